@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures.  Run ONCE in the build container:
+
+    python tests/golden/make_golden.py
+
+Needs /root/reference (the bundled TUM frames, standalone/rgb-d) and cv2 (genuine
+OpenCV 4.13).  Nothing here runs on the GPU box; only its outputs travel:
+
+  frames.npz        the reference's five bundled 640x480 RGB-D frames (data, re-encoded)
+  cv2_stages.json   sha256 of every genuine-OpenCV preprocessing stage output per frame
+                    (IPP disabled => OpenCV's portable code path), plus the
+                    IPP-enabled DT deviation for the record
+  numpy_pins.npz    an INDEPENDENT numpy restatement of the residual (Catmull-Rom bicubic,
+                    closed-form Jacobian) evaluated on pair 1->3, and scipy least_squares
+                    optima for 1->3 and 1->5 (sanity anchors, different optimiser)
+  solver_golden.npz outputs of the C++ oracle (Ceres restatement) for all 20 ordered pairs:
+                    regression pins for the GPU parity tests
+"""
+import hashlib
+import json
+import os
+import sys
+
+import cv2
+import numpy as np
+import scipy.optimize
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+REF = "/root/reference/standalone/rgb-d/"
+K = (525.0, 525.0, 319.5, 239.5)  # standalone_edge_align.cpp:152
+ZSCALE = 5000.0                   # standalone_edge_align.cpp:160
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def cv2_stages(bgr, depth):
+    """The reference's OpenCV call sequence (utils.cpp:38-83, 201-281), genuine cv2."""
+    out = {}
+    blur = cv2.GaussianBlur(bgr, (3, 3), 0, 0, borderType=cv2.BORDER_DEFAULT)
+    gray = cv2.cvtColor(blur, cv2.COLOR_RGB2GRAY)
+    lap8 = cv2.convertScaleAbs(cv2.Laplacian(gray, cv2.CV_16S, ksize=3, scale=1, delta=0, borderType=cv2.BORDER_DEFAULT))
+    B = np.where(lap8 > 35, 0, 255).astype(np.uint8)
+    Bf = cv2.medianBlur(B, 3)
+    dist = cv2.distanceTransform(Bf, cv2.DIST_L2, 3)
+    nd = cv2.normalize(dist, None, 0, 1.0, cv2.NORM_MINMAX)
+    nd255 = cv2.normalize(dist, None, 0, 255.0, cv2.NORM_MINMAX)
+    vs, us = np.nonzero((lap8 > 35) & (depth > 0))
+    uvd = np.stack([us, vs, depth[vs, us]], 1).astype(np.int32)
+    out.update(blur=blur, gray=gray, lap8=lap8, mask=B, median=Bf, dt_raw=dist, dt_norm=nd, dt_norm255=nd255, uvd=uvd)
+    out["half_bgr"] = cv2.resize(bgr, None, fx=0.5, fy=0.5)
+    out["half_depth"] = cv2.resize(depth, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST)
+    out["box3"] = cv2.blur(bgr, (3, 3))
+    return out
+
+
+# ---- independent numpy restatement of the residual (not the C++ oracle) ----------
+def np_residual(xyz, dt, pose7, want_J=False):
+    q = pose7[:4]; t = pose7[4:]
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    Y = xyz @ R.T
+    p = Y + t
+    u = K[0] * p[:, 0] / p[:, 2] + K[2]
+    v = K[1] * p[:, 1] / p[:, 2] + K[3]
+    H, W = dt.shape
+    iu = np.floor(u).astype(int); iv = np.floor(v).astype(int)
+    fu = u - iu; fv = v - iv
+    D = dt.astype(np.float64)
+
+    def wts(s):  # Catmull-Rom basis and derivative
+        w0 = 0.5 * (-s**3 + 2 * s**2 - s); w1 = 0.5 * (3 * s**3 - 5 * s**2 + 2)
+        w2 = 0.5 * (-3 * s**3 + 4 * s**2 + s); w3 = 0.5 * (s**3 - s**2)
+        d0 = 0.5 * (-3 * s**2 + 4 * s - 1); d1 = 0.5 * (9 * s**2 - 10 * s)
+        d2 = 0.5 * (-9 * s**2 + 8 * s + 1); d3 = 0.5 * (3 * s**2 - 2 * s)
+        return np.stack([w0, w1, w2, w3]), np.stack([d0, d1, d2, d3])
+    wu, du = wts(fu); wv, dv = wts(fv)
+    f = np.zeros(len(u)); fdu = np.zeros(len(u)); fdv = np.zeros(len(u))
+    for a in range(4):
+        xi = np.clip(iu - 1 + a, 0, W - 1)
+        for b in range(4):
+            yi = np.clip(iv - 1 + b, 0, H - 1)
+            pix = D[yi, xi]
+            f += wu[a] * wv[b] * pix; fdu += du[a] * wv[b] * pix; fdv += wu[a] * dv[b] * pix
+    if not want_J:
+        return f
+    iz = 1.0 / p[:, 2]
+    g = np.stack([fdu * K[0] * iz, fdv * K[1] * iz, -(fdu * K[0] * p[:, 0] + fdv * K[1] * p[:, 1]) * iz * iz], 1)
+    J = np.concatenate([2.0 * np.cross(Y, g), g], 1)
+    return f, J
+
+
+def rotvec_pose(x6):
+    th = np.linalg.norm(x6[:3])
+    q = np.array([1.0, 0, 0, 0]) if th == 0 else np.concatenate([[np.cos(th / 2)], np.sin(th / 2) * x6[:3] / th])
+    return np.concatenate([q, x6[3:]])
+
+
+def main():
+    cv2.ipp.setUseIPP(False)
+    frames_bgr, frames_depth = [], []
+    for i in range(1, 6):
+        frames_bgr.append(cv2.imread(REF + "rgb/%d.png" % i))
+        frames_depth.append(cv2.imread(REF + "depth/%d.png" % i, cv2.IMREAD_ANYDEPTH))
+    bgr = np.stack(frames_bgr); depth = np.stack(frames_depth)
+    np.savez_compressed(os.path.join(HERE, "frames.npz"), bgr=bgr, depth=depth, K=np.array(K), zscale=ZSCALE)
+
+    stages = {"cv2_version": cv2.__version__, "ipp": False, "frames": []}
+    for i in range(5):
+        s = cv2_stages(bgr[i], depth[i])
+        rec = {k: sha(v) for k, v in s.items()}
+        rec["n_points"] = int(len(s["uvd"])); rec["n_edge_now"] = int((s["median"] == 0).sum())
+        rec["dt_raw_max"] = float(s["dt_raw"].max())
+        cv2.ipp.setUseIPP(True)
+        d_ipp = cv2.distanceTransform(s["median"], cv2.DIST_L2, 3)
+        cv2.ipp.setUseIPP(False)
+        rec["dt_raw_ipp_max_abs_dev"] = float(np.abs(d_ipp - s["dt_raw"]).max())
+        stages["frames"].append(rec)
+    with open(os.path.join(HERE, "cv2_stages.json"), "w") as f:
+        json.dump(stages, f, indent=1)
+
+    # ---- independent numpy + scipy pins (pair 1->3 and 1->5, stride 30) -------------
+    pins = {}
+    xyz, _ = O.get_aX(bgr[0], depth[0], K, ZSCALE)          # point list itself is pinned by cv2 'uvd' hash
+    q = np.array([0.9999, 0.005, -0.008, 0.006]); q /= np.linalg.norm(q)
+    xpert = np.concatenate([q, [0.01, -0.02, 0.015]])
+    for j in (3, 5):
+        dt = cv2.normalize(cv2.distanceTransform(cv2_stages(bgr[j - 1], depth[j - 1])["median"], cv2.DIST_L2, 3), None, 0, 1.0, cv2.NORM_MINMAX)
+        sub = xyz[::30]
+        r0 = np_residual(sub, dt, np.array([1.0, 0, 0, 0, 0, 0, 0]))
+        r1, J1 = np_residual(sub, dt, xpert, want_J=True)
+        pins["np_r_identity_1_%d" % j] = r0; pins["np_r_pert_1_%d" % j] = r1; pins["np_J_pert_1_%d" % j] = J1
+        res = scipy.optimize.least_squares(lambda x6: np_residual(sub, dt, rotvec_pose(x6)), np.zeros(6), loss="cauchy",
+                                           f_scale=1.0, xtol=1e-12, ftol=1e-12, gtol=1e-12)
+        pins["scipy_pose_1_%d" % j] = rotvec_pose(res.x); pins["scipy_cost_1_%d" % j] = res.cost
+        print("scipy 1->%d" % j, rotvec_pose(res.x), res.cost)
+    pins["xpert"] = xpert
+    np.savez_compressed(os.path.join(HERE, "numpy_pins.npz"), **pins)
+
+    # ---- C++ oracle outputs for all 20 ordered pairs (regression pins for GPU parity) ----
+    gold = {}
+    I7 = np.array([1.0, 0, 0, 0, 0, 0, 0])
+    pts = [O.get_aX(bgr[i], depth[i], K, ZSCALE)[0] for i in range(5)]
+    dts = [O.get_distance_transform(bgr[i])[0] for i in range(5)]
+    for a in range(5):
+        for b in range(5):
+            if a == b:
+                continue
+            for loss, lname in ((O.LOSS_CAUCHY, "cauchy"), (O.LOSS_TRIVIAL, "trivial")):
+                o = O.default_options(loss_type=loss, loss_scale=1.0)
+                pose, s, tr = O.solve(pts[a], dts[b], K, I7, stride=30, options=o)
+                key = "%d_%d_%s" % (a + 1, b + 1, lname)
+                gold["pose_" + key] = pose
+                gold["summary_" + key] = np.array([s["initial_cost"], s["final_cost"], s["iterations"], s["accepted"], s["rejected"], s["termination"]])
+                gold["trace_cost_" + key] = tr[:, 0]
+            e = O.evaluate(pts[a], dts[b], K, xpert, stride=30, options=O.default_options(loss_type=O.LOSS_CAUCHY))
+            gold["eval_r_%d_%d" % (a + 1, b + 1)] = e["raw"]; gold["eval_sums_%d_%d" % (a + 1, b + 1)] = e["sums"]
+    # stride 1 full solve for the shipped configuration 1->3
+    pose, s, tr = O.solve(pts[0], dts[2], K, I7, stride=1)
+    gold["pose_1_3_cauchy_stride1"] = pose
+    gold["summary_1_3_cauchy_stride1"] = np.array([s["initial_cost"], s["final_cost"], s["iterations"], s["accepted"], s["rejected"], s["termination"]])
+    print("1->3 stride1", pose, s)
+    np.savez_compressed(os.path.join(HERE, "solver_golden.npz"), **gold)
+    for f in ("frames.npz", "cv2_stages.json", "numpy_pins.npz", "solver_golden.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()
