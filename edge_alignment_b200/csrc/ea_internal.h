@@ -1,0 +1,101 @@
+// Internal host-side declarations shared by the .cu translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "ea_device.cuh"
+
+struct EaSolveArgs {
+  const EaLevelDesc* ref_desc;  // [ref slots][EA_MAX_LEVELS]
+  const EaLevelDesc* now_desc;  // [now slots][EA_MAX_LEVELS]
+  const int32_t* ref_slots;     // [n_pairs] device
+  const int32_t* now_slots;     // [n_pairs] device
+  const int32_t* pose_index;    // [n_pairs] device or null (identity)
+  double* poses;                // [*][7] device, in/out
+  ea_summary* summaries;        // [n_pairs][n_levels] device or null
+  int n_pairs, n_levels, coarsest, finest;
+  double inv_depth_scale;
+  EaLevelGeom ref_geom[EA_MAX_LEVELS];
+  EaLevelGeom now_geom[EA_MAX_LEVELS];
+  int ref_cap[EA_MAX_LEVELS];   // point-list capacity per level (guards a truncated list)
+  ea_solve_params sp;
+};
+
+cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm_count, cudaStream_t stream);
+cudaError_t ea_launch_eval_points(const EaLevelDesc& rd, const EaLevelDesc& nd, const EaLevelGeom& rg,
+                                  const EaLevelGeom& ng, double inv_depth_scale, const ea_solve_params& sp,
+                                  const double* d_pose7, int n_res, double* d_raw, double* d_res, double* d_jac,
+                                  int* d_failed, cudaStream_t stream);
+cudaError_t ea_launch_eval_sums(const EaLevelDesc& rd, const EaLevelDesc& nd, const EaLevelGeom& rg,
+                                const EaLevelGeom& ng, double inv_depth_scale, const ea_solve_params& sp,
+                                const double* d_pose7, int n_res, int n_blocks, double* d_sums, cudaStream_t stream);
+
+// ---- preprocessing (ea_preprocess.cu) ---------------------------------------------------------------
+struct EaPrepLevel {            // device pointers of one pyramid level, slot-major pools
+  uint8_t* bgr;                 // [slots][h][w][3]   (level 0: null, the caller's input is read directly)
+  uint16_t* depth;              // [slots][h][w]      (level 0: null)
+  uint32_t* edge_bits;          // [slots][h][words]  raw Laplacian>threshold mask, 1 bit / pixel
+  uint32_t* ref_bits;           // [slots][h][words]  edge & depth>0
+  float* dt;                    // [slots][h][w]
+  float4* pts;                  // [slots][cap]
+  int w, h, words, cap;
+};
+struct EaPrepArgs {
+  EaPrepLevel lv[EA_MAX_LEVELS];
+  int n_levels;
+  const int32_t* slots;         // [n] device: destination slot of frame i
+  const uint8_t* in_bgr;        // [n][h0][w0][3]
+  const uint16_t* in_depth;     // [n][h0][w0] or null
+  int* n_pts;                   // [slots][EA_MAX_LEVELS]
+  unsigned* dt_minmax;          // [slots][EA_MAX_LEVELS][2]  (min,max of the fixed-point DT)
+  int* overflow;                // single flag: some point list was truncated
+  int n, roles, grad_threshold, use_median, dt_normalize;
+};
+// enqueue the whole preprocessing pipeline for n frames; returns number of kernel launches via *launches
+cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches);
+cudaError_t ea_launch_unpack_mask(const uint32_t* bits, int w, int h, int words, int median, uint8_t* out,
+                                  cudaStream_t stream);
+
+// ---- host-side objects behind the opaque ABI handles ------------------------------------------------
+struct ea_context {
+  int device = 0, sm_count = 0, cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t launches = 0;
+  // small scratch
+  double* d_pose = nullptr;      // [7]
+  int* d_failed = nullptr;
+  double* d_sums = nullptr;      // [max blocks][EA_SUMS]
+  int32_t* d_idx = nullptr;      // scratch slot indices
+  size_t idx_cap = 0;
+  void* d_tmp = nullptr;
+  size_t tmp_cap = 0;
+};
+
+struct ea_frameset {
+  ea_context* ctx = nullptr;
+  ea_frame_params p;
+  int n_slots = 0;
+  EaPrepLevel lv[EA_MAX_LEVELS];
+  EaLevelGeom geom[EA_MAX_LEVELS];
+  EaLevelDesc* d_desc = nullptr;          // [n_slots][EA_MAX_LEVELS]
+  std::vector<EaLevelDesc> h_desc;
+  int* d_npts = nullptr;                  // [n_slots][EA_MAX_LEVELS]
+  unsigned* d_minmax = nullptr;
+  int* d_overflow = nullptr;
+  uint8_t* stage_bgr = nullptr;           // [n_slots][h][w][3]  (host-upload staging)
+  uint16_t* stage_depth = nullptr;
+  std::vector<void*> allocs;
+};
+
+
+int ea_fail(int code, const char* fmt, ...);
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return ea_fail(EA_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+int ea_ensure_tmp(ea_context* c, size_t bytes);
+int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const uint16_t* d_depth, int roles);

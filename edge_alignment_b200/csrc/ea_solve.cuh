@@ -1,0 +1,179 @@
+// Device-side Levenberg-Marquardt state machine (one thread) -- replaces ceres::Solve's
+// TrustRegionMinimizer + LevenbergMarquardtStrategy + DenseQRSolver for the 6-DoF problem
+// assembled at standalone_edge_align.cpp:265-286.  Works purely on the 27 normal-equation
+// sums + cost (SURVEY.md A.4 "normal-equation form"): (S H S + diag/radius) y = S b by 6x6
+// Cholesky in fp64 instead of Householder QR on the (n+6)x6 stacked Jacobian.
+#pragma once
+#include <cfloat>
+
+#include "ea_device.cuh"
+
+#define EA_CMD_EVAL 0
+#define EA_CMD_DONE 1
+
+
+struct EaLmState {
+  double x[7];        // accepted iterate
+  double cand[7];     // candidate under evaluation
+  double H[21], b[6]; // normal equations at x (corrected, unscaled, local)
+  double scale[6], diag[6];
+  double cost, initial_cost, radius, decrease_factor, model_cost_change;
+  int phase, iter, accepted, rejected, invalid_run, reuse_diag, evals, term;
+};
+
+__device__ inline void ea_quat_plus(const double* x, const double* d, double* out) {
+  // ceres::QuaternionParameterization::Plus -- delta is a half-angle vector, left multiplication
+  const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (n > 0.0) {
+    const double s = sin(n) / n, c = cos(n);
+    const double q0 = c, q1 = s * d[0], q2 = s * d[1], q3 = s * d[2];
+    out[0] = q0 * x[0] - q1 * x[1] - q2 * x[2] - q3 * x[3];
+    out[1] = q0 * x[1] + q1 * x[0] + q2 * x[3] - q3 * x[2];
+    out[2] = q0 * x[2] - q1 * x[3] + q2 * x[0] + q3 * x[1];
+    out[3] = q0 * x[3] + q1 * x[2] - q2 * x[1] + q3 * x[0];
+  } else {
+    out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3];
+  }
+}
+__device__ inline void ea_pose_plus(const double* x, const double* d, double* out) {
+  ea_quat_plus(x, d, out);
+  out[4] = x[4] + d[3]; out[5] = x[5] + d[4]; out[6] = x[6] + d[5];
+}
+__device__ inline int ea_tri(int a, int c) { return a * 6 - (a * (a - 1)) / 2 + (c - a); }  // a <= c
+
+__device__ inline double ea_gradient_max_norm(const EaLmState& S) {
+  // || x - Plus(x, -g) ||_inf  (trust_region_minimizer.cc, EvaluateGradientAndJacobian)
+  double ng[6], xp[7];
+#pragma unroll 1
+  for (int j = 0; j < 6; ++j) ng[j] = -S.b[j];
+  ea_pose_plus(S.x, ng, xp);
+  double m = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < 7; ++i) m = fmax(m, fabs(S.x[i] - xp[i]));
+  return m;
+}
+
+// LevenbergMarquardtStrategy::ComputeStep on the normal equations.  Returns false on an invalid step.
+__device__ inline bool ea_lm_compute_step(EaLmState& S, const ea_solve_params& sp, double* delta) {
+  double A[6][6], bs[6], y[6];
+#pragma unroll 1
+  for (int a = 0; a < 6; ++a) {
+    bs[a] = S.scale[a] * S.b[a];
+#pragma unroll 1
+    for (int c = a; c < 6; ++c) { A[a][c] = S.scale[a] * S.H[ea_tri(a, c)] * S.scale[c]; A[c][a] = A[a][c]; }
+  }
+  if (!S.reuse_diag) {
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) S.diag[j] = fmin(fmax(A[j][j], sp.min_lm_diagonal), sp.max_lm_diagonal);
+  }
+  S.reuse_diag = 1;
+  // L L^T = H_s + diag/radius   (keep H_s in the strict upper triangle of A for the model cost)
+  double L[6][6];
+  bool ok = true;
+#pragma unroll 1
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j][j] + S.diag[j] / S.radius;
+#pragma unroll 1
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }
+    d = sqrt(d);
+    L[j][j] = d;
+#pragma unroll 1
+    for (int i = j + 1; i < 6; ++i) {
+      double s = A[i][j];
+#pragma unroll 1
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      L[i][j] = s / d;
+    }
+  }
+  if (!ok) return false;
+#pragma unroll 1
+  for (int i = 0; i < 6; ++i) {
+    double s = bs[i];
+#pragma unroll 1
+    for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
+    y[i] = s / L[i][i];
+  }
+#pragma unroll 1
+  for (int i = 5; i >= 0; --i) {
+    double s = y[i];
+#pragma unroll 1
+    for (int k = i + 1; k < 6; ++k) s -= L[k][i] * y[k];
+    y[i] = s / L[i][i];
+    if (!isfinite(y[i])) ok = false;
+  }
+  if (!ok) return false;
+  // step = -y ; model_cost_change = -(step^T b_s + 1/2 step^T H_s step)
+  double lin = 0.0, quad = 0.0;
+#pragma unroll 1
+  for (int a = 0; a < 6; ++a) {
+    const double sa = -y[a];
+    lin += sa * bs[a];
+    double row = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c) row += A[a][c] * (-y[c]);
+    quad += sa * row;
+    delta[a] = sa * S.scale[a];  // undo the Jacobi column scaling
+  }
+  S.model_cost_change = -(lin + 0.5 * quad);
+  return S.model_cost_change > 0.0;
+}
+
+// Advance the minimiser after an evaluation of S.cand produced `sums`.  Returns EA_CMD_EVAL with a
+// new S.cand, or EA_CMD_DONE with S.term set and S.x the final iterate.
+static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sums, const ea_solve_params& sp) {
+  const bool fail = sums[27] > 0.0;
+  S.evals++;
+  if (S.phase == 0) {  // IterationZero
+    if (fail) { S.term = EA_TERM_FAILURE_EVAL_X0; S.cost = 0.0; S.initial_cost = 0.0; return EA_CMD_DONE; }
+#pragma unroll 1
+    for (int k = 0; k < 21; ++k) S.H[k] = sums[k];
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) S.b[k] = sums[21 + k];
+    S.cost = S.initial_cost = sums[28];
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) S.scale[j] = sp.jacobi_scaling ? 1.0 / (1.0 + sqrt(S.H[ea_tri(j, j)])) : 1.0;
+    if (ea_gradient_max_norm(S) <= sp.gradient_tolerance) { S.term = EA_TERM_CONVERGENCE_GRADIENT; return EA_CMD_DONE; }
+    S.radius = sp.initial_trust_region_radius; S.decrease_factor = 2.0; S.reuse_diag = 0;
+    S.iter = 0; S.phase = 1;
+  } else {
+    const double cand_cost = fail ? DBL_MAX : sums[28];
+    double sn = 0.0, xn = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < 7; ++i) { const double d = S.x[i] - S.cand[i]; sn += d * d; xn += S.x[i] * S.x[i]; }
+    sn = sqrt(sn); xn = sqrt(xn);
+    if (sn <= sp.parameter_tolerance * (xn + sp.parameter_tolerance)) { S.term = EA_TERM_CONVERGENCE_PARAMETER; return EA_CMD_DONE; }
+    const double cost_change = S.cost - cand_cost;
+    if (fabs(cost_change) <= sp.function_tolerance * S.cost) { S.term = EA_TERM_CONVERGENCE_FUNCTION; return EA_CMD_DONE; }
+    const double rel = fail ? -DBL_MAX : cost_change / S.model_cost_change;
+    if (rel > sp.min_relative_decrease) {  // HandleSuccessfulStep (the fused pass already holds J at x_new)
+#pragma unroll 1
+      for (int i = 0; i < 7; ++i) S.x[i] = S.cand[i];
+#pragma unroll 1
+      for (int k = 0; k < 21; ++k) S.H[k] = sums[k];
+#pragma unroll 1
+      for (int k = 0; k < 6; ++k) S.b[k] = sums[21 + k];
+      S.cost = cand_cost;
+      const double t = 2.0 * rel - 1.0;
+      S.radius = fmin(sp.max_trust_region_radius, S.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+      S.decrease_factor = 2.0; S.reuse_diag = 0; S.accepted++;
+      if (ea_gradient_max_norm(S) <= sp.gradient_tolerance) { S.term = EA_TERM_CONVERGENCE_GRADIENT; return EA_CMD_DONE; }
+    } else {  // HandleUnsuccessfulStep
+      S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diag = 1; S.rejected++;
+    }
+  }
+  for (;;) {
+    if (S.iter >= sp.max_num_iterations) { S.term = EA_TERM_NO_CONVERGENCE; return EA_CMD_DONE; }
+    if (S.radius < sp.min_trust_region_radius) { S.term = EA_TERM_CONVERGENCE_MIN_RADIUS; return EA_CMD_DONE; }
+    S.iter++;
+    double delta[6];
+    if (!ea_lm_compute_step(S, sp, delta)) {  // HandleInvalidStep
+      if (++S.invalid_run >= sp.max_consecutive_invalid_steps) { S.term = EA_TERM_FAILURE_INVALID_STEPS; return EA_CMD_DONE; }
+      S.radius *= 0.5; S.reuse_diag = 0; S.rejected++;
+      continue;
+    }
+    S.invalid_run = 0;
+    ea_pose_plus(S.x, delta, S.cand);
+    return EA_CMD_EVAL;
+  }
+}

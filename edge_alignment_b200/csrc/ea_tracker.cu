@@ -1,0 +1,136 @@
+// Multi-stream frame-to-keyframe tracker: the caller of the pose-solve path, re-stated from the reference's
+// consumer loop (src/ea.cpp:87-131) and SolveEA's setRefFrame / setNowFrame / setAsCERESProblem sequence
+// (src/ea.cpp:184-199), batched over n_streams independent cameras.  Every frame is preprocessed once
+// (its DT when it arrives, its edge points only if it becomes a key frame); poses are warm-started from the
+// previous frame and never leave the device between steps.
+#include <cstring>
+#include <new>
+
+#include "ea_internal.h"
+
+struct ea_tracker {
+  ea_context* ctx = nullptr;
+  ea_frameset* fs = nullptr;       // 2 * n_streams slots: stream s owns slots 2s and 2s+1
+  ea_solve_params sp;
+  int n_streams = 0, interval = 1, n_levels = 1;
+  int frame = 0;                   // frames seen so far
+  int key_parity = 0;              // slot parity currently holding the key frames
+  int32_t* d_slots[2] = {nullptr, nullptr};   // [n_streams] slot ids of parity 0 / 1
+  double* d_poses = nullptr;       // warm-start table [n_streams][7]
+  double* d_result = nullptr;      // poses of the latest step [n_streams][7]
+  double* d_identity = nullptr;    // [n_streams][7]
+  ea_summary* d_summaries = nullptr;
+};
+
+extern "C" {
+
+int ea_tracker_create(ea_context* ctx, const ea_frame_params* fp, const ea_solve_params* sp, int n_streams,
+                      int keyframe_interval, ea_tracker** out) {
+  if (!ctx || !fp || !sp || !out) return ea_fail(EA_ERR_INVALID_ARG, "ea_tracker_create: null argument");
+  *out = nullptr;
+  if (n_streams <= 0 || keyframe_interval <= 0) return ea_fail(EA_ERR_INVALID_ARG, "n_streams and keyframe_interval must be positive");
+  ea_tracker* t = new (std::nothrow) ea_tracker();
+  if (!t) return ea_fail(EA_ERR_INVALID_ARG, "out of host memory");
+  t->ctx = ctx; t->sp = *sp; t->n_streams = n_streams; t->interval = keyframe_interval; t->n_levels = fp->n_levels;
+  int rc = ea_frameset_create(ctx, fp, 2 * n_streams, &t->fs);
+  if (rc) { delete t; return rc; }
+  std::vector<int32_t> s0(n_streams), s1(n_streams);
+  std::vector<double> id(size_t(n_streams) * 7, 0.0);
+  for (int i = 0; i < n_streams; ++i) { s0[i] = 2 * i; s1[i] = 2 * i + 1; id[size_t(i) * 7] = 1.0; }
+  CU(cudaMalloc((void**)&t->d_slots[0], n_streams * sizeof(int32_t)));
+  CU(cudaMalloc((void**)&t->d_slots[1], n_streams * sizeof(int32_t)));
+  CU(cudaMalloc((void**)&t->d_poses, id.size() * 8));
+  CU(cudaMalloc((void**)&t->d_result, id.size() * 8));
+  CU(cudaMalloc((void**)&t->d_identity, id.size() * 8));
+  CU(cudaMalloc((void**)&t->d_summaries, size_t(n_streams) * fp->n_levels * sizeof(ea_summary)));
+  CU(cudaMemcpy(t->d_slots[0], s0.data(), n_streams * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(t->d_slots[1], s1.data(), n_streams * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(t->d_identity, id.data(), id.size() * 8, cudaMemcpyHostToDevice));
+  *out = t;
+  return ea_tracker_reset(t);
+}
+
+int ea_tracker_destroy(ea_tracker* t) {
+  if (!t) return EA_OK;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->ctx->stream);
+  cudaFree(t->d_slots[0]); cudaFree(t->d_slots[1]); cudaFree(t->d_poses); cudaFree(t->d_result);
+  cudaFree(t->d_identity); cudaFree(t->d_summaries);
+  ea_frameset_destroy(t->fs);
+  delete t;
+  return EA_OK;
+}
+
+int ea_tracker_reset(ea_tracker* t) {
+  if (!t) return ea_fail(EA_ERR_INVALID_ARG, "null tracker");
+  cudaStream_t s = t->ctx->stream;
+  const size_t pb = size_t(t->n_streams) * 7 * 8;
+  t->frame = 0; t->key_parity = 0;
+  CU(cudaMemcpyAsync(t->d_poses, t->d_identity, pb, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(t->d_result, t->d_identity, pb, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemsetAsync(t->d_summaries, 0, size_t(t->n_streams) * t->n_levels * sizeof(ea_summary), s));
+  return EA_OK;
+}
+
+int ea_tracker_step_device(ea_tracker* t, const uint8_t* d_bgr, const uint16_t* d_depth) {
+  if (!t || !d_bgr) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
+  ea_context* c = t->ctx;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const bool first = (t->frame == 0);
+  const bool becomes_key = (t->frame % t->interval) == 0;
+  if (becomes_key && !d_depth) return ea_fail(EA_ERR_INVALID_ARG, "frame %d becomes a key frame and needs depth", t->frame);
+  // the new frame lands in the slots NOT holding the key frames
+  const int cur = first ? t->key_parity : (t->key_parity ^ 1);
+  const int roles = (first ? 0 : EA_ROLE_NOW) | (becomes_key ? EA_ROLE_REF : 0);
+  int rc = ea_preprocess_impl(t->fs, t->n_streams, t->d_slots[cur], d_bgr, d_depth, roles);
+  if (rc) return rc;
+  const size_t pb = size_t(t->n_streams) * 7 * 8;
+  if (!first) {
+    rc = ea_solve_batch_device(c, t->n_streams, t->fs, t->d_slots[t->key_parity], t->fs, t->d_slots[cur], t->d_poses, nullptr,
+                               &t->sp, t->d_summaries);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(t->d_result, t->d_poses, pb, cudaMemcpyDeviceToDevice, s));
+  }
+  if (becomes_key) {
+    t->key_parity = cur;
+    CU(cudaMemcpyAsync(t->d_poses, t->d_identity, pb, cudaMemcpyDeviceToDevice, s));  // pose is relative to the new key frame
+  }
+  t->frame++;
+  return EA_OK;
+}
+
+int ea_tracker_get_poses(ea_tracker* t, double* poses7, ea_summary* summaries) {
+  if (!t) return ea_fail(EA_ERR_INVALID_ARG, "null tracker");
+  cudaStream_t s = t->ctx->stream;
+  if (poses7) CU(cudaMemcpyAsync(poses7, t->d_result, size_t(t->n_streams) * 7 * 8, cudaMemcpyDeviceToHost, s));
+  if (summaries) CU(cudaMemcpyAsync(summaries, t->d_summaries, size_t(t->n_streams) * t->n_levels * sizeof(ea_summary), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return EA_OK;
+}
+
+int ea_tracker_step_host(ea_tracker* t, const uint8_t* bgr, const uint16_t* depth, double* poses7, ea_summary* summaries) {
+  if (!t || !bgr) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
+  ea_context* c = t->ctx;
+  ea_frameset* fs = t->fs;
+  CU(cudaSetDevice(c->device));
+  const size_t px = size_t(fs->p.width) * fs->p.height;
+  const int n = t->n_streams;
+  if (!fs->stage_bgr) CU(cudaMalloc((void**)&fs->stage_bgr, px * 3 * fs->n_slots));
+  if (depth && !fs->stage_depth) CU(cudaMalloc((void**)&fs->stage_depth, px * 2 * fs->n_slots));
+  CU(cudaMemcpyAsync(fs->stage_bgr, bgr, px * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  const bool becomes_key = (t->frame % t->interval) == 0;
+  if (depth && becomes_key) CU(cudaMemcpyAsync(fs->stage_depth, depth, px * 2 * n, cudaMemcpyHostToDevice, c->stream));
+  int rc = ea_tracker_step_device(t, fs->stage_bgr, (depth && becomes_key) ? fs->stage_depth : nullptr);
+  if (rc) return rc;
+  if (poses7 || summaries) return ea_tracker_get_poses(t, poses7, summaries);
+  return EA_OK;
+}
+
+int ea_tracker_frame_index(ea_tracker* t, int* n) {
+  if (!t || !n) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
+  *n = t->frame;
+  return EA_OK;
+}
+
+}  // extern "C"

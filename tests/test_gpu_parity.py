@@ -1,0 +1,291 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the
+CPU oracle on the same inputs and against the committed golden fixtures.
+
+Tolerances (BASELINE.json north_star):
+  * integer / byte / index work (masks, point lists, order, distance transform): bit exact
+  * per-point residuals: |gpu - oracle| <= 1e-5 * max(|r|, R_FLOOR)  (R_FLOOR: "relative" is meaningless as r -> 0
+    on an edge; 0.05 of the normalised DT range ~ 4 px)
+  * converged poses: 1e-4 rad, 1e-4 m
+"""
+import numpy as np
+import pytest
+
+from conftest import IDENTITY, rot_angle_between, sha
+
+pytestmark = pytest.mark.gpu
+R_FLOOR = 0.05
+
+
+@pytest.fixture(scope="module")
+def ea():
+    import edge_alignment_b200 as ea
+    return ea
+
+
+@pytest.fixture(scope="module")
+def ctx(ea):
+    c = ea.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def fs5(ea, ctx, frames):
+    """The five bundled frames preprocessed on the GPU for both roles (single level, reference defaults)."""
+    fs = ea.FrameSet(ctx, ea.frame_params(), 5)
+    fs.preprocess_host(np.arange(5), frames["bgr"], frames["depth"], ea.ROLE_BOTH)
+    yield fs
+    fs.close()
+
+
+# ---------------------------------------------------------------------------------------------- preprocessing
+@pytest.mark.parametrize("i", range(5))
+def test_preprocess_bit_exact(ea, fs5, frames, cv2_stages, oracle, i):
+    g = cv2_stages["frames"][i]
+    assert sha(fs5.edge_mask(i, 0, median=False)) == g["mask"]       # Laplacian>35 mask == genuine OpenCV
+    assert sha(fs5.edge_mask(i, 0, median=True)) == g["median"]      # medianBlur 3
+    pts = fs5.points(i)
+    assert len(pts) == g["n_points"]
+    assert sha(pts[:, :3].astype(np.int32)) == g["uvd"]              # ordered compaction == get_aX order
+    assert np.all(pts[:, 3] == 1.0)
+    dt = fs5.dt(i)
+    assert sha(dt) == g["dt_norm"]                                   # chamfer DT + normalize, bit exact
+    odt, _ = oracle.get_distance_transform(frames["bgr"][i])
+    np.testing.assert_array_equal(dt, odt)
+
+
+def test_preprocess_pyramid_and_variants(ea, ctx, frames, oracle):
+    O = oracle
+    fp = ea.frame_params(n_levels=3)
+    fs = ea.FrameSet(ctx, fp, 2)
+    try:
+        fs.preprocess_host([1, 0], frames["bgr"][[0, 2]], frames["depth"][[0, 2]], ea.ROLE_BOTH)   # scrambled slots
+        for slot, fi in ((1, 0), (0, 2)):
+            bgr, dep = frames["bgr"][fi], frames["depth"][fi]
+            for l in range(3):
+                w, h, K = fs.level_geometry(l)
+                assert (w, h) == (640 >> l, 480 >> l)
+                s = 1.0 / (1 << l)
+                np.testing.assert_allclose(K, (525 * s, 525 * s, (319.5 + .5) * s - .5, (239.5 + .5) * s - .5), rtol=0, atol=1e-12)
+                xyz, uvd = O.get_aX(bgr, dep, K)
+                np.testing.assert_array_equal(fs.points(slot, l)[:, :3].astype(np.int32), uvd)
+                odt, omask = O.get_distance_transform(bgr)
+                np.testing.assert_array_equal(fs.edge_mask(slot, l, median=True), omask)
+                np.testing.assert_array_equal(fs.dt(slot, l), odt)
+                bgr, dep = O.half_linear(bgr), O.half_nearest(dep)
+    finally:
+        fs.close()
+    # no median, [0,255] normalisation, other threshold
+    fs = ea.FrameSet(ctx, ea.frame_params(use_median=0, dt_normalize=ea.NORM_255, grad_threshold=60), 1)
+    try:
+        fs.preprocess_host([0], frames["bgr"][3:4], frames["depth"][3:4], ea.ROLE_BOTH)
+        odt, omask = O.get_distance_transform(frames["bgr"][3], thresh=60, use_median=0, norm_mode=2)
+        np.testing.assert_array_equal(fs.dt(0), odt)
+        _, uvd = O.get_aX(frames["bgr"][3], frames["depth"][3], frames["K"], thresh=60)
+        np.testing.assert_array_equal(fs.points(0)[:, :3].astype(np.int32), uvd)
+    finally:
+        fs.close()
+
+
+def test_preprocess_edge_cases(ea, ctx, oracle):
+    O = oracle
+    rng = np.random.default_rng(3)
+    for (w, h) in ((64, 48), (40, 24), (352, 16), (1280, 32)):   # ragged widths (not multiples of 32), multi-chunk rows
+        fp = ea.frame_params(width=w, height=h, fx=50.0, fy=50.0, cx=w / 2.0, cy=h / 2.0, max_points=w * h)
+        fs = ea.FrameSet(ctx, fp, 3)
+        try:
+            bgr = np.stack([rng.integers(0, 256, (h, w, 3)), np.full((h, w, 3), 90), rng.integers(0, 256, (h, w, 3))]).astype(np.uint8)
+            bgr[2] = (bgr[2] // 64) * 64
+            dep = rng.integers(0, 3, (3, h, w)).astype(np.uint16) * 700   # many invalid (zero) depths
+            fs.preprocess_host([0, 1, 2], bgr, dep, ea.ROLE_BOTH)
+            for s in range(3):
+                odt, omask = O.get_distance_transform(bgr[s])
+                np.testing.assert_array_equal(fs.edge_mask(s, 0, median=True), omask)
+                np.testing.assert_array_equal(fs.dt(s), odt)
+                _, uvd = O.get_aX(bgr[s], dep[s], (50.0, 50.0, w / 2.0, h / 2.0))
+                assert fs.num_points(s) == len(uvd)
+                np.testing.assert_array_equal(fs.points(s)[:, :3].astype(np.int32).reshape(-1, 3), uvd.reshape(-1, 3))
+            assert fs.num_points(1) == 0 and np.all(fs.dt(1) == 0)     # flat image: no edges, DT saturates then normalises to 0
+        finally:
+            fs.close()
+    # capacity overflow is reported, not silent
+    fp = ea.frame_params(width=64, height=48, max_points=100)
+    fs = ea.FrameSet(ctx, fp, 1)
+    try:
+        bgr = rng.integers(0, 256, (1, 48, 64, 3)).astype(np.uint8)
+        fs.preprocess_host([0], bgr, np.full((1, 48, 64), 1000, np.uint16), ea.ROLE_BOTH)
+        with pytest.raises(ea.EaError) as e:
+            fs.num_points(0)
+        assert e.value.code == 4
+    finally:
+        fs.close()
+
+
+# ------------------------------------------------------------------------------------------------- evaluation
+def _assert_residual_parity(gpu_raw, ref_raw):
+    tol = 1e-5 * np.maximum(np.abs(ref_raw), R_FLOOR)
+    bad = np.abs(gpu_raw - ref_raw) > tol
+    assert not bad.any(), "max excess %g" % (np.abs(gpu_raw - ref_raw) / tol).max()
+
+
+@pytest.mark.parametrize("a,b", [(1, 3), (1, 5), (3, 1), (4, 2)])
+@pytest.mark.parametrize("stride", [30, 1])
+def test_eval_parity(ea, ctx, fs5, frames, oracle, numpy_pins, a, b, stride):
+    O = oracle
+    K = frames["K"]
+    xyz, _ = O.get_aX(frames["bgr"][a - 1], frames["depth"][a - 1], K)
+    dt, _ = O.get_distance_transform(frames["bgr"][b - 1])
+    for pose in (IDENTITY, numpy_pins["xpert"]):
+        for loss, scale in ((ea.LOSS_TRIVIAL, 1.0), (ea.LOSS_CAUCHY, 1.0), (ea.LOSS_HUBER, 0.1)):
+            sp = ea.solve_params(point_stride=stride, loss_type=loss, loss_scale=scale)
+            g = ctx.eval(fs5, a - 1, fs5, b - 1, pose, sp)
+            o = O.evaluate(xyz, dt, K, pose, stride=stride, options=O.default_options(loss_type=loss, loss_scale=scale))
+            assert g["failed"] == 0 and g["n_residuals"] == len(o["raw"])
+            _assert_residual_parity(g["raw"], o["raw"])
+            _assert_residual_parity(g["residuals"], o["residuals"])
+            jscale = np.abs(o["J"]).max(0)
+            assert (np.abs(g["J"] - o["J"]) <= 2e-5 * jscale + 2e-5 * np.abs(o["J"])).all()
+            # 27 normal-equation sums + cost through the production reduction tree
+            np.testing.assert_allclose(g["cost"], o["cost"], rtol=2e-6)
+            np.testing.assert_allclose(g["H"], o["H"], rtol=0, atol=2e-6 * np.abs(np.diag(o["H"])).max())
+            np.testing.assert_allclose(g["b"], o["b"], rtol=0, atol=2e-6 * (np.abs(o["J"]) * np.abs(o["residuals"])[:, None]).sum(0).max())
+
+
+def test_eval_bypass_hooks_and_xyz_mode(ea, ctx, frames, oracle, numpy_pins):
+    """Oracle-made inputs through ea_frameset_set_points / set_dt: pixel stream and fp32 XYZ stream."""
+    O = oracle
+    K = frames["K"]
+    xyz, uvd = O.get_aX(frames["bgr"][0], frames["depth"][0], K)
+    dt, _ = O.get_distance_transform(frames["bgr"][2])
+    fs = ea.FrameSet(ctx, ea.frame_params(), 2)
+    try:
+        fs.set_dt(0, dt); fs.set_dt(1, dt)
+        fs.set_points(0, ea.pixel_points(uvd), mode=ea.POINTS_PIXEL)
+        p4 = np.ones((len(xyz), 4), np.float32); p4[:, :3] = xyz
+        fs.set_points(1, p4, mode=ea.POINTS_XYZ)
+        sp = ea.solve_params(point_stride=7, loss_type=ea.LOSS_TRIVIAL)
+        o = O.evaluate(xyz, dt, K, numpy_pins["xpert"], stride=7, options=O.default_options(loss_type=0))
+        g = ctx.eval(fs, 0, fs, 0, numpy_pins["xpert"], sp)
+        _assert_residual_parity(g["raw"], o["raw"])
+        # XYZ points are rounded to fp32 (6e-8 relative): compare against the oracle on the same rounded points
+        o32 = O.evaluate(p4[:, :3].astype(np.float64), dt, K, numpy_pins["xpert"], stride=7, options=O.default_options(loss_type=0))
+        g = ctx.eval(fs, 1, fs, 0, numpy_pins["xpert"], sp)
+        _assert_residual_parity(g["raw"], o32["raw"])
+    finally:
+        fs.close()
+
+
+def test_eval_out_of_image_and_z_guard(ea, ctx, oracle):
+    O = oracle
+    rng = np.random.default_rng(5)
+    w, h = 64, 48
+    K = (40.0, 40.0, 31.5, 23.5)
+    fs = ea.FrameSet(ctx, ea.frame_params(width=w, height=h, fx=K[0], fy=K[1], cx=K[2], cy=K[3], depth_scale=1000.0, max_points=w * h), 1)
+    try:
+        dt = rng.random((h, w)).astype(np.float32)
+        fs.set_dt(0, dt)
+        # points that project far outside, onto the border band, and behind the camera (no bounds test in utils.h:77)
+        p4 = np.ones((400, 4), np.float32)
+        p4[:, 0] = rng.uniform(-3, 3, 400); p4[:, 1] = rng.uniform(-3, 3, 400); p4[:, 2] = rng.uniform(0.5, 2.0, 400)
+        p4[::7, 2] *= -1
+        fs.set_points(0, p4, mode=ea.POINTS_XYZ)
+        sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_TRIVIAL)
+        pose = np.array([0.9987502603949663, 0.03, -0.02, 0.03, 0.1, -0.1, 0.2]); pose[:4] /= np.linalg.norm(pose[:4])
+        g = ctx.eval(fs, 0, fs, 0, pose, sp)
+        o = O.evaluate(p4[:, :3].astype(np.float64), dt, K, pose, stride=1, options=O.default_options(loss_type=0))
+        assert g["failed"] == 0 and o["ok"]
+        np.testing.assert_allclose(g["raw"], o["raw"], rtol=0, atol=2e-5)   # random field: slope ~1/px, fp64 frac keeps it tight
+        # |z'| < 0.01 => evaluation failure (utils.h:70-73)
+        p4[5, :3] = (0.1, 0.1, 0.005 - pose[6])
+        fs.set_points(0, p4, mode=ea.POINTS_XYZ)
+        g = ctx.eval(fs, 0, fs, 0, np.array([1, 0, 0, 0, 0.1, -0.1, pose[6]]), sp)
+        assert g["failed"] == 1
+        poses, S = ctx.solve_batch(fs, [0], fs, [0], [np.array([1, 0, 0, 0, 0.1, -0.1, pose[6]])], sp)
+        assert S[0][0]["termination_name"] == "FAILURE_EVAL_X0"
+    finally:
+        fs.close()
+
+
+# ------------------------------------------------------------------------------------------------------ solve
+def _check_solution(pose, summ, gpose, gsum, it_slack=2):
+    assert rot_angle_between(pose[:4], gpose[:4]) < 1e-4, "rotation off by %g rad" % rot_angle_between(pose[:4], gpose[:4])
+    assert np.abs(pose[4:] - gpose[4:]).max() < 1e-4
+    assert abs(summ["final_cost"] - gsum[1]) <= 1e-5 * gsum[1]
+    assert abs(summ["initial_cost"] - gsum[0]) <= 1e-5 * gsum[0]
+    assert abs(summ["iterations"] - int(gsum[2])) <= it_slack
+    assert summ["termination"] == int(gsum[5])
+
+
+@pytest.mark.parametrize("loss", ["cauchy", "trivial"])
+def test_solve_all_bundled_pairs_vs_golden(ea, ctx, fs5, solver_golden, loss):
+    """All 20 ordered pairs of the bundled frames in ONE batched launch (stride 30, Ceres defaults;
+    edge_align_test1 is the pair 1->3) against the oracle's frozen results."""
+    pairs = [(a, b) for a in range(5) for b in range(5) if a != b]
+    sp = ea.solve_params(point_stride=30, loss_type=ea.LOSS_CAUCHY if loss == "cauchy" else ea.LOSS_TRIVIAL)
+    poses, S = ctx.solve_batch(fs5, [p[0] for p in pairs], fs5, [p[1] for p in pairs], None, sp)
+    for i, (a, b) in enumerate(pairs):
+        key = "%d_%d_%s" % (a + 1, b + 1, loss)
+        _check_solution(poses[i], S[i][0], solver_golden["pose_" + key], solver_golden["summary_" + key])
+        assert S[i][0]["n_residuals"] == (fs5.num_points(a) + 29) // 30
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_solve_cluster_sizes_and_stride1(ea, ctx, fs5, solver_golden, cluster):
+    sp = ea.solve_params(point_stride=1, cluster_size=cluster)
+    poses, S = ctx.solve_batch(fs5, [0], fs5, [2], None, sp)
+    _check_solution(poses[0], S[0][0], solver_golden["pose_1_3_cauchy_stride1"], solver_golden["summary_1_3_cauchy_stride1"])
+    assert S[0][0]["n_residuals"] == 44458
+    sp30 = ea.solve_params(point_stride=30, cluster_size=cluster)
+    poses, S = ctx.solve_batch(fs5, [0, 0, 3], fs5, [2, 4, 1], None, sp30)
+    for i, key in enumerate(["1_3_cauchy", "1_5_cauchy", "4_2_cauchy"]):
+        _check_solution(poses[i], S[i][0], solver_golden["pose_" + key], solver_golden["summary_" + key])
+
+
+def test_solve_matches_live_oracle_pyramid_huber(ea, ctx, frames, oracle):
+    """3-level coarse-to-fine with Huber loss (the bench configuration) against the oracle run live."""
+    O = oracle
+    K = frames["K"]
+    fs = ea.FrameSet(ctx, ea.frame_params(n_levels=3), 5)
+    try:
+        fs.preprocess_host(np.arange(5), frames["bgr"], frames["depth"], ea.ROLE_BOTH)
+        sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=0.1)
+        pairs = [(0, 2), (0, 4), (2, 0), (3, 4)]
+        poses, S = ctx.solve_batch(fs, [p[0] for p in pairs], fs, [p[1] for p in pairs], None, sp)
+        cfg = O.pair_cfg(640, 480, K, n_levels=3, stride=1)
+        opts = O.default_options(loss_type=O.LOSS_HUBER, loss_scale=0.1)
+        for i, (a, b) in enumerate(pairs):
+            op, oS = O.align_pair(frames["bgr"][a], frames["depth"][a], frames["bgr"][b], cfg, IDENTITY, opts)
+            assert rot_angle_between(poses[i][:4], op[:4]) < 1e-4 and np.abs(poses[i][4:] - op[4:]).max() < 1e-4
+            for l in range(3):
+                assert S[i][l]["n_residuals"] == oS[l]["n_residuals"]
+                assert abs(S[i][l]["iterations"] - oS[l]["iterations"]) <= 2
+                assert abs(S[i][l]["final_cost"] - oS[l]["final_cost"]) <= 2e-5 * oS[l]["final_cost"]
+    finally:
+        fs.close()
+
+
+def test_solve_edge_cases(ea, ctx, frames):
+    fs = ea.FrameSet(ctx, ea.frame_params(), 2)
+    try:
+        flat = np.full((1, 480, 640, 3), 128, np.uint8)
+        fs.preprocess_host([0], flat, np.full((1, 480, 640), 5000, np.uint16), ea.ROLE_BOTH)
+        fs.preprocess_host([1], frames["bgr"][:1], frames["depth"][:1], ea.ROLE_BOTH)
+        # no reference points => level skipped, pose untouched
+        start = np.array([1.0, 0, 0, 0, 0.01, 0.02, 0.03])
+        poses, S = ctx.solve_batch(fs, [0], fs, [1], [start], ea.solve_params())
+        assert S[0][0]["termination_name"] == "SKIPPED_NO_POINTS" and np.array_equal(poses[0], start)
+        # a now-frame without edges: constant DT, zero gradient => immediate gradient convergence
+        poses, S = ctx.solve_batch(fs, [1], fs, [0], None, ea.solve_params())
+        assert S[0][0]["termination_name"] == "CONVERGENCE_GRADIENT" and np.array_equal(poses[0], IDENTITY)
+        # max_num_iterations is honoured
+        poses, S = ctx.solve_batch(fs, [1], fs, [1], [np.array([1.0, 0, 0, 0, 0.02, 0, 0])], ea.solve_params(max_num_iterations=3))
+        assert S[0][0]["iterations"] <= 3
+        # argument errors
+        with pytest.raises(ea.EaError):
+            ctx.solve_batch(fs, [0], fs, [5], None, ea.solve_params())
+        with pytest.raises(ea.EaError):
+            ctx.solve_batch(fs, [0], fs, [1], [np.array([2.0, 0, 0, 0, 0, 0, 0])], ea.solve_params())
+        with pytest.raises(ea.EaError):
+            ctx.solve_batch(fs, [0], fs, [1], None, ea.solve_params(point_stride=0))
+    finally:
+        fs.close()
