@@ -140,7 +140,8 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
   for (int l = 0; l < p->n_levels && rc == EA_OK; ++l) {
     EaPrepLevel& L = fs->lv[l];
     L.w = p->width >> l; L.h = p->height >> l; L.words = (L.w + 31) / 32;
-    L.cap = std::max(64, std::min(L.w * L.h, cap0 >> (2 * l)));
+    // coarse levels have a much higher edge density (and are small): give them every pixel
+    L.cap = (l == 0) ? std::max(64, std::min(L.w * L.h, cap0)) : std::min(L.w * L.h, std::max(cap0, 64));
     const size_t px = size_t(L.w) * L.h;
     L.bgr = nullptr; L.depth = nullptr;
     if (l > 0) {
