@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pair alignments/sec at 640x480 (BASELINE.json metric) on BASELINE configs[1]:
+synthetic TUM-fr1-shaped 640x480 RGB-D sequences, frame-to-keyframe tracking, 3-level pyramid, Huber loss.
+
+One *step* = every one of S independent camera streams receives one new frame, which is preprocessed
+(edge mask -> distance-transform pyramid; edge points too when it becomes a key frame) and aligned to the stream's
+key frame with the on-device LM solve (warm-started from the previous pose).  S alignments per step per GPU.
+
+  value  whole-job alignments/s with the frames already resident in HBM (device-timed, max over ranks)
+  e2e    the same through the tracker's HOST entry point: pinned-host -> device copy of every step's frames and a
+         device -> host read of the step's poses inside the timed region
+  roofline  dominant kernel = the fused residual/Jacobian/LM kernel; algorithmic bytes = 80 B per point-evaluation
+         (16 B float4 point stream + 64 B = 4x4 f32 DT gather) x point-evaluations per launch
+  cpu_baseline  the oracle (CPU restatement of the reference's Ceres/OpenCV path) on a bounded sample, all host cores
+
+`--impl reference` times that CPU restatement alone on the same workload shape (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+W, H = 640, 480
+N_LEVELS = 3
+HUBER_A = 0.1
+KEYFRAME_INTERVAL = 10
+BYTES_PER_POINT_EVAL = 80.0
+METRIC = "frame-pair alignments/sec at 640x480"
+
+
+def workload_name(streams):
+    return ("configs[1]: synthetic TUM-fr1-shaped 640x480 RGB-D sequences, frame-to-keyframe tracking "
+            "(key frame every %d frames), 3-level pyramid, Huber(%.1f), stride 1, Ceres-default LM; %d streams/GPU"
+            % (KEYFRAME_INTERVAL, HUBER_A, streams))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.samples = []; self._stop = threading.Event(); self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+                if self._stop.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(n_streams, steps, warmup, threads, make_frames):
+    """The reference's CPU path (oracle restatement) as a tracker over n_streams streams: returns
+    (alignments/s over the timed steps, seconds, total alignments)."""
+    from oracle import oracle as O
+    import synth
+    bgr, depth = make_frames(n_streams, warmup + steps + 1)
+    cfg = O.pair_cfg(W, H, synth.TUM_K, n_levels=N_LEVELS, stride=1)
+    opts = O.default_options(loss_type=O.LOSS_HUBER, loss_scale=HUBER_A)
+    poses = np.tile(np.array([1.0, 0, 0, 0, 0, 0, 0]), (n_streams, 1))
+    key = 0
+    T = bgr.shape[0]
+    flat_b = bgr.reshape(T * n_streams, H, W, 3); flat_d = depth.reshape(T * n_streams, H, W)
+    timed = 0.0
+    for t in range(1, warmup + steps + 1):
+        ref_idx = [key * n_streams + s for s in range(n_streams)]
+        now_idx = [t * n_streams + s for s in range(n_streams)]
+        poses, _, sec = O.align_batch(flat_b, flat_d, ref_idx, now_idx, cfg, poses, opts, n_threads=threads, include_preprocess=True)
+        if t > warmup:
+            timed += sec
+        if t % KEYFRAME_INTERVAL == 0:
+            key = t
+            poses = np.tile(np.array([1.0, 0, 0, 0, 0, 0, 0]), (n_streams, 1))
+    return n_streams * steps / timed, timed, n_streams * steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=296, help="camera streams per GPU (2 per SM)")
+    ap.add_argument("--cluster", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import torch
+    import synth
+
+    def make_frames_host(n_streams, n_frames, seed=1234):
+        dev = "cuda:%d" % local_rank if torch.cuda.is_available() else "cpu"   # GPU only synthesises the data
+        b, d, _ = synth.make_sequences(n_streams, n_frames, seed=seed, device=dev)
+        return b.cpu().numpy(), d.cpu().numpy()
+
+    # ------------------------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import oracle as O
+        O.build()
+        threads = O.hardware_threads()
+        n_streams = max(1, min(threads, 128))
+        t0 = time.time()
+        val, sec, n_al = cpu_reference_run(n_streams, args.steps, args.warmup, threads, make_frames_host)
+        out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "alignments/s", "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload_name(n_streams), "note": "CPU restatement of the reference's Ceres/OpenCV path "
+                          "(the reference itself needs Ceres+OpenCV C++, not installable here); bounded sample: one stream per host thread"},
+               "cpu_baseline": {"value": val, "unit": "alignments/s", "cores": threads, "kind": "port",
+                                "sample": "%d alignments (%d streams x %d steps), %.1f s" % (n_al, n_streams, args.steps, sec)},
+               "e2e": {"value": val, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0, "wall_s": time.time() - t0}
+        print(json.dumps(out))
+        return 0
+
+    # ------------------------------------------------------------------------------------------ our arm (GPU)
+    import edge_alignment_b200 as ea
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    S, K, Wm = args.streams, args.steps, args.warmup
+    T = Wm + K + 1
+    bgr_d, depth_d, _ = synth.make_sequences(S, T, seed=1234 + rank, device=dev)      # [T,S,h,w,3] / [T,S,h,w] resident in HBM
+    torch.cuda.synchronize()
+
+    ctx = ea.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    fp = ea.frame_params(n_levels=N_LEVELS)
+    sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=HUBER_A, cluster_size=args.cluster)
+    tracker = ea.Tracker(ctx, fp, sp, S, KEYFRAME_INTERVAL)
+    frame_b = W * H * 3 * S; frame_d = W * H * 2 * S
+
+    def run_device(first, last):
+        for t in range(first, last):
+            tracker.step_device(bgr_d.data_ptr() + t * frame_b, depth_d.data_ptr() + t * frame_d)
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------------------
+    tracker.reset()
+    run_device(0, Wm + 1)                       # frame 0 = key frame, then W warm-up steps
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ctx.profile_enable(True); ctx.profile_read()
+    l0 = ctx.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run_device(Wm + 1, T)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    prof = ctx.profile_read(); ctx.profile_enable(False)
+    clocks = sampler.stop()
+    if dist is not None:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * S * K / (ms * 1e-3)
+
+    # ---- accounting pass (untimed): point-evaluations per solve launch from the per-step summaries ------------
+    tracker.reset()
+    run_device(0, Wm + 1)
+    point_evals = 0; iters = 0; n_sum = 0; terms = {}
+    for t in range(Wm + 1, T):
+        run_device(t, t + 1)
+        _, Ss = tracker.poses()
+        for s in Ss:
+            point_evals += s.n_residuals * s.evaluations; iters += s.iterations; n_sum += 1
+            terms[s.termination] = terms.get(s.termination, 0) + 1
+    solve_ms_avg = prof["solve_ms"] / max(1, prof["n_solve"])
+    pe_per_launch = point_evals / max(1, K)
+    peak, peak_src = measured_peak_hbm()
+    achieved = pe_per_launch * BYTES_PER_POINT_EVAL / (solve_ms_avg * 1e-3) / 1e9 if solve_ms_avg > 0 else 0.0
+
+    # ---- e2e: host buffers through the tracker's host entry point --------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hb = torch.empty((T, S, H, W, 3), dtype=torch.uint8, pin_memory=True); hb.copy_(bgr_d)
+        hd = torch.empty((T, S, H, W), dtype=torch.uint16, pin_memory=True); hd.copy_(depth_d)
+        torch.cuda.synchronize()
+        tracker.reset()
+        for t in range(0, Wm + 1):
+            tracker.step_host(hb.data_ptr() + t * frame_b, hd.data_ptr() + t * frame_d, fetch=True)
+        barrier()
+        e0.record(stream)
+        for t in range(Wm + 1, T):
+            poses, _ = tracker.step_host(hb.data_ptr() + t * frame_b, hd.data_ptr() + t * frame_d, fetch=True)
+        e1.record(stream)
+        barrier()
+        ms_e = e0.elapsed_time(e1)
+        if dist is not None:
+            tms = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms_e = float(tms.item())
+        # depth only travels for frames that become key frames (1 in KEYFRAME_INTERVAL)
+        n_key = sum(1 for t in range(Wm + 1, T) if t % KEYFRAME_INTERVAL == 0)
+        h2d = (frame_b * K + frame_d * n_key) / K
+        d2h = S * (7 * 8 + N_LEVELS * 40)
+        e2e = {"value": world * S * K / (ms_e * 1e-3), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / K}
+        del hb, hd
+
+    if rank != 0:
+        return 0
+    # ---- CPU baseline (oracle restatement on the host cores, bounded sample) ---------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        threads = O.hardware_threads()
+        ns = max(1, min(threads, 128)); steps_cpu = 3
+        val, sec, n_al = cpu_reference_run(ns, steps_cpu, 0, threads, make_frames_host)
+        cpu = {"value": val, "unit": "alignments/s", "cores": threads, "kind": "port",
+               "sample": "%d alignments (%d streams x %d tracker steps, same generator), %.1f s of wall time" % (n_al, ns, steps_cpu, sec)}
+
+    out = {"metric": METRIC, "value": value, "unit": "alignments/s", "n_gpus": world, "steps": K, "warmup": Wm,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+           "data": "synthetic",
+           "config": {"workload": workload_name(S), "streams_per_gpu": S, "cluster_size": args.cluster,
+                      "l2": "every step reads %d MB of new frames per GPU (> 126 MB L2): inputs larger than L2" % (frame_b // 2**20),
+                      "point_evals_per_s": world * point_evals / (ms * 1e-3), "mean_lm_iterations_per_level": iters / max(1, n_sum),
+                      "terminations": {ea._lib.TERMINATION.get(k, str(k)): v for k, v in terms.items()}},
+           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "kernel": "ea_k_solve_batch", "peak_source": peak_src, "kernel_ms_per_launch": solve_ms_avg,
+                        "point_evals_per_launch": pe_per_launch, "bytes_per_point_eval": BYTES_PER_POINT_EVAL,
+                        "kernel_share_of_step": (prof["solve_ms"] / ms) if ms > 0 else None,
+                        "preprocess_ms_per_step": prof["preprocess_ms"] / max(1, K)},
+           "cpu_baseline": cpu}
+    print(json.dumps(out))
+    tracker.close(); ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "ea_host_alloc": (_i, [C.POINTER(_vp), C.c_size_t]),
     "ea_host_free": (_i, [_vp]),
     "ea_launch_count": (_i, [_vp, C.POINTER(C.c_int64)]),
+    "ea_profile_enable": (_i, [_vp, _i]),
+    "ea_profile_read": (_i, [_vp, _f64p, _pi, _f64p, _pi]),
     "ea_frame_params_default": (None, [C.POINTER(FrameParams)]),
     "ea_solve_params_default": (None, [C.POINTER(SolveParams)]),
     "ea_frameset_create": (_i, [_vp, C.POINTER(FrameParams), _i, C.POINTER(_vp)]),

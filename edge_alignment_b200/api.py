@@ -72,6 +72,14 @@ class Context:
         _check(L.lib().ea_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def profile_enable(self, on=True):
+        _check(L.lib().ea_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        a, b = C.c_double(), C.c_double(); na, nb = C.c_int(), C.c_int()
+        _check(L.lib().ea_profile_read(self._h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
+        return dict(preprocess_ms=a.value, n_preprocess=na.value, solve_ms=b.value, n_solve=nb.value)
+
     # ---- evaluation / solve -------------------------------------------------------------------------
     def eval(self, ref, ref_slot, now, now_slot, pose7, sp=None, level=0, want_jac=True):
         sp = sp or solve_params()

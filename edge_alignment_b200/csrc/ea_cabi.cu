@@ -98,6 +98,31 @@ int ea_launch_count(ea_context* c, int64_t* n) {
   return EA_OK;
 }
 
+int ea_profile_enable(ea_context* c, int on) {
+  if (!c) return ea_fail(EA_ERR_INVALID_ARG, "null context");
+  c->profile = on != 0;
+  return EA_OK;
+}
+int ea_profile_read(ea_context* c, double* pre_ms, int* n_pre, double* solve_ms, int* n_solve) {
+  if (!c) return ea_fail(EA_ERR_INVALID_ARG, "null context");
+  CU(cudaStreamSynchronize(c->stream));
+  double tot[2] = {0, 0}; int cnt[2] = {0, 0};
+  for (int k = 0; k < 2; ++k) {
+    for (size_t i = 0; i + 1 < c->ev[k].size(); i += 2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->ev[k][i], c->ev[k][i + 1]);
+      tot[k] += ms; cnt[k]++;
+    }
+    for (cudaEvent_t e : c->ev[k]) cudaEventDestroy(e);
+    c->ev[k].clear();
+  }
+  if (pre_ms) *pre_ms = tot[0];
+  if (n_pre) *n_pre = cnt[0];
+  if (solve_ms) *solve_ms = tot[1];
+  if (n_solve) *n_solve = cnt[1];
+  return EA_OK;
+}
+
 void ea_frame_params_default(ea_frame_params* p) {
   if (!p) return;
   std::memset(p, 0, sizeof *p);
@@ -211,6 +236,7 @@ int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uin
   A.n = n; A.roles = roles; A.grad_threshold = fs->p.grad_threshold; A.use_median = fs->p.use_median;
   A.dt_normalize = fs->p.dt_normalize;
   int nl = 0;
+  EaProfileScope prof(c, 0);
   cudaError_t e = ea_launch_preprocess(A, c->sm_count, c->stream, &nl);
   c->launches += nl;
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "preprocess launch: %s", cudaGetErrorString(e));
@@ -457,6 +483,7 @@ int ea_solve_batch_device(ea_context* c, int n, ea_frameset* ref, const int32_t*
   CU(cudaSetDevice(c->device));
   A.ref_slots = d_ref_slots; A.now_slots = d_now_slots; A.pose_index = d_pose_index; A.poses = d_poses7;
   A.summaries = d_summaries; A.n_pairs = n;
+  EaProfileScope prof(c, 1);
   cudaError_t e = ea_launch_solve_batch(A, auto_cluster(c, n, cluster), c->sm_count, c->stream);
   c->launches++;
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "solve launch: %s", cudaGetErrorString(e));

@@ -72,6 +72,18 @@ struct ea_context {
   size_t idx_cap = 0;
   void* d_tmp = nullptr;
   size_t tmp_cap = 0;
+  // optional profiling: event pairs around preprocessing pipelines [0] and solve launches [1]
+  bool profile = false;
+  std::vector<cudaEvent_t> ev[2];
+};
+struct EaProfileScope {   // records a start/stop event pair on the context stream when profiling is on
+  ea_context* c; int kind;
+  EaProfileScope(ea_context* c_, int kind_) : c(c_), kind(kind_) {
+    if (c->profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); c->ev[kind].push_back(e); }
+  }
+  ~EaProfileScope() {
+    if (c->profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); c->ev[kind].push_back(e); }
+  }
 };
 
 struct ea_frameset {

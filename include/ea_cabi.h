@@ -139,6 +139,11 @@ int ea_host_free(void* p);
 /* number of kernel launches issued by this context since creation (bench.py gpu_launches) */
 int ea_launch_count(ea_context* ctx, int64_t* n);
 
+/* Optional device-side timing (CUDA events on the context stream around each preprocessing pipeline and each
+ * solve launch).  ea_profile_read syncs, returns the totals since the last read and resets them. */
+int ea_profile_enable(ea_context* ctx, int on);
+int ea_profile_read(ea_context* ctx, double* preprocess_ms, int* n_preprocess, double* solve_ms, int* n_solve);
+
 void ea_frame_params_default(ea_frame_params* p);
 void ea_solve_params_default(ea_solve_params* p);
 
