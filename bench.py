@@ -50,7 +50,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index = index; self.samples = []; self._stop = threading.Event(); self.proc = None
+        self.index = index; self.samples = []; self._halt = threading.Event(); self.proc = None
 
     def run(self):
         try:
@@ -58,13 +58,13 @@ class ClockSampler(threading.Thread):
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.samples.append(line.strip())
-                if self._stop.is_set():
+                if self._halt.is_set():
                     break
         except Exception:
             pass
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)

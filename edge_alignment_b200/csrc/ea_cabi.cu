@@ -175,6 +175,7 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
     }
     if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.edge_bits, size_t(L.h) * L.words * 4 * n_slots);
     if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.ref_bits, size_t(L.h) * L.words * 4 * n_slots);
+    if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.med_bits, size_t(L.h) * L.words * 4 * n_slots);
     if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.dt, px * 4 * n_slots);
     if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.pts, size_t(L.cap) * 16 * n_slots);
     const double s = 1.0 / double(1 << l);

@@ -38,6 +38,7 @@ struct EaPrepLevel {            // device pointers of one pyramid level, slot-ma
   uint16_t* depth;              // [slots][h][w]      (level 0: null)
   uint32_t* edge_bits;          // [slots][h][words]  raw Laplacian>threshold mask, 1 bit / pixel
   uint32_t* ref_bits;           // [slots][h][words]  edge & depth>0
+  uint32_t* med_bits;           // [slots][h][words]  3x3 median of edge_bits
   float* dt;                    // [slots][h][w]
   float4* pts;                  // [slots][cap]
   int w, h, words, cap;

@@ -143,187 +143,225 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const uint32_t* __restri
   }
 }
 
-// ---- 3x3 median on the binary mask, bit-parallel -----------------------------------------------------------
-// a, b, c: bit fields of rows y-1, y, y+1 where bit k+1 <-> pixel x0+k (bit 0 is x0-1).  Returns the field of
-// "at least 5 of the 9 neighbours are edge" aligned so that bit k <-> pixel x0+k.
-__device__ __forceinline__ unsigned median3_bits(unsigned a, unsigned b, unsigned c) {
-  const unsigned s0 = a ^ b ^ c, s1 = (a & b) | (c & (a ^ b));  // per-column vertical count = s0 + 2 s1
-  const unsigned A0 = s0, B0 = s0 >> 1, C0 = s0 >> 2, A1 = s1, B1 = s1 >> 1, C1 = s1 >> 2;
-  const unsigned lo = A0 ^ B0 ^ C0, carry = (A0 & B0) | (C0 & (A0 ^ B0));
+// ---- 3x3 median on the binary mask (cv::medianBlur(B,3), BORDER_REPLICATE), bit-parallel -------------------
+// a, b, c: bit fields of rows y-1, y, y+1 where field bit p <-> pixel x0+p-1.  Returns the field of
+// "at least 5 of the 9 neighbours are edge", bit k <-> pixel x0+k.
+__device__ __forceinline__ unsigned long long median3_bits64(unsigned long long a, unsigned long long b, unsigned long long c) {
+  const unsigned long long s0 = a ^ b ^ c, s1 = (a & b) | (c & (a ^ b));  // per-column vertical count = s0 + 2 s1
+  const unsigned long long A0 = s0, B0 = s0 >> 1, C0 = s0 >> 2, A1 = s1, B1 = s1 >> 1, C1 = s1 >> 2;
+  const unsigned long long lo = A0 ^ B0 ^ C0, carry = (A0 & B0) | (C0 & (A0 ^ B0));
   // m = A1 + B1 + C1 + carry ; total = lo + 2 m >= 5  <=>  m >= 3 or (m == 2 and lo)
-  const unsigned t = A1 ^ B1, u = A1 & B1, v = C1 ^ carry, wv = C1 & carry;
-  const unsigned m0 = t ^ v, tv = t & v;
-  const unsigned ge1 = u | wv | tv, eq2 = u & wv;          // number of "twos": >=1, ==2
-  const unsigned m_ge3 = eq2 | (ge1 & m0);
-  const unsigned m_eq2 = ge1 & ~eq2 & ~m0;
+  const unsigned long long t = A1 ^ B1, u = A1 & B1, v = C1 ^ carry, wv = C1 & carry;
+  const unsigned long long m0 = t ^ v, tv = t & v;
+  const unsigned long long ge1 = u | wv | tv, eq2 = u & wv;
+  const unsigned long long m_ge3 = eq2 | (ge1 & m0);
+  const unsigned long long m_eq2 = ge1 & ~eq2 & ~m0;
   return m_ge3 | (m_eq2 & lo);
 }
-
-// bits [x_start-1, x_start+P] of a mask row as a field (bit 0 <-> x_start-1), with BORDER_REPLICATE in x
-__device__ __forceinline__ unsigned row_field(const uint32_t* __restrict__ row, int words, int w, int x_start, int nbits) {
-  unsigned f = 0;
-  // fast path: fully interior
-  const int xs = x_start - 1;
-  if (xs >= 0 && xs + nbits <= w) {
-    const int wi = xs >> 5, sh = xs & 31;
-    const unsigned lo = row[wi], hi = (wi + 1 < words) ? row[wi + 1] : 0u;
-    f = __funnelshift_r(lo, hi, sh);
-  } else {
-    for (int k = 0; k < nbits; ++k) {
-      int x = min(max(xs + k, 0), w - 1);
-      f |= ((row[x >> 5] >> (x & 31)) & 1u) << k;
-    }
-  }
-  return nbits >= 32 ? f : (f & ((1u << nbits) - 1u));
+__device__ __forceinline__ unsigned long long row_field64(const uint32_t* __restrict__ row, int wi, int words, int w) {
+  const unsigned word = row[wi];
+  const int nvalid = min(32, w - 32 * wi);
+  const unsigned left = (wi > 0) ? (row[wi - 1] >> 31) : (word & 1u);
+  unsigned right;
+  if (nvalid == 32 && wi + 1 < words) right = row[wi + 1] & 1u;
+  else right = (word >> (nvalid - 1)) & 1u;                         // replicate the last image column
+  return (static_cast<unsigned long long>(word) << 1) | left | (static_cast<unsigned long long>(right) << (nvalid + 1));
+}
+__global__ void __launch_bounds__(256) k_median_bits(const __grid_constant__ EaPrepArgs A) {
+  const int level = blockIdx.z;
+  const EaPrepLevel& L = A.lv[level];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L.h * L.words) return;
+  const int slot = A.slots[blockIdx.y];
+  const uint32_t* bits = L.edge_bits + size_t(slot) * L.h * L.words;
+  const int y = idx / L.words, wi = idx % L.words;
+  const unsigned long long f0 = row_field64(bits + size_t(max(y - 1, 0)) * L.words, wi, L.words, L.w);
+  const unsigned long long f1 = row_field64(bits + size_t(y) * L.words, wi, L.words, L.w);
+  const unsigned long long f2 = row_field64(bits + size_t(min(y + 1, L.h - 1)) * L.words, wi, L.words, L.w);
+  const int nvalid = min(32, L.w - 32 * wi);
+  unsigned m = unsigned(median3_bits64(f0, f1, f2));
+  if (nvalid < 32) m &= (1u << nvalid) - 1u;
+  L.med_bits[size_t(slot) * L.h * L.words + idx] = m;
 }
 
 // ---- chamfer 3x3 distance transform, OpenCV's fixed-point two-pass recurrence (distanceTransform_3x3) -------
-// One warp per frame; rows are sequential, each row is a lane-blocked min-plus scan.  Integer min/+ is
-// associative, so the scan reproduces the raster recurrence bit for bit.
-#define DT_HV 62587u        // cvRound(0.955f  * 65536)
-#define DT_DG 89738u        // cvRound(1.3693f * 65536)
+// One CTA per (frame, level); rows are sequential, each row is a block-wide min-plus scan (thread-local P
+// pixels -> warp shuffle scan -> cross-warp carry through shared memory, ONE barrier per row).  Integer min/+
+// is associative, so the scan reproduces the raster recurrence bit for bit.  The previous row lives in
+// registers; only warp totals / boundary pixels go through shared memory (parity double-buffered).
+#define DT_HV 62587         // cvRound(0.955f  * 65536)
+#define DT_DG 89738         // cvRound(1.3693f * 65536)
 #define DT_INF 0x3FFFFFFF   // internal "no seed yet"; written out as OpenCV's DIST_MAX
-#define DT_DISTMAX (0xFFFFFFFFu - DT_DG)
+#define DT_DISTMAX (0xFFFFFFFFu - 89738u)
 
-template <int P>
-__global__ void __launch_bounds__(32) k_chamfer_dt(const uint32_t* __restrict__ edge_bits, const int32_t* __restrict__ dst_slots,
-                                                   float* __restrict__ dt, unsigned* __restrict__ minmax, int level, int w, int h,
-                                                   int words, int use_median) {
-  extern __shared__ int smem[];
-  int* bufA = smem;            // [w + 2], index x+1
-  int* bufB = smem + (w + 2);
-  const int lane = threadIdx.x;
-  const int slot = dst_slots[blockIdx.x];
-  const uint32_t* bits = edge_bits + size_t(slot) * h * words;
-  int* gi = reinterpret_cast<int*>(dt + size_t(slot) * w * h);
-  float* gf = dt + size_t(slot) * w * h;
-  const int chunk = 32 * P, n_chunks = (w + chunk - 1) / chunk;
-  for (int i = lane; i < w + 2; i += 32) { bufA[i] = DT_INF; bufB[i] = DT_INF; }
-  __syncwarp();
-  int* prev = bufA;
-  int* cur = bufB;
-  // ---------------- forward pass ----------------
-  for (int y = 0; y < h; ++y) {
-    const uint32_t* r0 = bits + size_t(max(y - 1, 0)) * words;
-    const uint32_t* r1 = bits + size_t(y) * words;
-    const uint32_t* r2 = bits + size_t(min(y + 1, h - 1)) * words;
-    int carry = DT_INF;  // value of the pixel left of the chunk
-    for (int c = 0; c < n_chunks; ++c) {
-      const int xl = c * chunk + lane * P;   // first pixel of this lane
-      unsigned ef = 0;
-      if (xl < w) {
-        if (use_median) ef = median3_bits(row_field(r0, words, w, xl, P + 2), row_field(r1, words, w, xl, P + 2), row_field(r2, words, w, xl, P + 2));
-        else ef = row_field(r1, words, w, xl, P + 2) >> 1;
-      }
-      int d[P];
-      int run = DT_INF;
-      int pl = (xl < w) ? prev[xl] : DT_INF, pc = (xl < w) ? prev[xl + 1] : DT_INF;   // prev[x-1], prev[x] (index shift 1)
+template <int P, bool BACKWARD>
+__device__ __forceinline__ void dt_row_scan(int (&d)[P], const int (&cval)[P], int lane, int warp, int n_warps, int par,
+                                            int (*tot)[32], int (*first)[32], int& left_bnd, int& right_bnd) {
+  // local scan inside the thread (scan direction: increasing k for the forward pass, decreasing for the backward)
+  int dl[P];
+  int run = DT_INF;
 #pragma unroll
-      for (int k = 0; k < P; ++k) {
-        const int x = xl + k;
-        const int pr = (x < w) ? prev[x + 2] : DT_INF;
-        int cval = min(min(pl, pr) + int(DT_DG), pc + int(DT_HV));
-        if ((ef >> k) & 1u) cval = 0;
-        run = min(cval, run + int(DT_HV));
-        d[k] = run;
-        pl = pc; pc = pr;
-      }
-      // carry chain across lanes: out_i = min(L_i, out_{i-1} + HV*P)
-      const int step = int(DT_HV) * P;
-      int e = min(run, DT_INF) - step * lane;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, e, o); if (lane >= o) e = min(e, t); }
-      // include the chunk carry (acts like a lane -1 with out = carry)
-      const int with_carry = min(e + step * lane, carry + step * (lane + 1));
-      int cin = __shfl_up_sync(0xffffffffu, with_carry, 1);
-      if (lane == 0) cin = carry;
-      cin = min(cin, DT_INF);
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        const int x = xl + k;
-        const int v = min(min(d[k], cin + int(DT_HV) * (k + 1)), DT_INF);
-        if (x < w) cur[x + 1] = v;
-      }
-      carry = min(__shfl_sync(0xffffffffu, with_carry, 31), DT_INF);
-    }
-    __syncwarp();
-    int* grow = gi + size_t(y) * w;
-    for (int i = lane; i < w; i += 32) grow[i] = cur[i + 1];
-    int* t = prev; prev = cur; cur = t;
-    __syncwarp();
+  for (int kk = 0; kk < P; ++kk) {
+    const int k = BACKWARD ? (P - 1 - kk) : kk;
+    run = min(cval[k], run + DT_HV);
+    dl[k] = run;
   }
-  // ---------------- backward pass ----------------
-  for (int i = lane; i < w + 2; i += 32) prev[i] = DT_INF;   // "row below the image"
-  __syncwarp();
-  unsigned vmax = 0, vmin = 0xFFFFFFFFu;
-  for (int y = h - 1; y >= 0; --y) {
-    const int* grow = gi + size_t(y) * w;
-    for (int i = lane; i < w; i += 32) cur[i + 1] = grow[i];
-    __syncwarp();
-    int carry = DT_INF;  // value of the pixel right of the chunk
-    for (int c = n_chunks - 1; c >= 0; --c) {
-      // mirrored lane order: lane 0 owns the right-most block of the chunk
-      const int xr = c * chunk + (31 - lane) * P + (P - 1);  // right-most pixel of this lane
-      int d[P];
-      int run = DT_INF;
-      // below[x+1], below[x]; the buffers hold pixels -1..w at indices 0..w+1 (borders stay INF)
-      int pr = (xr + 2 <= w + 1) ? prev[xr + 2] : DT_INF, pc = (xr + 1 <= w + 1) ? prev[xr + 1] : DT_INF;
+  // warp scan of the thread totals; "upstream" = lower lanes (forward) / higher lanes (backward)
+  const int pos = BACKWARD ? (31 - lane) : lane;   // position along the scan direction
+  const int stepP = DT_HV * P;
+  int e = min(run, DT_INF) - stepP * pos;
 #pragma unroll
-      for (int k = 0; k < P; ++k) {
-        const int x = xr - k;
-        const int pl = (x <= w + 1) ? prev[x] : DT_INF;   // below[x-1]
-        const int t0 = (x < w) ? cur[x + 1] : DT_INF;
-        const int cval = min(t0, min(min(pl, pr) + int(DT_DG), pc + int(DT_HV)));
-        run = min(cval, run + int(DT_HV));
-        d[k] = run;
-        pr = pc; pc = pl;
-      }
-      const int step = int(DT_HV) * P;
-      int e = min(run, DT_INF) - step * lane;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, e, o); if (lane >= o) e = min(e, t); }
-      const int with_carry = min(e + step * lane, carry + step * (lane + 1));
-      int cin = __shfl_up_sync(0xffffffffu, with_carry, 1);
-      if (lane == 0) cin = carry;
-      cin = min(cin, DT_INF);
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        const int x = xr - k;
-        const int v = min(min(d[k], cin + int(DT_HV) * (k + 1)), DT_INF);
-        if (x < w && x >= 0) cur[x + 1] = v;
-      }
-      carry = min(__shfl_sync(0xffffffffu, with_carry, 31), DT_INF);
-    }
-    __syncwarp();
-    float* frow = gf + size_t(y) * w;
-    for (int i = lane; i < w; i += 32) {
-      const int v = cur[i + 1];
-      const unsigned t0 = (v >= DT_INF) ? DT_DISTMAX : unsigned(v);
-      vmax = max(vmax, t0); vmin = min(vmin, t0);
-      frow[i] = float(t0) * (1.0f / 65536.0f);
-    }
-    int* t = prev; prev = cur; cur = t;
-    __syncwarp();
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = BACKWARD ? __shfl_down_sync(0xffffffffu, e, o) : __shfl_up_sync(0xffffffffu, e, o);
+    if (pos >= o) e = min(e, t);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+  const int out = e + stepP * pos;                 // value of this thread's last pixel, ignoring the block carry
+  int carry_local = BACKWARD ? __shfl_down_sync(0xffffffffu, out, 1) : __shfl_up_sync(0xffffffffu, out, 1);
+  if (pos == 0) carry_local = DT_INF;
+  const int Lw = __shfl_sync(0xffffffffu, out, BACKWARD ? 0 : 31);
+  const int f0 = __shfl_sync(0xffffffffu, BACKWARD ? dl[P - 1] : dl[0], BACKWARD ? 31 : 0);
+  if (lane == 0) { tot[par][warp] = min(Lw, DT_INF); first[par][warp] = min(f0, DT_INF); }
+  __syncthreads();
+  // block carry: final value of the pixel just upstream of this warp
+  const int wpos = BACKWARD ? (n_warps - 1 - warp) : warp;
+  const int stepW = stepP * 32;
+  int cand = DT_INF;
+  if (lane < wpos) {
+    const int src = BACKWARD ? (n_warps - 1 - lane) : lane;
+    cand = tot[par][src] + stepW * (wpos - 1 - lane);
   }
-  if (lane == 0) { minmax[(slot * EA_MAX_LEVELS + level) * 2] = vmin; minmax[(slot * EA_MAX_LEVELS + level) * 2 + 1] = vmax; }
+  const int cw = min(__reduce_min_sync(0xffffffffu, cand), DT_INF);
+#pragma unroll
+  for (int kk = 0; kk < P; ++kk) {
+    const int k = BACKWARD ? (P - 1 - kk) : kk;
+    const int v = min(min(dl[k], carry_local + DT_HV * (kk + 1)), cw + DT_HV * (pos * P + kk + 1));
+    d[k] = min(v, DT_INF);
+  }
+  // boundaries the NEXT row needs: upstream neighbour's last pixel (== cw) and downstream neighbour's first pixel
+  const int out_w = min(min(Lw, cw + stepW), DT_INF);
+  const int dn = BACKWARD ? warp - 1 : warp + 1;
+  const int dn_first = (dn >= 0 && dn < n_warps) ? min(first[par][dn], out_w + DT_HV) : DT_INF;
+  if (BACKWARD) { right_bnd = cw; left_bnd = dn_first; }
+  else { left_bnd = cw; right_bnd = dn_first; }
 }
 
-// ---- cv::normalize(NORM_MINMAX, alpha=0, beta) on CV_32F -----------------------------------------------------
-__global__ void __launch_bounds__(256) k_dt_normalize(float* __restrict__ dt, const int32_t* __restrict__ dst_slots,
-                                                      const unsigned* __restrict__ minmax, int level, int npx, double beta) {
-  const int slot = dst_slots[blockIdx.y];
-  const float mn = float(minmax[(slot * EA_MAX_LEVELS + level) * 2]) * (1.0f / 65536.0f);
-  const float mx = float(minmax[(slot * EA_MAX_LEVELS + level) * 2 + 1]) * (1.0f / 65536.0f);
+template <int P>
+__global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaPrepArgs A) {
+  __shared__ int tot[2][32], first[2][32];
+  __shared__ unsigned red[2][32];
+  const int level = blockIdx.y;
+  const EaPrepLevel& L = A.lv[level];
+  const int w = L.w, h = L.h, words = L.words;
+  const int slot = A.slots[blockIdx.x];
+  const uint32_t* bits = (A.use_median ? L.med_bits : L.edge_bits) + size_t(slot) * h * words;
+  int* gi = reinterpret_cast<int*>(L.dt + size_t(slot) * w * h);
+  float* gf = L.dt + size_t(slot) * w * h;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_warps = ((w + P - 1) / P + 31) / 32;          // warps that own pixels at this level
+  const bool warp_on = warp < n_warps;
+  const int x0 = tid * P;
+  int d[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) d[k] = DT_INF;
+  int left_bnd = DT_INF, right_bnd = DT_INF;
+  int par = 0;
+  // ---------------- forward pass: rows top -> bottom, scan left -> right ----------------
+  for (int y = 0; y < h; ++y, par ^= 1) {
+    if (!warp_on) { __syncthreads(); continue; }
+    unsigned ebits = 0;
+    if (x0 < w) ebits = bits[size_t(y) * words + (x0 >> 5)] >> (x0 & 31);
+    int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
+    int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
+    if (lane == 0) pl = left_bnd;
+    if (lane == 31) pr = right_bnd;
+    int cval[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const int a = (k == 0) ? pl : d[k - 1];
+      const int c = (k == P - 1) ? pr : d[k + 1];
+      int v = min(min(a, c) + DT_DG, d[k] + DT_HV);
+      if ((ebits >> k) & 1u) v = 0;
+      if (x0 + k >= w) v = DT_INF;                           // beyond the image: stays "border"
+      cval[k] = min(v, DT_INF);
+    }
+    dt_row_scan<P, false>(d, cval, lane, warp, n_warps, par, tot, first, left_bnd, right_bnd);
+#pragma unroll
+    for (int k = 0; k < P; ++k) if (x0 + k >= w) d[k] = DT_INF;
+    if (x0 < w) {
+      int* g = gi + size_t(y) * w + x0;
+      if (P == 2 && x0 + 1 < w && ((size_t(y) * w + x0) & 1) == 0) *reinterpret_cast<int2*>(g) = make_int2(d[0], d[1 % P]);
+      else {
+#pragma unroll
+        for (int k = 0; k < P; ++k) if (x0 + k < w) g[k] = d[k];
+      }
+    }
+  }
+  // ---------------- backward pass: rows bottom -> top, scan right -> left ----------------
+#pragma unroll
+  for (int k = 0; k < P; ++k) d[k] = DT_INF;
+  left_bnd = DT_INF; right_bnd = DT_INF;
+  unsigned vmax = 0, vmin = 0xFFFFFFFFu;
+  for (int y = h - 1; y >= 0; --y, par ^= 1) {
+    if (!warp_on) { __syncthreads(); continue; }
+    int t0[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) t0[k] = (x0 + k < w) ? gi[size_t(y) * w + x0 + k] : DT_INF;
+    int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
+    int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
+    if (lane == 0) pl = left_bnd;
+    if (lane == 31) pr = right_bnd;
+    int cval[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const int a = (k == 0) ? pl : d[k - 1];
+      const int c = (k == P - 1) ? pr : d[k + 1];
+      int v = min(t0[k], min(min(a, c) + DT_DG, d[k] + DT_HV));
+      if (x0 + k >= w) v = DT_INF;
+      cval[k] = min(v, DT_INF);
+    }
+    dt_row_scan<P, true>(d, cval, lane, warp, n_warps, par, tot, first, left_bnd, right_bnd);
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      if (x0 + k >= w) { d[k] = DT_INF; continue; }
+      const unsigned t = (d[k] >= DT_INF) ? DT_DISTMAX : unsigned(d[k]);
+      vmax = max(vmax, t); vmin = min(vmin, t);
+      gf[size_t(y) * w + x0 + k] = float(t) * (1.0f / 65536.0f);
+    }
+  }
+  vmax = __reduce_max_sync(0xffffffffu, vmax);
+  vmin = __reduce_min_sync(0xffffffffu, vmin);
+  if (lane == 0) { red[0][warp] = vmin; red[1][warp] = vmax; }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned mn = 0xFFFFFFFFu, mx = 0;
+    for (int i = 0; i < n_warps; ++i) { mn = min(mn, red[0][i]); mx = max(mx, red[1][i]); }
+    A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2] = mn;
+    A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2 + 1] = mx;
+  }
+}
+
+// ---- cv::normalize(NORM_MINMAX, alpha=0, beta) on CV_32F, every level in one launch ------------------------
+__global__ void __launch_bounds__(256) k_dt_normalize(const __grid_constant__ EaPrepArgs A, double beta) {
+  const int level = blockIdx.z;
+  const EaPrepLevel& L = A.lv[level];
+  const int npx = L.w * L.h;
+  const int slot = A.slots[blockIdx.y];
+  const float mn = float(A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2]) * (1.0f / 65536.0f);
+  const float mx = float(A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2 + 1]) * (1.0f / 65536.0f);
   const double range = double(mx) - double(mn);
   const double scale = beta * (range > 2.220446049250313e-16 ? 1.0 / range : 0.0);
   const float fs = float(scale), fb = float(0.0 - double(mn) * scale);
-  float* d = dt + size_t(slot) * npx;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) d[i] = __fadd_rn(__fmul_rn(d[i], fs), fb);
+  float4* d4 = reinterpret_cast<float4*>(L.dt + size_t(slot) * npx);   // npx is a multiple of 4 (w, h >= 8, even)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx / 4; i += gridDim.x * blockDim.x) {
+    float4 v = d4[i];
+    v.x = __fadd_rn(__fmul_rn(v.x, fs), fb); v.y = __fadd_rn(__fmul_rn(v.y, fs), fb);
+    v.z = __fadd_rn(__fmul_rn(v.z, fs), fb); v.w = __fadd_rn(__fmul_rn(v.w, fs), fb);
+    d4[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (npx & 3)) {
+    float* d = L.dt + size_t(slot) * npx + (npx & ~3) + threadIdx.x;
+    *d = __fadd_rn(__fmul_rn(*d, fs), fb);
+  }
 }
 
 __global__ void __launch_bounds__(256) k_unpack_mask(const uint32_t* __restrict__ bits, int w, int h, int words, int median,
@@ -345,20 +383,10 @@ __global__ void __launch_bounds__(256) k_unpack_mask(const uint32_t* __restrict_
   }
 }
 
-template <int P>
-cudaError_t launch_dt(const EaPrepArgs& A, int l, cudaStream_t stream) {
-  const EaPrepLevel& L = A.lv[l];
-  const size_t smem = size_t(L.w + 2) * 2 * sizeof(int);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_chamfer_dt<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  k_chamfer_dt<P><<<A.n, 32, smem, stream>>>(L.edge_bits, A.slots, L.dt, A.dt_minmax, l, L.w, L.h, L.words, A.use_median);
-  return cudaGetLastError();
-}
-
 }  // namespace
 
 cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches) {
   int nl = 0;
-  cudaError_t err = cudaSuccess;
   const bool want_ref = (A.roles & EA_ROLE_REF) != 0, want_now = (A.roles & EA_ROLE_NOW) != 0;
   if (want_ref && !A.in_depth) return cudaErrorInvalidValue;
   const size_t px0 = size_t(A.lv[0].w) * A.lv[0].h;
@@ -384,19 +412,29 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
       k_compact<<<A.n, CP_THREADS, 0, stream>>>(L.ref_bits, d, pxl, ss, A.slots, L.pts, A.n_pts, l, A.overflow, L.w, L.h, L.words, L.cap);
       ++nl;
     }
-    if (want_now) {
-      if (L.w <= 160) err = launch_dt<5>(A, l, stream);
-      else if (L.w <= 352) err = launch_dt<11>(A, l, stream);
-      else err = launch_dt<21>(A, l, stream);
+  }
+  if (want_now) {
+    const EaPrepLevel& L0 = A.lv[0];
+    if (A.use_median) {
+      dim3 grid(unsigned((L0.h * L0.words + 255) / 256), unsigned(A.n), unsigned(A.n_levels));
+      k_median_bits<<<grid, 256, 0, stream>>>(A);
       ++nl;
-      if (err != cudaSuccess) return err;
-      if (A.dt_normalize != EA_NORM_NONE) {
-        int bx = int((pxl + 255) / 256);
-        const int cap = sm_count * 8;
-        if (bx > cap) bx = cap;
-        k_dt_normalize<<<dim3(unsigned(bx), unsigned(A.n)), 256, 0, stream>>>(L.dt, A.slots, A.dt_minmax, l, int(pxl), A.dt_normalize == EA_NORM_255 ? 255.0 : 1.0);
-        ++nl;
-      }
+    }
+    // every level of every frame in one launch: CTA (frame, level); block sized for level 0
+    const int P = (L0.w <= 2048) ? 2 : ((L0.w <= 4096) ? 4 : 8);
+    const int threads = (((L0.w + P - 1) / P + 31) / 32) * 32;
+    if (threads > 1024) return cudaErrorInvalidValue;
+    dim3 grid(unsigned(A.n), unsigned(A.n_levels));
+    if (P == 2) k_chamfer_dt<2><<<grid, threads, 0, stream>>>(A);
+    else if (P == 4) k_chamfer_dt<4><<<grid, threads, 0, stream>>>(A);
+    else k_chamfer_dt<8><<<grid, threads, 0, stream>>>(A);
+    ++nl;
+    if (A.dt_normalize != EA_NORM_NONE) {
+      int bx = int((px0 / 4 + 255) / 256);
+      const int cap = sm_count * 4;
+      if (bx > cap) bx = cap;
+      k_dt_normalize<<<dim3(unsigned(bx), unsigned(A.n), unsigned(A.n_levels)), 256, 0, stream>>>(A, A.dt_normalize == EA_NORM_255 ? 255.0 : 1.0);
+      ++nl;
     }
   }
   if (launches) *launches = nl;
