@@ -52,6 +52,7 @@ int ea_create(int device, ea_context** out) {
   c->own_stream = true;
   CU(cudaMalloc(&c->d_pose, 7 * sizeof(double)));
   CU(cudaMalloc(&c->d_failed, sizeof(int)));
+  CU(cudaMalloc(&c->d_work, sizeof(int)));
   CU(cudaMalloc(&c->d_sums, size_t(1024) * EA_SUMS * sizeof(double)));
   *out = c;
   return EA_OK;
@@ -60,7 +61,7 @@ int ea_destroy(ea_context* c) {
   if (!c) return EA_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
+  cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_work); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return EA_OK;
@@ -428,7 +429,7 @@ int ea_eval(ea_context* c, ea_frameset* ref, int ref_slot, ea_frameset* now, int
     for (int k = 0; k < 28; ++k) sums28[k] = 0.0;
     if (n_res > 0) {
       const int nb = std::max(1, std::min(c->sm_count, (n_res + 2047) / 2048));
-      cudaError_t e = ea_launch_eval_sums(rd, nd, ref->geom[level], now->geom[level], ids, *sp, c->d_pose, n_res, nb, c->d_sums, c->stream);
+      cudaError_t e = ea_launch_eval_sums(rd, nd, ref->geom[level], now->geom[level], ids, *sp, c->d_pose, nullptr, 0, n_res, nb, c->d_sums, c->stream);
       c->launches++;
       if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "eval sums launch: %s", cudaGetErrorString(e));
       std::vector<double> h(size_t(nb) * EA_SUMS);
@@ -483,7 +484,7 @@ int ea_solve_batch_device(ea_context* c, int n, ea_frameset* ref, const int32_t*
   if (rc) return rc;
   CU(cudaSetDevice(c->device));
   A.ref_slots = d_ref_slots; A.now_slots = d_now_slots; A.pose_index = d_pose_index; A.poses = d_poses7;
-  A.summaries = d_summaries; A.n_pairs = n;
+  A.summaries = d_summaries; A.n_pairs = n; A.work_counter = c->d_work;
   EaProfileScope prof(c, 1);
   cudaError_t e = ea_launch_solve_batch(A, auto_cluster(c, n, cluster), c->sm_count, c->stream);
   c->launches++;

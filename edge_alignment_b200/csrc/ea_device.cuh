@@ -33,28 +33,58 @@ struct EaLevelGeom {   // per level, identical for every slot of a frameset (ker
   int w, h;
 };
 
-struct EaPose {  // current rotation (Eigen un-normalised quaternion formula) and translation
-  double R[9];
-  double t[3];
+struct EaPose {  // per-evaluation uniform transform, fp64
+  // q = s * (A * a) + tt with A = K_now * R * B, tt = K_now * t; (u', v') = (q0, q1) / q2, z' = q2.
+  //   EA_POINTS_PIXEL: a = (u, v, 1), s = Z = raw depth / depth_scale, B = K_ref^-1 (back-projection utils.cpp:235-237)
+  //   EA_POINTS_XYZ:   a = (X, Y, Z), s = 1, B = I
+  double A[9];
+  double tt[3];
+  float t[3];        // translation, for y = p' - t in the Jacobian
+  float fx, fy, inv_fx, inv_fy;   // now-level intrinsics in fp32 (Jacobian)
+  double cx, cy;     // now-level principal point
 };
 
-// Eigen::Quaternion::toRotationMatrix(), as called at standalone/utils.h:51-53 (no normalisation).
-__device__ __forceinline__ void ea_pose_from_q(const double* x7, EaPose& P) {
+// Eigen::Quaternion::toRotationMatrix(), as called at standalone/utils.h:51-53 (no normalisation), folded with the
+// intrinsics of the reference level (back-projection) and of the now level (projection, utils.h:74-75).
+template <bool XYZ>
+__device__ __forceinline__ void ea_pose_setup(const double* x7, const EaLevelGeom& ref, const EaLevelGeom& now, EaPose& P) {
   const double qw = x7[0], qx = x7[1], qy = x7[2], qz = x7[3];
   const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
   const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
   const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
   const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-  P.R[0] = 1.0 - (tyy + tzz); P.R[1] = txy - twz;         P.R[2] = txz + twy;
-  P.R[3] = txy + twz;         P.R[4] = 1.0 - (txx + tzz); P.R[5] = tyz - twx;
-  P.R[6] = txz - twy;         P.R[7] = tyz + twx;         P.R[8] = 1.0 - (txx + tyy);
-  P.t[0] = x7[4]; P.t[1] = x7[5]; P.t[2] = x7[6];
+  double R[9];
+  R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz;         R[2] = txz + twy;
+  R[3] = txy + twz;         R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;         R[7] = tyz + twx;         R[8] = 1.0 - (txx + tyy);
+  double M[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (XYZ) { M[3 * i] = R[3 * i]; M[3 * i + 1] = R[3 * i + 1]; M[3 * i + 2] = R[3 * i + 2]; }
+    else {
+      M[3 * i] = R[3 * i] * ref.inv_fx;
+      M[3 * i + 1] = R[3 * i + 1] * ref.inv_fy;
+      M[3 * i + 2] = R[3 * i + 2] - ref.cx * M[3 * i] - ref.cy * M[3 * i + 1];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    P.A[j] = now.fx * M[j] + now.cx * M[6 + j];
+    P.A[3 + j] = now.fy * M[3 + j] + now.cy * M[6 + j];
+    P.A[6 + j] = M[6 + j];
+  }
+  P.tt[0] = now.fx * x7[4] + now.cx * x7[6];
+  P.tt[1] = now.fy * x7[5] + now.cy * x7[6];
+  P.tt[2] = x7[6];
+  P.t[0] = float(x7[4]); P.t[1] = float(x7[5]); P.t[2] = float(x7[6]);
+  P.fx = float(now.fx); P.fy = float(now.fy); P.inv_fx = float(now.inv_fx); P.inv_fy = float(now.inv_fy);
+  P.cx = now.cx; P.cy = now.cy;
 }
 
 struct EaPointEval {
   float f, dfdu, dfdv;     // bicubic value and gradient (grid row == u, col == v: SEA:258)
-  float yx, yy, yz;        // R * X
-  float px, py, iz;        // transformed point (x', y') and 1/z'
+  float ub, vb;            // u' - cx, v' - cy
+  float pz, iz;            // z' and 1/z'
   bool fail;               // |z'| < 0.01  (utils.h:70-73)
 };
 
@@ -73,51 +103,62 @@ __device__ __forceinline__ float ea_cubic_val(float p0, float p1, float p2, floa
   return fmaf(x, fmaf(x, fmaf(x, a, b), c), p1);
 }
 
+// floor(x) and x - floor(x): exact for |x| < 2^31 (F2I.FLOOR, I2F, one fp64 subtract, one narrowing).  Wild values
+// (only possible when the z-guard has already failed the evaluation) give unspecified but in-bounds indices.
+__device__ __forceinline__ void ea_floor_frac(double x, int& i, float& frac) {
+  i = __double2int_rd(x);
+  frac = float(x - double(i));
+}
+
 // Warp, project, bicubic lookup for one edge point.
-//   ref: intrinsics of the level the point list was extracted at (back-projection, utils.cpp:235-237)
-//   now: intrinsics of the distance transform's level (projection, utils.h:74-75)
 template <bool XYZ>
-__device__ __forceinline__ void ea_point_eval(const float4 p, const EaLevelGeom& ref, const EaLevelGeom& now,
-                                              double inv_depth_scale, const EaPose& P, const float* __restrict__ dt,
-                                              EaPointEval& o) {
-  double X, Y, Z;
+__device__ __forceinline__ void ea_point_eval(const float4 p, const EaLevelGeom& now, double inv_depth_scale, const EaPose& P,
+                                              const float* __restrict__ dt, EaPointEval& o) {
+  const double a0 = double(p.x), a1 = double(p.y);
+  double q0, q1, q2;
   if (XYZ) {
-    X = double(p.x); Y = double(p.y); Z = double(p.z);
+    const double a2 = double(p.z);
+    q0 = fma(P.A[0], a0, fma(P.A[1], a1, fma(P.A[2], a2, P.tt[0])));
+    q1 = fma(P.A[3], a0, fma(P.A[4], a1, fma(P.A[5], a2, P.tt[1])));
+    q2 = fma(P.A[6], a0, fma(P.A[7], a1, fma(P.A[8], a2, P.tt[2])));
   } else {
-    Z = double(p.z) * inv_depth_scale;
-    X = (double(p.x) - ref.cx) * Z * ref.inv_fx;
-    Y = (double(p.y) - ref.cy) * Z * ref.inv_fy;
+    const double Z = double(p.z) * inv_depth_scale;
+    q0 = fma(Z, fma(P.A[0], a0, fma(P.A[1], a1, P.A[2])), P.tt[0]);
+    q1 = fma(Z, fma(P.A[3], a0, fma(P.A[4], a1, P.A[5])), P.tt[1]);
+    q2 = fma(Z, fma(P.A[6], a0, fma(P.A[7], a1, P.A[8])), P.tt[2]);
   }
-  const double yx = P.R[0] * X + P.R[1] * Y + P.R[2] * Z;
-  const double yy = P.R[3] * X + P.R[4] * Y + P.R[5] * Z;
-  const double yz = P.R[6] * X + P.R[7] * Y + P.R[8] * Z;
-  const double px = yx + P.t[0], py = yy + P.t[1], pz = yz + P.t[2];
-  o.fail = (pz < 0.01) && (pz > -0.01);
-  const double iz = 1.0 / pz;
-  const double u = now.fx * px * iz + now.cx;
-  const double v = now.fy * py * iz + now.cy;
-  // floor + fractional offsets in fp64, then hand fp32 to the interpolator
-  double fu = floor(u), fv = floor(v);
+  o.fail = (q2 < 0.01) && (q2 > -0.01);
+  const double iz = 1.0 / q2;
+  const double u = q0 * iz, v = q1 * iz;
   const int W = now.w, H = now.h;
-  // keep the 4x4 footprint arithmetic inside int range: anything this far out clamps to one edge texel
-  fu = fmin(fmax(fu, -4.0), double(W + 4));
-  fv = fmin(fmax(fv, -4.0), double(H + 4));
-  const int iu = int(fu), iv = int(fv);
-  float du = float(u - fu), dv = float(v - fv);
-  du = fminf(fmaxf(du, 0.0f), 1.0f);
-  dv = fminf(fmaxf(dv, 0.0f), 1.0f);
-  // Grid2D::GetValue clamp-to-edge
-  const int x0 = min(max(iu - 1, 0), W - 1), x1 = min(max(iu, 0), W - 1), x2 = min(max(iu + 1, 0), W - 1),
-            x3 = min(max(iu + 2, 0), W - 1);
-  const float* r0 = dt + size_t(min(max(iv - 1, 0), H - 1)) * W;
-  const float* r1 = dt + size_t(min(max(iv, 0), H - 1)) * W;
-  const float* r2 = dt + size_t(min(max(iv + 1, 0), H - 1)) * W;
-  const float* r3 = dt + size_t(min(max(iv + 2, 0), H - 1)) * W;
-  // 16 texel gather (L1/L2-resident); issue all loads before use
-  const float p00 = __ldg(r0 + x0), p01 = __ldg(r0 + x1), p02 = __ldg(r0 + x2), p03 = __ldg(r0 + x3);
-  const float p10 = __ldg(r1 + x0), p11 = __ldg(r1 + x1), p12 = __ldg(r1 + x2), p13 = __ldg(r1 + x3);
-  const float p20 = __ldg(r2 + x0), p21 = __ldg(r2 + x1), p22 = __ldg(r2 + x2), p23 = __ldg(r2 + x3);
-  const float p30 = __ldg(r3 + x0), p31 = __ldg(r3 + x1), p32 = __ldg(r3 + x2), p33 = __ldg(r3 + x3);
+  int iu, iv;
+  float du, dv;
+  ea_floor_frac(u, iu, du);
+  ea_floor_frac(v, iv, dv);
+  // the conversion saturates, so the 4x4 footprint arithmetic below cannot wrap for any input
+  iu = min(max(iu, -4), W + 4);
+  iv = min(max(iv, -4), H + 4);
+  float p00, p01, p02, p03, p10, p11, p12, p13, p20, p21, p22, p23, p30, p31, p32, p33;
+  const bool interior = (iu >= 1) && (iu <= W - 3) && (iv >= 1) && (iv <= H - 3);
+  if (__all_sync(0xffffffffu, interior)) {
+    // fast path: 4 contiguous texels per row, one 32-bit offset per row
+    const unsigned o0 = unsigned(iv - 1) * unsigned(W) + unsigned(iu - 1);
+    const unsigned o1 = o0 + unsigned(W), o2 = o1 + unsigned(W), o3 = o2 + unsigned(W);
+    p00 = __ldg(dt + o0); p01 = __ldg(dt + o0 + 1); p02 = __ldg(dt + o0 + 2); p03 = __ldg(dt + o0 + 3);
+    p10 = __ldg(dt + o1); p11 = __ldg(dt + o1 + 1); p12 = __ldg(dt + o1 + 2); p13 = __ldg(dt + o1 + 3);
+    p20 = __ldg(dt + o2); p21 = __ldg(dt + o2 + 1); p22 = __ldg(dt + o2 + 2); p23 = __ldg(dt + o2 + 3);
+    p30 = __ldg(dt + o3); p31 = __ldg(dt + o3 + 1); p32 = __ldg(dt + o3 + 2); p33 = __ldg(dt + o3 + 3);
+  } else {
+    // Grid2D::GetValue clamp-to-edge
+    const unsigned x0 = unsigned(min(max(iu - 1, 0), W - 1)), x1 = unsigned(min(max(iu, 0), W - 1)),
+                   x2 = unsigned(min(max(iu + 1, 0), W - 1)), x3 = unsigned(min(max(iu + 2, 0), W - 1));
+    const unsigned r0 = unsigned(min(max(iv - 1, 0), H - 1)) * unsigned(W), r1 = unsigned(min(max(iv, 0), H - 1)) * unsigned(W),
+                   r2 = unsigned(min(max(iv + 1, 0), H - 1)) * unsigned(W), r3 = unsigned(min(max(iv + 2, 0), H - 1)) * unsigned(W);
+    p00 = __ldg(dt + r0 + x0); p01 = __ldg(dt + r0 + x1); p02 = __ldg(dt + r0 + x2); p03 = __ldg(dt + r0 + x3);
+    p10 = __ldg(dt + r1 + x0); p11 = __ldg(dt + r1 + x1); p12 = __ldg(dt + r1 + x2); p13 = __ldg(dt + r1 + x3);
+    p20 = __ldg(dt + r2 + x0); p21 = __ldg(dt + r2 + x1); p22 = __ldg(dt + r2 + x2); p23 = __ldg(dt + r2 + x3);
+    p30 = __ldg(dt + r3 + x0); p31 = __ldg(dt + r3 + x1); p32 = __ldg(dt + r3 + x2); p33 = __ldg(dt + r3 + x3);
+  }
   // BiCubicInterpolator::Evaluate: for each grid row (== image column x_k) spline along c (== image y),
   // then spline the four results along r (== image x).
   float f0, f1, f2, f3, d0, d1, d2, d3;
@@ -127,8 +168,8 @@ __device__ __forceinline__ void ea_point_eval(const float4 p, const EaLevelGeom&
   ea_cubic(p03, p13, p23, p33, dv, f3, d3);
   ea_cubic(f0, f1, f2, f3, du, o.f, o.dfdu);
   o.dfdv = ea_cubic_val(d0, d1, d2, d3, du);
-  o.yx = float(yx); o.yy = float(yy); o.yz = float(yz);
-  o.px = float(px); o.py = float(py); o.iz = float(iz);
+  o.ub = float(u - P.cx); o.vb = float(v - P.cy);
+  o.pz = float(q2); o.iz = float(iz);
 }
 
 // Loss (ceres/loss_function.cc) + Corrector (rho'' <= 0 for all three => scale by sqrt(rho')) in fp32.
@@ -154,16 +195,20 @@ __device__ __forceinline__ float ea_loss_eval(int type, float a, float r, float&
   return 1.0f;
 }
 
-// Analytic local Jacobian (collapsed closed form of AutoDiff x QuaternionParameterization,
-// SURVEY.md A.3): g = dr/dp', J = [ 2 (R X) x g | g ], then robust re-weighting.
-__device__ __forceinline__ void ea_jacobian(const EaPointEval& e, const EaLevelGeom& now, float w, float J[6]) {
-  const float g0 = e.dfdu * float(now.fx) * e.iz;
-  const float g1 = e.dfdv * float(now.fy) * e.iz;
-  const float g2 = -(g0 * e.px + g1 * e.py) * e.iz;
-  J[0] = 2.0f * (e.yy * g2 - e.yz * g1) * w;
-  J[1] = 2.0f * (e.yz * g0 - e.yx * g2) * w;
-  J[2] = 2.0f * (e.yx * g1 - e.yy * g0) * w;
-  J[3] = g0 * w; J[4] = g1 * w; J[5] = g2 * w;
+// Analytic local Jacobian (collapsed closed form of AutoDiff x QuaternionParameterization):
+// g = dr/dp', J = [ 2 (R X) x g | g ], then robust re-weighting.  Everything is rebuilt in fp32 from the projected
+// coordinates: p' = z' (ub/fx, vb/fy, 1), R X = p' - t.
+__device__ __forceinline__ void ea_jacobian(const EaPointEval& e, const EaPose& P, float w, float J[6]) {
+  const float px = e.pz * e.ub * P.inv_fx, py = e.pz * e.vb * P.inv_fy;
+  const float yx = px - P.t[0], yy = py - P.t[1], yz = e.pz - P.t[2];
+  const float wi = w * e.iz;
+  const float g0 = e.dfdu * P.fx * wi;
+  const float g1 = e.dfdv * P.fy * wi;
+  const float g2 = -(e.dfdu * e.ub + e.dfdv * e.vb) * wi;
+  J[0] = 2.0f * (yy * g2 - yz * g1);
+  J[1] = 2.0f * (yz * g0 - yx * g2);
+  J[2] = 2.0f * (yx * g1 - yy * g0);
+  J[3] = g0; J[4] = g1; J[5] = g2;
 }
 
 // Transposing warp reduction: every lane holds 32 partial sums v[0..31]; afterwards lane L holds in v[0]

@@ -14,6 +14,7 @@ struct EaSolveArgs {
   const int32_t* now_slots;     // [n_pairs] device
   const int32_t* pose_index;    // [n_pairs] device or null (identity)
   double* poses;                // [*][7] device, in/out
+  int* work_counter;            // device: next pair index of the dynamic work queue (zeroed per launch)
   ea_summary* summaries;        // [n_pairs][n_levels] device or null
   int n_pairs, n_levels, coarsest, finest;
   double inv_depth_scale;
@@ -30,7 +31,8 @@ cudaError_t ea_launch_eval_points(const EaLevelDesc& rd, const EaLevelDesc& nd, 
                                   int* d_failed, cudaStream_t stream);
 cudaError_t ea_launch_eval_sums(const EaLevelDesc& rd, const EaLevelDesc& nd, const EaLevelGeom& rg,
                                 const EaLevelGeom& ng, double inv_depth_scale, const ea_solve_params& sp,
-                                const double* d_pose7, int n_res, int n_blocks, double* d_sums, cudaStream_t stream);
+                                const double* d_pose7, const int* d_done, int j_begin, int j_end, int n_blocks, double* d_sums,
+                                cudaStream_t stream);
 
 // ---- preprocessing (ea_preprocess.cu) ---------------------------------------------------------------
 struct EaPrepLevel {            // device pointers of one pyramid level, slot-major pools
@@ -68,6 +70,7 @@ struct ea_context {
   // small scratch
   double* d_pose = nullptr;      // [7]
   int* d_failed = nullptr;
+  int* d_work = nullptr;         // work-queue counter of the batched solve
   double* d_sums = nullptr;      // [max blocks][EA_SUMS]
   int32_t* d_idx = nullptr;      // scratch slot indices
   size_t idx_cap = 0;

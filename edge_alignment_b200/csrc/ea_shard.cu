@@ -55,62 +55,6 @@ struct ShardState {        // device-resident control block
   int done, started;
 };
 
-#define SH_THREADS 512
-struct ShardSmem {
-  double part[SH_THREADS / 32][EA_NSUM];
-  double cpart[SH_THREADS / 32];
-};
-
-// slice evaluation: same per-point device functions and reduction tree as ea_eval_slice (ea_solve.cu)
-template <bool XYZ>
-__global__ void __launch_bounds__(SH_THREADS) k_shard_eval(EaLevelDesc rd, EaLevelDesc nd, EaLevelGeom rg, EaLevelGeom ng,
-                                                           double inv_depth_scale, ea_solve_params sp, const ShardState* st,
-                                                           int j_begin, int j_end, double* partials /*[grid][EA_SUMS]*/) {
-  if (st->done) return;
-  __shared__ ShardSmem S;
-  EaPose P;
-  ea_pose_from_q(st->cand, P);
-  const int n = j_end - j_begin;
-  const int j0 = j_begin + int((long long)n * blockIdx.x / gridDim.x), j1 = j_begin + int((long long)n * (blockIdx.x + 1) / gridDim.x);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float acc[EA_NSUM];
-#pragma unroll
-  for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
-  double acc64 = 0.0, cost64 = 0.0;
-  int since = 0;
-  for (int base = j0 + warp * 32; base < j1; base += SH_THREADS) {
-    const int j = base + lane;
-    if (j < j1) {
-      const float4 p = __ldg(rd.pts + size_t(j) * sp.point_stride);
-      EaPointEval e;
-      ea_point_eval<XYZ>(p, rg, ng, inv_depth_scale, P, nd.dt, e);
-      float rho0;
-      const float w = ea_loss_eval(sp.loss_type, float(sp.loss_scale), e.f, rho0);
-      float J[6];
-      ea_jacobian(e, ng, w, J);
-      ea_accumulate(acc, J, e.f * w);
-      acc[27] += e.fail ? 1.0f : 0.0f;
-      cost64 += double(0.5f * rho0);
-    }
-    if (++since == 4) {
-      acc64 += double(ea_warp_transpose_reduce(acc, lane));
-#pragma unroll
-      for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
-      since = 0;
-    }
-  }
-  if (since) acc64 += double(ea_warp_transpose_reduce(acc, lane));
-  cost64 = ea_warp_sum(cost64);
-  S.part[warp][lane] = acc64;
-  if (lane == 0) S.cpart[warp] = cost64;
-  __syncthreads();
-  if (tid < EA_SUMS) {
-    double s = 0.0;
-    for (int w2 = 0; w2 < SH_THREADS / 32; ++w2) s += (tid < 28) ? S.part[w2][tid] : S.cpart[w2];
-    partials[size_t(blockIdx.x) * EA_SUMS + tid] = s;
-  }
-}
-
 __global__ void k_shard_reduce(const ShardState* st, const double* partials, int n_blocks, double* sums) {
   if (st->done) return;
   const int k = threadIdx.x;
@@ -233,10 +177,8 @@ int ea_shard_solve(ea_shard* s, ea_frameset* ref, int ref_slot, ea_frameset* now
   while (evals < max_evals && !*s->h_done) {
     const int chunk = std::min(8, max_evals - evals);
     for (int i = 0; i < chunk; ++i) {
-      if (rd.pts_mode == EA_POINTS_XYZ)
-        k_shard_eval<true><<<nb, SH_THREADS, 0, st>>>(rd, nd, ref->geom[level], now->geom[level], ids, *sp, s->d_state, j0, j1, s->d_partials);
-      else
-        k_shard_eval<false><<<nb, SH_THREADS, 0, st>>>(rd, nd, ref->geom[level], now->geom[level], ids, *sp, s->d_state, j0, j1, s->d_partials);
+      cudaError_t le = ea_launch_eval_sums(rd, nd, ref->geom[level], now->geom[level], ids, *sp, s->d_state->cand, &s->d_state->done, j0, j1, nb, s->d_partials, st);
+      if (le != cudaSuccess) return ea_fail(EA_ERR_CUDA, "shard eval launch: %s", cudaGetErrorString(le));
       k_shard_reduce<<<1, 32, 0, st>>>(s->d_state, s->d_partials, nb, s->d_sums);
       if (s->world > 1) NC(g_nccl.AllReduce(s->d_sums, s->d_sums, EA_SUMS, ncclDouble, ncclSum, s->comm, st));
       k_shard_lm<<<1, 1, 0, st>>>(s->d_state, s->d_sums, *sp);

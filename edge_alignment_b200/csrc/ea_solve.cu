@@ -4,6 +4,12 @@
 //
 // Replaces, for n pairs at once: the residual-block loop + ceres::Solve of
 // standalone_edge_align.cpp:265-291 (and src/SolveEA.cpp:163-198).
+//
+// Control flow: the "boss" (thread 0 of cluster rank 0) owns the LM state machine and the work queue.  Every loop
+// iteration of every CTA is exactly one evaluation: read the boss's message {point list, DT, candidate pose}, reduce
+// the CTA's slice of the points to 29 sums, hand them to the boss, who advances LM / the pyramid level / the pair
+// and publishes the next message.  Messages are parity double-buffered, so two barriers per evaluation suffice.
+// Several small CTAs share an SM, so one pair's serial LM step overlaps the other pairs' evaluations.
 #include <cooperative_groups.h>
 
 #include "ea_internal.h"
@@ -11,28 +17,42 @@
 
 namespace cg = cooperative_groups;
 
-#define EA_MAX_WARPS 32
-#define EA_FLUSH_EVERY 4  // points per thread between fp32->fp64 flushes of the normal-equation slots
+#ifndef EA_SOLVE_THREADS
+#define EA_SOLVE_THREADS 512
+#endif
+#define EA_SOLVE_WARPS (EA_SOLVE_THREADS / 32)
+#ifndef EA_SOLVE_MIN_CTAS
+#define EA_SOLVE_MIN_CTAS 1
+#endif
+#ifndef EA_FLUSH_EVERY
+#define EA_FLUSH_EVERY 8
+#endif
+// points per thread between fp32->fp64 flushes of the normal-equation slots
+#define EA_CMD_EXIT 2
 
-struct EaCtrl {  // double-buffered hand-off from the LM thread to every CTA of the cluster
+struct EaMsg {  // boss -> all threads of the cluster
   double cand[7];
-  int cmd, pad;
+  const float4* pts;
+  const float* dt;
+  int n_res, level, pts_mode, cmd;
 };
 
 struct EaSolveSmem {
-  EaCtrl ctrl[2];
-  double part[EA_MAX_WARPS][EA_NSUM];       // per-warp lane-slot sums
-  double cpart[EA_MAX_WARPS];               // per-warp cost
+  EaMsg msg[2];
+  double part[EA_SOLVE_WARPS][EA_NSUM];     // per-warp lane-slot sums
+  double cpart[EA_SOLVE_WARPS];             // per-warp cost
+  double sums[EA_SUMS + 3];                 // CTA totals
   double cluster_sums[8][EA_SUMS + 3];      // rank 0 only: one row per cluster rank
-  EaLmState lm;                             // rank 0 / thread 0 only
+  EaLmState lm;                             // boss only
+  int pair, level;                          // boss only
 };
 
-// Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads; leaves the CTA totals in
-// out[0..EA_SUMS) (valid for all threads after the trailing __syncthreads()).
+// Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads and leave per-warp partial
+// sums in S.part / S.cpart (caller synchronises).
 template <bool XYZ, int THREADS>
-__device__ __forceinline__ void ea_eval_slice(const EaLevelDesc& rd, const EaLevelDesc& nd, const EaLevelGeom& rg,
-                                              const EaLevelGeom& ng, double inv_depth_scale, const ea_solve_params& sp,
-                                              const EaPose& P, int j0, int j1, EaSolveSmem& S, double* out) {
+__device__ __forceinline__ void ea_eval_slice(const float4* __restrict__ pts, const float* __restrict__ dt, const EaLevelGeom& ng,
+                                              double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, int j0,
+                                              int j1, double (*part)[EA_NSUM], double* cpart) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float loss_a = float(sp.loss_scale);
   const int loss_type = sp.loss_type, stride = sp.point_stride;
@@ -41,20 +61,27 @@ __device__ __forceinline__ void ea_eval_slice(const EaLevelDesc& rd, const EaLev
   for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
   double acc64 = 0.0, cost64 = 0.0;
   int since_flush = 0;
+  int j = j0 + warp * 32 + lane;
+  float4 p_next = (j < j1) ? __ldg(pts + size_t(j) * stride) : make_float4(0.f, 0.f, 1.f, 0.f);
   for (int base = j0 + warp * 32; base < j1; base += THREADS) {
-    const int j = base + lane;
-    if (j < j1) {
-      const float4 p = __ldg(rd.pts + size_t(j) * stride);
-      EaPointEval e;
-      ea_point_eval<XYZ>(p, rg, ng, inv_depth_scale, P, nd.dt, e);
-      float rho0;
-      const float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
-      float J[6];
-      ea_jacobian(e, ng, w, J);
-      ea_accumulate(acc, J, e.f * w);
-      acc[27] += e.fail ? 1.0f : 0.0f;
-      cost64 += double(0.5f * rho0);
+    const float4 p = p_next;
+    const bool valid = j < j1;
+    j += THREADS;
+    if (j < j1) p_next = __ldg(pts + size_t(j) * stride);   // prefetch the next point before the gather
+    EaPointEval e;
+    ea_point_eval<XYZ>(p, ng, inv_depth_scale, P, dt, e);
+    float rho0;
+    float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
+    if (!valid) { w = 0.0f; rho0 = 0.0f; e.f = 0.0f; e.fail = false; }
+    float J[6];
+    ea_jacobian(e, P, w, J);
+    if (!valid) {   // padding lanes of the last iteration: the dummy point may project to inf/NaN
+#pragma unroll
+      for (int k = 0; k < 6; ++k) J[k] = 0.0f;
     }
+    ea_accumulate(acc, J, e.f * w);
+    acc[27] += e.fail ? 1.0f : 0.0f;
+    cost64 += double(0.5f * rho0);
     if (++since_flush == EA_FLUSH_EVERY) {
       acc64 += double(ea_warp_transpose_reduce(acc, lane));
 #pragma unroll
@@ -64,124 +91,150 @@ __device__ __forceinline__ void ea_eval_slice(const EaLevelDesc& rd, const EaLev
   }
   if (since_flush) acc64 += double(ea_warp_transpose_reduce(acc, lane));
   cost64 = ea_warp_sum(cost64);
-  S.part[warp][lane] = acc64;
-  if (lane == 0) S.cpart[warp] = cost64;
-  __syncthreads();
-  if (tid < EA_SUMS) {
-    double s = 0.0;
-    if (tid < 28) {
+  part[warp][lane] = acc64;
+  if (lane == 0) cpart[warp] = cost64;
+}
+
+// CTA totals from the per-warp partials: lane k of the calling warp returns slot k (k < EA_SUMS), fixed order.
+template <int WARPS>
+__device__ __forceinline__ double ea_cta_total(const double (*part)[EA_NSUM], const double* cpart, int lane) {
+  double s = 0.0;
+  if (lane < 28) {
+#pragma unroll
+    for (int w2 = 0; w2 < WARPS; ++w2) s += part[w2][lane];
+  } else if (lane == 28) {
+#pragma unroll
+    for (int w2 = 0; w2 < WARPS; ++w2) s += cpart[w2];
+  }
+  return s;
+}
+
+// Boss: move to the next (pair, level) that has points and publish its first evaluation, or EXIT.
+__device__ __noinline__ void ea_boss_next(const EaSolveArgs& A, EaSolveSmem& S, EaMsg& out, bool new_pair_needed) {
+  for (;;) {
+    if (new_pair_needed) {
+      const int pair = atomicAdd(A.work_counter, 1);
+      if (pair >= A.n_pairs) { out.cmd = EA_CMD_EXIT; S.pair = -1; return; }
+      S.pair = pair; S.level = A.coarsest;
+      const int pi = A.pose_index ? A.pose_index[pair] : pair;
 #pragma unroll 1
-      for (int w2 = 0; w2 < THREADS / 32; ++w2) s += S.part[w2][tid];
-    } else {
-#pragma unroll 1
-      for (int w2 = 0; w2 < THREADS / 32; ++w2) s += S.cpart[w2];
+      for (int i = 0; i < 7; ++i) S.lm.x[i] = A.poses[size_t(pi) * 7 + i];
+      new_pair_needed = false;
     }
-    out[tid] = s;
+    const int pair = S.pair, level = S.level;
+    if (level < A.finest) {  // pair finished: write the pose back, fetch another
+      const int pi = A.pose_index ? A.pose_index[pair] : pair;
+#pragma unroll 1
+      for (int i = 0; i < 7; ++i) A.poses[size_t(pi) * 7 + i] = S.lm.x[i];
+      new_pair_needed = true;
+      continue;
+    }
+    const EaLevelDesc rd = A.ref_desc[size_t(A.ref_slots[pair]) * EA_MAX_LEVELS + level];
+    const EaLevelDesc nd = A.now_desc[size_t(A.now_slots[pair]) * EA_MAX_LEVELS + level];
+    const int n_pts = min(*rd.n_pts, A.ref_cap[level]);
+    const int n_res = (n_pts + A.sp.point_stride - 1) / A.sp.point_stride;
+    if (n_res == 0) {
+      if (A.summaries) { ea_summary z = {}; z.termination = EA_TERM_SKIPPED_NO_POINTS; A.summaries[size_t(pair) * A.n_levels + level] = z; }
+      S.level = level - 1;
+      continue;
+    }
+    EaLmState& L = S.lm;
+    L.phase = 0; L.iter = 0; L.accepted = 0; L.rejected = 0; L.invalid_run = 0; L.evals = 0; L.term = EA_TERM_NONE;
+#pragma unroll 1
+    for (int i = 0; i < 7; ++i) { L.cand[i] = L.x[i]; out.cand[i] = L.x[i]; }
+    out.pts = rd.pts; out.dt = nd.dt; out.n_res = n_res; out.level = level; out.pts_mode = rd.pts_mode; out.cmd = EA_CMD_EVAL;
+    return;
   }
 }
 
+// Boss: consume the sums of one evaluation; fills `out` with the next message.
+__device__ __noinline__ void ea_boss_step(const EaSolveArgs& A, EaSolveSmem& S, const double* sums, const EaMsg& cur, EaMsg& out) {
+  const int cmd = ea_lm_advance(S.lm, sums, A.sp);
+  if (cmd == EA_CMD_EVAL) {
+#pragma unroll 1
+    for (int i = 0; i < 7; ++i) out.cand[i] = S.lm.cand[i];
+    out.pts = cur.pts; out.dt = cur.dt; out.n_res = cur.n_res; out.level = cur.level; out.pts_mode = cur.pts_mode; out.cmd = EA_CMD_EVAL;
+    return;
+  }
+  if (A.summaries) {
+    const EaLmState& L = S.lm;
+    ea_summary z;
+    z.termination = L.term; z.iterations = L.iter; z.accepted = L.accepted; z.rejected = L.rejected;
+    z.n_residuals = cur.n_res; z.evaluations = L.evals; z.initial_cost = L.initial_cost; z.final_cost = L.cost;
+    A.summaries[size_t(S.pair) * A.n_levels + cur.level] = z;
+  }
+  S.level = cur.level - 1;
+  ea_boss_next(A, S, out, false);
+}
+
 template <int THREADS, bool CLUSTER>
-__global__ void __launch_bounds__(THREADS) ea_k_solve_batch(const __grid_constant__ EaSolveArgs A) {
+__global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(const __grid_constant__ EaSolveArgs A) {
   __shared__ EaSolveSmem S;
-  __shared__ double cta_sums[EA_SUMS + 3];
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = CLUSTER ? cluster.block_rank() : 0u;
   const unsigned csize = CLUSTER ? cluster.num_blocks() : 1u;
-  const int cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool boss = (crank == 0 && tid == 0);
-  EaSolveSmem* S0 = CLUSTER ? cluster.map_shared_rank(&S, 0) : &S;
   auto sync_all = [&]() { if (CLUSTER) cluster.sync(); else __syncthreads(); };
-  unsigned g = 0;  // control-slot parity, uniform across the cluster
-
-  for (int pair = cluster_id; pair < A.n_pairs; pair += n_clusters) {
-    const int rs = A.ref_slots[pair], ns = A.now_slots[pair];
-    const int pi = A.pose_index ? A.pose_index[pair] : pair;
-    if (boss) {
-#pragma unroll 1
-      for (int i = 0; i < 7; ++i) S.lm.x[i] = A.poses[size_t(pi) * 7 + i];
+  auto publish = [&](const EaMsg& m, unsigned slot) {
+    for (unsigned r = 0; r < csize; ++r) {
+      EaSolveSmem* Sr = CLUSTER ? cluster.map_shared_rank(&S, r) : &S;
+      Sr->msg[slot] = m;
     }
-    for (int level = A.coarsest; level >= A.finest; --level) {
-      const EaLevelDesc rd = A.ref_desc[size_t(rs) * EA_MAX_LEVELS + level];
-      const EaLevelDesc nd = A.now_desc[size_t(ns) * EA_MAX_LEVELS + level];
-      const EaLevelGeom& rg = A.ref_geom[level];
-      const EaLevelGeom& ng = A.now_geom[level];
-      const int n_pts = min(*rd.n_pts, A.ref_cap[level]);
-      const int n_res = (n_pts + A.sp.point_stride - 1) / A.sp.point_stride;
-      ea_summary* sum_out = A.summaries ? A.summaries + (size_t(pair) * A.n_levels + level) : nullptr;
-      if (n_res == 0) {
-        if (boss && sum_out) { ea_summary z = {}; z.termination = EA_TERM_SKIPPED_NO_POINTS; *sum_out = z; }
-        continue;
-      }
-      const int j0 = int((long long)n_res * crank / csize), j1 = int((long long)n_res * (crank + 1) / csize);
-      // level start: publish x as the first candidate in a control slot nobody is reading
-      g += 1;
-      if (boss) {
-        EaLmState& L = S.lm;
-        L.phase = 0; L.iter = 0; L.accepted = 0; L.rejected = 0; L.invalid_run = 0; L.evals = 0; L.term = EA_TERM_NONE;
-#pragma unroll 1
-        for (int i = 0; i < 7; ++i) L.cand[i] = L.x[i];
-        for (unsigned r = 0; r < csize; ++r) {
-          EaSolveSmem* Sr = CLUSTER ? cluster.map_shared_rank(&S, r) : &S;
-#pragma unroll 1
-          for (int i = 0; i < 7; ++i) Sr->ctrl[g & 1].cand[i] = L.x[i];
-          Sr->ctrl[g & 1].cmd = EA_CMD_EVAL;
+  };
+  unsigned g = 0;
+  if (boss) {
+    EaMsg m;
+    ea_boss_next(A, S, m, true);
+    publish(m, 0);
+  }
+  sync_all();
+  for (;;) {
+    const EaMsg& M = S.msg[g & 1];
+    if (M.cmd == EA_CMD_EXIT) break;
+    const EaLevelGeom& rg = A.ref_geom[M.level];
+    const EaLevelGeom& ng = A.now_geom[M.level];
+    const int j0 = int((long long)M.n_res * crank / csize), j1 = int((long long)M.n_res * (crank + 1) / csize);
+    EaPose P;
+    if (M.pts_mode == EA_POINTS_XYZ) {
+      ea_pose_setup<true>(M.cand, rg, ng, P);
+      ea_eval_slice<true, THREADS>(M.pts, M.dt, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart);
+    } else {
+      ea_pose_setup<false>(M.cand, rg, ng, P);
+      ea_eval_slice<false, THREADS>(M.pts, M.dt, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const double tot = ea_cta_total<THREADS / 32>(S.part, S.cpart, lane);
+      if (CLUSTER) {
+        EaSolveSmem* S0 = cluster.map_shared_rank(&S, 0);
+        if (lane < EA_SUMS) S0->cluster_sums[crank][lane] = tot;
+      } else {
+        if (lane < EA_SUMS) S.sums[lane] = tot;
+        __syncwarp();
+        if (lane == 0) {
+          EaMsg m;
+          ea_boss_step(A, S, S.sums, M, m);
+          S.msg[(g + 1) & 1] = m;
         }
       }
-      sync_all();
-      for (;;) {
-        const EaCtrl& C = S.ctrl[g & 1];
-        if (C.cmd == EA_CMD_DONE) break;
-        EaPose P;
-        ea_pose_from_q(C.cand, P);
-        if (rd.pts_mode == EA_POINTS_XYZ)
-          ea_eval_slice<true, THREADS>(rd, nd, rg, ng, A.inv_depth_scale, A.sp, P, j0, j1, S, cta_sums);
-        else
-          ea_eval_slice<false, THREADS>(rd, nd, rg, ng, A.inv_depth_scale, A.sp, P, j0, j1, S, cta_sums);
-        if (CLUSTER) {
-          __syncthreads();
-          if (tid < EA_SUMS) S0->cluster_sums[crank][tid] = cta_sums[tid];
+    }
+    if (CLUSTER) {
+      cluster.sync();
+      if (crank == 0 && warp == 0) {
+        double s = 0.0;
+        if (lane < EA_SUMS) for (unsigned r = 0; r < csize; ++r) s += S.cluster_sums[r][lane];
+        if (lane < EA_SUMS) S.sums[lane] = s;
+        __syncwarp();
+        if (lane == 0) {
+          EaMsg m;
+          ea_boss_step(A, S, S.sums, M, m);
+          publish(m, (g + 1) & 1);
         }
-        sync_all();
-        if (boss) {
-          double sums[EA_SUMS];
-          if (CLUSTER) {
-#pragma unroll 1
-            for (int k = 0; k < EA_SUMS; ++k) {
-              double s = 0.0;
-              for (unsigned r = 0; r < csize; ++r) s += S.cluster_sums[r][k];
-              sums[k] = s;
-            }
-          } else {
-#pragma unroll 1
-            for (int k = 0; k < EA_SUMS; ++k) sums[k] = cta_sums[k];
-          }
-          const int cmd = ea_lm_advance(S.lm, sums, A.sp);
-          const unsigned nx = (g + 1) & 1;
-          for (unsigned r = 0; r < csize; ++r) {
-            EaSolveSmem* Sr = CLUSTER ? cluster.map_shared_rank(&S, r) : &S;
-            if (cmd == EA_CMD_EVAL) {
-#pragma unroll 1
-              for (int i = 0; i < 7; ++i) Sr->ctrl[nx].cand[i] = S.lm.cand[i];
-            }
-            Sr->ctrl[nx].cmd = cmd;
-          }
-        }
-        sync_all();
-        g += 1;
-      }
-      if (boss && sum_out) {
-        const EaLmState& L = S.lm;
-        ea_summary z;
-        z.termination = L.term; z.iterations = L.iter; z.accepted = L.accepted; z.rejected = L.rejected;
-        z.n_residuals = n_res; z.evaluations = L.evals; z.initial_cost = L.initial_cost; z.final_cost = L.cost;
-        *sum_out = z;
       }
     }
-    if (boss) {
-#pragma unroll 1
-      for (int i = 0; i < 7; ++i) A.poses[size_t(pi) * 7 + i] = S.lm.x[i];
-    }
+    sync_all();
+    g += 1;
   }
   if (CLUSTER) cluster.sync();  // no CTA may exit while a peer can still touch its shared memory
 }
@@ -192,15 +245,18 @@ __global__ void __launch_bounds__(256) ea_k_eval_points(EaLevelDesc rd, EaLevelD
                                                         double inv_depth_scale, ea_solve_params sp, const double* pose7,
                                                         int n_res, double* raw, double* res, double* jac, int* failed) {
   EaPose P;
-  ea_pose_from_q(pose7, P);
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_res; j += gridDim.x * blockDim.x) {
-    const float4 p = __ldg(rd.pts + size_t(j) * sp.point_stride);
+  ea_pose_setup<XYZ>(pose7, rg, ng, P);
+  const int n_round = (n_res + 31) & ~31;   // keep warps converged: the gather's fast path votes with __all_sync
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+    const bool valid = j < n_res;
+    const float4 p = valid ? __ldg(rd.pts + size_t(j) * sp.point_stride) : make_float4(0.f, 0.f, 1.f, 0.f);
     EaPointEval e;
-    ea_point_eval<XYZ>(p, rg, ng, inv_depth_scale, P, nd.dt, e);
+    ea_point_eval<XYZ>(p, ng, inv_depth_scale, P, nd.dt, e);
     float rho0;
     const float w = ea_loss_eval(sp.loss_type, float(sp.loss_scale), e.f, rho0);
     float J[6];
-    ea_jacobian(e, ng, w, J);
+    ea_jacobian(e, P, w, J);
+    if (!valid) continue;
     if (raw) raw[j] = double(e.f);
     if (res) res[j] = double(e.f * w);
     if (jac) {
@@ -211,41 +267,49 @@ __global__ void __launch_bounds__(256) ea_k_eval_points(EaLevelDesc rd, EaLevelD
   }
 }
 
-// Normal-equation sums through the production reduction path (one cluster-less CTA per call slice).
+// Normal-equation sums through the production reduction path (one CTA per slice of the points).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) ea_k_eval_sums(EaLevelDesc rd, EaLevelDesc nd, EaLevelGeom rg, EaLevelGeom ng,
-                                                          double inv_depth_scale, ea_solve_params sp,
-                                                          const double* pose7, int n_res, double* sums /*[grid][EA_SUMS]*/) {
-  __shared__ EaSolveSmem S;
-  __shared__ double cta_sums[EA_SUMS + 3];
+                                                          double inv_depth_scale, ea_solve_params sp, const double* pose7,
+                                                          const int* done, int j_begin, int j_end, double* sums /*[grid][EA_SUMS]*/) {
+  if (done && *done) return;
+  __shared__ double part[THREADS / 32][EA_NSUM];
+  __shared__ double cpart[THREADS / 32];
+  const int n = j_end - j_begin;
+  const int j0 = j_begin + int((long long)n * blockIdx.x / gridDim.x), j1 = j_begin + int((long long)n * (blockIdx.x + 1) / gridDim.x);
   EaPose P;
-  ea_pose_from_q(pose7, P);
-  const int j0 = int((long long)n_res * blockIdx.x / gridDim.x), j1 = int((long long)n_res * (blockIdx.x + 1) / gridDim.x);
-  if (rd.pts_mode == EA_POINTS_XYZ)
-    ea_eval_slice<true, THREADS>(rd, nd, rg, ng, inv_depth_scale, sp, P, j0, j1, S, cta_sums);
-  else
-    ea_eval_slice<false, THREADS>(rd, nd, rg, ng, inv_depth_scale, sp, P, j0, j1, S, cta_sums);
+  if (rd.pts_mode == EA_POINTS_XYZ) {
+    ea_pose_setup<true>(pose7, rg, ng, P);
+    ea_eval_slice<true, THREADS>(rd.pts, nd.dt, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
+  } else {
+    ea_pose_setup<false>(pose7, rg, ng, P);
+    ea_eval_slice<false, THREADS>(rd.pts, nd.dt, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
+  }
   __syncthreads();
-  if (threadIdx.x < EA_SUMS) sums[size_t(blockIdx.x) * EA_SUMS + threadIdx.x] = cta_sums[threadIdx.x];
+  if (threadIdx.x < 32) {
+    const double tot = ea_cta_total<THREADS / 32>(part, cpart, threadIdx.x);
+    if (threadIdx.x < EA_SUMS) sums[size_t(blockIdx.x) * EA_SUMS + threadIdx.x] = tot;
+  }
 }
 
 // ---- host launchers -----------------------------------------------------------------------------------
-#define EA_SOLVE_THREADS 512
-
 cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm_count, cudaStream_t stream) {
   if (A.n_pairs <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(A.work_counter, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(EA_SOLVE_THREADS);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   if (cluster_size <= 1) {
-    // persistent: at most one CTA per SM worth of pairs in flight; CTAs loop over pairs
-    cfg.gridDim = dim3(unsigned(A.n_pairs < sm_count * 2 ? A.n_pairs : sm_count * 2));
+    // persistent CTAs (EA_SOLVE_MIN_CTAS per SM) pulling pairs from the work queue
+    const int max_ctas = sm_count * EA_SOLVE_MIN_CTAS;
+    cfg.gridDim = dim3(unsigned(A.n_pairs < max_ctas ? A.n_pairs : max_ctas));
     cfg.numAttrs = 0;
     return cudaLaunchKernelEx(&cfg, ea_k_solve_batch<EA_SOLVE_THREADS, false>, A);
   }
   int n_clusters = A.n_pairs;
-  const int max_clusters = (sm_count / cluster_size) * 2;
+  const int max_clusters = (sm_count * EA_SOLVE_MIN_CTAS) / cluster_size;
   if (n_clusters > max_clusters) n_clusters = max_clusters;
   if (n_clusters < 1) n_clusters = 1;
   cfg.gridDim = dim3(unsigned(n_clusters * cluster_size));
@@ -273,8 +337,9 @@ cudaError_t ea_launch_eval_points(const EaLevelDesc& rd, const EaLevelDesc& nd, 
 
 cudaError_t ea_launch_eval_sums(const EaLevelDesc& rd, const EaLevelDesc& nd, const EaLevelGeom& rg,
                                 const EaLevelGeom& ng, double inv_depth_scale, const ea_solve_params& sp,
-                                const double* d_pose7, int n_res, int n_blocks, double* d_sums, cudaStream_t stream) {
-  if (n_res <= 0 || n_blocks <= 0) return cudaSuccess;
-  ea_k_eval_sums<EA_SOLVE_THREADS><<<n_blocks, EA_SOLVE_THREADS, 0, stream>>>(rd, nd, rg, ng, inv_depth_scale, sp, d_pose7, n_res, d_sums);
+                                const double* d_pose7, const int* d_done, int j_begin, int j_end, int n_blocks, double* d_sums,
+                                cudaStream_t stream) {
+  if (n_blocks <= 0) return cudaSuccess;
+  ea_k_eval_sums<EA_SOLVE_THREADS><<<n_blocks, EA_SOLVE_THREADS, 0, stream>>>(rd, nd, rg, ng, inv_depth_scale, sp, d_pose7, d_done, j_begin, j_end, d_sums);
   return cudaGetLastError();
 }

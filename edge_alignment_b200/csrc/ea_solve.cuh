@@ -41,78 +41,89 @@ __device__ inline void ea_pose_plus(const double* x, const double* d, double* ou
 }
 __device__ inline int ea_tri(int a, int c) { return a * 6 - (a * (a - 1)) / 2 + (c - a); }  // a <= c
 
-__device__ inline double ea_gradient_max_norm(const EaLmState& S) {
-  // || x - Plus(x, -g) ||_inf  (trust_region_minimizer.cc, EvaluateGradientAndJacobian)
+// true iff || x - Plus(x, -g) ||_inf <= tol  (trust_region_minimizer.cc, EvaluateGradientAndJacobian).
+// The translation block of Plus is a plain addition, so the norm is at least max|g_t| (up to one rounding of
+// x_t): unless that is already tiny the full quaternion update (sin/cos of |g|, possibly huge) is skipped.
+__device__ inline bool ea_gradient_converged(const EaLmState& S, double tol) {
+  double gt = fmax(fabs(S.b[3]), fmax(fabs(S.b[4]), fabs(S.b[5])));
+  double xt = fmax(fabs(S.x[4]), fmax(fabs(S.x[5]), fabs(S.x[6])));
+  if (gt > 2.0 * tol + 4.5e-16 * xt) return false;
   double ng[6], xp[7];
-#pragma unroll 1
+#pragma unroll
   for (int j = 0; j < 6; ++j) ng[j] = -S.b[j];
   ea_pose_plus(S.x, ng, xp);
   double m = 0.0;
-#pragma unroll 1
+#pragma unroll
   for (int i = 0; i < 7; ++i) m = fmax(m, fabs(S.x[i] - xp[i]));
-  return m;
+  return m <= tol;
 }
 
-// LevenbergMarquardtStrategy::ComputeStep on the normal equations.  Returns false on an invalid step.
+// LevenbergMarquardtStrategy::ComputeStep on the normal equations: (S H S + diag/radius) y = S b, step = -y.
+// 6x6 LDL^T in registers (fully unrolled; one reciprocal per pivot).  Returns false on an invalid step.
 __device__ inline bool ea_lm_compute_step(EaLmState& S, const ea_solve_params& sp, double* delta) {
-  double A[6][6], bs[6], y[6];
-#pragma unroll 1
+  double A[6][6], bs[6];
+#pragma unroll
   for (int a = 0; a < 6; ++a) {
     bs[a] = S.scale[a] * S.b[a];
-#pragma unroll 1
+#pragma unroll
     for (int c = a; c < 6; ++c) { A[a][c] = S.scale[a] * S.H[ea_tri(a, c)] * S.scale[c]; A[c][a] = A[a][c]; }
   }
   if (!S.reuse_diag) {
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < 6; ++j) S.diag[j] = fmin(fmax(A[j][j], sp.min_lm_diagonal), sp.max_lm_diagonal);
   }
   S.reuse_diag = 1;
-  // L L^T = H_s + diag/radius   (keep H_s in the strict upper triangle of A for the model cost)
-  double L[6][6];
+  const double inv_radius = 1.0 / S.radius;
+  // L D L^T = H_s + diag/radius  (unit lower L, D = 1/dinv)
+  double L[6][6], dinv[6], dval[6];
   bool ok = true;
-#pragma unroll 1
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double d = A[j][j] + S.diag[j] / S.radius;
-#pragma unroll 1
-    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-    if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }
-    d = sqrt(d);
-    L[j][j] = d;
-#pragma unroll 1
+    double d = fma(S.diag[j], inv_radius, A[j][j]);
+    double v[6];
+#pragma unroll
+    for (int k = 0; k < j; ++k) { v[k] = L[j][k] * dval[k]; d = fma(-L[j][k], v[k], d); }
+    ok = ok && (d > 0.0) && isfinite(d);
+    dval[j] = d;
+    dinv[j] = 1.0 / d;
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double s = A[i][j];
-#pragma unroll 1
-      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-      L[i][j] = s / d;
+#pragma unroll
+      for (int k = 0; k < j; ++k) s = fma(-L[i][k], v[k], s);
+      L[i][j] = s * dinv[j];
     }
   }
   if (!ok) return false;
-#pragma unroll 1
+  double y[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double s = bs[i];
-#pragma unroll 1
-    for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
-    y[i] = s / L[i][i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s = fma(-L[i][k], y[k], s);
+    y[i] = s;
   }
-#pragma unroll 1
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y[i] *= dinv[i];
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = y[i];
-#pragma unroll 1
-    for (int k = i + 1; k < 6; ++k) s -= L[k][i] * y[k];
-    y[i] = s / L[i][i];
-    if (!isfinite(y[i])) ok = false;
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s = fma(-L[k][i], y[k], s);
+    y[i] = s;
+    ok = ok && isfinite(s);
   }
   if (!ok) return false;
   // step = -y ; model_cost_change = -(step^T b_s + 1/2 step^T H_s step)
   double lin = 0.0, quad = 0.0;
-#pragma unroll 1
+#pragma unroll
   for (int a = 0; a < 6; ++a) {
     const double sa = -y[a];
-    lin += sa * bs[a];
+    lin = fma(sa, bs[a], lin);
     double row = 0.0;
-#pragma unroll 1
-    for (int c = 0; c < 6; ++c) row += A[a][c] * (-y[c]);
-    quad += sa * row;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) row = fma(A[a][c], -y[c], row);
+    quad = fma(sa, row, quad);
     delta[a] = sa * S.scale[a];  // undo the Jacobi column scaling
   }
   S.model_cost_change = -(lin + 0.5 * quad);
@@ -133,7 +144,7 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
     S.cost = S.initial_cost = sums[28];
 #pragma unroll 1
     for (int j = 0; j < 6; ++j) S.scale[j] = sp.jacobi_scaling ? 1.0 / (1.0 + sqrt(S.H[ea_tri(j, j)])) : 1.0;
-    if (ea_gradient_max_norm(S) <= sp.gradient_tolerance) { S.term = EA_TERM_CONVERGENCE_GRADIENT; return EA_CMD_DONE; }
+    if (ea_gradient_converged(S, sp.gradient_tolerance)) { S.term = EA_TERM_CONVERGENCE_GRADIENT; return EA_CMD_DONE; }
     S.radius = sp.initial_trust_region_radius; S.decrease_factor = 2.0; S.reuse_diag = 0;
     S.iter = 0; S.phase = 1;
   } else {
@@ -157,7 +168,7 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
       const double t = 2.0 * rel - 1.0;
       S.radius = fmin(sp.max_trust_region_radius, S.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
       S.decrease_factor = 2.0; S.reuse_diag = 0; S.accepted++;
-      if (ea_gradient_max_norm(S) <= sp.gradient_tolerance) { S.term = EA_TERM_CONVERGENCE_GRADIENT; return EA_CMD_DONE; }
+      if (ea_gradient_converged(S, sp.gradient_tolerance)) { S.term = EA_TERM_CONVERGENCE_GRADIENT; return EA_CMD_DONE; }
     } else {  // HandleUnsuccessfulStep
       S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diag = 1; S.rejected++;
     }
