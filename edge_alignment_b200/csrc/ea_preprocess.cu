@@ -92,6 +92,128 @@ __global__ void __launch_bounds__(256) k_edge_mask(const uint8_t* __restrict__ b
   }
 }
 
+// ---- v2 of the fused edge kernel: 128x32 output tile per CTA, packed pixels, separable rolling windows --------
+// Same arithmetic as k_edge_mask (bit exact); ~3x fewer instructions per pixel.  Needs w % 4 == 0 (32-bit row loads).
+#define E2_TW 128
+#define E2_TH 32
+#define E2_PW (E2_TW + 8)   // packed tile: image columns x0-4 .. x0+131
+#define E2_PH (E2_TH + 4)   // image rows y0-2 .. y0+33 (through REFLECT_101)
+#define E2_GW (E2_TW + 4)   // gray tile: columns x0-1 .. x0+128 (+2 pad)
+
+// packed pixel p = B | G<<8 | R<<16  ->  16-bit lanes {B, G} and {R}
+__device__ __forceinline__ void e2_expand(unsigned p, unsigned& bg, unsigned& r) {
+  bg = __byte_perm(p, 0, 0x4140);
+  r = __byte_perm(p, 0, 0x4442);
+}
+// 3x3 Gaussian rounding + RGB2GRAY (on BGR data) from vertical sums held in 16-bit lanes
+__device__ __forceinline__ unsigned e2_gray(unsigned v_bg, unsigned v_r) {
+  const unsigned b_bg = ((v_bg + 0x00080008u) >> 4) & 0x00FF00FFu;
+  const unsigned b_r = (v_r + 8u) >> 4;
+  const unsigned B = b_bg & 0xFFFFu, G = b_bg >> 16;
+  return (B * 9798u + G * 19235u + b_r * 3735u + 16384u) >> 15;
+}
+
+__global__ void __launch_bounds__(E2_TW) k_edge_mask2(const uint8_t* __restrict__ bgr, const uint16_t* __restrict__ depth,
+                                                      size_t frame_stride_px, const int32_t* __restrict__ src_slots,
+                                                      const int32_t* __restrict__ dst_slots, uint32_t* __restrict__ edge_bits,
+                                                      uint32_t* __restrict__ ref_bits, int w, int h, int words, int thresh) {
+  __shared__ unsigned tile[E2_PH][E2_PW];
+  __shared__ uint8_t gray[E2_TH + 2][E2_GW];
+  const int f = blockIdx.z;
+  const size_t sbase = (src_slots ? size_t(src_slots[f]) : size_t(f)) * frame_stride_px;
+  const int x0 = blockIdx.x * E2_TW, y0 = blockIdx.y * E2_TH;
+  const int t = threadIdx.x;
+  const unsigned* img = reinterpret_cast<const unsigned*>(bgr + sbase * 3);
+  const int row_words = (w * 3) >> 2;
+  // ---- phase 1: 32-bit row loads, 3 words -> 4 packed pixels ----
+  for (int i = t; i < E2_PH * (E2_PW / 4); i += E2_TW) {
+    const int r = i / (E2_PW / 4), g = i % (E2_PW / 4);
+    const int col = x0 - 4 + 4 * g;                      // first image column of the group (multiple of 4)
+    if (col < 0 || col + 3 >= w) continue;                // outside the image: never read (REFLECT_101 maps inside)
+    const int ry = reflect101(y0 - 2 + r, h);
+    const unsigned* src = img + size_t(ry) * row_words + (col * 3 >> 2);
+    const unsigned w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    uint4 px;
+    px.x = w0 & 0x00FFFFFFu;
+    px.y = (w0 >> 24) | ((w1 & 0x0000FFFFu) << 8);
+    px.z = (w1 >> 16) | ((w2 & 0x000000FFu) << 16);
+    px.w = w2 >> 8;
+    *reinterpret_cast<uint4*>(&tile[r][4 * g]) = px;
+  }
+  __syncthreads();
+  // ---- phase 2: per-column rolling 3x3 blur + gray ----
+  const int gx = x0 + t;
+  if (gx < w) {
+    const int cl = reflect101(gx - 1, w) - x0 + 4, cc = t + 4, cr = reflect101(gx + 1, w) - x0 + 4;
+    unsigned hbg0 = 0, hr0 = 0, hbg1 = 0, hr1 = 0;
+#pragma unroll 4
+    for (int r = 0; r < E2_PH; ++r) {
+      unsigned lbg, lr, cbg, crr, rbg, rr;
+      e2_expand(tile[r][cl], lbg, lr);
+      e2_expand(tile[r][cc], cbg, crr);
+      e2_expand(tile[r][cr], rbg, rr);
+      const unsigned hbg = lbg + rbg + (cbg << 1), hr = lr + rr + (crr << 1);
+      if (r >= 2) gray[r - 2][t + 1] = uint8_t(e2_gray(hbg0 + hbg + (hbg1 << 1), hr0 + hr + (hr1 << 1)));
+      hbg0 = hbg1; hr0 = hr1; hbg1 = hbg; hr1 = hr;
+    }
+  }
+  // the two halo gray columns (x0-1 and x0+128): 2 x 34 values, computed directly
+  if (t < 2 * (E2_TH + 2)) {
+    const int which = t / (E2_TH + 2), gy = t % (E2_TH + 2);
+    const int hx = which ? x0 + E2_TW : x0 - 1;
+    if (which == 0 || hx <= w) {                          // column w itself is still needed (reflect of w is w-2 ...)
+      const int cl = reflect101(hx - 1, w) - x0 + 4, cc = reflect101(hx, w) - x0 + 4, cr = reflect101(hx + 1, w) - x0 + 4;
+      if (cl >= 0 && cl < E2_PW && cc >= 0 && cc < E2_PW && cr >= 0 && cr < E2_PW) {
+        unsigned vbg = 0, vr = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          unsigned lbg, lr, cbg, crr, rbg, rr;
+          e2_expand(tile[gy + k][cl], lbg, lr);
+          e2_expand(tile[gy + k][cc], cbg, crr);
+          e2_expand(tile[gy + k][cr], rbg, rr);
+          const unsigned m = (k == 1) ? 1u : 0u;
+          vbg += (lbg + rbg + (cbg << 1)) << m;
+          vr += (lr + rr + (crr << 1)) << m;
+        }
+        gray[gy][which ? E2_TW + 1 : 0] = uint8_t(e2_gray(vbg, vr));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: Laplacian (ksize 3) + convertScaleAbs + threshold, one ballot word per warp row ----
+  const int x = x0 + t, lane = t & 31, wq = t >> 5;
+  const bool col_ok = x < w;
+  int gl = 0, gc = 0, gr = 0;
+  if (col_ok) {
+    gl = reflect101(x - 1, w) - x0 + 1; gc = t + 1; gr = reflect101(x + 1, w) - x0 + 1;
+  }
+  int s0 = 0, s1 = 0, c1 = 0;
+  if (col_ok) {
+    s0 = gray[0][gl] + gray[0][gr];
+    s1 = gray[1][gl] + gray[1][gr]; c1 = gray[1][gc];
+  }
+  const uint16_t* dep = depth ? depth + sbase : nullptr;
+  const size_t obase = size_t(dst_slots[f]) * h * words + (x0 >> 5) + wq;
+#pragma unroll 4
+  for (int r = 0; r < E2_TH; ++r) {
+    const int y = y0 + r;
+    int s2 = 0, c2 = 0;
+    if (col_ok) { s2 = gray[r + 2][gl] + gray[r + 2][gr]; c2 = gray[r + 2][gc]; }
+    int v = 2 * (s0 + s2) - 8 * c1;
+    v = v < 0 ? -v : v;
+    const bool edge = col_ok && (y < h) && (min(v, 255) > thresh);
+    bool valid = false;
+    if (edge && dep) valid = dep[size_t(y) * w + x] > 0;
+    const unsigned eb = __ballot_sync(0xffffffffu, edge);
+    const unsigned rb = __ballot_sync(0xffffffffu, edge && valid);
+    if (lane == 0 && y < h && (x0 >> 5) + wq < words) {
+      edge_bits[obase + size_t(y) * words] = eb;
+      if (ref_bits) ref_bits[obase + size_t(y) * words] = rb;
+    }
+    s0 = s1; s1 = s2; c1 = c2;
+  }
+}
+
 // ---- ordered compaction: one CTA per frame, row-major rank == reference's loop order (utils.cpp:268-280) ----
 #define CP_THREADS 1024
 __global__ void __launch_bounds__(CP_THREADS) k_compact(const uint32_t* __restrict__ ref_bits, const uint16_t* __restrict__ depth,
@@ -266,10 +388,11 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
   int left_bnd = DT_INF, right_bnd = DT_INF;
   int par = 0;
   // ---------------- forward pass: rows top -> bottom, scan left -> right ----------------
+  unsigned ebits_next = (warp_on && x0 < w) ? bits[x0 >> 5] : 0u;
   for (int y = 0; y < h; ++y, par ^= 1) {
     if (!warp_on) { __syncthreads(); continue; }
-    unsigned ebits = 0;
-    if (x0 < w) ebits = bits[size_t(y) * words + (x0 >> 5)] >> (x0 & 31);
+    const unsigned ebits = ebits_next >> (x0 & 31);
+    if (x0 < w && y + 1 < h) ebits_next = bits[size_t(y + 1) * words + (x0 >> 5)];   // prefetch the next row's mask word
     int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
     int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
     if (lane == 0) pl = left_bnd;
@@ -301,11 +424,18 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
   for (int k = 0; k < P; ++k) d[k] = DT_INF;
   left_bnd = DT_INF; right_bnd = DT_INF;
   unsigned vmax = 0, vmin = 0xFFFFFFFFu;
+  int t_next[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) t_next[k] = (warp_on && x0 + k < w) ? gi[size_t(h - 1) * w + x0 + k] : DT_INF;
   for (int y = h - 1; y >= 0; --y, par ^= 1) {
     if (!warp_on) { __syncthreads(); continue; }
     int t0[P];
 #pragma unroll
-    for (int k = 0; k < P; ++k) t0[k] = (x0 + k < w) ? gi[size_t(y) * w + x0 + k] : DT_INF;
+    for (int k = 0; k < P; ++k) t0[k] = t_next[k];
+    if (y > 0) {                                           // prefetch the forward values of the next row up
+#pragma unroll
+      for (int k = 0; k < P; ++k) if (x0 + k < w) t_next[k] = gi[size_t(y - 1) * w + x0 + k];
+    }
     int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
     int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
     if (lane == 0) pl = left_bnd;
@@ -405,8 +535,13 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
     const uint8_t* b = (l == 0) ? A.in_bgr : L.bgr;
     const uint16_t* d = want_ref ? ((l == 0) ? A.in_depth : L.depth) : nullptr;
     const int32_t* ss = (l == 0) ? nullptr : A.slots;
-    dim3 grid(unsigned((L.w + ET_W - 1) / ET_W), unsigned((L.h + ET_H - 1) / ET_H), unsigned(A.n));
-    k_edge_mask<<<grid, dim3(ET_W, ET_H), 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold);
+    if ((L.w & 3) == 0 && L.w >= 8 && L.h >= 4) {
+      dim3 grid(unsigned((L.w + E2_TW - 1) / E2_TW), unsigned((L.h + E2_TH - 1) / E2_TH), unsigned(A.n));
+      k_edge_mask2<<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold);
+    } else {   // generic byte path (any width)
+      dim3 grid(unsigned((L.w + ET_W - 1) / ET_W), unsigned((L.h + ET_H - 1) / ET_H), unsigned(A.n));
+      k_edge_mask<<<grid, dim3(ET_W, ET_H), 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold);
+    }
     ++nl;
     if (want_ref) {
       k_compact<<<A.n, CP_THREADS, 0, stream>>>(L.ref_bits, d, pxl, ss, A.slots, L.pts, A.n_pts, l, A.overflow, L.w, L.h, L.words, L.cap);
