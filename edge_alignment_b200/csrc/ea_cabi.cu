@@ -188,10 +188,15 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
   if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_npts, size_t(n_slots) * EA_MAX_LEVELS * sizeof(int));
   if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_minmax, size_t(n_slots) * EA_MAX_LEVELS * 2 * sizeof(unsigned));
   if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_overflow, sizeof(int));
+  if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_affine, size_t(n_slots) * EA_MAX_LEVELS * sizeof(float2));
   if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_desc, size_t(n_slots) * EA_MAX_LEVELS * sizeof(EaLevelDesc));
   if (rc != EA_OK) { ea_frameset_destroy(fs); return rc; }
   cudaMemsetAsync(fs->d_npts, 0, size_t(n_slots) * EA_MAX_LEVELS * sizeof(int), ctx->stream);
   cudaMemsetAsync(fs->d_overflow, 0, sizeof(int), ctx->stream);
+  {
+    std::vector<float2> ones(size_t(n_slots) * EA_MAX_LEVELS, make_float2(1.0f, 0.0f));
+    cudaMemcpy(fs->d_affine, ones.data(), ones.size() * sizeof(float2), cudaMemcpyHostToDevice);
+  }
   fs->h_desc.assign(size_t(n_slots) * EA_MAX_LEVELS, EaLevelDesc{});
   for (int s = 0; s < n_slots; ++s)
     for (int l = 0; l < p->n_levels; ++l) {
@@ -200,6 +205,7 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
       D.pts = L.pts + size_t(s) * L.cap;
       D.n_pts = fs->d_npts + size_t(s) * EA_MAX_LEVELS + l;
       D.dt = L.dt + size_t(s) * L.w * L.h;
+      D.dt_affine = fs->d_affine + size_t(s) * EA_MAX_LEVELS + l;
       D.w = L.w; D.h = L.h; D.pts_mode = EA_POINTS_PIXEL; D.pad = 0;
     }
   CU(cudaMemcpyAsync(fs->d_desc, fs->h_desc.data(), fs->h_desc.size() * sizeof(EaLevelDesc), cudaMemcpyHostToDevice, ctx->stream));
@@ -234,7 +240,7 @@ int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uin
   std::memset(&A, 0, sizeof A);
   for (int l = 0; l < fs->p.n_levels; ++l) A.lv[l] = fs->lv[l];
   A.n_levels = fs->p.n_levels; A.slots = d_slots; A.in_bgr = d_bgr; A.in_depth = d_depth;
-  A.n_pts = fs->d_npts; A.dt_minmax = fs->d_minmax; A.overflow = fs->d_overflow;
+  A.n_pts = fs->d_npts; A.dt_minmax = fs->d_minmax; A.dt_affine = fs->d_affine; A.overflow = fs->d_overflow;
   A.n = n; A.roles = roles; A.grad_threshold = fs->p.grad_threshold; A.use_median = fs->p.use_median;
   A.dt_normalize = fs->p.dt_normalize;
   int nl = 0;
@@ -310,6 +316,8 @@ int ea_frameset_set_dt(ea_frameset* fs, int slot, int level, const float* dt) {
   ea_context* c = fs->ctx;
   CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(L.dt + size_t(slot) * L.w * L.h, dt, size_t(L.w) * L.h * 4, cudaMemcpyHostToDevice, c->stream));
+  const float2 one = make_float2(1.0f, 0.0f);   // the caller's DT is used as is
+  CU(cudaMemcpyAsync(fs->d_affine + size_t(slot) * EA_MAX_LEVELS + level, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return EA_OK;
 }
@@ -346,7 +354,14 @@ int ea_frameset_get_dt(ea_frameset* fs, int slot, int level, float* dt) {
   const EaPrepLevel& L = fs->lv[level];
   ea_context* c = fs->ctx;
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(dt, L.dt + size_t(slot) * L.w * L.h, size_t(L.w) * L.h * 4, cudaMemcpyDeviceToHost, c->stream));
+  // the device keeps the raw chamfer DT plus the normalisation {scale, shift}; hand back the normalised image
+  rc = ea_ensure_tmp(c, size_t(L.w) * L.h * 4);
+  if (rc) return rc;
+  cudaError_t e = ea_launch_dt_normalized_copy(L.dt + size_t(slot) * L.w * L.h, fs->d_affine + size_t(slot) * EA_MAX_LEVELS + level,
+                                              L.w * L.h, (float*)c->d_tmp, c->stream);
+  c->launches++;
+  if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "dt copy: %s", cudaGetErrorString(e));
+  CU(cudaMemcpyAsync(dt, c->d_tmp, size_t(L.w) * L.h * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return EA_OK;
 }

@@ -22,7 +22,8 @@
 struct EaLevelDesc {   // one per (slot, level); lives in device memory
   const float4* pts;   // point stream (EA_POINTS_PIXEL: {u,v,raw depth,1}; EA_POINTS_XYZ: {X,Y,Z,1})
   const int* n_pts;    // device-resident count (written by the compaction kernel)
-  const float* dt;     // normalised distance transform [h][w] f32
+  const float* dt;     // raw chamfer distance transform [h][w] f32 (pixels)
+  const float2* dt_affine;  // {scale, shift} of cv::normalize(MINMAX): sampled value = raw * scale + shift
   int w, h;
   int pts_mode, pad;
 };
@@ -113,7 +114,7 @@ __device__ __forceinline__ void ea_floor_frac(double x, int& i, float& frac) {
 // Warp, project, bicubic lookup for one edge point.
 template <bool XYZ>
 __device__ __forceinline__ void ea_point_eval(const float4 p, const EaLevelGeom& now, double inv_depth_scale, const EaPose& P,
-                                              const float* __restrict__ dt, EaPointEval& o) {
+                                              const float* __restrict__ dt, const float2 affine, EaPointEval& o) {
   const double a0 = double(p.x), a1 = double(p.y);
   double q0, q1, q2;
   if (XYZ) {
@@ -166,8 +167,12 @@ __device__ __forceinline__ void ea_point_eval(const float4 p, const EaLevelGeom&
   ea_cubic(p01, p11, p21, p31, dv, f1, d1);
   ea_cubic(p02, p12, p22, p32, dv, f2, d2);
   ea_cubic(p03, p13, p23, p33, dv, f3, d3);
-  ea_cubic(f0, f1, f2, f3, du, o.f, o.dfdu);
-  o.dfdv = ea_cubic_val(d0, d1, d2, d3, du);
+  float fr, fdu;
+  ea_cubic(f0, f1, f2, f3, du, fr, fdu);
+  // cv::normalize(NORM_MINMAX) folded into the sampler: the interpolant is linear in the texels
+  o.f = fmaf(fr, affine.x, affine.y);
+  o.dfdu = fdu * affine.x;
+  o.dfdv = ea_cubic_val(d0, d1, d2, d3, du) * affine.x;
   o.ub = float(u - P.cx); o.vb = float(v - P.cy);
   o.pz = float(q2); o.iz = float(iz);
 }

@@ -53,11 +53,13 @@ struct EaPrepArgs {
   const uint16_t* in_depth;     // [n][h0][w0] or null
   int* n_pts;                   // [slots][EA_MAX_LEVELS]
   unsigned* dt_minmax;          // [slots][EA_MAX_LEVELS][2]  (min,max of the fixed-point DT)
+  float2* dt_affine;            // [slots][EA_MAX_LEVELS]     {scale, shift} of the min-max normalisation
   int* overflow;                // single flag: some point list was truncated
   int n, roles, grad_threshold, use_median, dt_normalize;
 };
 // enqueue the whole preprocessing pipeline for n frames; returns number of kernel launches via *launches
 cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches);
+cudaError_t ea_launch_dt_normalized_copy(const float* raw, const float2* affine, int npx, float* out, cudaStream_t stream);
 cudaError_t ea_launch_unpack_mask(const uint32_t* bits, int w, int h, int words, int median, uint8_t* out,
                                   cudaStream_t stream);
 
@@ -100,6 +102,7 @@ struct ea_frameset {
   std::vector<EaLevelDesc> h_desc;
   int* d_npts = nullptr;                  // [n_slots][EA_MAX_LEVELS]
   unsigned* d_minmax = nullptr;
+  float2* d_affine = nullptr;             // [n_slots][EA_MAX_LEVELS]
   int* d_overflow = nullptr;
   uint8_t* stage_bgr = nullptr;           // [n_slots][h][w][3]  (host-upload staging)
   uint16_t* stage_depth = nullptr;

@@ -7,6 +7,8 @@
 //                                                          normalize MINMAX)
 // Integer stages are bit-exact restatements of OpenCV's portable code paths (pinned in tests/golden).
 // HBM-bound byte/integer work: coalesced loads, shared-memory staging, no tensor cores.
+#include <cstdlib>
+
 #include "ea_internal.h"
 
 namespace {
@@ -467,31 +469,24 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
     for (int i = 0; i < n_warps; ++i) { mn = min(mn, red[0][i]); mx = max(mx, red[1][i]); }
     A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2] = mn;
     A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2 + 1] = mx;
+    // cv::normalize(NORM_MINMAX, alpha = 0, beta): scale = beta / (max - min), shift = -min * scale (double, then float)
+    float2 aff = make_float2(1.0f, 0.0f);
+    if (A.dt_normalize != EA_NORM_NONE) {
+      const double beta = (A.dt_normalize == EA_NORM_255) ? 255.0 : 1.0;
+      const float fmn = float(mn) * (1.0f / 65536.0f), fmx = float(mx) * (1.0f / 65536.0f);
+      const double range = double(fmx) - double(fmn);
+      const double scale = beta * (range > 2.220446049250313e-16 ? 1.0 / range : 0.0);
+      aff = make_float2(float(scale), float(0.0 - double(fmn) * scale));
+    }
+    A.dt_affine[slot * EA_MAX_LEVELS + level] = aff;
   }
 }
 
-// ---- cv::normalize(NORM_MINMAX, alpha=0, beta) on CV_32F, every level in one launch ------------------------
-__global__ void __launch_bounds__(256) k_dt_normalize(const __grid_constant__ EaPrepArgs A, double beta) {
-  const int level = blockIdx.z;
-  const EaPrepLevel& L = A.lv[level];
-  const int npx = L.w * L.h;
-  const int slot = A.slots[blockIdx.y];
-  const float mn = float(A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2]) * (1.0f / 65536.0f);
-  const float mx = float(A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2 + 1]) * (1.0f / 65536.0f);
-  const double range = double(mx) - double(mn);
-  const double scale = beta * (range > 2.220446049250313e-16 ? 1.0 / range : 0.0);
-  const float fs = float(scale), fb = float(0.0 - double(mn) * scale);
-  float4* d4 = reinterpret_cast<float4*>(L.dt + size_t(slot) * npx);   // npx is a multiple of 4 (w, h >= 8, even)
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx / 4; i += gridDim.x * blockDim.x) {
-    float4 v = d4[i];
-    v.x = __fadd_rn(__fmul_rn(v.x, fs), fb); v.y = __fadd_rn(__fmul_rn(v.y, fs), fb);
-    v.z = __fadd_rn(__fmul_rn(v.z, fs), fb); v.w = __fadd_rn(__fmul_rn(v.w, fs), fb);
-    d4[i] = v;
-  }
-  if (blockIdx.x == 0 && threadIdx.x < (npx & 3)) {
-    float* d = L.dt + size_t(slot) * npx + (npx & ~3) + threadIdx.x;
-    *d = __fadd_rn(__fmul_rn(*d, fs), fb);
-  }
+// ---- normalised copy of one DT (read-back for parity tests): dst = raw * scale + shift, exactly as cv::normalize ----
+__global__ void __launch_bounds__(256) k_dt_normalized_copy(const float* __restrict__ raw, const float2* __restrict__ affine, int npx,
+                                                            float* __restrict__ out) {
+  const float2 a = *affine;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) out[i] = __fadd_rn(__fmul_rn(raw[i], a.x), a.y);
 }
 
 __global__ void __launch_bounds__(256) k_unpack_mask(const uint32_t* __restrict__ bits, int w, int h, int words, int median,
@@ -556,7 +551,8 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
       ++nl;
     }
     // every level of every frame in one launch: CTA (frame, level); block sized for level 0
-    const int P = (L0.w <= 2048) ? 2 : ((L0.w <= 4096) ? 4 : 8);
+    int P = (L0.w <= 4096) ? 4 : 8;
+    if (const char* e = getenv("EA_DT_P")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v > P) P = v; }   // tuning knob
     const int threads = (((L0.w + P - 1) / P + 31) / 32) * 32;
     if (threads > 1024) return cudaErrorInvalidValue;
     dim3 grid(unsigned(A.n), unsigned(A.n_levels));
@@ -564,15 +560,13 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
     else if (P == 4) k_chamfer_dt<4><<<grid, threads, 0, stream>>>(A);
     else k_chamfer_dt<8><<<grid, threads, 0, stream>>>(A);
     ++nl;
-    if (A.dt_normalize != EA_NORM_NONE) {
-      int bx = int((px0 / 4 + 255) / 256);
-      const int cap = sm_count * 4;
-      if (bx > cap) bx = cap;
-      k_dt_normalize<<<dim3(unsigned(bx), unsigned(A.n), unsigned(A.n_levels)), 256, 0, stream>>>(A, A.dt_normalize == EA_NORM_255 ? 255.0 : 1.0);
-      ++nl;
-    }
   }
   if (launches) *launches = nl;
+  return cudaGetLastError();
+}
+
+cudaError_t ea_launch_dt_normalized_copy(const float* raw, const float2* affine, int npx, float* out, cudaStream_t stream) {
+  k_dt_normalized_copy<<<(npx + 255) / 256, 256, 0, stream>>>(raw, affine, npx, out);
   return cudaGetLastError();
 }
 

@@ -34,6 +34,7 @@ struct EaMsg {  // boss -> all threads of the cluster
   double cand[7];
   const float4* pts;
   const float* dt;
+  float2 affine;
   int n_res, level, pts_mode, cmd;
 };
 
@@ -50,7 +51,8 @@ struct EaSolveSmem {
 // Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads and leave per-warp partial
 // sums in S.part / S.cpart (caller synchronises).
 template <bool XYZ, int THREADS>
-__device__ __forceinline__ void ea_eval_slice(const float4* __restrict__ pts, const float* __restrict__ dt, const EaLevelGeom& ng,
+__device__ __forceinline__ void ea_eval_slice(const float4* __restrict__ pts, const float* __restrict__ dt, const float2 affine,
+                                              const EaLevelGeom& ng,
                                               double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, int j0,
                                               int j1, double (*part)[EA_NSUM], double* cpart) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -69,7 +71,7 @@ __device__ __forceinline__ void ea_eval_slice(const float4* __restrict__ pts, co
     j += THREADS;
     if (j < j1) p_next = __ldg(pts + size_t(j) * stride);   // prefetch the next point before the gather
     EaPointEval e;
-    ea_point_eval<XYZ>(p, ng, inv_depth_scale, P, dt, e);
+    ea_point_eval<XYZ>(p, ng, inv_depth_scale, P, dt, affine, e);
     float rho0;
     float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
     if (!valid) { w = 0.0f; rho0 = 0.0f; e.f = 0.0f; e.fail = false; }
@@ -142,7 +144,7 @@ __device__ __noinline__ void ea_boss_next(const EaSolveArgs& A, EaSolveSmem& S, 
     L.phase = 0; L.iter = 0; L.accepted = 0; L.rejected = 0; L.invalid_run = 0; L.evals = 0; L.term = EA_TERM_NONE;
 #pragma unroll 1
     for (int i = 0; i < 7; ++i) { L.cand[i] = L.x[i]; out.cand[i] = L.x[i]; }
-    out.pts = rd.pts; out.dt = nd.dt; out.n_res = n_res; out.level = level; out.pts_mode = rd.pts_mode; out.cmd = EA_CMD_EVAL;
+    out.pts = rd.pts; out.dt = nd.dt; out.affine = *nd.dt_affine; out.n_res = n_res; out.level = level; out.pts_mode = rd.pts_mode; out.cmd = EA_CMD_EVAL;
     return;
   }
 }
@@ -153,7 +155,7 @@ __device__ __noinline__ void ea_boss_step(const EaSolveArgs& A, EaSolveSmem& S, 
   if (cmd == EA_CMD_EVAL) {
 #pragma unroll 1
     for (int i = 0; i < 7; ++i) out.cand[i] = S.lm.cand[i];
-    out.pts = cur.pts; out.dt = cur.dt; out.n_res = cur.n_res; out.level = cur.level; out.pts_mode = cur.pts_mode; out.cmd = EA_CMD_EVAL;
+    out.pts = cur.pts; out.dt = cur.dt; out.affine = cur.affine; out.n_res = cur.n_res; out.level = cur.level; out.pts_mode = cur.pts_mode; out.cmd = EA_CMD_EVAL;
     return;
   }
   if (A.summaries) {
@@ -198,10 +200,10 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
     EaPose P;
     if (M.pts_mode == EA_POINTS_XYZ) {
       ea_pose_setup<true>(M.cand, rg, ng, P);
-      ea_eval_slice<true, THREADS>(M.pts, M.dt, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart);
+      ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart);
     } else {
       ea_pose_setup<false>(M.cand, rg, ng, P);
-      ea_eval_slice<false, THREADS>(M.pts, M.dt, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart);
+      ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart);
     }
     __syncthreads();
     if (warp == 0) {
@@ -246,12 +248,13 @@ __global__ void __launch_bounds__(256) ea_k_eval_points(EaLevelDesc rd, EaLevelD
                                                         int n_res, double* raw, double* res, double* jac, int* failed) {
   EaPose P;
   ea_pose_setup<XYZ>(pose7, rg, ng, P);
+  const float2 affine = *nd.dt_affine;
   const int n_round = (n_res + 31) & ~31;   // keep warps converged: the gather's fast path votes with __all_sync
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
     const bool valid = j < n_res;
     const float4 p = valid ? __ldg(rd.pts + size_t(j) * sp.point_stride) : make_float4(0.f, 0.f, 1.f, 0.f);
     EaPointEval e;
-    ea_point_eval<XYZ>(p, ng, inv_depth_scale, P, nd.dt, e);
+    ea_point_eval<XYZ>(p, ng, inv_depth_scale, P, nd.dt, affine, e);
     float rho0;
     const float w = ea_loss_eval(sp.loss_type, float(sp.loss_scale), e.f, rho0);
     float J[6];
@@ -280,10 +283,10 @@ __global__ void __launch_bounds__(THREADS) ea_k_eval_sums(EaLevelDesc rd, EaLeve
   EaPose P;
   if (rd.pts_mode == EA_POINTS_XYZ) {
     ea_pose_setup<true>(pose7, rg, ng, P);
-    ea_eval_slice<true, THREADS>(rd.pts, nd.dt, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
+    ea_eval_slice<true, THREADS>(rd.pts, nd.dt, *nd.dt_affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
   } else {
     ea_pose_setup<false>(pose7, rg, ng, P);
-    ea_eval_slice<false, THREADS>(rd.pts, nd.dt, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
+    ea_eval_slice<false, THREADS>(rd.pts, nd.dt, *nd.dt_affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
   }
   __syncthreads();
   if (threadIdx.x < 32) {
