@@ -3,6 +3,7 @@
 // ea_preprocess.cu / ea_solve.cu.  No CPU fallback: every entry point fails loudly without a device.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -53,6 +54,8 @@ int ea_create(int device, ea_context** out) {
   CU(cudaMalloc(&c->d_pose, 7 * sizeof(double)));
   CU(cudaMalloc(&c->d_failed, sizeof(int)));
   CU(cudaMalloc(&c->d_work, sizeof(int)));
+  CU(cudaMalloc(&c->d_queue, sizeof(EaQueue)));
+  CU(cudaMalloc(&c->d_slots, size_t(EA_QUEUE_CAP) * sizeof(unsigned long long)));
   CU(cudaMalloc(&c->d_sums, size_t(1024) * EA_SUMS * sizeof(double)));
   *out = c;
   return EA_OK;
@@ -61,7 +64,7 @@ int ea_destroy(ea_context* c) {
   if (!c) return EA_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_work); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
+  cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_work); cudaFree(c->d_queue); cudaFree(c->d_slots); cudaFree(c->d_states); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return EA_OK;
@@ -479,7 +482,7 @@ static int fill_solve_args(ea_context* c, ea_frameset* ref, ea_frameset* now, co
   return EA_OK;
 }
 
-static int auto_cluster(ea_context* c, int n_pairs, int requested) {
+[[maybe_unused]] static int auto_cluster(ea_context* c, int n_pairs, int requested) {
   if (requested > 0) return requested;
   // few pairs: spread each over a cluster so the whole GPU works on them; many pairs: one CTA per pair
   if (n_pairs * 8 <= c->sm_count) return 8;
@@ -501,7 +504,27 @@ int ea_solve_batch_device(ea_context* c, int n, ea_frameset* ref, const int32_t*
   A.ref_slots = d_ref_slots; A.now_slots = d_now_slots; A.pose_index = d_pose_index; A.poses = d_poses7;
   A.summaries = d_summaries; A.n_pairs = n; A.work_counter = c->d_work;
   EaProfileScope prof(c, 1);
-  cudaError_t e = ea_launch_solve_batch(A, auto_cluster(c, n, cluster), c->sm_count, c->stream);
+  cudaError_t e;
+  if (cluster >= 2) {
+    // explicit request: one thread-block cluster per pair (DSMEM reduction), ea_solve.cu
+    e = ea_launch_solve_batch(A, cluster, c->sm_count, c->stream);
+  } else {
+    // default: task-graph kernel -- (pair, chunk) evaluation tasks through a device-side queue, ea_solve_tasks.cu
+    if (c->states_cap < size_t(n)) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->d_states) cudaFree(c->d_states);
+      c->d_states = nullptr; c->states_cap = 0;
+      const size_t cap = std::max<size_t>(size_t(n), 64);
+      CU(cudaMalloc((void**)&c->d_states, cap * sizeof(EaPairState)));
+      c->states_cap = cap;
+    }
+    A.states = c->d_states; A.queue = c->d_queue; A.slots = c->d_slots;
+    static const int env_window = getenv("EA_SOLVE_WINDOW") ? atoi(getenv("EA_SOLVE_WINDOW")) : 0;     // tuning knobs
+    static const int env_chunk = getenv("EA_SOLVE_CHUNK") ? atoi(getenv("EA_SOLVE_CHUNK")) : 0;
+    A.window = env_window;
+    A.chunk_points = env_chunk > 0 ? env_chunk : 4096;
+    e = (cluster == 1) ? ea_launch_solve_batch(A, 1, c->sm_count, c->stream) : ea_launch_solve_tasks(A, c->sm_count, c->stream);
+  }
   c->launches++;
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "solve launch: %s", cudaGetErrorString(e));
   return EA_OK;

@@ -7,6 +7,8 @@
 
 #include "ea_device.cuh"
 
+#include "ea_solve_state.h"
+
 struct EaSolveArgs {
   const EaLevelDesc* ref_desc;  // [ref slots][EA_MAX_LEVELS]
   const EaLevelDesc* now_desc;  // [now slots][EA_MAX_LEVELS]
@@ -15,6 +17,11 @@ struct EaSolveArgs {
   const int32_t* pose_index;    // [n_pairs] device or null (identity)
   double* poses;                // [*][7] device, in/out
   int* work_counter;            // device: next pair index of the dynamic work queue (zeroed per launch)
+  // task-graph kernel (ea_solve_tasks.cu)
+  EaPairState* states;          // [n_pairs]
+  EaQueue* queue;
+  unsigned long long* slots;    // [EA_QUEUE_CAP]
+  int window, chunk_points;
   ea_summary* summaries;        // [n_pairs][n_levels] device or null
   int n_pairs, n_levels, coarsest, finest;
   double inv_depth_scale;
@@ -25,6 +32,7 @@ struct EaSolveArgs {
 };
 
 cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm_count, cudaStream_t stream);
+cudaError_t ea_launch_solve_tasks(const EaSolveArgs& A, int sm_count, cudaStream_t stream);
 cudaError_t ea_launch_eval_points(const EaLevelDesc& rd, const EaLevelDesc& nd, const EaLevelGeom& rg,
                                   const EaLevelGeom& ng, double inv_depth_scale, const ea_solve_params& sp,
                                   const double* d_pose7, int n_res, double* d_raw, double* d_res, double* d_jac,
@@ -73,6 +81,9 @@ struct ea_context {
   double* d_pose = nullptr;      // [7]
   int* d_failed = nullptr;
   int* d_work = nullptr;         // work-queue counter of the batched solve
+  EaPairState* d_states = nullptr; size_t states_cap = 0;   // task-graph solve: per-pair state
+  EaQueue* d_queue = nullptr;
+  unsigned long long* d_slots = nullptr;
   double* d_sums = nullptr;      // [max blocks][EA_SUMS]
   int32_t* d_idx = nullptr;      // scratch slot indices
   size_t idx_cap = 0;

@@ -24,9 +24,6 @@ namespace cg = cooperative_groups;
 #ifndef EA_SOLVE_MIN_CTAS
 #define EA_SOLVE_MIN_CTAS 1
 #endif
-#ifndef EA_FLUSH_EVERY
-#define EA_FLUSH_EVERY 8
-#endif
 // points per thread between fp32->fp64 flushes of the normal-equation slots
 #define EA_CMD_EXIT 2
 
@@ -47,69 +44,6 @@ struct EaSolveSmem {
   EaLmState lm;                             // boss only
   int pair, level;                          // boss only
 };
-
-// Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads and leave per-warp partial
-// sums in S.part / S.cpart (caller synchronises).
-template <bool XYZ, int THREADS>
-__device__ __forceinline__ void ea_eval_slice(const float4* __restrict__ pts, const float* __restrict__ dt, const float2 affine,
-                                              const EaLevelGeom& ng,
-                                              double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, int j0,
-                                              int j1, double (*part)[EA_NSUM], double* cpart) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float loss_a = float(sp.loss_scale);
-  const int loss_type = sp.loss_type, stride = sp.point_stride;
-  float acc[EA_NSUM];
-#pragma unroll
-  for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
-  double acc64 = 0.0, cost64 = 0.0;
-  int since_flush = 0;
-  int j = j0 + warp * 32 + lane;
-  float4 p_next = (j < j1) ? __ldg(pts + size_t(j) * stride) : make_float4(0.f, 0.f, 1.f, 0.f);
-  for (int base = j0 + warp * 32; base < j1; base += THREADS) {
-    const float4 p = p_next;
-    const bool valid = j < j1;
-    j += THREADS;
-    if (j < j1) p_next = __ldg(pts + size_t(j) * stride);   // prefetch the next point before the gather
-    EaPointEval e;
-    ea_point_eval<XYZ>(p, ng, inv_depth_scale, P, dt, affine, e);
-    float rho0;
-    float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
-    if (!valid) { w = 0.0f; rho0 = 0.0f; e.f = 0.0f; e.fail = false; }
-    float J[6];
-    ea_jacobian(e, P, w, J);
-    if (!valid) {   // padding lanes of the last iteration: the dummy point may project to inf/NaN
-#pragma unroll
-      for (int k = 0; k < 6; ++k) J[k] = 0.0f;
-    }
-    ea_accumulate(acc, J, e.f * w);
-    acc[27] += e.fail ? 1.0f : 0.0f;
-    cost64 += double(0.5f * rho0);
-    if (++since_flush == EA_FLUSH_EVERY) {
-      acc64 += double(ea_warp_transpose_reduce(acc, lane));
-#pragma unroll
-      for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
-      since_flush = 0;
-    }
-  }
-  if (since_flush) acc64 += double(ea_warp_transpose_reduce(acc, lane));
-  cost64 = ea_warp_sum(cost64);
-  part[warp][lane] = acc64;
-  if (lane == 0) cpart[warp] = cost64;
-}
-
-// CTA totals from the per-warp partials: lane k of the calling warp returns slot k (k < EA_SUMS), fixed order.
-template <int WARPS>
-__device__ __forceinline__ double ea_cta_total(const double (*part)[EA_NSUM], const double* cpart, int lane) {
-  double s = 0.0;
-  if (lane < 28) {
-#pragma unroll
-    for (int w2 = 0; w2 < WARPS; ++w2) s += part[w2][lane];
-  } else if (lane == 28) {
-#pragma unroll
-    for (int w2 = 0; w2 < WARPS; ++w2) s += cpart[w2];
-  }
-  return s;
-}
 
 // Boss: move to the next (pair, level) that has points and publish its first evaluation, or EXIT.
 __device__ __noinline__ void ea_boss_next(const EaSolveArgs& A, EaSolveSmem& S, EaMsg& out, bool new_pair_needed) {
