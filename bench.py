@@ -126,8 +126,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=296, help="camera streams per GPU (2 per SM)")
-    ap.add_argument("--cluster", type=int, default=1)
+    ap.add_argument("--streams", type=int, default=592, help="camera streams per GPU (4 per SM)")
+    ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -247,8 +247,13 @@ def main():
             tracker.step_host(hb.data_ptr() + t * frame_b, hd.data_ptr() + t * frame_d, fetch=True)
         barrier()
         e0.record(stream)
+        # pipelined: frame t is submitted (its upload overlaps the alignment of frame t-1), then the poses of frame
+        # t-1 are read on the host.  Every step's frames cross PCIe and every step's result is read back.
         for t in range(Wm + 1, T):
-            poses, _ = tracker.step_host(hb.data_ptr() + t * frame_b, hd.data_ptr() + t * frame_d, fetch=True)
+            tracker.step_host(hb.data_ptr() + t * frame_b, hd.data_ptr() + t * frame_d, fetch=False)
+            if t > Wm + 1:
+                poses, _ = tracker.wait(t - 1)
+        poses, _ = tracker.wait(T - 1)
         e1.record(stream)
         barrier()
         ms_e = e0.elapsed_time(e1)

@@ -208,6 +208,17 @@ class Tracker:
         _check(L.lib().ea_tracker_step_host(self._h, bgr_ptr, depth_ptr or None, None, None))
         return None
 
+    def wait(self, frame):
+        """Results of a frame submitted with step_host(..., fetch=False)."""
+        poses = np.empty((self.n_streams, 7)); S = (L.Summary * (self.n_streams * self.n_levels))()
+        _check(L.lib().ea_tracker_wait(self._h, frame, _ptr(poses, C.c_double), S))
+        return poses, S
+
+    def frame_index(self):
+        n = C.c_int()
+        _check(L.lib().ea_tracker_frame_index(self._h, C.byref(n)))
+        return n.value
+
     def step_device(self, d_bgr, d_depth=0):
         _check(L.lib().ea_tracker_step_device(self._h, d_bgr, d_depth or None))
 

@@ -401,7 +401,7 @@ static int check_solve_params(const ea_solve_params* sp) {
   if (!(sp->loss_scale > 0)) return ea_fail(EA_ERR_INVALID_ARG, "loss_scale must be positive");
   if (sp->max_num_iterations < 0) return ea_fail(EA_ERR_INVALID_ARG, "max_num_iterations must be >= 0");
   const int cs = sp->cluster_size;
-  if (!(cs == 0 || cs == 1 || cs == 2 || cs == 4 || cs == 8)) return ea_fail(EA_ERR_INVALID_ARG, "cluster_size must be 0,1,2,4 or 8");
+  if (!(cs == -1 || cs == 0 || cs == 1 || cs == 2 || cs == 4 || cs == 8)) return ea_fail(EA_ERR_INVALID_ARG, "cluster_size must be -1,0,1,2,4 or 8");
   return EA_OK;
 }
 static int check_pairable(ea_frameset* ref, ea_frameset* now) {
@@ -523,7 +523,10 @@ int ea_solve_batch_device(ea_context* c, int n, ea_frameset* ref, const int32_t*
     static const int env_chunk = getenv("EA_SOLVE_CHUNK") ? atoi(getenv("EA_SOLVE_CHUNK")) : 0;
     A.window = env_window;
     A.chunk_points = env_chunk > 0 ? env_chunk : 4096;
-    e = (cluster == 1) ? ea_launch_solve_batch(A, 1, c->sm_count, c->stream) : ea_launch_solve_tasks(A, c->sm_count, c->stream);
+    // auto: big batches keep one persistent CTA per pair (no scheduling overhead, best L1 locality: measured faster
+    // from ~sm_count/2 pairs up); small batches spread every evaluation over the GPU through the task queue
+    const bool tasks = (cluster == -1) || (cluster == 0 && n < c->sm_count / 2);
+    e = tasks ? ea_launch_solve_tasks(A, c->sm_count, c->stream) : ea_launch_solve_batch(A, 1, c->sm_count, c->stream);
   }
   c->launches++;
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "solve launch: %s", cudaGetErrorString(e));

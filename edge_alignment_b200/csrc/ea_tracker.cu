@@ -20,6 +20,14 @@ struct ea_tracker {
   double* d_result = nullptr;      // poses of the latest step [n_streams][7]
   double* d_identity = nullptr;    // [n_streams][7]
   ea_summary* d_summaries = nullptr;
+  // host-input pipeline: frame t+1 is uploaded on a copy stream while frame t is being aligned
+  cudaStream_t copy_stream = nullptr;
+  uint8_t* stage_bgr[2] = {nullptr, nullptr};
+  uint16_t* stage_depth[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_result[2] = {nullptr, nullptr};
+  double* h_poses[2] = {nullptr, nullptr};          // pinned result ring
+  ea_summary* h_summaries[2] = {nullptr, nullptr};
+  int result_frame[2] = {-1, -1};
 };
 
 extern "C" {
@@ -46,6 +54,14 @@ int ea_tracker_create(ea_context* ctx, const ea_frame_params* fp, const ea_solve
   CU(cudaMemcpy(t->d_slots[0], s0.data(), n_streams * sizeof(int32_t), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(t->d_slots[1], s1.data(), n_streams * sizeof(int32_t), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(t->d_identity, id.data(), id.size() * 8, cudaMemcpyHostToDevice));
+  CU(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CU(cudaEventCreateWithFlags(&t->ev_copied[b], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&t->ev_consumed[b], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&t->ev_result[b], cudaEventDisableTiming));
+    CU(cudaHostAlloc((void**)&t->h_poses[b], id.size() * 8, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&t->h_summaries[b], size_t(n_streams) * fp->n_levels * sizeof(ea_summary), cudaHostAllocDefault));
+  }
   *out = t;
   return ea_tracker_reset(t);
 }
@@ -56,6 +72,15 @@ int ea_tracker_destroy(ea_tracker* t) {
   cudaStreamSynchronize(t->ctx->stream);
   cudaFree(t->d_slots[0]); cudaFree(t->d_slots[1]); cudaFree(t->d_poses); cudaFree(t->d_result);
   cudaFree(t->d_identity); cudaFree(t->d_summaries);
+  if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(t->stage_bgr[b]); cudaFree(t->stage_depth[b]);
+    if (t->ev_copied[b]) cudaEventDestroy(t->ev_copied[b]);
+    if (t->ev_consumed[b]) cudaEventDestroy(t->ev_consumed[b]);
+    if (t->ev_result[b]) cudaEventDestroy(t->ev_result[b]);
+    if (t->h_poses[b]) cudaFreeHost(t->h_poses[b]);
+    if (t->h_summaries[b]) cudaFreeHost(t->h_summaries[b]);
+  }
   ea_frameset_destroy(t->fs);
   delete t;
   return EA_OK;
@@ -65,7 +90,7 @@ int ea_tracker_reset(ea_tracker* t) {
   if (!t) return ea_fail(EA_ERR_INVALID_ARG, "null tracker");
   cudaStream_t s = t->ctx->stream;
   const size_t pb = size_t(t->n_streams) * 7 * 8;
-  t->frame = 0; t->key_parity = 0;
+  t->frame = 0; t->key_parity = 0; t->result_frame[0] = t->result_frame[1] = -1;
   CU(cudaMemcpyAsync(t->d_poses, t->d_identity, pb, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(t->d_result, t->d_identity, pb, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemsetAsync(t->d_summaries, 0, size_t(t->n_streams) * t->n_levels * sizeof(ea_summary), s));
@@ -116,14 +141,36 @@ int ea_tracker_step_host(ea_tracker* t, const uint8_t* bgr, const uint16_t* dept
   CU(cudaSetDevice(c->device));
   const size_t px = size_t(fs->p.width) * fs->p.height;
   const int n = t->n_streams;
-  if (!fs->stage_bgr) CU(cudaMalloc((void**)&fs->stage_bgr, px * 3 * fs->n_slots));
-  if (depth && !fs->stage_depth) CU(cudaMalloc((void**)&fs->stage_depth, px * 2 * fs->n_slots));
-  CU(cudaMemcpyAsync(fs->stage_bgr, bgr, px * 3 * n, cudaMemcpyHostToDevice, c->stream));
-  const bool becomes_key = (t->frame % t->interval) == 0;
-  if (depth && becomes_key) CU(cudaMemcpyAsync(fs->stage_depth, depth, px * 2 * n, cudaMemcpyHostToDevice, c->stream));
-  int rc = ea_tracker_step_device(t, fs->stage_bgr, (depth && becomes_key) ? fs->stage_depth : nullptr);
+  const int frame = t->frame, b = frame & 1;
+  const bool becomes_key = (frame % t->interval) == 0;
+  if (becomes_key && !depth) return ea_fail(EA_ERR_INVALID_ARG, "frame %d becomes a key frame and needs depth", frame);
+  if (!t->stage_bgr[b]) CU(cudaMalloc((void**)&t->stage_bgr[b], px * 3 * n));
+  if (becomes_key && !t->stage_depth[b]) CU(cudaMalloc((void**)&t->stage_depth[b], px * 2 * n));
+  // upload on the copy stream once the kernels that read this staging buffer two frames ago are done
+  if (frame >= 2) CU(cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[b], 0));
+  CU(cudaMemcpyAsync(t->stage_bgr[b], bgr, px * 3 * n, cudaMemcpyHostToDevice, t->copy_stream));
+  if (becomes_key) CU(cudaMemcpyAsync(t->stage_depth[b], depth, px * 2 * n, cudaMemcpyHostToDevice, t->copy_stream));
+  CU(cudaEventRecord(t->ev_copied[b], t->copy_stream));
+  CU(cudaStreamWaitEvent(c->stream, t->ev_copied[b], 0));
+  int rc = ea_tracker_step_device(t, t->stage_bgr[b], becomes_key ? t->stage_depth[b] : nullptr);
   if (rc) return rc;
-  if (poses7 || summaries) return ea_tracker_get_poses(t, poses7, summaries);
+  CU(cudaEventRecord(t->ev_consumed[b], c->stream));
+  // results into the pinned ring; the caller reads them now (poses7 given) or later with ea_tracker_wait
+  CU(cudaMemcpyAsync(t->h_poses[b], t->d_result, size_t(n) * 7 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(t->h_summaries[b], t->d_summaries, size_t(n) * t->n_levels * sizeof(ea_summary), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(t->ev_result[b], c->stream));
+  t->result_frame[b] = frame;
+  if (poses7 || summaries) return ea_tracker_wait(t, frame, poses7, summaries);
+  return EA_OK;
+}
+
+int ea_tracker_wait(ea_tracker* t, int frame, double* poses7, ea_summary* summaries) {
+  if (!t) return ea_fail(EA_ERR_INVALID_ARG, "null tracker");
+  const int b = frame & 1;
+  if (frame < 0 || t->result_frame[b] != frame) return ea_fail(EA_ERR_STATE, "results of frame %d are not (or no longer) in the 2-deep ring", frame);
+  CU(cudaEventSynchronize(t->ev_result[b]));
+  if (poses7) std::memcpy(poses7, t->h_poses[b], size_t(t->n_streams) * 7 * 8);
+  if (summaries) std::memcpy(summaries, t->h_summaries[b], size_t(t->n_streams) * t->n_levels * sizeof(ea_summary));
   return EA_OK;
 }
 

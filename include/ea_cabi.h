@@ -100,7 +100,9 @@ typedef struct ea_solve_params {
   int32_t max_num_iterations; /* 50 (per pyramid level) */
   int32_t jacobi_scaling;     /* 1 */
   int32_t max_consecutive_invalid_steps; /* 5 */
-  int32_t cluster_size;       /* CTAs cooperating on one pair (1,2,4,8); 0 => auto */
+  int32_t cluster_size;       /* 1 = one persistent CTA per pair; 2,4,8 = thread-block cluster per pair (DSMEM
+                               * reduction); -1 = task-graph kernel ((pair,chunk) tasks through a device queue);
+                               * 0 = auto (task graph for small batches, CTA per pair for large ones) */
   int32_t coarsest_level;     /* first level solved; -1 => n_levels-1 */
   int32_t finest_level;       /* last level solved; 0 */
   double loss_scale;          /* 1.0 */
@@ -204,6 +206,11 @@ int ea_tracker_reset(ea_tracker* tr);
  * (HOST, may be NULL => fetch later with ea_tracker_get_poses); asynchronous unless poses7 given. */
 int ea_tracker_step_host(ea_tracker* tr, const uint8_t* bgr, const uint16_t* depth, double* poses7,
                          ea_summary* summaries);
+/* Pipelined use of ea_tracker_step_host: call it with poses7 == summaries == NULL (asynchronous: the upload of this
+ * frame overlaps the alignment of the previous one), then collect frame f's result with ea_tracker_wait(tr, f, ...).
+ * Results live in a 2-deep ring: wait for frame f before submitting frame f+2.  The host buffers of a submitted
+ * frame must stay valid until its results have been waited for. */
+int ea_tracker_wait(ea_tracker* tr, int frame, double* poses7, ea_summary* summaries);
 int ea_tracker_step_device(ea_tracker* tr, const uint8_t* d_bgr, const uint16_t* d_depth);
 int ea_tracker_get_poses(ea_tracker* tr, double* poses7, ea_summary* summaries); /* syncs */
 int ea_tracker_frame_index(ea_tracker* tr, int* n_frames_seen);

@@ -289,3 +289,94 @@ def test_solve_edge_cases(ea, ctx, frames):
             ctx.solve_batch(fs, [0], fs, [1], None, ea.solve_params(point_stride=0))
     finally:
         fs.close()
+
+
+# ----------------------------------------------------------------------------------------- kernels / tracker
+@pytest.mark.parametrize("kernel", [-1, 1, 2])
+def test_solve_kernel_variants_agree(ea, ctx, fs5, solver_golden, kernel):
+    """task-graph (-1), CTA-per-pair (1) and cluster (2) kernels are the same solver: same poses, costs, iterations."""
+    pairs = [(a, b) for a in range(5) for b in range(5) if a != b]
+    sp = ea.solve_params(point_stride=3, cluster_size=kernel)
+    poses, S = ctx.solve_batch(fs5, [p[0] for p in pairs], fs5, [p[1] for p in pairs], None, sp)
+    sp1 = ea.solve_params(point_stride=3, cluster_size=1)
+    ref, R = ctx.solve_batch(fs5, [p[0] for p in pairs], fs5, [p[1] for p in pairs], None, sp1)
+    for i in range(len(pairs)):
+        assert rot_angle_between(poses[i][:4], ref[i][:4]) < 2e-5 and np.abs(poses[i][4:] - ref[i][4:]).max() < 2e-5
+        assert abs(S[i][0]["iterations"] - R[i][0]["iterations"]) <= 2
+        assert abs(S[i][0]["final_cost"] - R[i][0]["final_cost"]) <= 1e-5 * R[i][0]["final_cost"]
+    if kernel == -1:   # the task-graph reduction order is fixed by chunk index: bitwise reproducible
+        poses2, _ = ctx.solve_batch(fs5, [p[0] for p in pairs], fs5, [p[1] for p in pairs], None, sp)
+        assert np.array_equal(poses, poses2)
+
+
+def test_tracker_matches_pairwise_solves_and_pipelined_host_path(ea, ctx, frames, oracle):
+    """Frame-to-keyframe tracker (2 streams, key frame every 2 frames) == the same solves issued pair by pair with the
+    oracle, and the pipelined host path (submit t, wait t-1) == the synchronous one."""
+    import torch
+    O = oracle
+    K = frames["K"]
+    order = [[0, 1, 2, 3, 4], [4, 3, 2, 1, 0]]                      # two streams walking the bundled frames
+    fp = ea.frame_params(n_levels=2)
+    sp = ea.solve_params(point_stride=4, loss_type=ea.LOSS_HUBER, loss_scale=0.1)
+    seq_b = np.stack([np.stack([frames["bgr"][order[s][t]] for s in range(2)]) for t in range(5)])     # [T,S,h,w,3]
+    seq_d = np.stack([np.stack([frames["depth"][order[s][t]] for s in range(2)]) for t in range(5)])
+    hb = torch.from_numpy(seq_b).pin_memory(); hd = torch.from_numpy(seq_d).pin_memory()
+    fb, fd = seq_b[0].nbytes, seq_d[0].nbytes
+    tr = ea.Tracker(ctx, fp, sp, 2, keyframe_interval=2)
+    try:
+        sync_poses = []
+        for t in range(5):
+            poses, _ = tr.step_host(hb.data_ptr() + t * fb, hd.data_ptr() + t * fd, fetch=True)
+            sync_poses.append(poses.copy())
+        # oracle replay of the same schedule
+        cfg = O.pair_cfg(640, 480, K, n_levels=2, stride=4)
+        opts = O.default_options(loss_type=O.LOSS_HUBER, loss_scale=0.1)
+        for s in range(2):
+            key, pose = 0, IDENTITY.copy()
+            for t in range(1, 5):
+                a, b = order[s][key], order[s][t]
+                pose, _ = O.align_pair(frames["bgr"][a], frames["depth"][a], frames["bgr"][b], cfg, pose, opts)
+                g = sync_poses[t][s]
+                assert rot_angle_between(g[:4], pose[:4]) < 1e-4 and np.abs(g[4:] - pose[4:]).max() < 1e-4, (s, t)
+                if t % 2 == 0:
+                    key, pose = t, IDENTITY.copy()
+        # pipelined submission gives identical results
+        tr.reset()
+        got = {}
+        for t in range(5):
+            tr.step_host(hb.data_ptr() + t * fb, hd.data_ptr() + t * fd, fetch=False)
+            if t >= 1:
+                got[t - 1] = tr.wait(t - 1)[0].copy()
+        got[4] = tr.wait(4)[0].copy()
+        for t in range(1, 5):
+            np.testing.assert_array_equal(got[t], sync_poses[t])
+        with pytest.raises(ea.EaError):
+            tr.wait(1)          # fell out of the 2-deep ring
+    finally:
+        tr.close()
+
+
+def test_tracker_on_synthetic_sequence_recovers_ground_truth(ea, ctx):
+    """Synthetic ray-cast sequence with known camera motion: the tracked keyframe_T_frame poses follow the ground truth
+    (edge alignment is a pixel-level method: a few mm / tenths of a degree on this scene)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import synth
+    S, T = 3, 7
+    bgr, depth, traj = synth.make_sequences(S, T, seed=7, device="cuda")
+    fp = ea.frame_params(n_levels=3)
+    sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=0.1)
+    tr = ea.Tracker(ctx, fp, sp, S, keyframe_interval=10)
+    try:
+        fb, fd = 640 * 480 * 3 * S, 640 * 480 * 2 * S
+        for t in range(T):
+            tr.step_device(bgr.data_ptr() + t * fb, depth.data_ptr() + t * fd)
+            if t == 0:
+                continue
+            poses, Ss = tr.poses()
+            for s in range(S):
+                gt = synth.relative_pose(traj[s][0], traj[s][1], 0, t)
+                assert np.degrees(rot_angle_between(poses[s][:4], gt[:4])) < 1.0, (s, t)
+                assert np.abs(poses[s][4:] - gt[4:]).max() < 0.03, (s, t)
+    finally:
+        tr.close()
