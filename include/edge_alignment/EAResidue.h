@@ -1,0 +1,38 @@
+// class EAResidue -- the per-point residual functor of the reference (standalone/utils.h:38-99; ROS twin
+// include/EAResidue.h:69-126), kept as a HOST-SIDE PROBE: same constructor shape (fx,fy,cx,cy, X,Y,Z, distance field)
+// and the same operator()(q, t, residue) contract (returns false when |z'| < 0.01, utils.h:70-73).  The Ceres
+// BiCubicInterpolator argument becomes a Frame holding the now-frame's distance transform; the evaluation runs the
+// production device function on a one-point list.  Meant for tests and for probing single points, not for speed.
+#pragma once
+#include "Frame.h"
+
+class EAResidue {
+ public:
+  EAResidue(double fx, double fy, double cx, double cy, double a_Xx, double a_Xy, double a_Xz, const Frame& now_frame)
+      : X_(a_Xx), Y_(a_Xy), Z_(a_Xz), now_(&now_frame) {
+    ea_frame_params p = now_frame.params();
+    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.max_points = 64;
+    pt_.init(p, now_frame.context());
+    const float p4[4] = {float(a_Xx), float(a_Xy), float(a_Xz), 1.0f};
+    ea::check(ea_frameset_set_points(pt_.handle(), 0, 0, p4, 1, EA_POINTS_XYZ), "set_points");
+    ea_solve_params_default(&sp_);
+    sp_.point_stride = 1; sp_.loss_type = EA_LOSS_TRIVIAL;
+  }
+  // residue[0] = DT(u, v); optional jacobian[6] = d residue / d (half-angle rotation, translation)
+  bool operator()(const double* quat_wxyz, const double* t, double* residue, double* jacobian6 = nullptr) const {
+    double pose[7] = {quat_wxyz[0], quat_wxyz[1], quat_wxyz[2], quat_wxyz[3], t[0], t[1], t[2]};
+    int n = 0, failed = 0;
+    double raw = 0, J[6];
+    ea::check(ea_eval(now_->context(), pt_.handle(), 0, now_->handle(), 0, 0, pose, &sp_, &n, &raw, nullptr, J, nullptr, &failed), "ea_eval");
+    if (failed) return false;
+    residue[0] = raw;
+    if (jacobian6) for (int i = 0; i < 6; ++i) jacobian6[i] = J[i];
+    return true;
+  }
+
+ private:
+  double X_, Y_, Z_;
+  const Frame* now_;
+  mutable Frame pt_;
+  ea_solve_params sp_{};
+};

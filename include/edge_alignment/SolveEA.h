@@ -1,0 +1,82 @@
+// class SolveEA -- drop-in for the reference facade (include/SolveEA.h:36-71, src/SolveEA.cpp): same method names,
+// argument meaning and call order (src/ea.cpp:184-199):
+//     SolveEA* ea = new SolveEA();  ea->setRefFrame(ref_im, ref_depth);  ea->setNowFrame(now_im, now_depth);
+//     ea->setAsCERESProblem();
+// Everything behind it runs on the GPU through the C ABI (ea_cabi.h).  Additive accessors return what the reference
+// only printed (SolveEA.cpp:204-213): getPose(), getSummary(), setK().
+//
+// Numerical behaviour = the standalone pipeline (standalone/utils.cpp, the version the reference's README says works):
+// Laplacian>35 edges, chamfer-3 DT.  The ROS-flavour literals of src/SolveEA.cpp are the defaults here where they are
+// plain parameters: half-TUM intrinsics (SolveEA.cpp:12-23), no sub-sampling (:163), NULL loss (:171), 25 iterations
+// (:185), DT normalised to [0,255] (:109), depth in metres as CV_32F with Z==0 -> 1.0 (:68-69).  Its Canny edges,
+// exact Euclidean DT and DOGLEG strategy are not part of this round (DESIGN.md "Out of scope").
+#pragma once
+#include "Frame.h"
+
+class SolveEA {
+ public:
+  SolveEA() {
+    ea_frame_params_default(&fp_);
+    fp_.width = 320; fp_.height = 240;                       // src/ea.cpp:38 feeds half-resolution frames
+    fp_.fx = .5 * 525.0; fp_.fy = .5 * 525.0; fp_.cx = .5 * 319.5; fp_.cy = .5 * 239.5;   // SolveEA.cpp:15-18
+    fp_.depth_scale = 5000.0; fp_.dt_normalize = EA_NORM_255;                             // SolveEA.cpp:109
+    ea_solve_params_default(&sp_);
+    sp_.point_stride = 1; sp_.loss_type = EA_LOSS_TRIVIAL; sp_.max_num_iterations = 25;    // SolveEA.cpp:163,171,185
+    pose_[0] = 1; for (int i = 1; i < 7; ++i) pose_[i] = 0;                               // SolveEA.cpp:130-131
+  }
+
+  // "TODO : Write a function to set K" (SolveEA.cpp:12)
+  void setK(double fx, double fy, double cx, double cy) { fp_.fx = fx; fp_.fy = fy; fp_.cx = cx; fp_.cy = cy; dirty_ = true; }
+  void setImageSize(int width, int height) { fp_.width = width; fp_.height = height; dirty_ = true; }
+  ea_frame_params& frameParams() { dirty_ = true; return fp_; }
+  ea_solve_params& solveParams() { return sp_; }
+
+  template <class MatT> void setRefFrame(const MatT& rgb, const MatT& depth) {           // SolveEA.cpp:29-82
+    ensure(rgb);
+    ref_.set(rgb, &depth, EA_ROLE_REF, /*zero_depth_to_one=*/true);
+    have_ref_ = true;
+  }
+  template <class MatT> void setNowFrame(const MatT& rgb, const MatT& /*depth: stored but unused, SolveEA.cpp:86-119*/) {
+    ensure(rgb);
+    now_.set(rgb, static_cast<const MatT*>(nullptr), EA_ROLE_NOW);
+    have_now_ = true;
+  }
+
+  // Builds and solves the problem (SolveEA.cpp:124-216).  Starts from q=(1,0,0,0), t=0 like the reference unless
+  // setInitialPose was called.  Throws if a frame is missing (the reference left that unchecked, SolveEA.cpp:122).
+  void setAsCERESProblem() {
+    if (!have_ref_ || !have_now_) throw std::runtime_error("SolveEA::setAsCERESProblem: call setRefFrame and setNowFrame first");
+    const int32_t zero = 0;
+    summaries_.assign(size_t(fp_.n_levels), ea_summary{});
+    ea::check(ea_solve_batch(ref_.context(), 1, ref_.handle(), &zero, now_.handle(), &zero, pose_, &sp_, summaries_.data()), "ea_solve_batch");
+  }
+
+  void setInitialPose(const double q_wxyz[4], const double t[3]) { for (int i = 0; i < 4; ++i) pose_[i] = q_wxyz[i]; for (int i = 0; i < 3; ++i) pose_[4 + i] = t[i]; }
+  void getPose(double q_wxyz[4], double t[3]) const { for (int i = 0; i < 4; ++i) q_wxyz[i] = pose_[i]; for (int i = 0; i < 3; ++i) t[i] = pose_[4 + i]; }
+  const std::vector<ea_summary>& getSummary() const { return summaries_; }
+
+  // _verify3dPts (SolveEA.cpp:275-306) re-stated without the imshow: fraction of the reference edge points that
+  // project inside the now image at identity.
+  double _verify3dPts() const {
+    std::vector<float> p = ref_.edgePoints(0);
+    const size_t n = p.size() / 4;
+    size_t inside = 0;
+    for (size_t i = 0; i < n; ++i) inside += (p[4 * i] >= 0 && p[4 * i] < fp_.width && p[4 * i + 1] >= 0 && p[4 * i + 1] < fp_.height);
+    return n ? double(inside) / double(n) : 0.0;
+  }
+
+  Frame& refFrame() { return ref_; }
+  Frame& nowFrame() { return now_; }
+
+ private:
+  template <class MatT> void ensure(const MatT& rgb) {
+    if (rgb.cols != fp_.width || rgb.rows != fp_.height) { fp_.width = rgb.cols; fp_.height = rgb.rows; dirty_ = true; }
+    if (dirty_ || !ref_.valid()) { ref_.init(fp_); now_.init(fp_); have_ref_ = have_now_ = false; dirty_ = false; }
+  }
+  ea_frame_params fp_{};
+  ea_solve_params sp_{};
+  Frame ref_, now_;
+  bool have_ref_ = false, have_now_ = false, dirty_ = true;
+  double pose_[7];
+  std::vector<ea_summary> summaries_;
+};

@@ -1,0 +1,55 @@
+// Compiled and run by tests/test_gpu_facade.py: drives the reference's call sequence (src/ea.cpp:184-199) through the
+// C++ facade and prints the pose so the Python test can compare it with the C-ABI / oracle result.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "edge_alignment/EAResidue.h"
+#include "edge_alignment/SolveEA.h"
+
+static std::vector<unsigned char> read_file(const char* path, size_t n) {
+  std::vector<unsigned char> b(n);
+  FILE* f = fopen(path, "rb");
+  if (!f || fread(b.data(), 1, n, f) != n) { fprintf(stderr, "cannot read %s\n", path); exit(2); }
+  fclose(f);
+  return b;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 6) { fprintf(stderr, "usage: facade_test ref.bgr ref.depth16 now.bgr W H\n"); return 2; }
+  const int W = atoi(argv[4]), H = atoi(argv[5]);
+  auto ref_bgr = read_file(argv[1], size_t(W) * H * 3);
+  auto ref_d = read_file(argv[2], size_t(W) * H * 2);
+  auto now_bgr = read_file(argv[3], size_t(W) * H * 3);
+  ea::Mat ref_im(H, W, ea::U8C3, ref_bgr.data()), ref_depth(H, W, ea::U16C1, ref_d.data());
+  ea::Mat now_im(H, W, ea::U8C3, now_bgr.data()), now_depth;
+  try {
+    SolveEA* ea = new SolveEA();                    // src/ea.cpp:184
+    ea->setK(525.0, 525.0, 319.5, 239.5);           // full-resolution TUM intrinsics (standalone_edge_align.cpp:152)
+    ea->frameParams().dt_normalize = EA_NORM_01;    // standalone flavour so the oracle fixtures apply
+    ea->solveParams().point_stride = 30; ea->solveParams().loss_type = EA_LOSS_CAUCHY; ea->solveParams().max_num_iterations = 50;
+    ea->setRefFrame(ref_im, ref_depth);             // src/ea.cpp:186
+    ea->setNowFrame(now_im, now_depth);             // src/ea.cpp:188
+    printf("inside %.6f\n", ea->_verify3dPts());    // src/ea.cpp:193
+    ea->setAsCERESProblem();                        // src/ea.cpp:196
+    double q[4], t[3];
+    ea->getPose(q, t);
+    const ea_summary& s = ea->getSummary()[0];
+    printf("pose %.15g %.15g %.15g %.15g %.15g %.15g %.15g\n", q[0], q[1], q[2], q[3], t[0], t[1], t[2]);
+    printf("summary %d %d %d %.15g %.15g\n", s.termination, s.iterations, s.n_residuals, s.initial_cost, s.final_cost);
+    printf("npts %d\n", ea->refFrame().numEdgePoints());
+    // EAResidue probe: first reference point at identity
+    std::vector<float> p = ea->refFrame().edgePoints();
+    const double Z = p[2] / 5000.0, X = (p[0] - 319.5) * Z / 525.0, Y = (p[1] - 239.5) * Z / 525.0;
+    EAResidue res(525.0, 525.0, 319.5, 239.5, X, Y, Z, ea->nowFrame());
+    const double qi[4] = {1, 0, 0, 0}, ti[3] = {0, 0, 0};
+    double r = -1, J[6];
+    const bool ok = res(qi, ti, &r, J);
+    printf("residue %d %.9g %.9g %.9g\n", int(ok), r, J[3], J[4]);
+    // calling order is enforced (the reference left it unchecked, SolveEA.cpp:122)
+    SolveEA fresh;
+    try { fresh.setAsCERESProblem(); printf("order unchecked\n"); } catch (const std::exception&) { printf("order checked\n"); }
+    delete ea;
+  } catch (const std::exception& e) { fprintf(stderr, "exception: %s\n", e.what()); return 1; }
+  return 0;
+}

@@ -1,0 +1,37 @@
+"""The C++ facade with the reference's class names (include/edge_alignment/{SolveEA,Frame,EAResidue}.h) driven through
+the reference's own call sequence (src/ea.cpp:184-199) by tests/cpp/facade_test.cpp, checked against the golden
+results of the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rot_angle_between
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cpp_facade_runs_reference_call_sequence(frames, solver_golden, tmp_path):
+    from edge_alignment_b200 import _lib as L
+    exe = str(tmp_path / "facade_test")
+    lib_dir = os.path.dirname(L.SO_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "facade_test.cpp"), "-o", exe,
+                           "-L", lib_dir, "-l:libea_b200.so", "-Wl,-rpath," + lib_dir, "-Wl,-rpath,/usr/local/cuda/lib64"])
+    frames["bgr"][0].tofile(tmp_path / "ref.bgr"); frames["depth"][0].tofile(tmp_path / "ref.d16"); frames["bgr"][2].tofile(tmp_path / "now.bgr")
+    out = subprocess.run([exe, str(tmp_path / "ref.bgr"), str(tmp_path / "ref.d16"), str(tmp_path / "now.bgr"), "640", "480"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    rec = {l.split()[0]: l.split()[1:] for l in out.stdout.strip().splitlines()}
+    pose = np.array([float(v) for v in rec["pose"]])
+    gp = solver_golden["pose_1_3_cauchy"]; gs = solver_golden["summary_1_3_cauchy"]
+    assert rot_angle_between(pose[:4], gp[:4]) < 1e-4 and np.abs(pose[4:] - gp[4:]).max() < 1e-4
+    term, its, nres = int(rec["summary"][0]), int(rec["summary"][1]), int(rec["summary"][2])
+    assert term == int(gs[5]) and abs(its - int(gs[2])) <= 2 and nres == 1482
+    assert abs(float(rec["summary"][4]) - gs[1]) < 1e-5 * gs[1]
+    assert int(rec["npts"][0]) == 44458 and float(rec["inside"][0]) == 1.0
+    # EAResidue probe at identity: first point's residual == SURVEY A.6 anchor (0.1514616 with the portable DT)
+    ok, r = int(rec["residue"][0]), float(rec["residue"][1])
+    assert ok == 1 and abs(r - 0.15146105) < 2e-6
+    assert "checked" in out.stdout.splitlines()[-1]
