@@ -168,6 +168,7 @@ def main():
 
     # ------------------------------------------------------------------------------------------ our arm (GPU)
     import edge_alignment_b200 as ea
+    from edge_alignment_b200 import sharding
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -215,10 +216,7 @@ def main():
     launches = ctx.launch_count() - l0
     prof = ctx.profile_read(); ctx.profile_enable(False)
     clocks = sampler.stop()
-    if dist is not None:
-        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    ms = sharding.reduce_max(ms, dist, dev)                 # slowest rank defines the step
     value = world * S * K / (ms * 1e-3)
 
     # ---- accounting pass (untimed): point-evaluations per solve launch from the per-step summaries ------------
@@ -257,10 +255,7 @@ def main():
         e1.record(stream)
         barrier()
         ms_e = e0.elapsed_time(e1)
-        if dist is not None:
-            tms = torch.tensor([ms_e], device=dev, dtype=torch.float64)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms_e = float(tms.item())
+        ms_e = sharding.reduce_max(ms_e, dist, dev)
         # depth only travels for frames that become key frames (1 in KEYFRAME_INTERVAL)
         n_key = sum(1 for t in range(Wm + 1, T) if t % KEYFRAME_INTERVAL == 0)
         h2d = (frame_b * K + frame_d * n_key) / K
