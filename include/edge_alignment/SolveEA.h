@@ -30,10 +30,13 @@ class SolveEA {
   void setImageSize(int width, int height) { fp_.width = width; fp_.height = height; dirty_ = true; }
   ea_frame_params& frameParams() { dirty_ = true; return fp_; }
   ea_solve_params& solveParams() { return sp_; }
+  // SolveEA.cpp:69 keeps edge pixels without depth by placing them at Z = 1.0 (default); false = drop them like
+  // the standalone get_aX does (utils.cpp:258 "Z > 0")
+  void setZeroDepthToOne(bool on) { zero_depth_to_one_ = on; }
 
   template <class MatT> void setRefFrame(const MatT& rgb, const MatT& depth) {           // SolveEA.cpp:29-82
     ensure(rgb);
-    ref_.set(rgb, &depth, EA_ROLE_REF, /*zero_depth_to_one=*/true);
+    ref_.set(rgb, &depth, EA_ROLE_REF, zero_depth_to_one_);
     have_ref_ = true;
   }
   template <class MatT> void setNowFrame(const MatT& rgb, const MatT& /*depth: stored but unused, SolveEA.cpp:86-119*/) {
@@ -76,7 +79,7 @@ class SolveEA {
   ea_frame_params fp_{};
   ea_solve_params sp_{};
   Frame ref_, now_;
-  bool have_ref_ = false, have_now_ = false, dirty_ = true;
+  bool have_ref_ = false, have_now_ = false, dirty_ = true, zero_depth_to_one_ = true;
   double pose_[7];
   std::vector<ea_summary> summaries_;
 };

@@ -27,6 +27,7 @@ int main(int argc, char** argv) {
     SolveEA* ea = new SolveEA();                    // src/ea.cpp:184
     ea->setK(525.0, 525.0, 319.5, 239.5);           // full-resolution TUM intrinsics (standalone_edge_align.cpp:152)
     ea->frameParams().dt_normalize = EA_NORM_01;    // standalone flavour so the oracle fixtures apply
+    ea->setZeroDepthToOne(false);                   // standalone get_aX drops Z == 0 (utils.cpp:258)
     ea->solveParams().point_stride = 30; ea->solveParams().loss_type = EA_LOSS_CAUCHY; ea->solveParams().max_num_iterations = 50;
     ea->setRefFrame(ref_im, ref_depth);             // src/ea.cpp:186
     ea->setNowFrame(now_im, now_depth);             // src/ea.cpp:188
