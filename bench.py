@@ -272,7 +272,7 @@ def main():
         from oracle import oracle as O
         O.build()
         threads = O.hardware_threads()
-        ns = max(1, min(threads, 128)); steps_cpu = 3
+        ns = max(1, min(threads, 128)); steps_cpu = 8      # ~20-30 core-seconds of CPU work
         val, sec, n_al = cpu_reference_run(ns, steps_cpu, 0, threads, make_frames_host)
         cpu = {"value": val, "unit": "alignments/s", "cores": threads, "kind": "port",
                "sample": "%d alignments (%d streams x %d tracker steps, same generator), %.1f s of wall time" % (n_al, ns, steps_cpu, sec)}
