@@ -233,6 +233,15 @@ def main():
     pe_per_launch = point_evals / max(1, K)
     peak, peak_src = measured_peak_hbm()
     achieved = pe_per_launch * BYTES_PER_POINT_EVAL / (solve_ms_avg * 1e-3) / 1e9 if solve_ms_avg > 0 else 0.0
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, "profiles", "solve_traffic.json")      # DRAM bytes per point-eval from the last ncu --set full capture
+    if os.path.exists(tj):
+        try:
+            tr_ = json.load(open(tj))
+            traffic = float(tr_["dram_bytes_per_point_eval"]) * pe_per_launch
+            traffic_src = tr_.get("source")
+        except Exception:
+            pass
 
     # ---- e2e: host buffers through the tracker's host entry point --------------------------------------------
     e2e = None
@@ -285,7 +294,7 @@ def main():
                       "point_evals_per_s": world * point_evals / (ms * 1e-3), "mean_lm_iterations_per_level": iters / max(1, n_sum),
                       "terminations": {ea._lib.TERMINATION.get(k, str(k)): v for k, v in terms.items()}},
            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                         "kernel": "ea_k_solve_batch", "peak_source": peak_src, "kernel_ms_per_launch": solve_ms_avg,
                         "point_evals_per_launch": pe_per_launch, "bytes_per_point_eval": BYTES_PER_POINT_EVAL,
                         "kernel_share_of_step": (prof["solve_ms"] / ms) if ms > 0 else None,

@@ -1,0 +1,156 @@
+"""BASELINE.json configs[2..4] at (or near) their full sizes, through size-independent properties plus oracle spot
+checks: batches of thousands of pairs, a dense 1280x720 coarse-to-fine solve, a 3840x2160 pair with millions of
+edge points solved point-sharded."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import IDENTITY, ROOT, rot_angle_between
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.fixture(scope="module")
+def ea():
+    import edge_alignment_b200 as ea
+    return ea
+
+
+def test_config3_batch_of_4096_pairs(ea, oracle):
+    """4096 independent 640x480 pairs (built from a pool of 64 synthetic frames): one batched launch is deterministic,
+    equals pair-by-pair solves, follows the ground truth, and agrees with the oracle on a random subset."""
+    import synth
+    O = oracle
+    ctx = ea.Context(0)
+    n_seq, T = 16, 4
+    bgr, depth, traj = synth.make_sequences(n_seq, T, seed=11, device="cuda")          # [T,S,...]
+    fs = ea.FrameSet(ctx, ea.frame_params(n_levels=3), n_seq * T)
+    try:
+        slots = np.arange(n_seq * T)                                                    # slot = t * n_seq + s
+        fs.preprocess_device(slots, bgr.data_ptr(), depth.data_ptr(), ea.ROLE_BOTH)
+        rng = np.random.default_rng(0)
+        s_idx = rng.integers(0, n_seq, 4096); ta = rng.integers(0, T, 4096); tb = (ta + rng.integers(1, 3, 4096)) % T
+        ref = ta * n_seq + s_idx; now = tb * n_seq + s_idx
+        sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=0.1)
+        poses, S = ctx.solve_batch(fs, ref, fs, now, None, sp)
+        poses2, _ = ctx.solve_batch(fs, ref, fs, now, None, sp)
+        assert np.array_equal(poses, poses2)                                            # deterministic reductions
+        # identical pairs inside the batch give identical answers; unit quaternions; sane terminations
+        key = ref * 1000 + now
+        first = {}
+        for i, k in enumerate(key):
+            if k in first:
+                assert np.array_equal(poses[i], poses[first[k]])
+            else:
+                first[k] = i
+        assert np.allclose(np.linalg.norm(poses[:, :4], axis=1), 1.0, atol=1e-12)
+        assert all(s[0]["termination"] in (1, 2, 3, 4, 5) for s in S)
+        # a sub-batch (what one rank of an 8-way shard would get) reproduces the same numbers
+        sub = slice(512, 1024)
+        p_sub, _ = ctx.solve_batch(fs, ref[sub], fs, now[sub], None, sp)
+        assert np.array_equal(p_sub, poses[sub])
+        # ground truth (edge alignment is pixel-level: loose) and oracle (tight) on a subset
+        hb, hd = bgr.cpu().numpy(), depth.cpu().numpy()
+        cfg = O.pair_cfg(640, 480, synth.TUM_K, n_levels=3, stride=1)
+        opts = O.default_options(loss_type=O.LOSS_HUBER, loss_scale=0.1)
+        n_ok = 0
+        for i in rng.choice(4096, 6, replace=False):
+            s, a, b = s_idx[i], ta[i], tb[i]
+            gt = synth.relative_pose(traj[s][0], traj[s][1], a, b)
+            if np.degrees(rot_angle_between(poses[i][:4], gt[:4])) < 1.0 and np.abs(poses[i][4:] - gt[4:]).max() < 0.03:
+                n_ok += 1
+            op, _ = O.align_pair(hb[a, s], hd[a, s], hb[b, s], cfg, IDENTITY, opts)
+            assert rot_angle_between(poses[i][:4], op[:4]) < 1e-4 and np.abs(poses[i][4:] - op[4:]).max() < 1e-4
+        assert n_ok >= 4
+    finally:
+        fs.close(); ctx.close()
+
+
+def test_config4_dense_1280x720_coarse_to_fine(ea, oracle):
+    """1280x720, dense edges (hundreds of thousands of edge points), 4-level coarse-to-fine LM: preprocessing bit exact
+    at this size (multi-word rows, 4 levels) and the solve within the pose tolerance of the oracle."""
+    import synth
+    O = oracle
+    w, h = 1280, 720
+    K = (525.0 * 2, 525.0 * 2, (w - 1) / 2.0, (h - 1) / 2.0)
+    Rw, tw = synth.trajectory(3, 5)
+    b, d = synth.render(Rw, tw, 5, w, h, K, device="cuda", cell=0.02, hole_frac=0.1)
+    hb, hd = b.cpu().numpy(), d.cpu().numpy()
+    ctx = ea.Context(0)
+    fp = ea.frame_params(width=w, height=h, n_levels=4, fx=K[0], fy=K[1], cx=K[2], cy=K[3], max_points=w * h)
+    fs = ea.FrameSet(ctx, fp, 2)
+    try:
+        fs.preprocess_host([0, 1], hb[[0, 2]], hd[[0, 2]], ea.ROLE_BOTH)
+        n0 = fs.num_points(0)
+        assert n0 > 150000
+        img, dep = hb[0], hd[0]
+        for l in range(4):
+            _, _, Kl = fs.level_geometry(l)
+            _, uvd = O.get_aX(img, dep, Kl)
+            np.testing.assert_array_equal(fs.points(0, l)[:, :3].astype(np.int32), uvd)
+            img, dep = O.half_linear(img), O.half_nearest(dep)
+        odt, _ = O.get_distance_transform(hb[2])
+        np.testing.assert_array_equal(fs.dt(1, 0), odt)
+        sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=0.1)
+        cfg = O.pair_cfg(w, h, K, n_levels=4, stride=1)
+        op, oS = O.align_pair(hb[0], hd[0], hb[2], cfg, IDENTITY, O.default_options(loss_type=O.LOSS_HUBER, loss_scale=0.1))
+        for kernel in (0, 1, 8):     # auto (task graph for a single pair), CTA per pair, cluster of 8
+            sp.cluster_size = kernel
+            poses, S = ctx.solve_batch(fs, [0], fs, [1], None, sp)
+            assert rot_angle_between(poses[0][:4], op[:4]) < 1e-4 and np.abs(poses[0][4:] - op[4:]).max() < 1e-4
+            assert [s["n_residuals"] for s in S[0]] == [s["n_residuals"] for s in oS]
+        gt = synth.relative_pose(Rw, tw, 0, 2)
+        assert np.degrees(rot_angle_between(poses[0][:4], gt[:4])) < 0.5 and np.abs(poses[0][4:] - gt[4:]).max() < 0.02
+    finally:
+        fs.close(); ctx.close()
+
+
+def test_config5_4k_pair_point_sharded(ea, oracle):
+    """3840x2160 pair with > 1e6 edge points, single level: the point-sharded solver (world 1 here; the NCCL 2-rank case is
+    in test_gpu_multi.py) equals the batched solver; residuals match the oracle on a strided subset."""
+    import synth
+    from edge_alignment_b200 import _lib as L
+    O = oracle
+    w, h = 3840, 2160
+    K = (525.0 * 6, 525.0 * 6, (w - 1) / 2.0, (h - 1) / 2.0)
+    Rw, tw = synth.trajectory(2, 9, max_rot_deg=0.3, max_trans=0.005)
+    b, d = synth.render(Rw, tw, 9, w, h, K, device="cuda", cell=0.03, hole_frac=0.1, chunk=1)
+    hb, hd = b.cpu().numpy(), d.cpu().numpy()
+    del b, d
+    ctx = ea.Context(0)
+    fp = ea.frame_params(width=w, height=h, n_levels=1, fx=K[0], fy=K[1], cx=K[2], cy=K[3], max_points=w * h // 2)
+    fs = ea.FrameSet(ctx, fp, 2)
+    try:
+        fs.preprocess_host([0, 1], hb, hd, ea.ROLE_BOTH)
+        n = fs.num_points(0)
+        assert n > 1_000_000
+        odt, _ = O.get_distance_transform(hb[1])
+        np.testing.assert_array_equal(fs.dt(1), odt)                      # 4K chamfer DT, bit exact
+        xyz, uvd = O.get_aX(hb[0], hd[0], K)
+        assert len(uvd) == n
+        np.testing.assert_array_equal(fs.points(0)[:, :3].astype(np.int32), uvd)
+        # residual parity on every 64th point at a perturbed pose
+        pose = np.array([0.99999, 0.003, -0.002, 0.001, 0.002, -0.001, 0.003]); pose[:4] /= np.linalg.norm(pose[:4])
+        sp = ea.solve_params(point_stride=64, loss_type=ea.LOSS_TRIVIAL)
+        g = ctx.eval(fs, 0, fs, 1, pose, sp, want_jac=False)
+        o = O.evaluate(xyz, odt, K, pose, stride=64, options=O.default_options(loss_type=0))
+        assert np.all(np.abs(g["raw"] - o["raw"]) <= 1e-5 * np.maximum(np.abs(o["raw"]), 0.05))
+        np.testing.assert_allclose(g["cost"], o["cost"], rtol=2e-6)
+        # sharded == batched, all points
+        sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=0.1)
+        poses, S = ctx.solve_batch(fs, [0], fs, [1], None, sp)
+        sh = C.c_void_p()
+        assert L.lib().ea_shard_create(ctx._h, None, 0, 1, C.byref(sh)) == 0
+        p2 = IDENTITY.copy(); s2 = L.Summary()
+        assert L.lib().ea_shard_solve(sh, fs._h, 0, fs._h, 1, 0, p2.ctypes.data_as(C.POINTER(C.c_double)), C.byref(sp), C.byref(s2)) == 0
+        L.lib().ea_shard_destroy(sh)
+        assert rot_angle_between(poses[0][:4], p2[:4]) < 2e-6 and np.abs(poses[0][4:] - p2[4:]).max() < 2e-6
+        assert abs(S[0][0]["iterations"] - s2.iterations) <= 1 and S[0][0]["n_residuals"] == n
+        gt = synth.relative_pose(Rw, tw, 0, 1)
+        assert np.degrees(rot_angle_between(p2[:4], gt[:4])) < 0.2 and np.abs(p2[4:] - gt[4:]).max() < 0.01
+    finally:
+        fs.close(); ctx.close()
