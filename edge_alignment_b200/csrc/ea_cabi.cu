@@ -494,6 +494,13 @@ static int fill_solve_args(ea_context* c, ea_frameset* ref, ea_frameset* now, co
 int ea_solve_batch_device(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now,
                           const int32_t* d_now_slots, double* d_poses7, const int32_t* d_pose_index,
                           const ea_solve_params* sp, ea_summary* d_summaries) {
+  return ea_solve_batch_device_ordered(c, n, ref, d_ref_slots, now, d_now_slots, d_poses7, d_pose_index, nullptr, sp, d_summaries);
+}
+}  // extern "C"
+
+int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now,
+                                  const int32_t* d_now_slots, double* d_poses7, const int32_t* d_pose_index,
+                                  const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries) {
   if (!c || !d_ref_slots || !d_now_slots || !d_poses7) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
   if (n <= 0) return EA_OK;
   EaSolveArgs A;
@@ -502,7 +509,7 @@ int ea_solve_batch_device(ea_context* c, int n, ea_frameset* ref, const int32_t*
   if (rc) return rc;
   CU(cudaSetDevice(c->device));
   A.ref_slots = d_ref_slots; A.now_slots = d_now_slots; A.pose_index = d_pose_index; A.poses = d_poses7;
-  A.summaries = d_summaries; A.n_pairs = n; A.work_counter = c->d_work;
+  A.summaries = d_summaries; A.n_pairs = n; A.work_counter = c->d_work; A.order = d_order;
   EaProfileScope prof(c, 1);
   cudaError_t e;
   if (cluster >= 2) {
@@ -532,6 +539,7 @@ int ea_solve_batch_device(ea_context* c, int n, ea_frameset* ref, const int32_t*
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "solve launch: %s", cudaGetErrorString(e));
   return EA_OK;
 }
+extern "C" {
 
 int ea_solve_batch(ea_context* c, int n, ea_frameset* ref, const int32_t* ref_slots, ea_frameset* now, const int32_t* now_slots,
                    double* poses7, const ea_solve_params* sp, ea_summary* summaries) {

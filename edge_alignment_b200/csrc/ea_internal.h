@@ -15,6 +15,7 @@ struct EaSolveArgs {
   const int32_t* ref_slots;     // [n_pairs] device
   const int32_t* now_slots;     // [n_pairs] device
   const int32_t* pose_index;    // [n_pairs] device or null (identity)
+  const int32_t* order;         // [n_pairs] device or null: processing order of the work queue (longest first)
   double* poses;                // [*][7] device, in/out
   int* work_counter;            // device: next pair index of the dynamic work queue (zeroed per launch)
   // task-graph kernel (ea_solve_tasks.cu)
@@ -128,4 +129,8 @@ int ea_fail(int code, const char* fmt, ...);
     if (e_ != cudaSuccess) return ea_fail(EA_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
   } while (0)
 int ea_ensure_tmp(ea_context* c, size_t bytes);
+int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now,
+                                   const int32_t* d_now_slots, double* d_poses7, const int32_t* d_pose_index,
+                                   const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries);
+cudaError_t ea_launch_order_by_work(const ea_summary* d_summaries, int n, int n_levels, int32_t* d_order, cudaStream_t stream);
 int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const uint16_t* d_depth, int roles);

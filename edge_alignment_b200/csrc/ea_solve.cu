@@ -49,8 +49,9 @@ struct EaSolveSmem {
 __device__ __noinline__ void ea_boss_next(const EaSolveArgs& A, EaSolveSmem& S, EaMsg& out, bool new_pair_needed) {
   for (;;) {
     if (new_pair_needed) {
-      const int pair = atomicAdd(A.work_counter, 1);
-      if (pair >= A.n_pairs) { out.cmd = EA_CMD_EXIT; S.pair = -1; return; }
+      const int ticket = atomicAdd(A.work_counter, 1);
+      if (ticket >= A.n_pairs) { out.cmd = EA_CMD_EXIT; S.pair = -1; return; }
+      const int pair = A.order ? A.order[ticket] : ticket;   // longest-expected-first when the caller knows better
       S.pair = pair; S.level = A.coarsest;
       const int pi = A.pose_index ? A.pose_index[pair] : pair;
 #pragma unroll 1
@@ -278,5 +279,46 @@ cudaError_t ea_launch_eval_sums(const EaLevelDesc& rd, const EaLevelDesc& nd, co
                                 cudaStream_t stream) {
   if (n_blocks <= 0) return cudaSuccess;
   ea_k_eval_sums<EA_SOLVE_THREADS><<<n_blocks, EA_SOLVE_THREADS, 0, stream>>>(rd, nd, rg, ng, inv_depth_scale, sp, d_pose7, d_done, j_begin, j_end, d_sums);
+  return cudaGetLastError();
+}
+
+// ---- longest-first ordering for the next launch: sort pairs by the work their last solve needed -----------------
+// One CTA, bitonic sort of (work, index) in shared memory; n <= 4096.
+__global__ void __launch_bounds__(1024) ea_k_order_by_work(const ea_summary* __restrict__ summaries, int n, int n_levels, int32_t* __restrict__ order) {
+  __shared__ unsigned long long key[4096];
+  int m = 1;
+  while (m < n) m <<= 1;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    unsigned long long k = 0;
+    if (i < n) {
+      unsigned long long work = 0;
+      for (int l = 0; l < n_levels; ++l) {
+        const ea_summary s = summaries[size_t(i) * n_levels + l];
+        work += (unsigned long long)(s.n_residuals > 0 ? s.n_residuals : 0) * (unsigned long long)(s.evaluations > 0 ? s.evaluations : 0);
+      }
+      if (work > 0xFFFFFFFFFFFull) work = 0xFFFFFFFFFFFull;
+      k = (work << 20) | (unsigned long long)(0xFFFFF - i);       // descending work, ascending index on ties
+    }
+    key[i] = k;
+  }
+  __syncthreads();
+  for (int size = 2; size <= m; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool desc = (i & size) == 0;
+          const unsigned long long a = key[i], b = key[j];
+          if (desc ? (a < b) : (a > b)) { key[i] = b; key[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) order[i] = int32_t(0xFFFFF - int(key[i] & 0xFFFFF));
+}
+
+cudaError_t ea_launch_order_by_work(const ea_summary* d_summaries, int n, int n_levels, int32_t* d_order, cudaStream_t stream) {
+  if (n <= 0 || n > 4096) return cudaErrorInvalidValue;
+  ea_k_order_by_work<<<1, 1024, 0, stream>>>(d_summaries, n, n_levels, d_order);
   return cudaGetLastError();
 }

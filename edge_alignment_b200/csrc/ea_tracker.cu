@@ -20,6 +20,8 @@ struct ea_tracker {
   double* d_result = nullptr;      // poses of the latest step [n_streams][7]
   double* d_identity = nullptr;    // [n_streams][7]
   ea_summary* d_summaries = nullptr;
+  int32_t* d_order = nullptr;      // longest-first processing order derived from the previous step's summaries
+  bool have_order = false;
   // host-input pipeline: frame t+1 is uploaded on a copy stream while frame t is being aligned
   cudaStream_t copy_stream = nullptr;
   uint8_t* stage_bgr[2] = {nullptr, nullptr};
@@ -51,6 +53,7 @@ int ea_tracker_create(ea_context* ctx, const ea_frame_params* fp, const ea_solve
   CU(cudaMalloc((void**)&t->d_result, id.size() * 8));
   CU(cudaMalloc((void**)&t->d_identity, id.size() * 8));
   CU(cudaMalloc((void**)&t->d_summaries, size_t(n_streams) * fp->n_levels * sizeof(ea_summary)));
+  CU(cudaMalloc((void**)&t->d_order, size_t(n_streams) * sizeof(int32_t)));
   CU(cudaMemcpy(t->d_slots[0], s0.data(), n_streams * sizeof(int32_t), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(t->d_slots[1], s1.data(), n_streams * sizeof(int32_t), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(t->d_identity, id.data(), id.size() * 8, cudaMemcpyHostToDevice));
@@ -71,7 +74,7 @@ int ea_tracker_destroy(ea_tracker* t) {
   cudaSetDevice(t->ctx->device);
   cudaStreamSynchronize(t->ctx->stream);
   cudaFree(t->d_slots[0]); cudaFree(t->d_slots[1]); cudaFree(t->d_poses); cudaFree(t->d_result);
-  cudaFree(t->d_identity); cudaFree(t->d_summaries);
+  cudaFree(t->d_identity); cudaFree(t->d_summaries); cudaFree(t->d_order);
   if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
   for (int b = 0; b < 2; ++b) {
     cudaFree(t->stage_bgr[b]); cudaFree(t->stage_depth[b]);
@@ -90,7 +93,7 @@ int ea_tracker_reset(ea_tracker* t) {
   if (!t) return ea_fail(EA_ERR_INVALID_ARG, "null tracker");
   cudaStream_t s = t->ctx->stream;
   const size_t pb = size_t(t->n_streams) * 7 * 8;
-  t->frame = 0; t->key_parity = 0; t->result_frame[0] = t->result_frame[1] = -1;
+  t->frame = 0; t->key_parity = 0; t->result_frame[0] = t->result_frame[1] = -1; t->have_order = false;
   CU(cudaMemcpyAsync(t->d_poses, t->d_identity, pb, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(t->d_result, t->d_identity, pb, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemsetAsync(t->d_summaries, 0, size_t(t->n_streams) * t->n_levels * sizeof(ea_summary), s));
@@ -112,9 +115,16 @@ int ea_tracker_step_device(ea_tracker* t, const uint8_t* d_bgr, const uint16_t* 
   if (rc) return rc;
   const size_t pb = size_t(t->n_streams) * 7 * 8;
   if (!first) {
-    rc = ea_solve_batch_device(c, t->n_streams, t->fs, t->d_slots[t->key_parity], t->fs, t->d_slots[cur], t->d_poses, nullptr,
-                               &t->sp, t->d_summaries);
+    // streams that needed the most work last frame go first: hides the launch tail behind the rest of the batch
+    rc = ea_solve_batch_device_ordered(c, t->n_streams, t->fs, t->d_slots[t->key_parity], t->fs, t->d_slots[cur], t->d_poses, nullptr,
+                                       t->have_order ? t->d_order : nullptr, &t->sp, t->d_summaries);
     if (rc) return rc;
+    if (t->n_streams > 1 && t->n_streams <= 4096) {
+      cudaError_t oe = ea_launch_order_by_work(t->d_summaries, t->n_streams, t->n_levels, t->d_order, s);
+      c->launches++;
+      if (oe != cudaSuccess) return ea_fail(EA_ERR_CUDA, "order kernel: %s", cudaGetErrorString(oe));
+      t->have_order = true;
+    }
     CU(cudaMemcpyAsync(t->d_result, t->d_poses, pb, cudaMemcpyDeviceToDevice, s));
   }
   if (becomes_key) {
