@@ -89,19 +89,22 @@ struct EaPointEval {
   bool fail;               // |z'| < 0.01  (utils.h:70-73)
 };
 
-// ceres CubicHermiteSpline<1> (Catmull-Rom), fp32.
-__device__ __forceinline__ void ea_cubic(float p0, float p1, float p2, float p3, float x, float& f, float& dfdx) {
-  const float a = 0.5f * (-p0 + 3.0f * p1 - 3.0f * p2 + p3);
-  const float b = 0.5f * (2.0f * p0 - 5.0f * p1 + 4.0f * p2 - p3);
-  const float c = 0.5f * (-p0 + p2);
-  f = fmaf(x, fmaf(x, fmaf(x, a, b), c), p1);
-  dfdx = fmaf(x, fmaf(3.0f * a, x, 2.0f * b), c);
+// ceres CubicHermiteSpline<1> (Catmull-Rom), fp32, with the 1/2 factors pulled out of the coefficients:
+//   a2 = -p0 + 3 p1 - 3 p2 + p3,  b2 = 2 p0 - 5 p1 + 4 p2 - p3,  c2 = p2 - p0
+//   f = p1 + (x/2) (c2 + x (b2 + x a2)),   f' = c2/2 + x (b2 + (3x/2) a2)
+// hx = x/2 and x15 = 3x/2 are shared by all splines evaluated at the same x.
+__device__ __forceinline__ void ea_cubic(float p0, float p1, float p2, float p3, float x, float hx, float x15, float& f, float& dfdx) {
+  const float a2 = fmaf(3.0f, p1 - p2, p3 - p0);
+  const float b2 = fmaf(4.0f, p2, fmaf(-5.0f, p1, fmaf(2.0f, p0, -p3)));
+  const float c2 = p2 - p0;
+  f = fmaf(hx, fmaf(x, fmaf(x, a2, b2), c2), p1);
+  dfdx = fmaf(x, fmaf(x15, a2, b2), 0.5f * c2);
 }
-__device__ __forceinline__ float ea_cubic_val(float p0, float p1, float p2, float p3, float x) {
-  const float a = 0.5f * (-p0 + 3.0f * p1 - 3.0f * p2 + p3);
-  const float b = 0.5f * (2.0f * p0 - 5.0f * p1 + 4.0f * p2 - p3);
-  const float c = 0.5f * (-p0 + p2);
-  return fmaf(x, fmaf(x, fmaf(x, a, b), c), p1);
+__device__ __forceinline__ float ea_cubic_val(float p0, float p1, float p2, float p3, float x, float hx) {
+  const float a2 = fmaf(3.0f, p1 - p2, p3 - p0);
+  const float b2 = fmaf(4.0f, p2, fmaf(-5.0f, p1, fmaf(2.0f, p0, -p3)));
+  const float c2 = p2 - p0;
+  return fmaf(hx, fmaf(x, fmaf(x, a2, b2), c2), p1);
 }
 
 // floor(x) and x - floor(x): exact for |x| < 2^31 (F2I.FLOOR, I2F, one fp64 subtract, one narrowing).  Wild values
@@ -163,16 +166,17 @@ __device__ __forceinline__ void ea_point_eval(const float4 p, const EaLevelGeom&
   // BiCubicInterpolator::Evaluate: for each grid row (== image column x_k) spline along c (== image y),
   // then spline the four results along r (== image x).
   float f0, f1, f2, f3, d0, d1, d2, d3;
-  ea_cubic(p00, p10, p20, p30, dv, f0, d0);
-  ea_cubic(p01, p11, p21, p31, dv, f1, d1);
-  ea_cubic(p02, p12, p22, p32, dv, f2, d2);
-  ea_cubic(p03, p13, p23, p33, dv, f3, d3);
+  const float hv = 0.5f * dv, v15 = 1.5f * dv, hu = 0.5f * du, u15 = 1.5f * du;
+  ea_cubic(p00, p10, p20, p30, dv, hv, v15, f0, d0);
+  ea_cubic(p01, p11, p21, p31, dv, hv, v15, f1, d1);
+  ea_cubic(p02, p12, p22, p32, dv, hv, v15, f2, d2);
+  ea_cubic(p03, p13, p23, p33, dv, hv, v15, f3, d3);
   float fr, fdu;
-  ea_cubic(f0, f1, f2, f3, du, fr, fdu);
+  ea_cubic(f0, f1, f2, f3, du, hu, u15, fr, fdu);
   // cv::normalize(NORM_MINMAX) folded into the sampler: the interpolant is linear in the texels
   o.f = fmaf(fr, affine.x, affine.y);
   o.dfdu = fdu * affine.x;
-  o.dfdv = ea_cubic_val(d0, d1, d2, d3, du) * affine.x;
+  o.dfdv = ea_cubic_val(d0, d1, d2, d3, du, hu) * affine.x;
   o.ub = float(u - P.cx); o.vb = float(v - P.cy);
   o.pz = float(q2); o.iz = float(iz);
 }
