@@ -50,6 +50,12 @@ class Summary(C.Structure):
         return d
 
 
+class View(C.Structure):
+    _fields_ = [("ref", C.c_void_p), ("ref_slot", C.c_int32), ("now", C.c_void_p), ("now_slot", C.c_int32),
+                ("use_distortion", C.c_int32), ("use_rig", C.c_int32), ("dist", C.c_double * 5),
+                ("cam_T_first", C.c_double * 12), ("first_T_cam", C.c_double * 12)]
+
+
 # every symbol include/ea_cabi.h declares: name -> (restype, argtypes)
 _vp, _i, _pi = C.c_void_p, C.c_int, C.POINTER(C.c_int)
 _i32p, _u8p, _u16p, _f32p, _f64p = (C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint16),
@@ -83,6 +89,8 @@ PROTOTYPES = {
     "ea_eval": (_i, [_vp, _vp, _i, _vp, _i, _i, _f64p, C.POINTER(SolveParams), _pi, _f64p, _f64p, _f64p, _f64p, _pi]),
     "ea_solve_batch": (_i, [_vp, _i, _vp, _i32p, _vp, _i32p, _f64p, C.POINTER(SolveParams), C.POINTER(Summary)]),
     "ea_solve_batch_device": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(SolveParams), _vp]),
+    "ea_eval_views": (_i, [_vp, _i, C.POINTER(View), _i, _f64p, C.POINTER(SolveParams), _pi, _f64p, _f64p, _f64p, _f64p, _pi]),
+    "ea_solve_views": (_i, [_vp, _i, C.POINTER(View), _i, _f64p, C.POINTER(SolveParams), C.POINTER(Summary)]),
     "ea_tracker_create": (_i, [_vp, C.POINTER(FrameParams), C.POINTER(SolveParams), _i, _i, C.POINTER(_vp)]),
     "ea_tracker_destroy": (_i, [_vp]),
     "ea_tracker_reset": (_i, [_vp]),

@@ -110,6 +110,47 @@ class Context:
         sums = [[S[i * nl + l].asdict() for l in range(nl)] for i in range(n)]
         return poses, sums
 
+    # ---- residual variants / multi-camera problems (standalone/utils.h:101-421) ------------------------------------
+    @staticmethod
+    def _views(views):
+        arr = (L.View * len(views))()
+        for i, v in enumerate(views):
+            a = arr[i]
+            a.ref = v["ref"]._h; a.ref_slot = v["ref_slot"]; a.now = v["now"]._h; a.now_slot = v["now_slot"]
+            d = v.get("dist"); T21 = v.get("T21")
+            a.use_distortion = 0 if d is None else 1
+            a.use_rig = 0 if T21 is None else 1
+            for k in range(5):
+                a.dist[k] = 0.0 if d is None else float(d[k])
+            t21 = np.eye(4) if T21 is None else np.asarray(T21, np.float64)
+            t12 = np.linalg.inv(t21)
+            for k in range(12):
+                a.cam_T_first[k] = float(t21[:3].flat[k]); a.first_T_cam[k] = float(t12[:3].flat[k])
+        return arr
+
+    def eval_views(self, views, pose7, sp=None, level=0):
+        """views: list of dict(ref, ref_slot, now, now_slot, dist=None (k1,k2,p1,p2,k3), T21=None (4x4 trans_1to2))."""
+        sp = sp or solve_params()
+        arr = self._views(views)
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        n = sum((v["ref"].num_points(v["ref_slot"], level) + sp.point_stride - 1) // sp.point_stride for v in views)
+        raw = np.empty(n); res = np.empty(n); jac = np.empty((n, 6)); sums = np.empty(28); nres = C.c_int(); failed = C.c_int()
+        _check(L.lib().ea_eval_views(self._h, len(views), arr, level, _ptr(pose7, C.c_double), C.byref(sp), C.byref(nres),
+                                     _ptr(raw, C.c_double), _ptr(res, C.c_double), _ptr(jac, C.c_double), _ptr(sums, C.c_double), C.byref(failed)))
+        H = np.zeros((6, 6)); k = 7
+        for a in range(6):
+            for c in range(a, 6):
+                H[a, c] = H[c, a] = sums[k]; k += 1
+        return dict(raw=raw, residuals=res, J=jac, cost=sums[0], b=sums[1:7].copy(), H=H, sums=sums, failed=failed.value, n_residuals=nres.value)
+
+    def solve_views(self, views, pose7=None, sp=None, level=0):
+        sp = sp or solve_params()
+        arr = self._views(views)
+        pose = np.array(IDENTITY if pose7 is None else pose7, np.float64)
+        s = L.Summary()
+        _check(L.lib().ea_solve_views(self._h, len(views), arr, level, _ptr(pose, C.c_double), C.byref(sp), C.byref(s)))
+        return pose, s.asdict()
+
     def solve_batch_device(self, n, ref, d_ref_slots, now, d_now_slots, d_poses, sp, d_pose_index=0, d_summaries=0):
         """All pointer arguments are raw device addresses (ints); asynchronous on the context stream."""
         _check(L.lib().ea_solve_batch_device(self._h, n, ref._h, d_ref_slots, now._h, d_now_slots, d_poses,

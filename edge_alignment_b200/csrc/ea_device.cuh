@@ -255,3 +255,163 @@ __device__ __forceinline__ void ea_accumulate(float (&acc)[EA_NSUM], const float
 #pragma unroll
   for (int a = 0; a < 6; ++a) acc[21 + a] = fmaf(J[a], rw, acc[21 + a]);
 }
+
+// =================================================================================================================
+// General per-point evaluation for the residual VARIANTS of the reference (standalone/utils.h:101-421):
+//   EAResidueEx           radial-tangential distortion between normalisation and K            (utils.h:140-149)
+//   EAResidueSecondCam    rigid rig: b_T_a_SecCam = T_1to2 * b_T_a * T_1to2_inv               (utils.h:244-256)
+//   EAResidueSecondCamEx  both
+// Same skeleton as ea_point_eval; not the batched hot path (used by ea_eval_views / ea_solve_views).
+// =================================================================================================================
+struct EaViewXf {            // kernel parameter
+  double T21[12], T12[12];   // trans_1to2 / trans_1to2_inv, 3x4 row-major [R | t]
+  double dist[5];            // k1, k2, p1, p2, k3
+  int use_rig, use_dist;
+};
+
+struct EaPoseG {
+  double A[9], tt[3];        // q = s * (A a) + tt ; camera coordinates when use_dist, else K-folded as in EaPose
+  double k1, k2, p1, p2, k3, fx, fy, cx, cy;
+  float Rt21[9];             // R21^T (identity without rig): pulls the gradient back into the first camera
+  float t21[3], t[3];
+  float fxf, fyf, inv_fx, inv_fy;
+  int use_dist, use_rig;
+};
+
+template <bool XYZ>
+__device__ __forceinline__ void ea_pose_setup_general(const double* x7, const EaLevelGeom& ref, const EaLevelGeom& now,
+                                                      const EaViewXf& V, EaPoseG& P) {
+  const double qw = x7[0], qx = x7[1], qy = x7[2], qz = x7[3];
+  const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+  const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  double R[9] = {1.0 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.0 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1.0 - (txx + tyy)};
+  double t[3] = {x7[4], x7[5], x7[6]};
+  double Rp[9], tp[3];
+  if (V.use_rig) {   // R' = R21 R R12 ; t' = R21 (R t12 + t) + t21
+    double RR[9], v[3];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) RR[3 * i + j] = R[3 * i] * V.T12[j] + R[3 * i + 1] * V.T12[4 + j] + R[3 * i + 2] * V.T12[8 + j];
+      v[i] = R[3 * i] * V.T12[3] + R[3 * i + 1] * V.T12[7] + R[3 * i + 2] * V.T12[11] + t[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) Rp[3 * i + j] = V.T21[4 * i] * RR[j] + V.T21[4 * i + 1] * RR[3 + j] + V.T21[4 * i + 2] * RR[6 + j];
+      tp[i] = V.T21[4 * i] * v[0] + V.T21[4 * i + 1] * v[1] + V.T21[4 * i + 2] * v[2] + V.T21[4 * i + 3];
+    }
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) P.Rt21[3 * i + j] = float(V.T21[4 * j + i]); P.t21[i] = float(V.T21[4 * i + 3]); }
+  } else {
+    for (int i = 0; i < 9; ++i) Rp[i] = R[i];
+    for (int i = 0; i < 3; ++i) tp[i] = t[i];
+    for (int i = 0; i < 9; ++i) P.Rt21[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    P.t21[0] = P.t21[1] = P.t21[2] = 0.0f;
+  }
+  double M[9];
+  for (int i = 0; i < 3; ++i) {
+    if (XYZ) { M[3 * i] = Rp[3 * i]; M[3 * i + 1] = Rp[3 * i + 1]; M[3 * i + 2] = Rp[3 * i + 2]; }
+    else {
+      M[3 * i] = Rp[3 * i] * ref.inv_fx;
+      M[3 * i + 1] = Rp[3 * i + 1] * ref.inv_fy;
+      M[3 * i + 2] = Rp[3 * i + 2] - ref.cx * M[3 * i] - ref.cy * M[3 * i + 1];
+    }
+  }
+  if (V.use_dist) {
+    for (int i = 0; i < 9; ++i) P.A[i] = M[i];
+    for (int i = 0; i < 3; ++i) P.tt[i] = tp[i];
+  } else {
+    for (int j = 0; j < 3; ++j) {
+      P.A[j] = now.fx * M[j] + now.cx * M[6 + j];
+      P.A[3 + j] = now.fy * M[3 + j] + now.cy * M[6 + j];
+      P.A[6 + j] = M[6 + j];
+    }
+    P.tt[0] = now.fx * tp[0] + now.cx * tp[2]; P.tt[1] = now.fy * tp[1] + now.cy * tp[2]; P.tt[2] = tp[2];
+  }
+  P.k1 = V.dist[0]; P.k2 = V.dist[1]; P.p1 = V.dist[2]; P.p2 = V.dist[3]; P.k3 = V.dist[4];
+  P.fx = now.fx; P.fy = now.fy; P.cx = now.cx; P.cy = now.cy;
+  P.t[0] = float(t[0]); P.t[1] = float(t[1]); P.t[2] = float(t[2]);
+  P.fxf = float(now.fx); P.fyf = float(now.fy); P.inv_fx = float(now.inv_fx); P.inv_fy = float(now.inv_fy);
+  P.use_dist = V.use_dist; P.use_rig = V.use_rig;
+}
+
+// value f, robust weight and local Jacobian of one point for any variant; returns the failure flag
+template <bool XYZ>
+__device__ __forceinline__ bool ea_point_eval_general(const float4 p, const EaLevelGeom& now, double inv_depth_scale, const EaPoseG& P,
+                                                      const float* __restrict__ dt, const float2 affine, int loss_type, float loss_a,
+                                                      float& f_out, float& w_out, float& rho0, float J[6]) {
+  const double a0 = double(p.x), a1 = double(p.y);
+  double q0, q1, q2;
+  if (XYZ) {
+    const double a2 = double(p.z);
+    q0 = fma(P.A[0], a0, fma(P.A[1], a1, fma(P.A[2], a2, P.tt[0])));
+    q1 = fma(P.A[3], a0, fma(P.A[4], a1, fma(P.A[5], a2, P.tt[1])));
+    q2 = fma(P.A[6], a0, fma(P.A[7], a1, fma(P.A[8], a2, P.tt[2])));
+  } else {
+    const double Z = double(p.z) * inv_depth_scale;
+    q0 = fma(Z, fma(P.A[0], a0, fma(P.A[1], a1, P.A[2])), P.tt[0]);
+    q1 = fma(Z, fma(P.A[3], a0, fma(P.A[4], a1, P.A[5])), P.tt[1]);
+    q2 = fma(Z, fma(P.A[6], a0, fma(P.A[7], a1, P.A[8])), P.tt[2]);
+  }
+  const bool fail = (q2 < 0.01) && (q2 > -0.01);
+  const double iz = 1.0 / q2;
+  double u, v;
+  float Dxx = 1.f, Dxy = 0.f, Dyx = 0.f, Dyy = 1.f, xn, yn;   // d(distorted)/d(normalised)
+  if (P.use_dist) {
+    const double x = q0 * iz, y = q1 * iz;
+    const double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    const double radial = 1.0 + P.k1 * r2 + P.k2 * r4 + P.k3 * r6;
+    const double dx = x * radial + 2.0 * P.p1 * x * y + P.p2 * (r2 + 2.0 * x * x);
+    const double dy = y * radial + 2.0 * P.p2 * x * y + P.p1 * (r2 + 2.0 * y * y);
+    u = P.fx * dx + P.cx; v = P.fy * dy + P.cy;
+    const double rd = P.k1 + 2.0 * P.k2 * r2 + 3.0 * P.k3 * r4;
+    Dxx = float(radial + 2.0 * x * x * rd + 2.0 * P.p1 * y + 6.0 * P.p2 * x);
+    Dxy = float(2.0 * x * y * rd + 2.0 * P.p1 * x + 2.0 * P.p2 * y);
+    Dyx = float(2.0 * x * y * rd + 2.0 * P.p2 * y + 2.0 * P.p1 * x);
+    Dyy = float(radial + 2.0 * y * y * rd + 2.0 * P.p2 * x + 6.0 * P.p1 * y);
+    xn = float(x); yn = float(y);
+  } else {
+    u = q0 * iz; v = q1 * iz;
+    xn = float((u - P.cx)) * P.inv_fx; yn = float((v - P.cy)) * P.inv_fy;
+  }
+  const int W = now.w, H = now.h;
+  int iu, iv;
+  float du, dv;
+  ea_floor_frac(u, iu, du);
+  ea_floor_frac(v, iv, dv);
+  iu = min(max(iu, -4), W + 4); iv = min(max(iv, -4), H + 4);
+  float tex[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const unsigned row = unsigned(min(max(iv - 1 + r, 0), H - 1)) * unsigned(W);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tex[4 * r + c] = __ldg(dt + row + unsigned(min(max(iu - 1 + c, 0), W - 1)));
+  }
+  float f0, f1, f2, f3, d0, d1, d2, d3, fr, fdu;
+  const float hv = 0.5f * dv, v15 = 1.5f * dv, hu = 0.5f * du, u15 = 1.5f * du;
+  ea_cubic(tex[0], tex[4], tex[8], tex[12], dv, hv, v15, f0, d0);
+  ea_cubic(tex[1], tex[5], tex[9], tex[13], dv, hv, v15, f1, d1);
+  ea_cubic(tex[2], tex[6], tex[10], tex[14], dv, hv, v15, f2, d2);
+  ea_cubic(tex[3], tex[7], tex[11], tex[15], dv, hv, v15, f3, d3);
+  ea_cubic(f0, f1, f2, f3, du, hu, u15, fr, fdu);
+  const float f = fmaf(fr, affine.x, affine.y);
+  const float gu = fdu * affine.x * P.fxf;                                          // dr/d(distorted x)
+  const float gv = ea_cubic_val(d0, d1, d2, d3, du, hu) * affine.x * P.fyf;         // dr/d(distorted y)
+  const float w = ea_loss_eval(loss_type, loss_a, f, rho0);
+  // chain rule: distorted -> normalised -> p' (this camera) -> first camera
+  const float gx = gu * Dxx + gv * Dyx, gy = gu * Dxy + gv * Dyy;
+  const float pz = float(q2), izf = float(iz), wi = w * izf;
+  const float g0 = gx * wi, g1 = gy * wi, g2 = -(gx * xn + gy * yn) * wi;
+  const float h0 = P.Rt21[0] * g0 + P.Rt21[1] * g1 + P.Rt21[2] * g2;
+  const float h1 = P.Rt21[3] * g0 + P.Rt21[4] * g1 + P.Rt21[5] * g2;
+  const float h2 = P.Rt21[6] * g0 + P.Rt21[7] * g1 + P.Rt21[8] * g2;
+  // y1 = R X1 = R21^T (p' - t21) - t
+  const float px = xn * pz - P.t21[0], py = yn * pz - P.t21[1], pzz = pz - P.t21[2];
+  const float yx = P.Rt21[0] * px + P.Rt21[1] * py + P.Rt21[2] * pzz - P.t[0];
+  const float yy = P.Rt21[3] * px + P.Rt21[4] * py + P.Rt21[5] * pzz - P.t[1];
+  const float yz = P.Rt21[6] * px + P.Rt21[7] * py + P.Rt21[8] * pzz - P.t[2];
+  J[0] = 2.0f * (yy * h2 - yz * h1);
+  J[1] = 2.0f * (yz * h0 - yx * h2);
+  J[2] = 2.0f * (yx * h1 - yy * h0);
+  J[3] = h0; J[4] = h1; J[5] = h2;
+  f_out = f; w_out = w;
+  return fail;
+}

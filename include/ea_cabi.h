@@ -194,6 +194,28 @@ int ea_solve_batch_device(ea_context* ctx, int n, ea_frameset* ref, const int32_
                           const int32_t* d_now_slots, double* d_poses7, const int32_t* d_pose_index,
                           const ea_solve_params* sp, ea_summary* d_summaries);
 
+/* ---- residual variants / multi-camera problems (standalone/utils.h:101-421) ------------------------------------------
+ * Every view adds its residual blocks to the same 6-DoF problem, as the reference does with one AddResidualBlock loop per
+ * camera (standalone_edge_align.cpp:791-803, 3204-3219):
+ *   plain view                      EAResidue             utils.h:38-99
+ *   use_distortion                  EAResidueEx           utils.h:101-178  (k1,k2,p1,p2,k3 as the functor takes them)
+ *   use_rig                         EAResidueSecondCam    utils.h:180-298  b_T_a_SecCam = cam_T_first * b_T_a * first_T_cam
+ *   use_rig + use_distortion        EAResidueSecondCamEx  utils.h:300-421
+ * Intrinsics of a view are those of its `now` frameset.  Transforms are 3x4 row-major [R | t]. */
+typedef struct ea_view {
+  ea_frameset* ref; int32_t ref_slot;
+  ea_frameset* now; int32_t now_slot;
+  int32_t use_distortion, use_rig;
+  double dist[5];         /* k1, k2, p1, p2, k3 */
+  double cam_T_first[12]; /* trans_1to2     (standalone_edge_align.cpp: trans_1to2) */
+  double first_T_cam[12]; /* trans_1to2_inv */
+} ea_view;
+int ea_eval_views(ea_context* ctx, int n_views, const ea_view* views, int level, const double* pose7,
+                  const ea_solve_params* sp, int* n_residuals, double* raw, double* residuals, double* jac,
+                  double* sums28, int* failed);
+int ea_solve_views(ea_context* ctx, int n_views, const ea_view* views, int level, double* pose7,
+                   const ea_solve_params* sp, ea_summary* summary);
+
 /* ---- tracker: the caller of the path (src/ea.cpp:87-131 consumer loop, re-stated) ------ */
 /* n_streams independent cameras; every step each stream gets one new frame which is aligned
  * to that stream's key frame (warm-started from the previous pose); every keyframe_interval-th

@@ -321,6 +321,52 @@ struct EAResidue {
   }
 };
 
+// standalone/utils.h:101-421  EAResidueEx (radial-tangential distortion, :140-149), EAResidueSecondCam (rigid rig,
+// :244-256: b_T_a_SecCam = T_1to2 * b_T_a * T_1to2_inv) and EAResidueSecondCamEx (both) -- one functor, same arithmetic
+// order as the reference's three classes; use_rig / use_dist select the variant.
+struct EAResidueVariant {
+  double fx, fy, cx, cy, X, Y, Z;
+  const DtGrid* grid;
+  bool use_dist; double k1, k2, p1, p2, k3;          // functor argument order (k1,k2,p1,p2,k3), utils.h:106
+  bool use_rig; const double* T21; const double* T12;   // row-major 4x4: trans_1to2, trans_1to2_inv
+  template <typename T>
+  bool operator()(const T* quat, const T* t, T* residue) const {
+    const T qw = quat[0], qx = quat[1], qy = quat[2], qz = quat[3];
+    const T tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+    const T twx = tx * qw, twy = ty * qw, twz = tz * qw;
+    const T txx = tx * qx, txy = ty * qx, txz = tz * qx;
+    const T tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    T M[4][4];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) M[i][j] = T(0.0);
+    M[0][0] = 1.0 - (tyy + tzz); M[0][1] = txy - twz;         M[0][2] = txz + twy;
+    M[1][0] = txy + twz;         M[1][1] = 1.0 - (txx + tzz); M[1][2] = tyz - twx;
+    M[2][0] = txz - twy;         M[2][1] = tyz + twx;         M[2][2] = 1.0 - (txx + tyy);
+    M[0][3] = t[0]; M[1][3] = t[1]; M[2][3] = t[2]; M[3][3] = T(1.0);
+    if (use_rig) {   // Eigen evaluates (A * B) * C
+      T AB[4][4], ABC[4][4];
+      for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { T s = T(0.0); for (int k = 0; k < 4; ++k) s = s + M[k][j] * T21[i * 4 + k]; AB[i][j] = s; }
+      for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { T s = T(0.0); for (int k = 0; k < 4; ++k) s = s + AB[i][k] * T12[k * 4 + j]; ABC[i][j] = s; }
+      for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) M[i][j] = ABC[i][j];
+    }
+    T bX[3];
+    for (int i = 0; i < 3; ++i) bX[i] = M[i][0] * X + M[i][1] * Y + M[i][2] * Z + M[i][3];
+    if (scalar_part(bX[2]) < 0.01 && scalar_part(bX[2]) > -0.01) return false;
+    T u, v;
+    if (use_dist) {
+      T x = bX[0] / bX[2], y = bX[1] / bX[2];
+      T r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+      T radial = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+      T dx = x * radial + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+      T dy = y * radial + 2.0 * p2 * x * y + p1 * (r2 + 2.0 * y * y);
+      u = fx * dx + cx; v = fy * dy + cy;
+    } else {
+      u = fx * bX[0] / bX[2] + cx; v = fy * bX[1] / bX[2] + cy;
+    }
+    interp(*grid, u, v, residue);
+    return true;
+  }
+};
+
 enum { LOSS_TRIVIAL = 0, LOSS_CAUCHY = 1, LOSS_HUBER = 2 };
 // ceres/loss_function.cc
 inline void loss_eval(int type, double a, double s, double rho[3]) {
@@ -381,31 +427,52 @@ enum Termination { TERM_CONVERGENCE_GRADIENT = 1, TERM_CONVERGENCE_FUNCTION = 2,
                    TERM_CONVERGENCE_MIN_RADIUS = 4, TERM_NO_CONVERGENCE = 5, TERM_FAILURE_EVAL_X0 = 6,
                    TERM_FAILURE_INVALID_STEPS = 7 };
 
-struct Problem {
-  const double* pts;  // xyz xyz ... (already strided selection applied by caller index)
-  int n_total; int stride;
+struct View {          // one camera's residual blocks (standalone_edge_align.cpp:791-803 adds one loop per camera)
+  const double* pts; int n_total; int stride;
   double fx, fy, cx, cy;
   DtGrid grid;
+  bool use_dist = false; double dist[5] = {0, 0, 0, 0, 0};
+  bool use_rig = false; double T21[16], T12[16];
   int n_res() const { return (n_total + stride - 1) / stride; }
+};
+struct Problem {
+  std::vector<View> views;
+  Problem() {}
+  Problem(const double* pts, int n_total, int stride, double fx, double fy, double cx, double cy, DtGrid g) {
+    View v; v.pts = pts; v.n_total = n_total; v.stride = stride; v.fx = fx; v.fy = fy; v.cx = cx; v.cy = cy; v.grid = g;
+    views.push_back(v);
+  }
+  int n_res() const { int n = 0; for (const View& v : views) n += v.n_res(); return n; }
+  const View& locate(int bi, int* local) const {
+    size_t k = 0;
+    while (bi >= views[k].n_res()) { bi -= views[k].n_res(); ++k; }
+    *local = bi;
+    return views[k];
+  }
 };
 
 // One residual block: autodiff via Jet<7>, local-parameterisation product, loss+corrector.
 // Returns false if the functor returns false (|z|<0.01).
 inline bool eval_block(const Problem& p, int bi, const double x[7], const Options& o, double* cost, double* r_out,
                        double* J_out /*6 or null*/, double* raw_r /*unrobustified, or null*/) {
-  const double* P3 = p.pts + size_t(bi) * p.stride * 3;
-  EAResidue f{p.fx, p.fy, p.cx, p.cy, P3[0], P3[1], P3[2], &p.grid};
+  int li;
+  const View& V = p.locate(bi, &li);
+  const double* P3 = V.pts + size_t(li) * V.stride * 3;
+  const bool plain = !V.use_dist && !V.use_rig;
+  EAResidue f{V.fx, V.fy, V.cx, V.cy, P3[0], P3[1], P3[2], &V.grid};
+  EAResidueVariant fv{V.fx, V.fy, V.cx, V.cy, P3[0], P3[1], P3[2], &V.grid, V.use_dist, V.dist[0], V.dist[1], V.dist[2], V.dist[3], V.dist[4],
+                      V.use_rig, V.T21, V.T12};
   double r, Jq[4] = {0, 0, 0, 0}, Jt[3] = {0, 0, 0};
   if (J_out) {
     Jet<7> q[4], t[3], res;
     for (int i = 0; i < 4; ++i) q[i] = Jet<7>(x[i], i);
     for (int i = 0; i < 3; ++i) t[i] = Jet<7>(x[4 + i], 4 + i);
-    if (!f(q, t, &res)) return false;
+    if (!(plain ? f(q, t, &res) : fv(q, t, &res))) return false;
     r = res.a;
     for (int i = 0; i < 4; ++i) Jq[i] = res.v[i];
     for (int i = 0; i < 3; ++i) Jt[i] = res.v[4 + i];
   } else {
-    if (!f(x, x + 4, &r)) return false;
+    if (!(plain ? f(x, x + 4, &r) : fv(x, x + 4, &r))) return false;
   }
   if (raw_r) *raw_r = r;
   const double sq = r * r;
@@ -708,7 +775,7 @@ int eo_eval(const double* pts, int n_total, int stride, const float* dt, int w, 
             double cy, const double* pose7, const eo_options* eo, double* residuals, double* raw, double* J,
             double* sums) {
   Options o = to_opts(eo);
-  Problem p{pts, n_total, stride, fx, fy, cx, cy, DtGrid{dt, w, h}};
+  Problem p(pts, n_total, stride, fx, fy, cx, cy, DtGrid{dt, w, h});
   const int n = p.n_res();
   double cost = 0, b[6] = {0}, H[21] = {0};
   for (int i = 0; i < n; ++i) {
@@ -729,11 +796,11 @@ int eo_eval(const double* pts, int n_total, int stride, const float* dt, int w, 
 // candidate cost): residuals raw (unrobustified).  Also returns dfdu, dfdv per point.
 int eo_eval_raw(const double* pts, int n_total, int stride, const float* dt, int w, int h, double fx, double fy,
                 double cx, double cy, const double* pose7, double* raw, double* uv) {
-  Problem p{pts, n_total, stride, fx, fy, cx, cy, DtGrid{dt, w, h}};
+  Problem p(pts, n_total, stride, fx, fy, cx, cy, DtGrid{dt, w, h});
   const int n = p.n_res();
   for (int i = 0; i < n; ++i) {
     const double* P3 = pts + size_t(i) * stride * 3;
-    EAResidue f{fx, fy, cx, cy, P3[0], P3[1], P3[2], &p.grid};
+    EAResidue f{fx, fy, cx, cy, P3[0], P3[1], P3[2], &p.views[0].grid};
     double r;
     if (!f(pose7, pose7 + 4, &r)) return 1;
     raw[i] = r;
@@ -769,7 +836,7 @@ int eo_solve(const double* pts, int n_total, int stride, const float* dt, int w,
              double cy, double* pose7, const eo_options* eo, eo_summary* summary, double* trace, int trace_cap,
              int* trace_n) {
   Options o = to_opts(eo);
-  Problem p{pts, n_total, stride, fx, fy, cx, cy, DtGrid{dt, w, h}};
+  Problem p(pts, n_total, stride, fx, fy, cx, cy, DtGrid{dt, w, h});
   std::vector<IterRecord> tr(trace_cap > 0 ? trace_cap : 0);
   int tn = 0;
   SolveSummary S = lm_solve(p, pose7, o, tr.data(), trace_cap, &tn);
@@ -779,6 +846,52 @@ int eo_solve(const double* pts, int n_total, int stride, const float* dt, int w,
     d[4] = tr[i].relative_decrease; d[5] = tr[i].radius; d[6] = tr[i].accepted;
   }
   if (trace_n) *trace_n = tn;
+  fill(summary, S);
+  return 0;
+}
+
+// ---- multi-camera problems: residual variants of standalone/utils.h:101-421 -----------------------------------
+// One eo_view per camera; all views constrain the same pose (standalone_edge_align.cpp:791-803, 3204-3219).
+struct eo_view {
+  const double* pts; int n_total, stride; const float* dt; int w, h;
+  double fx, fy, cx, cy;
+  int use_dist; double dist[5];       // k1,k2,p1,p2,k3
+  int use_rig; double T21[16], T12[16];  // trans_1to2, trans_1to2_inv (row-major 4x4)
+};
+static Problem views_problem(const eo_view* v, int n_views) {
+  Problem p;
+  for (int i = 0; i < n_views; ++i) {
+    View V; V.pts = v[i].pts; V.n_total = v[i].n_total; V.stride = v[i].stride; V.fx = v[i].fx; V.fy = v[i].fy; V.cx = v[i].cx; V.cy = v[i].cy;
+    V.grid = DtGrid{v[i].dt, v[i].w, v[i].h};
+    V.use_dist = v[i].use_dist != 0; for (int k = 0; k < 5; ++k) V.dist[k] = v[i].dist[k];
+    V.use_rig = v[i].use_rig != 0; for (int k = 0; k < 16; ++k) { V.T21[k] = v[i].T21[k]; V.T12[k] = v[i].T12[k]; }
+    p.views.push_back(V);
+  }
+  return p;
+}
+int eo_eval_views(const eo_view* views, int n_views, const double* pose7, const eo_options* eo, double* residuals, double* raw,
+                  double* J, double* sums) {
+  Options o = to_opts(eo);
+  Problem p = views_problem(views, n_views);
+  const int n = p.n_res();
+  double cost = 0, b[6] = {0}, H[21] = {0};
+  for (int i = 0; i < n; ++i) {
+    double ci, ri, Ji[6], rr;
+    if (!eval_block(p, i, pose7, o, &ci, &ri, Ji, &rr)) return 1;
+    cost += ci;
+    if (residuals) residuals[i] = ri;
+    if (raw) raw[i] = rr;
+    if (J) std::memcpy(J + size_t(i) * 6, Ji, sizeof(Ji));
+    int k = 0;
+    for (int a = 0; a < 6; ++a) { b[a] += Ji[a] * ri; for (int c = a; c < 6; ++c) H[k++] += Ji[a] * Ji[c]; }
+  }
+  if (sums) { sums[0] = cost; std::memcpy(sums + 1, b, sizeof(b)); std::memcpy(sums + 7, H, sizeof(H)); }
+  return 0;
+}
+int eo_solve_views(const eo_view* views, int n_views, double* pose7, const eo_options* eo, eo_summary* summary) {
+  Options o = to_opts(eo);
+  Problem p = views_problem(views, n_views);
+  SolveSummary S = lm_solve(p, pose7, o, nullptr, 0, nullptr);
   fill(summary, S);
   return 0;
 }
@@ -816,10 +929,10 @@ static void build_levels(const uint8_t* bgr, const uint16_t* depth, const eo_pai
 static void solve_levels(const std::vector<Level>& R, const std::vector<Level>& N, const eo_pair_cfg& c, const Options& o,
                          double* pose7, eo_summary* summaries) {
   for (int l = c.n_levels - 1; l >= 0; --l) {
-    Problem p{R[l].pts.data(), int(R[l].pts.size() / 3), c.stride, N[l].fx, N[l].fy, N[l].cx, N[l].cy,
-              DtGrid{N[l].dt.data(), N[l].w, N[l].h}};
+    Problem p(R[l].pts.data(), int(R[l].pts.size() / 3), c.stride, N[l].fx, N[l].fy, N[l].cx, N[l].cy,
+              DtGrid{N[l].dt.data(), N[l].w, N[l].h});
     SolveSummary S{};
-    if (p.n_total > 0) S = lm_solve(p, pose7, o, nullptr, 0, nullptr);
+    if (p.n_res() > 0) S = lm_solve(p, pose7, o, nullptr, 0, nullptr);
     if (summaries) fill(summaries + l, S);
   }
 }

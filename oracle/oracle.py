@@ -221,3 +221,59 @@ def quat_plus(x7, d6):
     x7 = np.ascontiguousarray(x7, np.float64); d6 = np.ascontiguousarray(d6, np.float64); out = np.empty(7)
     lib().eo_quat_plus(_p(x7, C.c_double), _p(d6, C.c_double), _p(out, C.c_double))
     return out
+
+
+# ---- multi-camera problems / residual variants (standalone/utils.h:101-421) ------------------------------------
+class ViewC(C.Structure):
+    _fields_ = [("pts", C.POINTER(C.c_double)), ("n_total", C.c_int), ("stride", C.c_int), ("dt", C.POINTER(C.c_float)),
+                ("w", C.c_int), ("h", C.c_int), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("use_dist", C.c_int), ("dist", C.c_double * 5), ("use_rig", C.c_int), ("T21", C.c_double * 16),
+                ("T12", C.c_double * 16)]
+
+
+def make_views(views):
+    """views: list of dict(xyz, dt, K, stride=1, dist=None (k1,k2,p1,p2,k3), T21=None (4x4), T12=None)."""
+    arr = (ViewC * len(views))()
+    keep = []
+    for i, v in enumerate(views):
+        xyz = np.ascontiguousarray(v["xyz"], np.float64); dt = np.ascontiguousarray(v["dt"], np.float32)
+        keep += [xyz, dt]
+        a = arr[i]
+        a.pts = _p(xyz, C.c_double); a.n_total = len(xyz); a.stride = int(v.get("stride", 1)); a.dt = _p(dt, C.c_float)
+        a.h, a.w = dt.shape
+        a.fx, a.fy, a.cx, a.cy = [float(k) for k in v["K"]]
+        d = v.get("dist")
+        a.use_dist = 0 if d is None else 1
+        for k in range(5):
+            a.dist[k] = 0.0 if d is None else float(d[k])
+        T21 = v.get("T21")
+        a.use_rig = 0 if T21 is None else 1
+        t21 = np.eye(4) if T21 is None else np.asarray(T21, np.float64)
+        t12 = np.linalg.inv(t21) if v.get("T12") is None else np.asarray(v["T12"], np.float64)
+        for k in range(16):
+            a.T21[k] = float(t21.flat[k]); a.T12[k] = float(t12.flat[k])
+    return arr, keep
+
+
+def evaluate_views(views, pose7, options=None):
+    arr, keep = make_views(views)
+    n = sum((len(v["xyz"]) + int(v.get("stride", 1)) - 1) // int(v.get("stride", 1)) for v in views)
+    pose7 = np.ascontiguousarray(pose7, np.float64)
+    r = np.empty(n); raw = np.empty(n); J = np.empty((n, 6)); sums = np.empty(28)
+    o = options or default_options()
+    rc = lib().eo_eval_views(arr, len(views), _p(pose7, C.c_double), C.byref(o), _p(r, C.c_double), _p(raw, C.c_double),
+                             _p(J, C.c_double), _p(sums, C.c_double))
+    H = np.zeros((6, 6)); k = 7
+    for a in range(6):
+        for c in range(a, 6):
+            H[a, c] = H[c, a] = sums[k]; k += 1
+    return dict(residuals=r, raw=raw, J=J, cost=sums[0], b=sums[1:7].copy(), H=H, sums=sums, ok=(rc == 0))
+
+
+def solve_views(views, pose7, options=None):
+    arr, keep = make_views(views)
+    pose = np.array(pose7, np.float64)
+    o = options or default_options()
+    s = Summary()
+    lib().eo_solve_views(arr, len(views), _p(pose, C.c_double), C.byref(o), C.byref(s))
+    return pose, s.asdict()

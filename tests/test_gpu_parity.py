@@ -380,3 +380,45 @@ def test_tracker_on_synthetic_sequence_recovers_ground_truth(ea, ctx):
                 assert np.abs(poses[s][4:] - gt[4:]).max() < 0.03, (s, t)
     finally:
         tr.close()
+
+
+# --------------------------------------------------------------------- residual variants (standalone/utils.h:101-421)
+def test_residual_variants_and_two_camera_solve(ea, ctx, fs5, frames, oracle, numpy_pins):
+    """EAResidueEx (distortion), EAResidueSecondCam (rig), EAResidueSecondCamEx (both) against the oracle's Jet
+    restatement: per-point residuals, Jacobians, normal equations, and a two-camera solve of one pose."""
+    O = oracle
+    K = frames["K"]
+    x = numpy_pins["xpert"]
+    ang = 0.05
+    T21 = np.eye(4); T21[:3, :3] = [[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]; T21[:3, 3] = [-0.1, 0.01, 0.02]
+    dist = (0.1, -0.2, 0.001, -0.002, 0.05)
+    pts = {i: O.get_aX(frames["bgr"][i], frames["depth"][i], K)[0] for i in (0, 1)}
+    dts = {i: O.get_distance_transform(frames["bgr"][i])[0] for i in (2, 3)}
+    for stride in (30, 1):
+        for kw in (dict(), dict(dist=dist), dict(T21=T21), dict(dist=dist, T21=T21)):
+            for loss, scale in ((ea.LOSS_TRIVIAL, 1.0), (ea.LOSS_HUBER, 0.1)):
+                sp = ea.solve_params(point_stride=stride, loss_type=loss, loss_scale=scale)
+                g = ctx.eval_views([dict(ref=fs5, ref_slot=0, now=fs5, now_slot=2, **kw)], x, sp)
+                o = O.evaluate_views([dict(xyz=pts[0], dt=dts[2], K=K, stride=stride, **kw)], x, O.default_options(loss_type=loss, loss_scale=scale))
+                assert g["failed"] == 0 and o["ok"] and g["n_residuals"] == len(o["raw"])
+                _assert_residual_parity(g["raw"], o["raw"])
+                jscale = np.abs(o["J"]).max(0)
+                assert (np.abs(g["J"] - o["J"]) <= 3e-5 * jscale + 3e-5 * np.abs(o["J"])).all()
+                np.testing.assert_allclose(g["cost"], o["cost"], rtol=3e-6)
+                np.testing.assert_allclose(g["H"], o["H"], rtol=0, atol=3e-6 * np.abs(np.diag(o["H"])).max())
+    # two cameras, one pose (SEA:791-803): camera 1 plain, camera 2 through the rig with distortion
+    sp = ea.solve_params(point_stride=10)
+    gv = [dict(ref=fs5, ref_slot=0, now=fs5, now_slot=2), dict(ref=fs5, ref_slot=1, now=fs5, now_slot=3, T21=T21, dist=dist)]
+    ov = [dict(xyz=pts[0], dt=dts[2], K=K, stride=10), dict(xyz=pts[1], dt=dts[3], K=K, stride=10, T21=T21, dist=dist)]
+    g = ctx.eval_views(gv, x, sp); o = O.evaluate_views(ov, x, O.default_options())
+    _assert_residual_parity(g["raw"], o["raw"])
+    np.testing.assert_allclose(g["cost"], o["cost"], rtol=3e-6)
+    pose, s = ctx.solve_views(gv, None, sp)
+    op, os_ = O.solve_views(ov, IDENTITY, O.default_options())
+    assert rot_angle_between(pose[:4], op[:4]) < 1e-4 and np.abs(pose[4:] - op[4:]).max() < 1e-4
+    assert abs(s["iterations"] - os_["iterations"]) <= 2 and s["n_residuals"] == os_["n_residuals"]
+    assert abs(s["final_cost"] - os_["final_cost"]) <= 1e-5 * os_["final_cost"]
+    # a single plain view through the views API == the batched solver
+    p1, s1 = ctx.solve_views(gv[:1], None, ea.solve_params(point_stride=30))
+    p2, s2 = ctx.solve_batch(fs5, [0], fs5, [2], None, ea.solve_params(point_stride=30))
+    assert rot_angle_between(p1[:4], p2[0][:4]) < 2e-6 and np.abs(p1[4:] - p2[0][4:]).max() < 2e-6

@@ -171,3 +171,40 @@ def test_pyramid_and_batch_entry_points(oracle, frames):
     poses, sums, sec = O.align_batch(frames["bgr"], frames["depth"], [0, 0, 1], [2, 2, 3], cfg3, np.tile(IDENTITY, (3, 1)), opts, n_threads=2)
     np.testing.assert_array_equal(poses[0], p3); np.testing.assert_array_equal(poses[1], p3)
     assert sec > 0
+
+
+def test_residual_variants_jet_vs_finite_differences(oracle, pair13, frames, numpy_pins):
+    """EAResidueEx / SecondCam / SecondCamEx restatements (standalone/utils.h:101-421): Jet Jacobians agree with central
+    differences through Plus(); the plain view equals the single-camera entry point; identity rig / zero distortion
+    reduce to EAResidue."""
+    O = oracle
+    xyz, dt = pair13
+    K = frames["K"]
+    x = numpy_pins["xpert"]
+    opt = O.default_options(loss_type=O.LOSS_TRIVIAL)
+    base = O.evaluate(xyz, dt, K, x, stride=30, options=opt)
+    ang = 0.05
+    T21 = np.eye(4); T21[:3, :3] = [[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]; T21[:3, 3] = [-0.1, 0.01, 0.02]
+    dist = (0.1, -0.2, 0.001, -0.002, 0.05)
+    for kw in (dict(), dict(dist=(0, 0, 0, 0, 0)), dict(T21=np.eye(4))):
+        e = O.evaluate_views([dict(xyz=xyz, dt=dt, K=K, stride=30, **kw)], x, opt)
+        np.testing.assert_allclose(e["raw"], base["raw"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(e["J"], base["J"], rtol=0, atol=1e-9)
+    for kw in (dict(dist=dist), dict(T21=T21), dict(dist=dist, T21=T21)):
+        views = [dict(xyz=xyz, dt=dt, K=K, stride=30, **kw)]
+        e = O.evaluate_views(views, x, opt)
+        assert e["ok"] and np.abs(e["raw"] - base["raw"]).max() > 1e-3          # the variant really changes the projection
+        h = 1e-6
+        for k in range(6):
+            d = np.zeros(6); d[k] = h
+            rp = O.evaluate_views(views, O.quat_plus(x, d), opt)["raw"]; rm = O.evaluate_views(views, O.quat_plus(x, -d), opt)["raw"]
+            fd = (rp - rm) / (2 * h)
+            ok = np.abs(e["J"][:, k] - fd) <= 1e-5 * np.abs(fd) + 5e-5
+            assert ok.mean() > 0.99          # bicubic is only C1: a few probes straddle a cell boundary
+    # two cameras constrain one pose: sums add up
+    v2 = [dict(xyz=xyz, dt=dt, K=K, stride=30), dict(xyz=xyz[5:], dt=dt, K=K, stride=30, T21=T21, dist=dist)]
+    e2 = O.evaluate_views(v2, x, opt)
+    ea_, eb_ = O.evaluate_views(v2[:1], x, opt), O.evaluate_views(v2[1:], x, opt)
+    np.testing.assert_allclose(e2["sums"], ea_["sums"] + eb_["sums"], rtol=1e-12)
+    pose, s = O.solve_views(v2, IDENTITY, O.default_options())
+    assert s["termination"] in (1, 2, 3) and s["n_residuals"] == len(e2["raw"])
