@@ -207,6 +207,91 @@ void half_nearest_u16(const uint16_t* s, int w, int h, uint16_t* d) {
     for (int x = 0; x < w2; ++x) d[size_t(y) * w2 + x] = s[size_t(2 * y) * w + 2 * x];
 }
 
+// cv::Canny(src, dst, t1, t2, 3, L2gradient) -- OpenCV's portable algorithm (canny.cpp): Sobel 3x3 with
+// BORDER_REPLICATE per channel, per pixel the channel with the largest magnitude (first on ties), non-maximum
+// suppression with the fixed-point tan(22.5 deg) test, hysteresis over 8-neighbours.  cn = 1 or 3.
+// Call sites: standalone/utils.cpp:94 (gray, 30/90, L1), src/SolveEA.cpp:46,102 (colour, 150/100 swapped, L2).
+void canny_u8(const uint8_t* src, int w, int h, int cn, double t1, double t2, bool l2, uint8_t* dst) {
+  if (t1 > t2) std::swap(t1, t2);
+  if (l2) {
+    t1 = std::min(32767.0, t1); t2 = std::min(32767.0, t2);
+    if (t1 > 0) t1 *= t1;
+    if (t2 > 0) t2 *= t2;
+  }
+  const int low = int(std::floor(t1)), high = int(std::floor(t2));
+  std::vector<int> mag(size_t(w + 2) * (h + 2), 0);
+  std::vector<short> gx(size_t(w) * h), gy(size_t(w) * h);
+  auto px = [&](int x, int y, int c) { return int(src[(size_t(replicate(y, h)) * w + replicate(x, w)) * cn + c]); };
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int best = -1, bdx = 0, bdy = 0;
+      for (int c = 0; c < cn; ++c) {
+        const int dx = (px(x + 1, y - 1, c) + 2 * px(x + 1, y, c) + px(x + 1, y + 1, c)) - (px(x - 1, y - 1, c) + 2 * px(x - 1, y, c) + px(x - 1, y + 1, c));
+        const int dy = (px(x - 1, y + 1, c) + 2 * px(x, y + 1, c) + px(x + 1, y + 1, c)) - (px(x - 1, y - 1, c) + 2 * px(x, y - 1, c) + px(x + 1, y - 1, c));
+        const int m = l2 ? dx * dx + dy * dy : std::abs(dx) + std::abs(dy);
+        if (m > best) { best = m; bdx = dx; bdy = dy; }
+      }
+      mag[size_t(y + 1) * (w + 2) + x + 1] = best; gx[size_t(y) * w + x] = short(bdx); gy[size_t(y) * w + x] = short(bdy);
+    }
+  // map: 1 = not an edge, 0 = candidate, 2 = edge; 1-pixel border of 1s
+  std::vector<uint8_t> map(size_t(w + 2) * (h + 2), 1);
+  std::vector<int> stack;
+  const int TG22 = 13573, ms = w + 2;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const int* M = &mag[size_t(y + 1) * ms + x + 1];
+      const int m = M[0];
+      bool is_max = false;
+      if (m > low) {
+        const int xs = gx[size_t(y) * w + x], ys = gy[size_t(y) * w + x];
+        const int ax = std::abs(xs), ay = std::abs(ys) << 15;
+        const int tg22x = ax * TG22;
+        if (ay < tg22x) is_max = (m > M[-1] && m >= M[1]);
+        else {
+          const int tg67x = tg22x + (ax << 16);
+          if (ay > tg67x) is_max = (m > M[-ms] && m >= M[ms]);
+          else { const int sg = (xs ^ ys) < 0 ? -1 : 1; is_max = (m > M[-ms - sg] && m > M[ms + sg]); }
+        }
+      }
+      uint8_t& c = map[size_t(y + 1) * ms + x + 1];
+      if (is_max) { if (m > high) { c = 2; stack.push_back(int(&c - map.data())); } else c = 0; }
+      else c = 1;
+    }
+  while (!stack.empty()) {
+    const int i = stack.back(); stack.pop_back();
+    const int nb[8] = {-ms - 1, -ms, -ms + 1, -1, 1, ms - 1, ms, ms + 1};
+    for (int k = 0; k < 8; ++k) if (map[i + nb[k]] == 0) { map[i + nb[k]] = 2; stack.push_back(i + nb[k]); }
+  }
+  for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) dst[size_t(y) * w + x] = map[size_t(y + 1) * ms + x + 1] == 2 ? 255 : 0;
+}
+
+// cv::distanceTransform(src, dst, DIST_L2, DIST_MASK_PRECISE) -- OpenCV's trueDistTrans (distransform.cpp): a column pass
+// (vertical distance to the nearest zero pixel; "infinite" when a column has none) and a row pass taking the lower
+// envelope of the parabolas.  All quantities are integers < 2^24, so the envelope value is the
+// exact integer minimum and the result is sqrtf of it.   Call site: src/SolveEA.cpp:108.
+void exact_edt(const uint8_t* src, int w, int h, float* dst) {
+  const int INF = 1 << 20;                 // "no zero pixel in this column"
+  std::vector<int> g(size_t(w) * h);
+  for (int x = 0; x < w; ++x) {
+    int dist = INF;
+    for (int y = h - 1; y >= 0; --y) { dist = src[size_t(y) * w + x] == 0 ? 0 : std::min(dist + 1, INF); g[size_t(y) * w + x] = dist; }
+    dist = INF;
+    for (int y = 0; y < h; ++y) { dist = src[size_t(y) * w + x] == 0 ? 0 : std::min(dist + 1, INF); g[size_t(y) * w + x] = std::min(g[size_t(y) * w + x], dist); }
+  }
+  for (int y = 0; y < h; ++y) {
+    const int* gr = &g[size_t(y) * w];
+    for (int q = 0; q < w; ++q) {
+      long long best = -1;
+      for (int p = 0; p < w; ++p) {
+        if (gr[p] >= INF) continue;
+        const long long v = (long long)(q - p) * (q - p) + (long long)gr[p] * gr[p];
+        if (best < 0 || v < best) best = v;
+      }
+      dst[size_t(y) * w + q] = best < 0 ? 65536.0f : std::sqrt(float(best));   // OpenCV's value when the image has no zero pixel
+    }
+  }
+}
+
 // gradient magnitude image shared by get_aX and get_distance_transform
 void laplacian_edge_strength(const uint8_t* bgr, int w, int h, uint8_t* lap8) {
   std::vector<uint8_t> blur(size_t(w) * h * 3), gray(size_t(w) * h);
@@ -747,6 +832,8 @@ void eo_normalize_minmax(float* d, int n, double a, double b) { normalize_minmax
 void eo_half_linear_u8c3(const uint8_t* s, int w, int h, uint8_t* d) { half_linear_u8c3(s, w, h, d); }
 void eo_half_nearest_u16(const uint16_t* s, int w, int h, uint16_t* d) { half_nearest_u16(s, w, h, d); }
 
+void eo_canny(const uint8_t* s, int w, int h, int cn, double t1, double t2, int l2, uint8_t* d) { canny_u8(s, w, h, cn, t1, t2, l2 != 0, d); }
+void eo_exact_edt(const uint8_t* s, int w, int h, float* d) { exact_edt(s, w, h, d); }
 // get_aX (utils.cpp:201-281): returns N; fills xyz (3N doubles) and uvd (3N ints) up to cap points.
 int eo_get_aX(const uint8_t* bgr, const uint16_t* depth, int w, int h, double fx, double fy, double cx, double cy,
               double zscale, int thresh, double* xyz, int* uvd, int cap) {

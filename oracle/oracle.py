@@ -98,6 +98,19 @@ def chamfer3_dt(mask): return _stage("eo_chamfer3_dt", mask, mask.shape, np.floa
 def half_linear(bgr): return _stage("eo_half_linear_u8c3", bgr, (bgr.shape[0] // 2, bgr.shape[1] // 2, 3))
 
 
+def canny(img, t1, t2, l2=False):
+    """cv::Canny(img, t1, t2, 3, l2) on 8UC1 or 8UC3."""
+    img = _u8(img)
+    h, w = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty((h, w), np.uint8)
+    lib().eo_canny(_p(img, C.c_uint8), w, h, cn, C.c_double(t1), C.c_double(t2), 1 if l2 else 0, _p(out, C.c_uint8))
+    return out
+
+
+def exact_edt(mask): return _stage("eo_exact_edt", mask, mask.shape, np.float32)
+
+
 def half_nearest(depth):
     depth = np.ascontiguousarray(depth, dtype=np.uint16)
     h, w = depth.shape

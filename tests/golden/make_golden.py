@@ -56,6 +56,19 @@ def cv2_stages(bgr, depth):
     out["half_bgr"] = cv2.resize(bgr, None, fx=0.5, fy=0.5)
     out["half_depth"] = cv2.resize(depth, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST)
     out["box3"] = cv2.blur(bgr, (3, 3))
+    # SolveEA flavour (src/SolveEA.cpp:46,102-109): Canny on the colour image, thresholds given as (150, 100), L2 gradient,
+    # exact Euclidean DT of the inverted edge map, normalised to [0, 255]
+    cc = cv2.Canny(bgr, 150, 100, apertureSize=3, L2gradient=True)
+    out["canny_color_l2"] = cc
+    edt = cv2.distanceTransform(255 - cc, cv2.DIST_L2, cv2.DIST_MASK_PRECISE)
+    out["edt_precise"] = edt
+    out["edt_precise_norm255"] = cv2.normalize(edt, None, 0.0, 255.0, cv2.NORM_MINMAX)
+    # standalone Canny variants (utils.cpp:85-106, 371-462): box blur 3x3 -> gray -> Canny(30, 90), L1 gradient
+    cg = cv2.Canny(cv2.cvtColor(out["box3"], cv2.COLOR_RGB2GRAY), 30, 90)
+    out["canny_gray_l1"] = cg
+    out["dt2_norm"] = cv2.normalize(cv2.distanceTransform(cv2.threshold(cg, 127, 255, cv2.THRESH_BINARY_INV)[1], cv2.DIST_L2, 3), None, 0, 1.0, cv2.NORM_MINMAX)
+    vs2, us2 = np.nonzero((cg > 0) & (depth > 0))
+    out["uvd_canny"] = np.stack([us2, vs2, depth[vs2, us2]], 1).astype(np.int32)
     return out
 
 
@@ -117,6 +130,7 @@ def main():
         s = cv2_stages(bgr[i], depth[i])
         rec = {k: sha(v) for k, v in s.items()}
         rec["n_points"] = int(len(s["uvd"])); rec["n_edge_now"] = int((s["median"] == 0).sum())
+        rec["n_canny_color"] = int((s["canny_color_l2"] > 0).sum()); rec["n_points_canny"] = int(len(s["uvd_canny"]))
         rec["dt_raw_max"] = float(s["dt_raw"].max())
         cv2.ipp.setUseIPP(True)
         d_ipp = cv2.distanceTransform(s["median"], cv2.DIST_L2, 3)

@@ -69,3 +69,30 @@ def test_edge_cases_tiny_and_empty(oracle):
     adx, ady = abs(xx - 5), abs(yy - 4)
     expect = ((HV * abs(adx - ady) + DG * np.minimum(adx, ady)).astype(np.float32) / np.float32(65536)).astype(np.float32)
     np.testing.assert_array_equal(d, expect)
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_canny_and_exact_edt_bit_exact_vs_cv2(oracle, frames, cv2_stages, i):
+    """SolveEA flavour (src/SolveEA.cpp:46,102-109) and the standalone Canny variants (utils.cpp:85-106): Canny and the
+    exact Euclidean DT restatements reproduce genuine OpenCV bit for bit."""
+    O = oracle
+    g = cv2_stages["frames"][i]
+    bgr = frames["bgr"][i]
+    cc = O.canny(bgr, 150, 100, l2=True)                       # thresholds swapped inside, as OpenCV does
+    assert sha(cc) == g["canny_color_l2"] and int((cc > 0).sum()) == g["n_canny_color"]
+    edt = O.exact_edt(255 - cc)
+    assert sha(edt) == g["edt_precise"]
+    assert sha(O.normalize_minmax(edt, 0, 255)) == g["edt_precise_norm255"]
+    cg = O.canny(O.rgb2gray(O.box3(bgr)), 30, 90, l2=False)
+    assert sha(cg) == g["canny_gray_l1"]
+    inv = np.where(cg > 127, 0, 255).astype(np.uint8)
+    assert sha(O.normalize_minmax(O.chamfer3_dt(inv), 0, 1)) == g["dt2_norm"]
+
+
+def test_exact_edt_edge_cases(oracle):
+    O = oracle
+    m = np.full((20, 300), 255, np.uint8); m[0, 0] = 0           # columns without any zero pixel are "infinite", not capped
+    yy, xx = np.mgrid[0:20, 0:300]
+    np.testing.assert_array_equal(O.exact_edt(m), np.sqrt((xx ** 2 + yy ** 2).astype(np.float32)))
+    assert (O.exact_edt(np.full((12, 16), 255, np.uint8)) == 65536.0).all()   # OpenCV's value for an image without zeros
+    assert (O.exact_edt(np.zeros((12, 16), np.uint8)) == 0).all()
