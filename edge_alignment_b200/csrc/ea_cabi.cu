@@ -133,6 +133,7 @@ void ea_frame_params_default(ea_frame_params* p) {
   p->width = 640; p->height = 480; p->n_levels = 1; p->grad_threshold = 35; p->use_median = 1;
   p->dt_normalize = EA_NORM_01; p->max_points = 0;
   p->fx = 525.0; p->fy = 525.0; p->cx = 319.5; p->cy = 239.5; p->depth_scale = 5000.0;
+  p->edge_detector = EA_EDGE_LAPLACIAN; p->canny_l2 = 0; p->canny_low = 30.0; p->canny_high = 90.0; p->dt_kind = EA_DT_CHAMFER3;
 }
 void ea_solve_params_default(ea_solve_params* p) {
   if (!p) return;
@@ -160,6 +161,7 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
   if ((p->width % (1 << (p->n_levels - 1))) || (p->height % (1 << (p->n_levels - 1))))
     return ea_fail(EA_ERR_INVALID_ARG, "width/height must be divisible by 2^(n_levels-1)");
   if (!(p->fx > 0) || !(p->fy > 0) || !(p->depth_scale > 0)) return ea_fail(EA_ERR_INVALID_ARG, "fx, fy, depth_scale must be positive");
+  if (p->edge_detector < 0 || p->edge_detector > EA_EDGE_CANNY_COLOR || p->dt_kind < 0 || p->dt_kind > EA_DT_EXACT) return ea_fail(EA_ERR_INVALID_ARG, "unknown edge_detector / dt_kind");
   CU(cudaSetDevice(ctx->device));
   ea_frameset* fs = new (std::nothrow) ea_frameset();
   if (!fs) return ea_fail(EA_ERR_INVALID_ARG, "out of host memory");
@@ -187,6 +189,14 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
     G.fx = p->fx * s; G.fy = p->fy * s;
     G.cx = (p->cx + 0.5) * s - 0.5; G.cy = (p->cy + 0.5) * s - 0.5;   // pixel-centre convention (DESIGN.md "Pyramid")
     G.inv_fx = 1.0 / G.fx; G.inv_fy = 1.0 / G.fy; G.w = L.w; G.h = L.h;
+  }
+  if (rc == EA_OK && (p->edge_detector != EA_EDGE_LAPLACIAN || p->dt_kind == EA_DT_EXACT)) {
+    const size_t px0 = size_t(p->width) * p->height;
+    fs->scratch.stride = px0;
+    rc = fs_alloc(fs, (void**)&fs->scratch.gray, px0 * n_slots);
+    if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->scratch.mag, px0 * 4 * n_slots);
+    if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->scratch.dxy, px0 * 4 * n_slots);
+    if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->scratch.map, px0 * n_slots);
   }
   if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_npts, size_t(n_slots) * EA_MAX_LEVELS * sizeof(int));
   if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_minmax, size_t(n_slots) * EA_MAX_LEVELS * 2 * sizeof(unsigned));
@@ -246,6 +256,11 @@ int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uin
   A.n_pts = fs->d_npts; A.dt_minmax = fs->d_minmax; A.dt_affine = fs->d_affine; A.overflow = fs->d_overflow;
   A.n = n; A.roles = roles; A.grad_threshold = fs->p.grad_threshold; A.use_median = fs->p.use_median;
   A.dt_normalize = fs->p.dt_normalize;
+  A.edge_detector = fs->p.edge_detector; A.dt_kind = fs->p.dt_kind;
+  A.canny.low = fs->p.canny_low; A.canny.high = fs->p.canny_high; A.canny.l2 = fs->p.canny_l2;
+  A.canny.on_color = (fs->p.edge_detector == EA_EDGE_CANNY_COLOR);
+  A.scratch = fs->scratch;
+  if (A.edge_detector != EA_EDGE_LAPLACIAN) A.use_median = 0;   // the Canny pipelines of the reference have no median step
   int nl = 0;
   EaProfileScope prof(c, 0);
   cudaError_t e = ea_launch_preprocess(A, c->sm_count, c->stream, &nl);

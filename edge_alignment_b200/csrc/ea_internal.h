@@ -54,6 +54,10 @@ struct EaPrepLevel {            // device pointers of one pyramid level, slot-ma
   float4* pts;                  // [slots][cap]
   int w, h, words, cap;
 };
+struct EaCannyCfg { double low, high; int l2, on_color; };
+struct EaScratch {              // Canny / exact-EDT work buffers, [n_slots][stride] each (stride = level-0 pixels)
+  uint8_t* gray; int* mag; short2* dxy; uint8_t* map; size_t stride;
+};
 struct EaPrepArgs {
   EaPrepLevel lv[EA_MAX_LEVELS];
   int n_levels;
@@ -65,10 +69,16 @@ struct EaPrepArgs {
   float2* dt_affine;            // [slots][EA_MAX_LEVELS]     {scale, shift} of the min-max normalisation
   int* overflow;                // single flag: some point list was truncated
   int n, roles, grad_threshold, use_median, dt_normalize;
+  int edge_detector, dt_kind;
+  EaCannyCfg canny;
+  EaScratch scratch;
 };
 // enqueue the whole preprocessing pipeline for n frames; returns number of kernel launches via *launches
 cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches);
 cudaError_t ea_launch_dt_normalized_copy(const float* raw, const float2* affine, int npx, float* out, cudaStream_t stream);
+cudaError_t ea_launch_canny_level(const EaPrepArgs& A, int l, const uint8_t* bgr, const uint16_t* depth, size_t frame_stride_px,
+                                  bool slot_indexed, const EaCannyCfg& cfg, const EaScratch& S, cudaStream_t stream, int* launches);
+cudaError_t ea_launch_exact_edt_level(const EaPrepArgs& A, int l, const EaScratch& S, cudaStream_t stream, int* launches);
 cudaError_t ea_launch_unpack_mask(const uint32_t* bits, int w, int h, int words, int median, uint8_t* out,
                                   cudaStream_t stream);
 
@@ -118,6 +128,7 @@ struct ea_frameset {
   int* d_overflow = nullptr;
   uint8_t* stage_bgr = nullptr;           // [n_slots][h][w][3]  (host-upload staging)
   uint16_t* stage_depth = nullptr;
+  EaScratch scratch{};                    // only allocated for Canny / exact EDT
   std::vector<void*> allocs;
 };
 

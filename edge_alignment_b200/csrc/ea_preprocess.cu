@@ -530,7 +530,12 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
     const uint8_t* b = (l == 0) ? A.in_bgr : L.bgr;
     const uint16_t* d = want_ref ? ((l == 0) ? A.in_depth : L.depth) : nullptr;
     const int32_t* ss = (l == 0) ? nullptr : A.slots;
-    if ((L.w & 3) == 0 && L.w >= 8 && L.h >= 4) {
+    if (A.edge_detector != EA_EDGE_LAPLACIAN) {
+      int k = 0;
+      cudaError_t ce = ea_launch_canny_level(A, l, b, d, pxl, l != 0, A.canny, A.scratch, stream, &k);
+      nl += k - 1;
+      if (ce != cudaSuccess) return ce;
+    } else if ((L.w & 3) == 0 && L.w >= 8 && L.h >= 4) {
       dim3 grid(unsigned((L.w + E2_TW - 1) / E2_TW), unsigned((L.h + E2_TH - 1) / E2_TH), unsigned(A.n));
       k_edge_mask2<<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold);
     } else {   // generic byte path (any width)
@@ -543,7 +548,12 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
       ++nl;
     }
   }
-  if (want_now) {
+  if (want_now && A.dt_kind == EA_DT_EXACT) {
+    for (int l = 0; l < A.n_levels; ++l) {
+      cudaError_t ee = ea_launch_exact_edt_level(A, l, A.scratch, stream, &nl);
+      if (ee != cudaSuccess) return ee;
+    }
+  } else if (want_now) {
     const EaPrepLevel& L0 = A.lv[0];
     if (A.use_median) {
       dim3 grid(unsigned((L0.h * L0.words + 255) / 256), unsigned(A.n), unsigned(A.n_levels));

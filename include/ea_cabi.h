@@ -53,6 +53,17 @@ typedef enum ea_loss { EA_LOSS_TRIVIAL = 0, EA_LOSS_CAUCHY = 1, EA_LOSS_HUBER = 
  * utils.cpp:142-165 none */
 typedef enum ea_norm { EA_NORM_NONE = 0, EA_NORM_01 = 1, EA_NORM_255 = 2 } ea_norm;
 
+/* edge detector feeding both roles */
+typedef enum ea_edge {
+  EA_EDGE_LAPLACIAN = 0,   /* GaussianBlur3 -> gray -> |Laplacian| > grad_threshold (+ median for the DT): utils.cpp:49-75, 214-220 */
+  EA_EDGE_CANNY_GRAY = 1,  /* blur 3x3 -> gray -> Canny(low, high): get_distance_transform2 / get_aX_canny, utils.cpp:85-106, 371-462 */
+  EA_EDGE_CANNY_COLOR = 2  /* Canny on the BGR image itself: src/SolveEA.cpp:46,102 */
+} ea_edge;
+typedef enum ea_dt {
+  EA_DT_CHAMFER3 = 0,      /* cv::distanceTransform(DIST_L2, 3): utils.cpp:80 */
+  EA_DT_EXACT = 1          /* cv::distanceTransform(DIST_L2, DIST_MASK_PRECISE): src/SolveEA.cpp:108 */
+} ea_dt;
+
 /* what a frame is preprocessed for */
 typedef enum ea_role {
   EA_ROLE_REF = 1, /* edge points with depth   (get_aX, utils.cpp:201-281) */
@@ -91,6 +102,12 @@ typedef struct ea_frame_params {
   int32_t reserved;
   double fx, fy, cx, cy;  /* 525,525,319.5,239.5: standalone_edge_align.cpp:152 */
   double depth_scale;     /* 5000: standalone_edge_align.cpp:160 */
+  /* edge detector / distance transform selection (defaults 0 = the standalone test1 pipeline) */
+  int32_t edge_detector;  /* ea_edge */
+  int32_t canny_l2;       /* L2gradient flag of cv::Canny (src/SolveEA.cpp:46: true) */
+  double canny_low, canny_high; /* cv::Canny thresholds as passed (swapped if low > high, like OpenCV) */
+  int32_t dt_kind;        /* ea_dt */
+  int32_t reserved2;
 } ea_frame_params;
 
 /* Problem assembly + ceres::Solver::Options (standalone_edge_align.cpp:265-286; Ceres defaults). */

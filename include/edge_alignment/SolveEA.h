@@ -5,11 +5,13 @@
 // Everything behind it runs on the GPU through the C ABI (ea_cabi.h).  Additive accessors return what the reference
 // only printed (SolveEA.cpp:204-213): getPose(), getSummary(), setK().
 //
-// Numerical behaviour = the standalone pipeline (standalone/utils.cpp, the version the reference's README says works):
-// Laplacian>35 edges, chamfer-3 DT.  The ROS-flavour literals of src/SolveEA.cpp are the defaults here where they are
-// plain parameters: half-TUM intrinsics (SolveEA.cpp:12-23), no sub-sampling (:163), NULL loss (:171), 25 iterations
-// (:185), DT normalised to [0,255] (:109), depth in metres as CV_32F with Z==0 -> 1.0 (:68-69).  Its Canny edges,
-// exact Euclidean DT and DOGLEG strategy are not part of this round (DESIGN.md "Out of scope").
+// Defaults = the literals of src/SolveEA.cpp: half-TUM intrinsics (:12-23), cv::Canny(rgb, 150, 100, 3, true) on the
+// colour image (:46,102), exact Euclidean distance transform of the inverted edge map (:108) normalised to [0,255]
+// (:109), every edge point (:163), NULL loss (:171), 25 iterations (:185), depth in metres as CV_32F with Z==0 -> 1.0
+// (:68-69), start at identity (:130-131).  Two repairs of reference defects: the distance field is sampled
+// as one channel with the standalone's (row == u, col == v) convention, and the trust-region strategy is
+// Levenberg-Marquardt (the reference asks for DOGLEG, :192).  useStandalonePipeline() switches to the edge detector /
+// DT / loss of standalone/utils.cpp + edge_align_test1.
 #pragma once
 #include "Frame.h"
 
@@ -20,6 +22,9 @@ class SolveEA {
     fp_.width = 320; fp_.height = 240;                       // src/ea.cpp:38 feeds half-resolution frames
     fp_.fx = .5 * 525.0; fp_.fy = .5 * 525.0; fp_.cx = .5 * 319.5; fp_.cy = .5 * 239.5;   // SolveEA.cpp:15-18
     fp_.depth_scale = 5000.0; fp_.dt_normalize = EA_NORM_255;                             // SolveEA.cpp:109
+    fp_.edge_detector = EA_EDGE_CANNY_COLOR; fp_.canny_low = 150.0; fp_.canny_high = 100.0; fp_.canny_l2 = 1;   // :46
+    fp_.dt_kind = EA_DT_EXACT;                                                            // SolveEA.cpp:108
+    fp_.max_points = 0;
     ea_solve_params_default(&sp_);
     sp_.point_stride = 1; sp_.loss_type = EA_LOSS_TRIVIAL; sp_.max_num_iterations = 25;    // SolveEA.cpp:163,171,185
     pose_[0] = 1; for (int i = 1; i < 7; ++i) pose_[i] = 0;                               // SolveEA.cpp:130-131
@@ -33,6 +38,13 @@ class SolveEA {
   // SolveEA.cpp:69 keeps edge pixels without depth by placing them at Z = 1.0 (default); false = drop them like
   // the standalone get_aX does (utils.cpp:258 "Z > 0")
   void setZeroDepthToOne(bool on) { zero_depth_to_one_ = on; }
+  // the working pipeline of standalone/: Laplacian>35 edges (+median for the DT), chamfer-3 DT in [0,1], Cauchy(1),
+  // every 30th point, 50 iterations, edge pixels without depth dropped  (utils.cpp:38-83,201-281; SEA:256-286)
+  void useStandalonePipeline() {
+    fp_.edge_detector = EA_EDGE_LAPLACIAN; fp_.dt_kind = EA_DT_CHAMFER3; fp_.dt_normalize = EA_NORM_01; fp_.use_median = 1;
+    sp_.point_stride = 30; sp_.loss_type = EA_LOSS_CAUCHY; sp_.loss_scale = 1.0; sp_.max_num_iterations = 50;
+    zero_depth_to_one_ = false; dirty_ = true;
+  }
 
   template <class MatT> void setRefFrame(const MatT& rgb, const MatT& depth) {           // SolveEA.cpp:29-82
     ensure(rgb);
@@ -74,6 +86,7 @@ class SolveEA {
  private:
   template <class MatT> void ensure(const MatT& rgb) {
     if (rgb.cols != fp_.width || rgb.rows != fp_.height) { fp_.width = rgb.cols; fp_.height = rgb.rows; dirty_ = true; }
+    if (fp_.max_points <= 0 || dirty_) fp_.max_points = fp_.width * fp_.height;   // Z==0 -> 1 keeps every edge pixel
     if (dirty_ || !ref_.valid()) { ref_.init(fp_); now_.init(fp_); have_ref_ = have_now_ = false; dirty_ = false; }
   }
   ea_frame_params fp_{};

@@ -26,9 +26,7 @@ int main(int argc, char** argv) {
   try {
     SolveEA* ea = new SolveEA();                    // src/ea.cpp:184
     ea->setK(525.0, 525.0, 319.5, 239.5);           // full-resolution TUM intrinsics (standalone_edge_align.cpp:152)
-    ea->frameParams().dt_normalize = EA_NORM_01;    // standalone flavour so the oracle fixtures apply
-    ea->setZeroDepthToOne(false);                   // standalone get_aX drops Z == 0 (utils.cpp:258)
-    ea->solveParams().point_stride = 30; ea->solveParams().loss_type = EA_LOSS_CAUCHY; ea->solveParams().max_num_iterations = 50;
+    ea->useStandalonePipeline();                    // edge_align_test1 settings so the oracle's golden results apply
     ea->setRefFrame(ref_im, ref_depth);             // src/ea.cpp:186
     ea->setNowFrame(now_im, now_depth);             // src/ea.cpp:188
     printf("inside %.6f\n", ea->_verify3dPts());    // src/ea.cpp:193
@@ -47,6 +45,20 @@ int main(int argc, char** argv) {
     double r = -1, J[6];
     const bool ok = res(qi, ti, &r, J);
     printf("residue %d %.9g %.9g %.9g\n", int(ok), r, J[3], J[4]);
+    // the reference's own (ROS) flavour: Canny colour + exact DT [0,255] + every point + no loss + 25 iterations
+    {
+      SolveEA ros;
+      ros.setK(525.0, 525.0, 319.5, 239.5);
+      ros.setZeroDepthToOne(false);
+      ros.setRefFrame(ref_im, ref_depth);
+      ros.setNowFrame(now_im, now_depth);
+      ros.setAsCERESProblem();
+      double rq[4], rt[3];
+      ros.getPose(rq, rt);
+      const ea_summary& rs = ros.getSummary()[0];
+      printf("rospose %.15g %.15g %.15g %.15g %.15g %.15g %.15g\n", rq[0], rq[1], rq[2], rq[3], rt[0], rt[1], rt[2]);
+      printf("rossummary %d %d %d %.15g %.15g\n", rs.termination, rs.iterations, rs.n_residuals, rs.initial_cost, rs.final_cost);
+    }
     // calling order is enforced (the reference left it unchecked, SolveEA.cpp:122)
     SolveEA fresh;
     try { fresh.setAsCERESProblem(); printf("order unchecked\n"); } catch (const std::exception&) { printf("order checked\n"); }

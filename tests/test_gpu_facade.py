@@ -35,3 +35,16 @@ def test_cpp_facade_runs_reference_call_sequence(frames, solver_golden, tmp_path
     ok, r = int(rec["residue"][0]), float(rec["residue"][1])
     assert ok == 1 and abs(r - 0.15146105) < 2e-6
     assert "checked" in out.stdout.splitlines()[-1]
+    # ROS-flavour defaults (src/SolveEA.cpp literals) against the oracle fed with the same stages
+    from oracle import oracle as O
+    K = frames["K"]
+    cc = O.canny(frames["bgr"][0], 150, 100, l2=True)
+    vs, us = np.nonzero((cc > 0) & (frames["depth"][0] > 0))
+    Z = frames["depth"][0][vs, us] / 5000.0
+    xyz = np.stack([(us - K[2]) * Z / K[0], (vs - K[3]) * Z / K[1], Z], 1)
+    dt = O.normalize_minmax(O.exact_edt(255 - O.canny(frames["bgr"][2], 150, 100, l2=True)), 0, 255)
+    op, os_, _ = O.solve(xyz, dt, K, np.array([1.0, 0, 0, 0, 0, 0, 0]), stride=1,
+                         options=O.default_options(loss_type=O.LOSS_TRIVIAL, max_num_iterations=25))
+    rp = np.array([float(v) for v in rec["rospose"]])
+    assert rot_angle_between(rp[:4], op[:4]) < 1e-4 and np.abs(rp[4:] - op[4:]).max() < 1e-4
+    assert int(rec["rossummary"][2]) == len(xyz) and abs(int(rec["rossummary"][1]) - os_["iterations"]) <= 2

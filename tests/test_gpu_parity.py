@@ -422,3 +422,82 @@ def test_residual_variants_and_two_camera_solve(ea, ctx, fs5, frames, oracle, nu
     p1, s1 = ctx.solve_views(gv[:1], None, ea.solve_params(point_stride=30))
     p2, s2 = ctx.solve_batch(fs5, [0], fs5, [2], None, ea.solve_params(point_stride=30))
     assert rot_angle_between(p1[:4], p2[0][:4]) < 2e-6 and np.abs(p1[4:] - p2[0][4:]).max() < 2e-6
+
+
+# ----------------------------------------------------- Canny + exact Euclidean DT (src/SolveEA.cpp:46,102-109 flavour)
+@pytest.mark.parametrize("i", [0, 2, 4])
+def test_canny_and_exact_edt_bit_exact(ea, ctx, frames, cv2_stages, oracle, i):
+    O = oracle
+    g = cv2_stages["frames"][i]
+    # SolveEA flavour: Canny(colour, 150, 100, 3, L2), exact DT of the inverted map, normalised to [0, 255]
+    fp = ea.frame_params(edge_detector=ea.EDGE_CANNY_COLOR, canny_low=150.0, canny_high=100.0, canny_l2=1,
+                         dt_kind=ea.DT_EXACT, dt_normalize=ea.NORM_255, max_points=640 * 480)
+    fs = ea.FrameSet(ctx, fp, 1)
+    try:
+        fs.preprocess_host([0], frames["bgr"][i:i + 1], frames["depth"][i:i + 1], ea.ROLE_BOTH)
+        mask = fs.edge_mask(0, 0, median=False)                         # 0 on edges (reference convention)
+        assert sha((255 - mask).astype(np.uint8)) == g["canny_color_l2"]
+        assert sha(fs.dt(0)) == g["edt_precise_norm255"]
+        cc = O.canny(frames["bgr"][i], 150, 100, l2=True)
+        vs, us = np.nonzero((cc > 0) & (frames["depth"][i] > 0))
+        np.testing.assert_array_equal(fs.points(0)[:, :3].astype(np.int32), np.stack([us, vs, frames["depth"][i][vs, us]], 1))
+    finally:
+        fs.close()
+    # standalone Canny variant: blur 3x3 -> gray -> Canny(30, 90) L1, chamfer DT normalised to [0, 1]  (utils.cpp:85-106, 371-462)
+    fp = ea.frame_params(edge_detector=ea.EDGE_CANNY_GRAY, canny_low=30.0, canny_high=90.0, canny_l2=0, max_points=640 * 480)
+    fs = ea.FrameSet(ctx, fp, 1)
+    try:
+        fs.preprocess_host([0], frames["bgr"][i:i + 1], frames["depth"][i:i + 1], ea.ROLE_BOTH)
+        assert sha((255 - fs.edge_mask(0, 0)).astype(np.uint8)) == g["canny_gray_l1"]
+        assert sha(fs.dt(0)) == g["dt2_norm"]
+        assert fs.num_points(0) == g["n_points_canny"] and sha(fs.points(0)[:, :3].astype(np.int32)) == g["uvd_canny"]
+    finally:
+        fs.close()
+
+
+def test_solveea_flavour_pipeline_matches_oracle(ea, ctx, frames, oracle):
+    """Canny(colour) + exact DT [0,255] + no loss + every point + 25 iterations (src/SolveEA.cpp:124-198, with LM instead of
+    DOGLEG) on a 2-level pyramid and ragged sizes, against the oracle fed with the same stages."""
+    O = oracle
+    K = frames["K"]
+    fp = ea.frame_params(edge_detector=ea.EDGE_CANNY_COLOR, canny_low=150.0, canny_high=100.0, canny_l2=1,
+                         dt_kind=ea.DT_EXACT, dt_normalize=ea.NORM_255, max_points=640 * 480, n_levels=2)
+    fs = ea.FrameSet(ctx, fp, 2)
+    try:
+        fs.preprocess_host([0, 1], frames["bgr"][[0, 2]], frames["depth"][[0, 2]], ea.ROLE_BOTH)
+        # level 1 of the pyramid through the same kernels
+        hb, hd = O.half_linear(frames["bgr"][0]), O.half_nearest(frames["depth"][0])
+        c1 = O.canny(hb, 150, 100, l2=True)
+        vs, us = np.nonzero((c1 > 0) & (hd > 0))
+        np.testing.assert_array_equal(fs.points(0, 1)[:, :3].astype(np.int32), np.stack([us, vs, hd[vs, us]], 1))
+        e1 = O.normalize_minmax(O.exact_edt(255 - O.canny(O.half_linear(frames["bgr"][2]), 150, 100, l2=True)), 0, 255)
+        np.testing.assert_array_equal(fs.dt(1, 1), e1)
+        # level-0 solve, SolveEA settings
+        cc = O.canny(frames["bgr"][0], 150, 100, l2=True)
+        vs, us = np.nonzero((cc > 0) & (frames["depth"][0] > 0))
+        Z = frames["depth"][0][vs, us] / 5000.0
+        xyz = np.stack([(us - K[2]) * Z / K[0], (vs - K[3]) * Z / K[1], Z], 1)
+        dt = O.normalize_minmax(O.exact_edt(255 - O.canny(frames["bgr"][2], 150, 100, l2=True)), 0, 255)
+        opts = O.default_options(loss_type=O.LOSS_TRIVIAL, max_num_iterations=25)
+        op, os_, _ = O.solve(xyz, dt, K, IDENTITY, stride=1, options=opts)
+        sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_TRIVIAL, max_num_iterations=25, coarsest_level=0)
+        poses, S = ctx.solve_batch(fs, [0], fs, [1], None, sp)
+        assert rot_angle_between(poses[0][:4], op[:4]) < 1e-4 and np.abs(poses[0][4:] - op[4:]).max() < 1e-4
+        assert S[0][0]["n_residuals"] == len(xyz) and abs(S[0][0]["iterations"] - os_["iterations"]) <= 2
+    finally:
+        fs.close()
+    rng = np.random.default_rng(2)
+    for (w, h) in ((72, 40), (200, 24)):
+        fp = ea.frame_params(width=w, height=h, fx=50.0, fy=50.0, cx=w / 2.0, cy=h / 2.0, edge_detector=ea.EDGE_CANNY_GRAY,
+                             canny_low=30.0, canny_high=90.0, dt_kind=ea.DT_EXACT, dt_normalize=ea.NORM_NONE, max_points=w * h)
+        fs = ea.FrameSet(ctx, fp, 2)
+        try:
+            bgr = (rng.integers(0, 4, (2, h, w, 3)) * 80).astype(np.uint8); bgr[1] = 60       # random blocks / flat image
+            dep = rng.integers(0, 2, (2, h, w)).astype(np.uint16) * 900
+            fs.preprocess_host([0, 1], bgr, dep, ea.ROLE_BOTH)
+            for s_ in range(2):
+                cg = O.canny(O.rgb2gray(O.box3(bgr[s_])), 30, 90, l2=False)
+                np.testing.assert_array_equal(255 - fs.edge_mask(s_, 0), cg)
+                np.testing.assert_array_equal(fs.dt(s_), O.exact_edt(255 - cg))
+        finally:
+            fs.close()
