@@ -181,6 +181,14 @@ class FrameSet:
                                                    None if depth is None else depth.ctypes.data, roles))
         self.ctx.sync()   # numpy buffers may be pageable and short-lived
 
+    def preprocess_masked(self, slots, bgr, depth, mask, roles=L.ROLE_BOTH):
+        """get_aX_mask (utils.cpp:283-369): reference points only where mask > 0."""
+        slots = np.ascontiguousarray(slots, np.int32)
+        bgr = np.ascontiguousarray(bgr, np.uint8); depth = np.ascontiguousarray(depth, np.uint16); mask = np.ascontiguousarray(mask, np.uint8)
+        _check(L.lib().ea_frameset_preprocess_masked(self._h, len(slots), _ptr(slots, C.c_int32), bgr.ctypes.data, depth.ctypes.data,
+                                                     mask.ctypes.data, roles))
+        self.ctx.sync()
+
     def preprocess_device(self, slots, d_bgr, d_depth=0, roles=L.ROLE_BOTH):
         slots = np.ascontiguousarray(slots, np.int32)
         _check(L.lib().ea_frameset_preprocess_device(self._h, len(slots), _ptr(slots, C.c_int32), d_bgr, d_depth or None, roles))

@@ -216,6 +216,24 @@ __global__ void __launch_bounds__(E2_TW) k_edge_mask2(const uint8_t* __restrict_
   }
 }
 
+// ---- get_aX_mask (utils.cpp:283-369): keep reference edge points only where mask > 0 (level l samples mask(x<<l, y<<l)) ----
+__global__ void __launch_bounds__(256) k_mask_ref_bits(uint32_t* __restrict__ ref_bits, const int32_t* __restrict__ dst_slots,
+                                                       const uint8_t* __restrict__ mask, int w0, int h0, int w, int h, int words, int level) {
+  const int f = blockIdx.y;
+  uint32_t* bits = ref_bits + size_t(dst_slots[f]) * h * words;
+  const uint8_t* m = mask + size_t(f) * w0 * h0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h * words; i += gridDim.x * blockDim.x) {
+    const int y = i / words, x0 = (i % words) * 32;
+    unsigned keep = 0;
+    unsigned b = bits[i];
+    for (unsigned t = b; t; t &= t - 1) {
+      const int k = __ffs(t) - 1;
+      if (m[size_t(y << level) * w0 + ((x0 + k) << level)] > 0) keep |= 1u << k;
+    }
+    bits[i] = keep;
+  }
+}
+
 // ---- ordered compaction: one CTA per frame, row-major rank == reference's loop order (utils.cpp:268-280) ----
 #define CP_THREADS 1024
 __global__ void __launch_bounds__(CP_THREADS) k_compact(const uint32_t* __restrict__ ref_bits, const uint16_t* __restrict__ depth,
@@ -543,6 +561,10 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
       k_edge_mask<<<grid, dim3(ET_W, ET_H), 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold);
     }
     ++nl;
+    if (want_ref && A.in_mask) {
+      k_mask_ref_bits<<<dim3(unsigned((L.h * L.words + 255) / 256), unsigned(A.n)), 256, 0, stream>>>(L.ref_bits, A.slots, A.in_mask, A.lv[0].w, A.lv[0].h, L.w, L.h, L.words, l);
+      ++nl;
+    }
     if (want_ref) {
       k_compact<<<A.n, CP_THREADS, 0, stream>>>(L.ref_bits, d, pxl, ss, A.slots, L.pts, A.n_pts, l, A.overflow, L.w, L.h, L.words, L.cap);
       ++nl;

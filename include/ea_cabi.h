@@ -178,6 +178,9 @@ int ea_frameset_destroy(ea_frameset* fs);
  * Asynchronous on the context stream (host buffers should be pinned for true overlap). */
 int ea_frameset_preprocess_host(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr,
                                 const uint16_t* depth, int roles);
+/* get_aX_mask (utils.cpp:283-369): as above from HOST buffers, reference points only where mask [n][h][w] u8 is > 0 */
+int ea_frameset_preprocess_masked(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr,
+                                  const uint16_t* depth, const uint8_t* mask, int roles);
 /* same, inputs already resident in device memory */
 int ea_frameset_preprocess_device(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* d_bgr,
                                   const uint16_t* d_depth, int roles);

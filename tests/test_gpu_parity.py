@@ -501,3 +501,24 @@ def test_solveea_flavour_pipeline_matches_oracle(ea, ctx, frames, oracle):
                 np.testing.assert_array_equal(fs.dt(s_), O.exact_edt(255 - cg))
         finally:
             fs.close()
+
+
+def test_masked_reference_points(ea, ctx, frames, oracle):
+    """get_aX_mask (utils.cpp:283-369): point list restricted to mask > 0, same order; pyramid levels sample the mask."""
+    O = oracle
+    rng = np.random.default_rng(4)
+    mask = np.zeros((480, 640), np.uint8); mask[100:400, 150:500] = 7; mask[rng.integers(0, 480, 5000), rng.integers(0, 640, 5000)] = 0
+    fs = ea.FrameSet(ctx, ea.frame_params(n_levels=2), 1)
+    try:
+        fs.preprocess_masked([0], frames["bgr"][:1], frames["depth"][:1], mask[None], ea.ROLE_BOTH)
+        _, uvd = O.get_aX(frames["bgr"][0], frames["depth"][0], frames["K"])
+        keep = mask[uvd[:, 1], uvd[:, 0]] > 0
+        np.testing.assert_array_equal(fs.points(0)[:, :3].astype(np.int32), uvd[keep])
+        hb, hd = O.half_linear(frames["bgr"][0]), O.half_nearest(frames["depth"][0])
+        _, uvd1 = O.get_aX(hb, hd, fs.level_geometry(1)[2])
+        keep1 = mask[uvd1[:, 1] * 2, uvd1[:, 0] * 2] > 0
+        np.testing.assert_array_equal(fs.points(0, 1)[:, :3].astype(np.int32), uvd1[keep1])
+        odt, _ = O.get_distance_transform(frames["bgr"][0])
+        np.testing.assert_array_equal(fs.dt(0), odt)              # the mask does not touch the now role
+    finally:
+        fs.close()
