@@ -523,7 +523,7 @@ static int fill_solve_args(ea_context* c, ea_frameset* ref, ea_frameset* now, co
   return EA_OK;
 }
 
-[[maybe_unused]] static int auto_cluster(ea_context* c, int n_pairs, int requested) {
+static int auto_cluster(ea_context* c, int n_pairs, int requested) {
   if (requested > 0) return requested;
   // few pairs: spread each over a cluster so the whole GPU works on them; many pairs: one CTA per pair
   if (n_pairs * 8 <= c->sm_count) return 8;
@@ -553,11 +553,11 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
   A.summaries = d_summaries; A.n_pairs = n; A.work_counter = c->d_work; A.order = d_order;
   EaProfileScope prof(c, 1);
   cudaError_t e;
-  if (cluster >= 2) {
-    // explicit request: one thread-block cluster per pair (DSMEM reduction), ea_solve.cu
-    e = ea_launch_solve_batch(A, cluster, c->sm_count, c->stream);
-  } else {
-    // default: task-graph kernel -- (pair, chunk) evaluation tasks through a device-side queue, ea_solve_tasks.cu
+  // auto (measured): few pairs -> a thread-block cluster per pair so the whole GPU works on them and the
+  // per-iteration latency drops (config 1, stride 1: 0.58 ms with clusters of 8 vs 2.4 ms on one CTA); big batches -> one
+  // persistent CTA per pair (no scheduling overhead, best L1 locality).  -1 asks for the task-graph kernel explicitly.
+  if (cluster == 0) cluster = auto_cluster(c, n, 0);
+  if (cluster == -1) {
     if (c->states_cap < size_t(n)) {
       CU(cudaStreamSynchronize(c->stream));
       if (c->d_states) cudaFree(c->d_states);
@@ -571,10 +571,9 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
     static const int env_chunk = getenv("EA_SOLVE_CHUNK") ? atoi(getenv("EA_SOLVE_CHUNK")) : 0;
     A.window = env_window;
     A.chunk_points = env_chunk > 0 ? env_chunk : 4096;
-    // auto: big batches keep one persistent CTA per pair (no scheduling overhead, best L1 locality: measured faster
-    // from ~sm_count/2 pairs up); small batches spread every evaluation over the GPU through the task queue
-    const bool tasks = (cluster == -1) || (cluster == 0 && n < c->sm_count / 2);
-    e = tasks ? ea_launch_solve_tasks(A, c->sm_count, c->stream) : ea_launch_solve_batch(A, 1, c->sm_count, c->stream);
+    e = ea_launch_solve_tasks(A, c->sm_count, c->stream);
+  } else {
+    e = ea_launch_solve_batch(A, cluster, c->sm_count, c->stream);
   }
   c->launches++;
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "solve launch: %s", cudaGetErrorString(e));

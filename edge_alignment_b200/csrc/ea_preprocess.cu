@@ -387,6 +387,28 @@ __device__ __forceinline__ void dt_row_scan(int (&d)[P], const int (&cval)[P], i
   else { left_bnd = cw; right_bnd = dn_first; }
 }
 
+// P consecutive 32-bit values of one row: 128-bit accesses when the row layout allows it (w % 4 == 0, P % 4 == 0)
+template <int P, typename T>
+__device__ __forceinline__ void dt_store_row(T* __restrict__ row, int x0, int w, const T (&v)[P], bool vec_ok) {
+  if (vec_ok && x0 + P <= w) {
+#pragma unroll
+    for (int k = 0; k < P; k += 4) *reinterpret_cast<int4*>(row + x0 + k) = *reinterpret_cast<const int4*>(&v[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < P; ++k) if (x0 + k < w) row[x0 + k] = v[k];
+  }
+}
+template <int P>
+__device__ __forceinline__ void dt_load_row(const int* __restrict__ row, int x0, int w, int (&v)[P], bool vec_ok) {
+  if (vec_ok && x0 + P <= w) {
+#pragma unroll
+    for (int k = 0; k < P; k += 4) *reinterpret_cast<int4*>(&v[k]) = *reinterpret_cast<const int4*>(row + x0 + k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < P; ++k) v[k] = (x0 + k < w) ? row[x0 + k] : DT_INF;
+  }
+}
+
 template <int P>
 __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaPrepArgs A) {
   __shared__ int tot[2][32], first[2][32];
@@ -402,6 +424,7 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
   const int n_warps = ((w + P - 1) / P + 31) / 32;          // warps that own pixels at this level
   const bool warp_on = warp < n_warps;
   const int x0 = tid * P;
+  const bool vec_ok = (P % 4 == 0) && ((w & 3) == 0);
   int d[P];
 #pragma unroll
   for (int k = 0; k < P; ++k) d[k] = DT_INF;
@@ -430,14 +453,7 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
     dt_row_scan<P, false>(d, cval, lane, warp, n_warps, par, tot, first, left_bnd, right_bnd);
 #pragma unroll
     for (int k = 0; k < P; ++k) if (x0 + k >= w) d[k] = DT_INF;
-    if (x0 < w) {
-      int* g = gi + size_t(y) * w + x0;
-      if (P == 2 && x0 + 1 < w && ((size_t(y) * w + x0) & 1) == 0) *reinterpret_cast<int2*>(g) = make_int2(d[0], d[1 % P]);
-      else {
-#pragma unroll
-        for (int k = 0; k < P; ++k) if (x0 + k < w) g[k] = d[k];
-      }
-    }
+    if (x0 < w) dt_store_row<P, int>(gi + size_t(y) * w, x0, w, d, vec_ok);
   }
   // ---------------- backward pass: rows bottom -> top, scan right -> left ----------------
 #pragma unroll
@@ -446,16 +462,14 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
   unsigned vmax = 0, vmin = 0xFFFFFFFFu;
   int t_next[P];
 #pragma unroll
-  for (int k = 0; k < P; ++k) t_next[k] = (warp_on && x0 + k < w) ? gi[size_t(h - 1) * w + x0 + k] : DT_INF;
+  for (int k = 0; k < P; ++k) t_next[k] = DT_INF;
+  if (warp_on && x0 < w) dt_load_row<P>(gi + size_t(h - 1) * w, x0, w, t_next, vec_ok);
   for (int y = h - 1; y >= 0; --y, par ^= 1) {
     if (!warp_on) { __syncthreads(); continue; }
     int t0[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) t0[k] = t_next[k];
-    if (y > 0) {                                           // prefetch the forward values of the next row up
-#pragma unroll
-      for (int k = 0; k < P; ++k) if (x0 + k < w) t_next[k] = gi[size_t(y - 1) * w + x0 + k];
-    }
+    if (y > 0 && x0 < w) dt_load_row<P>(gi + size_t(y - 1) * w, x0, w, t_next, vec_ok);   // prefetch the next row up
     int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
     int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
     if (lane == 0) pl = left_bnd;
@@ -470,13 +484,16 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
       cval[k] = min(v, DT_INF);
     }
     dt_row_scan<P, true>(d, cval, lane, warp, n_warps, par, tot, first, left_bnd, right_bnd);
+    float outv[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) {
+      outv[k] = 0.0f;
       if (x0 + k >= w) { d[k] = DT_INF; continue; }
       const unsigned t = (d[k] >= DT_INF) ? DT_DISTMAX : unsigned(d[k]);
       vmax = max(vmax, t); vmin = min(vmin, t);
-      gf[size_t(y) * w + x0 + k] = float(t) * (1.0f / 65536.0f);
+      outv[k] = float(t) * (1.0f / 65536.0f);
     }
+    if (x0 < w) dt_store_row<P, float>(gf + size_t(y) * w, x0, w, outv, vec_ok);
   }
   vmax = __reduce_max_sync(0xffffffffu, vmax);
   vmin = __reduce_min_sync(0xffffffffu, vmin);
