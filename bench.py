@@ -55,7 +55,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.samples.append(line.strip())
                 if self._halt.is_set():
@@ -247,17 +247,21 @@ def main():
     e2e = None
     if not args.no_e2e:
         hb = torch.empty((T, S, H, W, 3), dtype=torch.uint8, pin_memory=True); hb.copy_(bgr_d)
-        hd = torch.empty((T, S, H, W), dtype=torch.uint16, pin_memory=True); hd.copy_(depth_d)
+        # depth only travels for frames that become key frames: pin just those
+        hd = {t: torch.empty((S, H, W), dtype=torch.uint16, pin_memory=True) for t in range(T) if t % KEYFRAME_INTERVAL == 0}
+        for t, buf in hd.items():
+            buf.copy_(depth_d[t])
         torch.cuda.synchronize()
+        dptr = lambda t: hd[t].data_ptr() if t in hd else 0
         tracker.reset()
         for t in range(0, Wm + 1):
-            tracker.step_host(hb.data_ptr() + t * frame_b, hd.data_ptr() + t * frame_d, fetch=True)
+            tracker.step_host(hb.data_ptr() + t * frame_b, dptr(t), fetch=True)
         barrier()
         e0.record(stream)
         # pipelined: frame t is submitted (its upload overlaps the alignment of frame t-1), then the poses of frame
         # t-1 are read on the host.  Every step's frames cross PCIe and every step's result is read back.
         for t in range(Wm + 1, T):
-            tracker.step_host(hb.data_ptr() + t * frame_b, hd.data_ptr() + t * frame_d, fetch=False)
+            tracker.step_host(hb.data_ptr() + t * frame_b, dptr(t), fetch=False)
             if t > Wm + 1:
                 poses, _ = tracker.wait(t - 1)
         poses, _ = tracker.wait(T - 1)

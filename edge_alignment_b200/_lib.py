@@ -17,6 +17,7 @@ NORM_NONE, NORM_01, NORM_255 = 0, 1, 2
 ROLE_REF, ROLE_NOW, ROLE_BOTH = 1, 2, 3
 EDGE_LAPLACIAN, EDGE_CANNY_GRAY, EDGE_CANNY_COLOR = 0, 1, 2
 DT_CHAMFER3, DT_EXACT = 0, 1
+DEPTH_U16, DEPTH_F32 = 0, 1
 POINTS_PIXEL, POINTS_XYZ = 0, 1
 TERMINATION = {0: "NONE", 1: "CONVERGENCE_GRADIENT", 2: "CONVERGENCE_FUNCTION", 3: "CONVERGENCE_PARAMETER",
                4: "CONVERGENCE_MIN_RADIUS", 5: "NO_CONVERGENCE", 6: "FAILURE_EVAL_X0", 7: "FAILURE_INVALID_STEPS",
@@ -26,9 +27,9 @@ TERMINATION = {0: "NONE", 1: "CONVERGENCE_GRADIENT", 2: "CONVERGENCE_FUNCTION", 
 class FrameParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("n_levels", C.c_int32), ("grad_threshold", C.c_int32),
                 ("use_median", C.c_int32), ("dt_normalize", C.c_int32), ("max_points", C.c_int32),
-                ("reserved", C.c_int32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double),
+                ("depth_type", C.c_int32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double),
                 ("cy", C.c_double), ("depth_scale", C.c_double), ("edge_detector", C.c_int32), ("canny_l2", C.c_int32),
-                ("canny_low", C.c_double), ("canny_high", C.c_double), ("dt_kind", C.c_int32), ("reserved2", C.c_int32)]
+                ("canny_low", C.c_double), ("canny_high", C.c_double), ("dt_kind", C.c_int32), ("zero_depth_to_one", C.c_int32)]
 
 
 class SolveParams(C.Structure):

@@ -175,7 +175,7 @@ class FrameSet:
     def preprocess_host(self, slots, bgr, depth=None, roles=L.ROLE_BOTH):
         slots = np.ascontiguousarray(slots, np.int32)
         bgr = np.ascontiguousarray(bgr, np.uint8)
-        depth = None if depth is None else np.ascontiguousarray(depth, np.uint16)
+        depth = None if depth is None else np.ascontiguousarray(depth, np.float32 if self.params.depth_type == L.DEPTH_F32 else np.uint16)
         assert bgr.size == len(slots) * self.params.width * self.params.height * 3
         _check(L.lib().ea_frameset_preprocess_host(self._h, len(slots), _ptr(slots, C.c_int32), bgr.ctypes.data,
                                                    None if depth is None else depth.ctypes.data, roles))
@@ -184,7 +184,8 @@ class FrameSet:
     def preprocess_masked(self, slots, bgr, depth, mask, roles=L.ROLE_BOTH):
         """get_aX_mask (utils.cpp:283-369): reference points only where mask > 0."""
         slots = np.ascontiguousarray(slots, np.int32)
-        bgr = np.ascontiguousarray(bgr, np.uint8); depth = np.ascontiguousarray(depth, np.uint16); mask = np.ascontiguousarray(mask, np.uint8)
+        bgr = np.ascontiguousarray(bgr, np.uint8); mask = np.ascontiguousarray(mask, np.uint8)
+        depth = np.ascontiguousarray(depth, np.float32 if self.params.depth_type == L.DEPTH_F32 else np.uint16)
         _check(L.lib().ea_frameset_preprocess_masked(self._h, len(slots), _ptr(slots, C.c_int32), bgr.ctypes.data, depth.ctypes.data,
                                                      mask.ctypes.data, roles))
         self.ctx.sync()

@@ -162,10 +162,13 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
     return ea_fail(EA_ERR_INVALID_ARG, "width/height must be divisible by 2^(n_levels-1)");
   if (!(p->fx > 0) || !(p->fy > 0) || !(p->depth_scale > 0)) return ea_fail(EA_ERR_INVALID_ARG, "fx, fy, depth_scale must be positive");
   if (p->edge_detector < 0 || p->edge_detector > EA_EDGE_CANNY_COLOR || p->dt_kind < 0 || p->dt_kind > EA_DT_EXACT) return ea_fail(EA_ERR_INVALID_ARG, "unknown edge_detector / dt_kind");
+  if (p->depth_type < 0 || p->depth_type > EA_DEPTH_F32) return ea_fail(EA_ERR_INVALID_ARG, "unknown depth_type");
   CU(cudaSetDevice(ctx->device));
   ea_frameset* fs = new (std::nothrow) ea_frameset();
   if (!fs) return ea_fail(EA_ERR_INVALID_ARG, "out of host memory");
   fs->ctx = ctx; fs->p = *p; fs->n_slots = n_slots;
+  fs->depth_elem = (p->depth_type == EA_DEPTH_F32) ? 4 : 2;
+  fs->inv_depth_unit = (p->depth_type == EA_DEPTH_F32) ? 1.0 : 1.0 / p->depth_scale;
   const int cap0 = p->max_points > 0 ? p->max_points : (p->width * p->height) / 4;
   int rc = EA_OK;
   for (int l = 0; l < p->n_levels && rc == EA_OK; ++l) {
@@ -177,7 +180,7 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
     L.bgr = nullptr; L.depth = nullptr;
     if (l > 0) {
       rc = fs_alloc(fs, (void**)&L.bgr, px * 3 * n_slots);
-      if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.depth, px * 2 * n_slots);
+      if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.depth, px * (p->depth_type == EA_DEPTH_F32 ? 4 : 2) * n_slots);
     }
     if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.edge_bits, size_t(L.h) * L.words * 4 * n_slots);
     if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.ref_bits, size_t(L.h) * L.words * 4 * n_slots);
@@ -247,7 +250,7 @@ static int check_slots(ea_frameset* fs, int n, const int32_t* slots) {
 }
 
 }  // extern "C"
-int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const uint16_t* d_depth, int roles,
+int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const void* d_depth, int roles,
                        const uint8_t* d_mask) {
   ea_context* c = fs->ctx;
   EaPrepArgs A;
@@ -261,6 +264,8 @@ int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uin
   A.canny.low = fs->p.canny_low; A.canny.high = fs->p.canny_high; A.canny.l2 = fs->p.canny_l2;
   A.canny.on_color = (fs->p.edge_detector == EA_EDGE_CANNY_COLOR);
   A.scratch = fs->scratch;
+  A.depth_type = fs->p.depth_type; A.zero_to_one = fs->p.zero_depth_to_one;
+  A.depth_one = fs->p.depth_type == EA_DEPTH_F32 ? 1.0f : float(fs->p.depth_scale);
   if (A.edge_detector != EA_EDGE_LAPLACIAN) A.use_median = 0;   // the Canny pipelines of the reference have no median step
   int nl = 0;
   EaProfileScope prof(c, 0);
@@ -271,7 +276,7 @@ int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uin
 }
 
 extern "C" {
-int ea_frameset_preprocess_device(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* d_bgr, const uint16_t* d_depth, int roles) {
+int ea_frameset_preprocess_device(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* d_bgr, const void* d_depth, int roles) {
   int rc = check_slots(fs, n, slots);
   if (rc) return rc;
   if (!d_bgr) return ea_fail(EA_ERR_INVALID_ARG, "bgr is null");
@@ -288,7 +293,7 @@ int ea_frameset_preprocess_device(ea_frameset* fs, int n, const int32_t* slots, 
   return rc;
 }
 
-int ea_frameset_preprocess_masked(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr, const uint16_t* depth,
+int ea_frameset_preprocess_masked(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr, const void* depth,
                                   const uint8_t* mask, int roles) {
   int rc = check_slots(fs, n, slots);
   if (rc) return rc;
@@ -298,13 +303,13 @@ int ea_frameset_preprocess_masked(ea_frameset* fs, int n, const int32_t* slots, 
   CU(cudaSetDevice(c->device));
   const size_t px = size_t(fs->p.width) * fs->p.height;
   if (!fs->stage_bgr) CU(cudaMalloc((void**)&fs->stage_bgr, px * 3 * fs->n_slots));
-  if (!fs->stage_depth) CU(cudaMalloc((void**)&fs->stage_depth, px * 2 * fs->n_slots));
+  if (!fs->stage_depth) CU(cudaMalloc((void**)&fs->stage_depth, px * fs->depth_elem * fs->n_slots));
   uint8_t* d_mask = nullptr;
   int32_t* d_slots = nullptr;
   CU(cudaMallocAsync((void**)&d_mask, px * n, c->stream));
   CU(cudaMallocAsync((void**)&d_slots, size_t(n) * sizeof(int32_t), c->stream));
   CU(cudaMemcpyAsync(fs->stage_bgr, bgr, px * 3 * n, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(fs->stage_depth, depth, px * 2 * n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(fs->stage_depth, depth, px * fs->depth_elem * n, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(d_mask, mask, px * n, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(d_slots, slots, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   rc = ea_preprocess_impl(fs, n, d_slots, fs->stage_bgr, fs->stage_depth, roles, d_mask);
@@ -313,7 +318,7 @@ int ea_frameset_preprocess_masked(ea_frameset* fs, int n, const int32_t* slots, 
   return rc;
 }
 
-int ea_frameset_preprocess_host(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr, const uint16_t* depth, int roles) {
+int ea_frameset_preprocess_host(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr, const void* depth, int roles) {
   int rc = check_slots(fs, n, slots);
   if (rc) return rc;
   if (!bgr) return ea_fail(EA_ERR_INVALID_ARG, "bgr is null");
@@ -322,9 +327,9 @@ int ea_frameset_preprocess_host(ea_frameset* fs, int n, const int32_t* slots, co
   CU(cudaSetDevice(c->device));
   const size_t px = size_t(fs->p.width) * fs->p.height;
   if (!fs->stage_bgr) CU(cudaMalloc((void**)&fs->stage_bgr, px * 3 * fs->n_slots));
-  if (depth && !fs->stage_depth) CU(cudaMalloc((void**)&fs->stage_depth, px * 2 * fs->n_slots));
+  if (depth && !fs->stage_depth) CU(cudaMalloc((void**)&fs->stage_depth, px * fs->depth_elem * fs->n_slots));
   CU(cudaMemcpyAsync(fs->stage_bgr, bgr, px * 3 * n, cudaMemcpyHostToDevice, c->stream));
-  if (depth) CU(cudaMemcpyAsync(fs->stage_depth, depth, px * 2 * n, cudaMemcpyHostToDevice, c->stream));
+  if (depth) CU(cudaMemcpyAsync(fs->stage_depth, depth, px * fs->depth_elem * n, cudaMemcpyHostToDevice, c->stream));
   return ea_frameset_preprocess_device(fs, n, slots, fs->stage_bgr, depth ? fs->stage_depth : nullptr, roles);
 }
 
@@ -471,7 +476,7 @@ int ea_eval(ea_context* c, ea_frameset* ref, int ref_slot, ea_frameset* now, int
   const EaLevelDesc& nd = now->h_desc[size_t(now_slot) * EA_MAX_LEVELS + level];
   CU(cudaMemcpyAsync(c->d_pose, pose7, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemsetAsync(c->d_failed, 0, sizeof(int), c->stream));
-  const double ids = 1.0 / ref->p.depth_scale;
+  const double ids = ref->inv_depth_unit;
   if (n_res > 0 && (raw || residuals || jac || failed)) {
     rc = ea_ensure_tmp(c, size_t(n_res) * 8 * sizeof(double));
     if (rc) return rc;
@@ -515,7 +520,7 @@ static int fill_solve_args(ea_context* c, ea_frameset* ref, ea_frameset* now, co
   A.coarsest = sp->coarsest_level < 0 ? ref->p.n_levels - 1 : sp->coarsest_level;
   A.finest = sp->finest_level;
   if (A.coarsest >= ref->p.n_levels || A.finest < 0 || A.finest > A.coarsest) return ea_fail(EA_ERR_INVALID_ARG, "bad level range [%d..%d]", A.coarsest, A.finest);
-  A.inv_depth_scale = 1.0 / ref->p.depth_scale;
+  A.inv_depth_scale = ref->inv_depth_unit;
   for (int l = 0; l < ref->p.n_levels; ++l) { A.ref_geom[l] = ref->geom[l]; A.now_geom[l] = now->geom[l]; A.ref_cap[l] = ref->lv[l].cap; }
   A.sp = *sp;
   *cluster = sp->cluster_size;

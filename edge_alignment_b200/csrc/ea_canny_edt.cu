@@ -92,10 +92,11 @@ __global__ void __launch_bounds__(256) k_canny_nms(const int* __restrict__ mag, 
 
 // hysteresis: one CTA per frame promotes candidates that touch a strong pixel until nothing changes (the fixed point
 // is the 8-connected closure of the strong pixels, independent of visiting order), then packs the bit planes.
-__global__ void __launch_bounds__(1024) k_canny_hysteresis(uint8_t* __restrict__ map, size_t scratch_stride_px, const uint16_t* __restrict__ depth,
+template <typename D>
+__global__ void __launch_bounds__(1024) k_canny_hysteresis(uint8_t* __restrict__ map, size_t scratch_stride_px, const D* __restrict__ depth,
                                                            size_t depth_stride_px, const int32_t* __restrict__ depth_slots, bool depth_slot_indexed,
                                                            const int32_t* __restrict__ dst_slots, uint32_t* __restrict__ edge_bits,
-                                                           uint32_t* __restrict__ ref_bits, int w, int h, int words) {
+                                                           uint32_t* __restrict__ ref_bits, int w, int h, int words, int zero_to_one) {
   const int f = blockIdx.x;
   uint8_t* P = map + size_t(f) * scratch_stride_px;
   const int n = w * h, per = (n + blockDim.x - 1) / blockDim.x;
@@ -121,14 +122,14 @@ __global__ void __launch_bounds__(1024) k_canny_hysteresis(uint8_t* __restrict__
     if (!__syncthreads_or(changed)) break;
   }
   __syncthreads();
-  const uint16_t* dep = depth ? depth + ((depth_slot_indexed && depth_slots) ? size_t(depth_slots[f]) : size_t(f)) * depth_stride_px : nullptr;
+  const D* dep = depth ? depth + ((depth_slot_indexed && depth_slots) ? size_t(depth_slots[f]) : size_t(f)) * depth_stride_px : nullptr;
   const size_t obase = size_t(dst_slots[f]) * h * words;
   for (int wi = threadIdx.x; wi < h * words; wi += blockDim.x) {
     const int y = wi / words, x0 = (wi % words) * 32;
     unsigned eb = 0, rb = 0;
     for (int k = 0; k < 32 && x0 + k < w; ++k) {
       const size_t i = size_t(y) * w + x0 + k;
-      if (P[i] == 2) { eb |= 1u << k; if (dep && dep[i] > 0) rb |= 1u << k; }
+      if (P[i] == 2) { eb |= 1u << k; if (dep && (zero_to_one || dep[i] > D(0))) rb |= 1u << k; }
     }
     edge_bits[obase + wi] = eb;
     if (ref_bits) ref_bits[obase + wi] = rb;
@@ -210,7 +211,7 @@ __global__ void k_edt_affine(const unsigned* fminmax, const int32_t* dst_slots, 
 
 // Edge planes of level l by Canny.  src = BGR of that level.  scratch: gray u8 | mag i32 | dxy short2 | map u8, each
 // [n][stride] with stride = level-0 pixels.
-cudaError_t ea_launch_canny_level(const EaPrepArgs& A, int l, const uint8_t* bgr, const uint16_t* depth, size_t frame_stride_px,
+cudaError_t ea_launch_canny_level(const EaPrepArgs& A, int l, const uint8_t* bgr, const void* depth, size_t frame_stride_px,
                                   bool slot_indexed, const EaCannyCfg& cfg, const EaScratch& S, cudaStream_t stream, int* launches) {
   const EaPrepLevel& L = A.lv[l];
   const int npx = L.w * L.h;
@@ -233,8 +234,12 @@ cudaError_t ea_launch_canny_level(const EaPrepArgs& A, int l, const uint8_t* bgr
   }
   k_canny_nms<<<grid, 256, 0, stream>>>(S.mag, S.dxy, S.map, S.stride, L.w, L.h, low, high);
   const bool want_ref = (A.roles & EA_ROLE_REF) != 0;
-  k_canny_hysteresis<<<A.n, 1024, 0, stream>>>(S.map, S.stride, want_ref ? depth : nullptr, frame_stride_px, A.slots, slot_indexed, A.slots,
-                                               L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words);
+  if (A.depth_type == 1)
+    k_canny_hysteresis<float><<<A.n, 1024, 0, stream>>>(S.map, S.stride, want_ref ? static_cast<const float*>(depth) : nullptr, frame_stride_px, A.slots, slot_indexed, A.slots,
+                                                        L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.zero_to_one);
+  else
+    k_canny_hysteresis<uint16_t><<<A.n, 1024, 0, stream>>>(S.map, S.stride, want_ref ? static_cast<const uint16_t*>(depth) : nullptr, frame_stride_px, A.slots, slot_indexed, A.slots,
+                                                           L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.zero_to_one);
   *launches += 2;
   return cudaGetLastError();
 }

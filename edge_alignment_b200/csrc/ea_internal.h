@@ -46,7 +46,7 @@ cudaError_t ea_launch_eval_sums(const EaLevelDesc& rd, const EaLevelDesc& nd, co
 // ---- preprocessing (ea_preprocess.cu) ---------------------------------------------------------------
 struct EaPrepLevel {            // device pointers of one pyramid level, slot-major pools
   uint8_t* bgr;                 // [slots][h][w][3]   (level 0: null, the caller's input is read directly)
-  uint16_t* depth;              // [slots][h][w]      (level 0: null)
+  void* depth;                  // [slots][h][w] u16 or f32 (level 0: null)
   uint32_t* edge_bits;          // [slots][h][words]  raw Laplacian>threshold mask, 1 bit / pixel
   uint32_t* ref_bits;           // [slots][h][words]  edge & depth>0
   uint32_t* med_bits;           // [slots][h][words]  3x3 median of edge_bits
@@ -63,7 +63,7 @@ struct EaPrepArgs {
   int n_levels;
   const int32_t* slots;         // [n] device: destination slot of frame i
   const uint8_t* in_bgr;        // [n][h0][w0][3]
-  const uint16_t* in_depth;     // [n][h0][w0] or null
+  const void* in_depth;         // [n][h0][w0] u16 raw units or f32 metres (depth_type), or null
   const uint8_t* in_mask;       // [n][h0][w0] or null: reference points only where mask > 0 (get_aX_mask, utils.cpp:283-369)
   int* n_pts;                   // [slots][EA_MAX_LEVELS]
   unsigned* dt_minmax;          // [slots][EA_MAX_LEVELS][2]  (min,max of the fixed-point DT)
@@ -71,13 +71,16 @@ struct EaPrepArgs {
   int* overflow;                // single flag: some point list was truncated
   int n, roles, grad_threshold, use_median, dt_normalize;
   int edge_detector, dt_kind;
+  int depth_type;               // 0 = u16 raw units, 1 = f32 metres
+  int zero_to_one;              // src/SolveEA.cpp:69: an edge pixel without depth is kept at Z = 1
+  float depth_one;              // the stored value meaning Z = 1 (depth_scale for u16, 1.0 for f32)
   EaCannyCfg canny;
   EaScratch scratch;
 };
 // enqueue the whole preprocessing pipeline for n frames; returns number of kernel launches via *launches
 cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches);
 cudaError_t ea_launch_dt_normalized_copy(const float* raw, const float2* affine, int npx, float* out, cudaStream_t stream);
-cudaError_t ea_launch_canny_level(const EaPrepArgs& A, int l, const uint8_t* bgr, const uint16_t* depth, size_t frame_stride_px,
+cudaError_t ea_launch_canny_level(const EaPrepArgs& A, int l, const uint8_t* bgr, const void* depth, size_t frame_stride_px,
                                   bool slot_indexed, const EaCannyCfg& cfg, const EaScratch& S, cudaStream_t stream, int* launches);
 cudaError_t ea_launch_exact_edt_level(const EaPrepArgs& A, int l, const EaScratch& S, cudaStream_t stream, int* launches);
 cudaError_t ea_launch_unpack_mask(const uint32_t* bits, int w, int h, int words, int median, uint8_t* out,
@@ -128,7 +131,9 @@ struct ea_frameset {
   float2* d_affine = nullptr;             // [n_slots][EA_MAX_LEVELS]
   int* d_overflow = nullptr;
   uint8_t* stage_bgr = nullptr;           // [n_slots][h][w][3]  (host-upload staging)
-  uint16_t* stage_depth = nullptr;
+  void* stage_depth = nullptr;
+  size_t depth_elem = 2;                  // bytes per depth sample (2: u16, 4: f32)
+  double inv_depth_unit = 1.0 / 5000.0;   // metres per stored depth unit
   EaScratch scratch{};                    // only allocated for Canny / exact EDT
   std::vector<void*> allocs;
 };
@@ -145,5 +150,5 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
                                    const int32_t* d_now_slots, double* d_poses7, const int32_t* d_pose_index,
                                    const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries);
 cudaError_t ea_launch_order_by_work(const ea_summary* d_summaries, int n, int n_levels, int32_t* d_order, cudaStream_t stream);
-int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const uint16_t* d_depth, int roles,
+int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const void* d_depth, int roles,
                        const uint8_t* d_mask = nullptr);

@@ -20,9 +20,10 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 // ---- pyramid: cv::resize(0.5) INTER_LINEAR on BGR (== 2x2 mean, +2 >> 2), INTER_NEAREST on depth ---------
-__global__ void __launch_bounds__(256) k_pyr_down(const uint8_t* __restrict__ src_bgr, const uint16_t* __restrict__ src_depth,
+template <typename D>
+__global__ void __launch_bounds__(256) k_pyr_down(const uint8_t* __restrict__ src_bgr, const D* __restrict__ src_depth,
                                                   size_t src_frame_stride_px, const int32_t* __restrict__ src_slots,
-                                                  uint8_t* __restrict__ dst_bgr, uint16_t* __restrict__ dst_depth,
+                                                  uint8_t* __restrict__ dst_bgr, D* __restrict__ dst_depth,
                                                   const int32_t* __restrict__ dst_slots, int sw, int sh) {
   const int dw = sw >> 1, dh = sh >> 1;
   const int f = blockIdx.y;
@@ -43,10 +44,11 @@ __global__ void __launch_bounds__(256) k_pyr_down(const uint8_t* __restrict__ sr
 // Block = 32x8 pixels; one ballot word per warp row.
 #define ET_W 32
 #define ET_H 8
-__global__ void __launch_bounds__(256) k_edge_mask(const uint8_t* __restrict__ bgr, const uint16_t* __restrict__ depth,
+template <typename D>
+__global__ void __launch_bounds__(256) k_edge_mask(const uint8_t* __restrict__ bgr, const D* __restrict__ depth,
                                                    size_t frame_stride_px, const int32_t* __restrict__ src_slots,
                                                    const int32_t* __restrict__ dst_slots, uint32_t* __restrict__ edge_bits,
-                                                   uint32_t* __restrict__ ref_bits, int w, int h, int words, int thresh) {
+                                                   uint32_t* __restrict__ ref_bits, int w, int h, int words, int thresh, int zero_to_one) {
   __shared__ uint8_t tile[ET_H + 4][(ET_W + 4) * 3 + 4];
   __shared__ uint8_t gray[ET_H + 2][ET_W + 2 + 2];
   const int f = blockIdx.z;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(256) k_edge_mask(const uint8_t* __restrict__ b
     int v = 2 * (gray[gy - 1][gx - 1] + gray[gy - 1][gx + 1] + gray[gy + 1][gx - 1] + gray[gy + 1][gx + 1]) - 8 * gray[gy][gx];
     v = v < 0 ? -v : v;                             // Laplacian ksize 3 + convertScaleAbs
     edge = min(v, 255) > thresh;
-    if (depth) valid = depth[sbase + size_t(y) * w + x] > 0;
+    if (depth) valid = zero_to_one || depth[sbase + size_t(y) * w + x] > D(0);
   }
   const unsigned eb = __ballot_sync(0xffffffffu, edge);
   const unsigned rb = __ballot_sync(0xffffffffu, edge && valid);
@@ -115,10 +117,11 @@ __device__ __forceinline__ unsigned e2_gray(unsigned v_bg, unsigned v_r) {
   return (B * 9798u + G * 19235u + b_r * 3735u + 16384u) >> 15;
 }
 
-__global__ void __launch_bounds__(E2_TW) k_edge_mask2(const uint8_t* __restrict__ bgr, const uint16_t* __restrict__ depth,
+template <typename D>
+__global__ void __launch_bounds__(E2_TW) k_edge_mask2(const uint8_t* __restrict__ bgr, const D* __restrict__ depth,
                                                       size_t frame_stride_px, const int32_t* __restrict__ src_slots,
                                                       const int32_t* __restrict__ dst_slots, uint32_t* __restrict__ edge_bits,
-                                                      uint32_t* __restrict__ ref_bits, int w, int h, int words, int thresh) {
+                                                      uint32_t* __restrict__ ref_bits, int w, int h, int words, int thresh, int zero_to_one) {
   __shared__ unsigned tile[E2_PH][E2_PW];
   __shared__ uint8_t gray[E2_TH + 2][E2_GW];
   const int f = blockIdx.z;
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(E2_TW) k_edge_mask2(const uint8_t* __restrict_
     s0 = gray[0][gl] + gray[0][gr];
     s1 = gray[1][gl] + gray[1][gr]; c1 = gray[1][gc];
   }
-  const uint16_t* dep = depth ? depth + sbase : nullptr;
+  const D* dep = depth ? depth + sbase : nullptr;
   const size_t obase = size_t(dst_slots[f]) * h * words + (x0 >> 5) + wq;
 #pragma unroll 4
   for (int r = 0; r < E2_TH; ++r) {
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(E2_TW) k_edge_mask2(const uint8_t* __restrict_
     v = v < 0 ? -v : v;
     const bool edge = col_ok && (y < h) && (min(v, 255) > thresh);
     bool valid = false;
-    if (edge && dep) valid = dep[size_t(y) * w + x] > 0;
+    if (edge && dep) valid = zero_to_one || dep[size_t(y) * w + x] > D(0);
     const unsigned eb = __ballot_sync(0xffffffffu, edge);
     const unsigned rb = __ballot_sync(0xffffffffu, edge && valid);
     if (lane == 0 && y < h && (x0 >> 5) + wq < words) {
@@ -236,16 +239,17 @@ __global__ void __launch_bounds__(256) k_mask_ref_bits(uint32_t* __restrict__ re
 
 // ---- ordered compaction: one CTA per frame, row-major rank == reference's loop order (utils.cpp:268-280) ----
 #define CP_THREADS 1024
-__global__ void __launch_bounds__(CP_THREADS) k_compact(const uint32_t* __restrict__ ref_bits, const uint16_t* __restrict__ depth,
+template <typename D>
+__global__ void __launch_bounds__(CP_THREADS) k_compact(const uint32_t* __restrict__ ref_bits, const D* __restrict__ depth,
                                                         size_t frame_stride_px, const int32_t* __restrict__ src_slots,
                                                         const int32_t* __restrict__ dst_slots, float4* __restrict__ pts,
                                                         int* __restrict__ n_pts, int level, int* __restrict__ overflow,
-                                                        int w, int h, int words, int cap) {
+                                                        int w, int h, int words, int cap, int zero_to_one, float depth_one) {
   __shared__ int warp_sums[CP_THREADS / 32];
   __shared__ int total_s;
   const int f = blockIdx.x, slot = dst_slots[f];
   const uint32_t* bits = ref_bits + size_t(slot) * h * words;
-  const uint16_t* dep = depth + (src_slots ? size_t(src_slots[f]) : size_t(f)) * frame_stride_px;
+  const D* dep = depth + (src_slots ? size_t(src_slots[f]) : size_t(f)) * frame_stride_px;
   float4* out = pts + size_t(slot) * cap;
   const int nw = h * words;
   const int per = (nw + CP_THREADS - 1) / CP_THREADS;
@@ -275,7 +279,11 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const uint32_t* __restri
       const int bit = __ffs(m) - 1;
       m &= m - 1;
       const int x = xb + bit;
-      if (rank < cap) out[rank] = make_float4(float(x), float(y), float(dep[size_t(y) * w + x]), 1.0f);
+      if (rank < cap) {
+        float dz = float(dep[size_t(y) * w + x]);
+        if (zero_to_one && dz == 0.0f) dz = depth_one;               // src/SolveEA.cpp:69
+        out[rank] = make_float4(float(x), float(y), dz, 1.0f);
+      }
       ++rank;
     }
   }
@@ -545,25 +553,25 @@ __global__ void __launch_bounds__(256) k_unpack_mask(const uint32_t* __restrict_
 
 }  // namespace
 
-cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches) {
-  int nl = 0;
-  const bool want_ref = (A.roles & EA_ROLE_REF) != 0, want_now = (A.roles & EA_ROLE_NOW) != 0;
-  if (want_ref && !A.in_depth) return cudaErrorInvalidValue;
+template <typename D>
+static cudaError_t launch_edges_and_points(const EaPrepArgs& A, cudaStream_t stream, int& nl) {
+  const bool want_ref = (A.roles & EA_ROLE_REF) != 0;
   const size_t px0 = size_t(A.lv[0].w) * A.lv[0].h;
+  const D* in_depth = static_cast<const D*>(A.in_depth);
   for (int l = 0; l < A.n_levels; ++l) {
     const EaPrepLevel& L = A.lv[l];
     const size_t pxl = size_t(L.w) * L.h;
     if (l > 0) {
       const EaPrepLevel& S = A.lv[l - 1];
       const uint8_t* sb = (l == 1) ? A.in_bgr : S.bgr;
-      const uint16_t* sd = want_ref ? ((l == 1) ? A.in_depth : S.depth) : nullptr;
+      const D* sd = want_ref ? ((l == 1) ? in_depth : static_cast<const D*>(S.depth)) : nullptr;
       const size_t sstride = (l == 1) ? px0 : size_t(S.w) * S.h;
       dim3 grid(unsigned((pxl + 255) / 256), unsigned(A.n));
-      k_pyr_down<<<grid, 256, 0, stream>>>(sb, sd, sstride, (l == 1) ? nullptr : A.slots, L.bgr, L.depth, A.slots, S.w, S.h);
+      k_pyr_down<D><<<grid, 256, 0, stream>>>(sb, sd, sstride, (l == 1) ? nullptr : A.slots, L.bgr, static_cast<D*>(L.depth), A.slots, S.w, S.h);
       ++nl;
     }
     const uint8_t* b = (l == 0) ? A.in_bgr : L.bgr;
-    const uint16_t* d = want_ref ? ((l == 0) ? A.in_depth : L.depth) : nullptr;
+    const D* d = want_ref ? ((l == 0) ? in_depth : static_cast<const D*>(L.depth)) : nullptr;
     const int32_t* ss = (l == 0) ? nullptr : A.slots;
     if (A.edge_detector != EA_EDGE_LAPLACIAN) {
       int k = 0;
@@ -572,10 +580,10 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
       if (ce != cudaSuccess) return ce;
     } else if ((L.w & 3) == 0 && L.w >= 8 && L.h >= 4) {
       dim3 grid(unsigned((L.w + E2_TW - 1) / E2_TW), unsigned((L.h + E2_TH - 1) / E2_TH), unsigned(A.n));
-      k_edge_mask2<<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold);
+      k_edge_mask2<D><<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
     } else {   // generic byte path (any width)
       dim3 grid(unsigned((L.w + ET_W - 1) / ET_W), unsigned((L.h + ET_H - 1) / ET_H), unsigned(A.n));
-      k_edge_mask<<<grid, dim3(ET_W, ET_H), 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold);
+      k_edge_mask<D><<<grid, dim3(ET_W, ET_H), 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
     }
     ++nl;
     if (want_ref && A.in_mask) {
@@ -583,10 +591,20 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
       ++nl;
     }
     if (want_ref) {
-      k_compact<<<A.n, CP_THREADS, 0, stream>>>(L.ref_bits, d, pxl, ss, A.slots, L.pts, A.n_pts, l, A.overflow, L.w, L.h, L.words, L.cap);
+      k_compact<D><<<A.n, CP_THREADS, 0, stream>>>(L.ref_bits, d, pxl, ss, A.slots, L.pts, A.n_pts, l, A.overflow, L.w, L.h, L.words, L.cap, A.zero_to_one, A.depth_one);
       ++nl;
     }
   }
+  return cudaGetLastError();
+}
+
+cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches) {
+  int nl = 0;
+  const bool want_ref = (A.roles & EA_ROLE_REF) != 0, want_now = (A.roles & EA_ROLE_NOW) != 0;
+  if (want_ref && !A.in_depth) return cudaErrorInvalidValue;
+  (void)sm_count;
+  cudaError_t pe = (A.depth_type == 1) ? launch_edges_and_points<float>(A, stream, nl) : launch_edges_and_points<uint16_t>(A, stream, nl);
+  if (pe != cudaSuccess) return pe;
   if (want_now && A.dt_kind == EA_DT_EXACT) {
     for (int l = 0; l < A.n_levels; ++l) {
       cudaError_t ee = ea_launch_exact_edt_level(A, l, A.scratch, stream, &nl);

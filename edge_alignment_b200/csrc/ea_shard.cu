@@ -227,7 +227,7 @@ int ea_shard_solve(ea_shard* s, ea_frameset* ref, int ref_slot, ea_frameset* now
   const int j0 = int((long long)n_res * s->rank / s->world), j1 = int((long long)n_res * (s->rank + 1) / s->world);
   const EaLevelDesc& rd = ref->h_desc[size_t(ref_slot) * EA_MAX_LEVELS + level];
   const EaLevelDesc& nd = now->h_desc[size_t(now_slot) * EA_MAX_LEVELS + level];
-  const double ids = 1.0 / ref->p.depth_scale;
+  const double ids = ref->inv_depth_unit;
   int nb = s->n_blocks;
   const int per_block = 2048;
   if ((j1 - j0 + per_block - 1) / per_block < nb) nb = std::max(1, (j1 - j0 + per_block - 1) / per_block);
@@ -312,7 +312,7 @@ int ea_eval_views(ea_context* c, int n_views, const ea_view* views, int level, c
     const EaLevelDesc& rd = v.ref->h_desc[size_t(v.ref_slot) * EA_MAX_LEVELS + level];
     const EaLevelDesc& nd = v.now->h_desc[size_t(v.now_slot) * EA_MAX_LEVELS + level];
     EaViewXf X; view_xf(v, X);
-    const double ids = 1.0 / v.ref->p.depth_scale;
+    const double ids = v.ref->inv_depth_unit;
     if (nres[i] > 0) {
       const int blocks = (nres[i] + 255) / 256;
       if (rd.pts_mode == EA_POINTS_XYZ)
@@ -388,7 +388,7 @@ int ea_solve_views(ea_context* c, int n_views, const ea_view* views, int level, 
         const EaLevelDesc& rd = v.ref->h_desc[size_t(v.ref_slot) * EA_MAX_LEVELS + level];
         const EaLevelDesc& nd = v.now->h_desc[size_t(v.now_slot) * EA_MAX_LEVELS + level];
         EaViewXf X; view_xf(v, X);
-        const double ids = 1.0 / v.ref->p.depth_scale;
+        const double ids = v.ref->inv_depth_unit;
         if (rd.pts_mode == EA_POINTS_XYZ)
           k_view_eval_sums<true><<<nb[i], GV_THREADS, 0, st>>>(rd, nd, v.ref->geom[level], v.now->geom[level], X, ids, *sp, d_state->cand, &d_state->done, 0, nres[i], d_partials + size_t(boff) * EA_SUMS);
         else

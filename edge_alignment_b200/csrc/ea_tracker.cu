@@ -25,7 +25,7 @@ struct ea_tracker {
   // host-input pipeline: frame t+1 is uploaded on a copy stream while frame t is being aligned
   cudaStream_t copy_stream = nullptr;
   uint8_t* stage_bgr[2] = {nullptr, nullptr};
-  uint16_t* stage_depth[2] = {nullptr, nullptr};
+  void* stage_depth[2] = {nullptr, nullptr};
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_result[2] = {nullptr, nullptr};
   double* h_poses[2] = {nullptr, nullptr};          // pinned result ring
   ea_summary* h_summaries[2] = {nullptr, nullptr};
@@ -100,7 +100,7 @@ int ea_tracker_reset(ea_tracker* t) {
   return EA_OK;
 }
 
-int ea_tracker_step_device(ea_tracker* t, const uint8_t* d_bgr, const uint16_t* d_depth) {
+int ea_tracker_step_device(ea_tracker* t, const uint8_t* d_bgr, const void* d_depth) {
   if (!t || !d_bgr) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
   ea_context* c = t->ctx;
   CU(cudaSetDevice(c->device));
@@ -144,7 +144,7 @@ int ea_tracker_get_poses(ea_tracker* t, double* poses7, ea_summary* summaries) {
   return EA_OK;
 }
 
-int ea_tracker_step_host(ea_tracker* t, const uint8_t* bgr, const uint16_t* depth, double* poses7, ea_summary* summaries) {
+int ea_tracker_step_host(ea_tracker* t, const uint8_t* bgr, const void* depth, double* poses7, ea_summary* summaries) {
   if (!t || !bgr) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
   ea_context* c = t->ctx;
   ea_frameset* fs = t->fs;
@@ -155,11 +155,11 @@ int ea_tracker_step_host(ea_tracker* t, const uint8_t* bgr, const uint16_t* dept
   const bool becomes_key = (frame % t->interval) == 0;
   if (becomes_key && !depth) return ea_fail(EA_ERR_INVALID_ARG, "frame %d becomes a key frame and needs depth", frame);
   if (!t->stage_bgr[b]) CU(cudaMalloc((void**)&t->stage_bgr[b], px * 3 * n));
-  if (becomes_key && !t->stage_depth[b]) CU(cudaMalloc((void**)&t->stage_depth[b], px * 2 * n));
+  if (becomes_key && !t->stage_depth[b]) CU(cudaMalloc((void**)&t->stage_depth[b], px * fs->depth_elem * n));
   // upload on the copy stream once the kernels that read this staging buffer two frames ago are done
   if (frame >= 2) CU(cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[b], 0));
   CU(cudaMemcpyAsync(t->stage_bgr[b], bgr, px * 3 * n, cudaMemcpyHostToDevice, t->copy_stream));
-  if (becomes_key) CU(cudaMemcpyAsync(t->stage_depth[b], depth, px * 2 * n, cudaMemcpyHostToDevice, t->copy_stream));
+  if (becomes_key) CU(cudaMemcpyAsync(t->stage_depth[b], depth, px * fs->depth_elem * n, cudaMemcpyHostToDevice, t->copy_stream));
   CU(cudaEventRecord(t->ev_copied[b], t->copy_stream));
   CU(cudaStreamWaitEvent(c->stream, t->ev_copied[b], 0));
   int rc = ea_tracker_step_device(t, t->stage_bgr[b], becomes_key ? t->stage_depth[b] : nullptr);

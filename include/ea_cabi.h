@@ -59,6 +59,7 @@ typedef enum ea_edge {
   EA_EDGE_CANNY_GRAY = 1,  /* blur 3x3 -> gray -> Canny(low, high): get_distance_transform2 / get_aX_canny, utils.cpp:85-106, 371-462 */
   EA_EDGE_CANNY_COLOR = 2  /* Canny on the BGR image itself: src/SolveEA.cpp:46,102 */
 } ea_edge;
+typedef enum ea_depth { EA_DEPTH_U16 = 0, EA_DEPTH_F32 = 1 } ea_depth;
 typedef enum ea_dt {
   EA_DT_CHAMFER3 = 0,      /* cv::distanceTransform(DIST_L2, 3): utils.cpp:80 */
   EA_DT_EXACT = 1          /* cv::distanceTransform(DIST_L2, DIST_MASK_PRECISE): src/SolveEA.cpp:108 */
@@ -99,7 +100,8 @@ typedef struct ea_frame_params {
   int32_t use_median;     /* 1: medianBlur(B,3) utils.cpp:75 */
   int32_t dt_normalize;   /* ea_norm; EA_NORM_01: utils.cpp:81 */
   int32_t max_points;     /* level-0 capacity of the point list; 0 => width*height/4 */
-  int32_t reserved;
+  int32_t depth_type;     /* ea_depth: EA_DEPTH_U16 raw units (/depth_scale = metres, utils.cpp:235) or EA_DEPTH_F32 metres
+                           * (src/SolveEA.cpp:27,68) */
   double fx, fy, cx, cy;  /* 525,525,319.5,239.5: standalone_edge_align.cpp:152 */
   double depth_scale;     /* 5000: standalone_edge_align.cpp:160 */
   /* edge detector / distance transform selection (defaults 0 = the standalone test1 pipeline) */
@@ -107,7 +109,7 @@ typedef struct ea_frame_params {
   int32_t canny_l2;       /* L2gradient flag of cv::Canny (src/SolveEA.cpp:46: true) */
   double canny_low, canny_high; /* cv::Canny thresholds as passed (swapped if low > high, like OpenCV) */
   int32_t dt_kind;        /* ea_dt */
-  int32_t reserved2;
+  int32_t zero_depth_to_one; /* src/SolveEA.cpp:69: edge pixels without depth are kept at Z = 1 instead of dropped */
 } ea_frame_params;
 
 /* Problem assembly + ceres::Solver::Options (standalone_edge_align.cpp:265-286; Ceres defaults). */
@@ -174,16 +176,17 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
 int ea_frameset_destroy(ea_frameset* fs);
 
 /* get_aX (utils.cpp:201-281) and/or get_distance_transform (utils.cpp:38-83) for n frames.
- * HOST buffers: bgr [n][h][w][3] u8, depth [n][h][w] u16 (may be NULL when roles==EA_ROLE_NOW).
+ * HOST buffers: bgr [n][h][w][3] u8, depth [n][h][w] u16 or f32 per ea_frame_params.depth_type (may be NULL when
+ * roles==EA_ROLE_NOW).
  * Asynchronous on the context stream (host buffers should be pinned for true overlap). */
 int ea_frameset_preprocess_host(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr,
-                                const uint16_t* depth, int roles);
+                                const void* depth, int roles);
 /* get_aX_mask (utils.cpp:283-369): as above from HOST buffers, reference points only where mask [n][h][w] u8 is > 0 */
 int ea_frameset_preprocess_masked(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr,
-                                  const uint16_t* depth, const uint8_t* mask, int roles);
+                                  const void* depth, const uint8_t* mask, int roles);
 /* same, inputs already resident in device memory */
 int ea_frameset_preprocess_device(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* d_bgr,
-                                  const uint16_t* d_depth, int roles);
+                                  const void* d_depth, int roles);
 
 /* Bypass hooks (parity on oracle-made inputs; CAD point sets as in edge_align_test5..8). */
 int ea_frameset_set_points(ea_frameset* fs, int slot, int level, const float* pts4, int n, int mode);
@@ -246,14 +249,14 @@ int ea_tracker_destroy(ea_tracker* tr);
 int ea_tracker_reset(ea_tracker* tr);
 /* HOST inputs [n_streams][h][w][3] / [n_streams][h][w]; poses7 out [n_streams][7] = keyframe_T_frame
  * (HOST, may be NULL => fetch later with ea_tracker_get_poses); asynchronous unless poses7 given. */
-int ea_tracker_step_host(ea_tracker* tr, const uint8_t* bgr, const uint16_t* depth, double* poses7,
+int ea_tracker_step_host(ea_tracker* tr, const uint8_t* bgr, const void* depth, double* poses7,
                          ea_summary* summaries);
 /* Pipelined use of ea_tracker_step_host: call it with poses7 == summaries == NULL (asynchronous: the upload of this
  * frame overlaps the alignment of the previous one), then collect frame f's result with ea_tracker_wait(tr, f, ...).
  * Results live in a 2-deep ring: wait for frame f before submitting frame f+2.  The host buffers of a submitted
  * frame must stay valid until its results have been waited for. */
 int ea_tracker_wait(ea_tracker* tr, int frame, double* poses7, ea_summary* summaries);
-int ea_tracker_step_device(ea_tracker* tr, const uint8_t* d_bgr, const uint16_t* d_depth);
+int ea_tracker_step_device(ea_tracker* tr, const uint8_t* d_bgr, const void* d_depth);
 int ea_tracker_get_poses(ea_tracker* tr, double* poses7, ea_summary* summaries); /* syncs */
 int ea_tracker_frame_index(ea_tracker* tr, int* n_frames_seen);
 

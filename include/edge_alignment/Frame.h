@@ -44,32 +44,32 @@ class Frame {
   ea_frameset* handle() const { return fs_; }
   ea_context* context() const { return ctx_; }
 
-  // rgb: 8UC3 (BGR as cv::imread gives it); depth: 16UC1 raw units, or 32FC1 metres (SolveEA.cpp:27,68 -- converted
-  // with depth_scale, and zero_depth_to_one applies SolveEA.cpp:69 "Z==0 -> 1.0"); depth may be empty for now-only.
+  // rgb: 8UC3 (BGR as cv::imread gives it); depth: 16UC1 raw units or 32FC1 metres (SolveEA.cpp:27,68), converted to the
+  // frameset's own depth_type when they differ; depth may be null for a now-only frame.  The "Z==0 -> 1.0" rule of
+  // SolveEA.cpp:69 is a frameset parameter (zero_depth_to_one) applied on the device.
   template <class MatT>
-  void set(const MatT& rgb, const MatT* depth, int roles, bool zero_depth_to_one = false) {
+  void set(const MatT& rgb, const MatT* depth, int roles) {
     if (!fs_) throw std::runtime_error("Frame::set before init");
     if (rgb.rows != params_.height || rgb.cols != params_.width) throw std::runtime_error("Frame::set: image size differs from ea_frame_params");
     const size_t W = size_t(params_.width), H = size_t(params_.height);
     bgr_.resize(W * H * 3);
     for (size_t y = 0; y < H; ++y) std::copy(rgb.data + y * size_t(rgb.step), rgb.data + y * size_t(rgb.step) + W * 3, bgr_.begin() + y * W * 3);
-    const uint16_t* dptr = nullptr;
+    const void* dptr = nullptr;
     if (depth && depth->data) {
-      depth_.resize(W * H);
+      const bool want_f32 = params_.depth_type == EA_DEPTH_F32, have_f32 = depth->type() == ea::F32C1;
+      depth_.resize(W * H * (want_f32 ? 4 : 2));
       for (size_t y = 0; y < H; ++y) {
         const unsigned char* row = depth->data + y * size_t(depth->step);
         for (size_t x = 0; x < W; ++x) {
-          uint16_t v;
-          if (depth->type() == ea::F32C1) {
-            float z = reinterpret_cast<const float*>(row)[x];
-            if (zero_depth_to_one && z == 0.0f) z = 1.0f;
-            const double r = double(z) * params_.depth_scale + 0.5;
-            v = r <= 0 ? 0 : (r >= 65535.0 ? 65535 : uint16_t(r));
+          if (want_f32) {
+            const float z = have_f32 ? reinterpret_cast<const float*>(row)[x] : float(double(reinterpret_cast<const uint16_t*>(row)[x]) / params_.depth_scale);
+            reinterpret_cast<float*>(depth_.data())[y * W + x] = z;
           } else {
-            v = reinterpret_cast<const uint16_t*>(row)[x];
-            if (zero_depth_to_one && v == 0) v = uint16_t(params_.depth_scale);
+            uint16_t v;
+            if (have_f32) { const double r = double(reinterpret_cast<const float*>(row)[x]) * params_.depth_scale + 0.5; v = r <= 0 ? 0 : (r >= 65535.0 ? 65535 : uint16_t(r)); }
+            else v = reinterpret_cast<const uint16_t*>(row)[x];
+            reinterpret_cast<uint16_t*>(depth_.data())[y * W + x] = v;
           }
-          depth_[y * W + x] = v;
         }
       }
       dptr = depth_.data();
@@ -80,7 +80,7 @@ class Frame {
   }
 
   int numEdgePoints(int level = 0) const { int n = 0; ea::check(ea_frameset_get_num_points(fs_, 0, level, &n), "get_num_points"); return n; }
-  // list_edge_ref as {u, v, raw depth, 1} rows (reference: 3xN X,Y,Z doubles, SolveEA.h:63)
+  // list_edge_ref as {u, v, depth (raw units or metres per depth_type), 1} rows (reference: 3xN X,Y,Z doubles, SolveEA.h:63)
   std::vector<float> edgePoints(int level = 0) const {
     int n = numEdgePoints(level);
     std::vector<float> p(size_t(n) * 4);
@@ -101,5 +101,5 @@ class Frame {
   ea_frameset* fs_ = nullptr;
   ea_frame_params params_{};
   std::vector<uint8_t> bgr_;
-  std::vector<uint16_t> depth_;
+  std::vector<unsigned char> depth_;
 };

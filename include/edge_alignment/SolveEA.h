@@ -25,6 +25,7 @@ class SolveEA {
     fp_.edge_detector = EA_EDGE_CANNY_COLOR; fp_.canny_low = 150.0; fp_.canny_high = 100.0; fp_.canny_l2 = 1;   // :46
     fp_.dt_kind = EA_DT_EXACT;                                                            // SolveEA.cpp:108
     fp_.max_points = 0;
+    fp_.depth_type = EA_DEPTH_F32; fp_.zero_depth_to_one = 1;                             // SolveEA.cpp:27,68-69
     ea_solve_params_default(&sp_);
     sp_.point_stride = 1; sp_.loss_type = EA_LOSS_TRIVIAL; sp_.max_num_iterations = 25;    // SolveEA.cpp:163,171,185
     pose_[0] = 1; for (int i = 1; i < 7; ++i) pose_[i] = 0;                               // SolveEA.cpp:130-131
@@ -37,18 +38,18 @@ class SolveEA {
   ea_solve_params& solveParams() { return sp_; }
   // SolveEA.cpp:69 keeps edge pixels without depth by placing them at Z = 1.0 (default); false = drop them like
   // the standalone get_aX does (utils.cpp:258 "Z > 0")
-  void setZeroDepthToOne(bool on) { zero_depth_to_one_ = on; }
+  void setZeroDepthToOne(bool on) { fp_.zero_depth_to_one = on ? 1 : 0; dirty_ = true; }
   // the working pipeline of standalone/: Laplacian>35 edges (+median for the DT), chamfer-3 DT in [0,1], Cauchy(1),
   // every 30th point, 50 iterations, edge pixels without depth dropped  (utils.cpp:38-83,201-281; SEA:256-286)
   void useStandalonePipeline() {
     fp_.edge_detector = EA_EDGE_LAPLACIAN; fp_.dt_kind = EA_DT_CHAMFER3; fp_.dt_normalize = EA_NORM_01; fp_.use_median = 1;
     sp_.point_stride = 30; sp_.loss_type = EA_LOSS_CAUCHY; sp_.loss_scale = 1.0; sp_.max_num_iterations = 50;
-    zero_depth_to_one_ = false; dirty_ = true;
+    fp_.zero_depth_to_one = 0; fp_.depth_type = EA_DEPTH_U16; dirty_ = true;
   }
 
   template <class MatT> void setRefFrame(const MatT& rgb, const MatT& depth) {           // SolveEA.cpp:29-82
     ensure(rgb);
-    ref_.set(rgb, &depth, EA_ROLE_REF, zero_depth_to_one_);
+    ref_.set(rgb, &depth, EA_ROLE_REF);
     have_ref_ = true;
   }
   template <class MatT> void setNowFrame(const MatT& rgb, const MatT& /*depth: stored but unused, SolveEA.cpp:86-119*/) {
@@ -92,7 +93,7 @@ class SolveEA {
   ea_frame_params fp_{};
   ea_solve_params sp_{};
   Frame ref_, now_;
-  bool have_ref_ = false, have_now_ = false, dirty_ = true, zero_depth_to_one_ = true;
+  bool have_ref_ = false, have_now_ = false, dirty_ = true;
   double pose_[7];
   std::vector<ea_summary> summaries_;
 };

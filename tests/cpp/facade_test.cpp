@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
     printf("npts %d\n", ea->refFrame().numEdgePoints());
     // EAResidue probe: first reference point at identity
     std::vector<float> p = ea->refFrame().edgePoints();
-    const double Z = p[2] / 5000.0, X = (p[0] - 319.5) * Z / 525.0, Y = (p[1] - 239.5) * Z / 525.0;
+    const double Z = p[2] / 5000.0 /* standalone pipeline keeps raw u16 depth */, X = (p[0] - 319.5) * Z / 525.0, Y = (p[1] - 239.5) * Z / 525.0;
     EAResidue res(525.0, 525.0, 319.5, 239.5, X, Y, Z, ea->nowFrame());
     const double qi[4] = {1, 0, 0, 0}, ti[3] = {0, 0, 0};
     double r = -1, J[6];

@@ -522,3 +522,38 @@ def test_masked_reference_points(ea, ctx, frames, oracle):
         np.testing.assert_array_equal(fs.dt(0), odt)              # the mask does not touch the now role
     finally:
         fs.close()
+
+
+def test_float_depth_and_zero_depth_policy(ea, ctx, frames, oracle):
+    """SolveEA's depth convention (src/SolveEA.cpp:27,68-69): CV_32F metres, edge pixels without depth kept at Z = 1."""
+    O = oracle
+    K = frames["K"]
+    depth_m = (frames["depth"][0].astype(np.float32) / np.float32(5000.0)).astype(np.float32)
+    fp = ea.frame_params(depth_type=ea.DEPTH_F32, zero_depth_to_one=1, max_points=640 * 480, n_levels=2)
+    fs = ea.FrameSet(ctx, fp, 2)
+    try:
+        fs.preprocess_host([0], frames["bgr"][:1], depth_m[None], ea.ROLE_BOTH)
+        fs.preprocess_host([1], frames["bgr"][2:3], None, ea.ROLE_NOW)
+        lap = O.laplacian3_abs(O.rgb2gray(O.gaussian3(frames["bgr"][0])))
+        vs, us = np.nonzero(lap > 35)                                   # every edge pixel is kept
+        z = depth_m[vs, us].copy(); z[z == 0] = 1.0
+        pts = fs.points(0)
+        np.testing.assert_array_equal(pts[:, 0], us.astype(np.float32)); np.testing.assert_array_equal(pts[:, 1], vs.astype(np.float32))
+        np.testing.assert_array_equal(pts[:, 2], z)                      # metres, bit for bit
+        # residuals against the oracle on X = Z (u - cx) / fx built from the same float depths
+        Z = z.astype(np.float64)
+        xyz = np.stack([(us - K[2]) * Z / K[0], (vs - K[3]) * Z / K[1], Z], 1)
+        dt, _ = O.get_distance_transform(frames["bgr"][2])
+        pose = np.array([0.99995, 0.006, -0.004, 0.005, 0.01, -0.01, 0.02]); pose[:4] /= np.linalg.norm(pose[:4])
+        sp = ea.solve_params(point_stride=3, loss_type=ea.LOSS_TRIVIAL)
+        g = ctx.eval(fs, 0, fs, 1, pose, sp)
+        o = O.evaluate(xyz, dt, K, pose, stride=3, options=O.default_options(loss_type=0))
+        _assert_residual_parity(g["raw"], o["raw"])
+        # level 1: nearest-decimated float depth
+        hb = O.half_linear(frames["bgr"][0]); hd = depth_m[::2, ::2]
+        lap1 = O.laplacian3_abs(O.rgb2gray(O.gaussian3(hb)))
+        vs1, us1 = np.nonzero(lap1 > 35)
+        z1 = hd[vs1, us1].copy(); z1[z1 == 0] = 1.0
+        np.testing.assert_array_equal(fs.points(0, 1)[:, 2], z1)
+    finally:
+        fs.close()
