@@ -35,6 +35,15 @@ HUBER_A = 0.1
 KEYFRAME_INTERVAL = 10
 BYTES_PER_POINT_EVAL = 80.0
 METRIC = "frame-pair alignments/sec at 640x480"
+RING = 24          # distinct frames kept per stream; longer runs walk the sequence forwards then backwards (continuous motion)
+
+
+def ring_index(t, n):
+    """Frame shown at step t when only n distinct frames exist: 0,1,..,n-1,n-2,..,1,0,1,.. (camera retraces its path)."""
+    if n <= 1:
+        return 0
+    t %= 2 * (n - 1)
+    return t if t < n else 2 * (n - 1) - t
 
 
 def workload_name(streams):
@@ -51,26 +60,33 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index; self.samples = []; self._halt = threading.Event(); self.proc = None
+        self.t_begin = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.samples.append(line.strip())
+                self.samples.append((time.time(), line.strip()))
                 if self._halt.is_set():
                     break
         except Exception:
             pass
 
+    def begin(self):
+        """Start of the timed region: only samples taken from here to stop() are reported."""
+        self.t_begin = time.time()
+
     def stop(self):
+        t_end = time.time()
         self._halt.set()
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        inside = [x for ts, x in self.samples if self.t_begin is None or self.t_begin <= ts <= t_end + 0.05]
+        for s in inside:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 7:
                 continue
@@ -100,7 +116,7 @@ def cpu_reference_run(n_streams, steps, warmup, threads, make_frames):
     (alignments/s over the timed steps, seconds, total alignments)."""
     from oracle import oracle as O
     import synth
-    bgr, depth = make_frames(n_streams, warmup + steps + 1)
+    bgr, depth = make_frames(n_streams, min(warmup + steps + 1, RING))
     cfg = O.pair_cfg(W, H, synth.TUM_K, n_levels=N_LEVELS, stride=1)
     opts = O.default_options(loss_type=O.LOSS_HUBER, loss_scale=HUBER_A)
     poses = np.tile(np.array([1.0, 0, 0, 0, 0, 0, 0]), (n_streams, 1))
@@ -109,8 +125,8 @@ def cpu_reference_run(n_streams, steps, warmup, threads, make_frames):
     flat_b = bgr.reshape(T * n_streams, H, W, 3); flat_d = depth.reshape(T * n_streams, H, W)
     timed = 0.0
     for t in range(1, warmup + steps + 1):
-        ref_idx = [key * n_streams + s for s in range(n_streams)]
-        now_idx = [t * n_streams + s for s in range(n_streams)]
+        ref_idx = [ring_index(key, T) * n_streams + s for s in range(n_streams)]
+        now_idx = [ring_index(t, T) * n_streams + s for s in range(n_streams)]
         poses, _, sec = O.align_batch(flat_b, flat_d, ref_idx, now_idx, cfg, poses, opts, n_threads=threads, include_preprocess=True)
         if t > warmup:
             timed += sec
@@ -123,8 +139,8 @@ def cpu_reference_run(n_streams, steps, warmup, threads, make_frames):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=592, help="camera streams per GPU (4 per SM)")
     ap.add_argument("--cluster", type=int, default=0)
@@ -185,8 +201,10 @@ def main():
 
     S, K, Wm = args.streams, args.steps, args.warmup
     T = Wm + K + 1
-    bgr_d, depth_d, _ = synth.make_sequences(S, T, seed=1234 + rank, device=dev)      # [T,S,h,w,3] / [T,S,h,w] resident in HBM
+    NF = min(T, RING)
+    bgr_d, depth_d, _ = synth.make_sequences(S, NF, seed=1234 + rank, device=dev)     # [NF,S,h,w,3] / [NF,S,h,w] resident in HBM
     torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank); sampler.start()       # nvidia-smi is up and printing before the timed region
 
     ctx = ea.Context(local_rank)
     stream = torch.cuda.current_stream()
@@ -198,13 +216,14 @@ def main():
 
     def run_device(first, last):
         for t in range(first, last):
-            tracker.step_device(bgr_d.data_ptr() + t * frame_b, depth_d.data_ptr() + t * frame_d)
+            f = ring_index(t, NF)
+            tracker.step_device(bgr_d.data_ptr() + f * frame_b, depth_d.data_ptr() + f * frame_d)
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------------------
     tracker.reset()
     run_device(0, Wm + 1)                       # frame 0 = key frame, then W warm-up steps
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler.begin()
     ctx.profile_enable(True); ctx.profile_read()
     l0 = ctx.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -246,22 +265,24 @@ def main():
     # ---- e2e: host buffers through the tracker's host entry point --------------------------------------------
     e2e = None
     if not args.no_e2e:
-        hb = torch.empty((T, S, H, W, 3), dtype=torch.uint8, pin_memory=True); hb.copy_(bgr_d)
+        hb = torch.empty((NF, S, H, W, 3), dtype=torch.uint8, pin_memory=True); hb.copy_(bgr_d)
         # depth only travels for frames that become key frames: pin just those
-        hd = {t: torch.empty((S, H, W), dtype=torch.uint16, pin_memory=True) for t in range(T) if t % KEYFRAME_INTERVAL == 0}
-        for t, buf in hd.items():
-            buf.copy_(depth_d[t])
+        hd = {f: torch.empty((S, H, W), dtype=torch.uint16, pin_memory=True)
+              for f in sorted({ring_index(t, NF) for t in range(T) if t % KEYFRAME_INTERVAL == 0})}
+        for f, buf in hd.items():
+            buf.copy_(depth_d[f])
         torch.cuda.synchronize()
-        dptr = lambda t: hd[t].data_ptr() if t in hd else 0
+        bptr = lambda t: hb.data_ptr() + ring_index(t, NF) * frame_b
+        dptr = lambda t: hd[ring_index(t, NF)].data_ptr() if t % KEYFRAME_INTERVAL == 0 else 0
         tracker.reset()
         for t in range(0, Wm + 1):
-            tracker.step_host(hb.data_ptr() + t * frame_b, dptr(t), fetch=True)
+            tracker.step_host(bptr(t), dptr(t), fetch=True)
         barrier()
         e0.record(stream)
         # pipelined: frame t is submitted (its upload overlaps the alignment of frame t-1), then the poses of frame
         # t-1 are read on the host.  Every step's frames cross PCIe and every step's result is read back.
         for t in range(Wm + 1, T):
-            tracker.step_host(hb.data_ptr() + t * frame_b, dptr(t), fetch=False)
+            tracker.step_host(bptr(t), dptr(t), fetch=False)
             if t > Wm + 1:
                 poses, _ = tracker.wait(t - 1)
         poses, _ = tracker.wait(T - 1)
@@ -295,6 +316,7 @@ def main():
            "data": "synthetic",
            "config": {"workload": workload_name(S), "streams_per_gpu": S, "cluster_size": args.cluster,
                       "l2": "every step reads %d MB of new frames per GPU (> 126 MB L2): inputs larger than L2" % (frame_b // 2**20),
+                      "frames_resident": "%d distinct frames per stream, walked forwards then backwards" % NF,
                       "point_evals_per_s": world * point_evals / (ms * 1e-3), "mean_lm_iterations_per_level": iters / max(1, n_sum),
                       "terminations": {ea._lib.TERMINATION.get(k, str(k)): v for k, v in terms.items()}},
            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -13,6 +13,7 @@ SO_PATH = os.path.join(HERE, "libea_b200.so")
 EA_MAX_LEVELS = 4
 EA_OK = 0
 LOSS_TRIVIAL, LOSS_CAUCHY, LOSS_HUBER = 0, 1, 2
+STRATEGY_LM, STRATEGY_DOGLEG = 0, 1
 NORM_NONE, NORM_01, NORM_255 = 0, 1, 2
 ROLE_REF, ROLE_NOW, ROLE_BOTH = 1, 2, 3
 EDGE_LAPLACIAN, EDGE_CANNY_GRAY, EDGE_CANNY_COLOR = 0, 1, 2
@@ -40,7 +41,7 @@ class SolveParams(C.Structure):
                 ("parameter_tolerance", C.c_double), ("initial_trust_region_radius", C.c_double),
                 ("max_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double),
                 ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
-                ("max_lm_diagonal", C.c_double)]
+                ("max_lm_diagonal", C.c_double), ("trust_region_strategy", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Summary(C.Structure):

@@ -33,6 +33,8 @@ def frame_params(**kw):
     p = L.FrameParams()
     L.lib().ea_frame_params_default(C.byref(p))
     for k, v in kw.items():
+        if not hasattr(type(p), k):
+            raise TypeError('frame_params: unknown field %r' % k)
         setattr(p, k, v)
     return p
 
@@ -41,6 +43,8 @@ def solve_params(**kw):
     p = L.SolveParams()
     L.lib().ea_solve_params_default(C.byref(p))
     for k, v in kw.items():
+        if not hasattr(type(p), k):
+            raise TypeError('solve_params: unknown field %r' % k)
         setattr(p, k, v)
     return p
 

@@ -18,7 +18,9 @@ struct EaLmState {
   double H[21], b[6]; // normal equations at x (corrected, unscaled, local)
   double scale[6], diag[6];
   double cost, initial_cost, radius, decrease_factor, model_cost_change;
+  double dl_mu, dl_alpha, dl_step_norm, dl_grad[6], dl_gn[6];   // DoglegStrategy state (trust_region_strategy == 1)
   int phase, iter, accepted, rejected, invalid_run, reuse_diag, evals, term;
+  int dl_reuse, pad;
 };
 
 __device__ inline void ea_quat_plus(const double* x, const double* d, double* out) {
@@ -58,28 +60,13 @@ __device__ inline bool ea_gradient_converged(const EaLmState& S, double tol) {
   return m <= tol;
 }
 
-// LevenbergMarquardtStrategy::ComputeStep on the normal equations: (S H S + diag/radius) y = S b, step = -y.
-// 6x6 LDL^T in registers (fully unrolled; one reciprocal per pivot).  Returns false on an invalid step.
-__device__ inline bool ea_lm_compute_step(EaLmState& S, const ea_solve_params& sp, double* delta) {
-  double A[6][6], bs[6];
-#pragma unroll
-  for (int a = 0; a < 6; ++a) {
-    bs[a] = S.scale[a] * S.b[a];
-#pragma unroll
-    for (int c = a; c < 6; ++c) { A[a][c] = S.scale[a] * S.H[ea_tri(a, c)] * S.scale[c]; A[c][a] = A[a][c]; }
-  }
-  if (!S.reuse_diag) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) S.diag[j] = fmin(fmax(A[j][j], sp.min_lm_diagonal), sp.max_lm_diagonal);
-  }
-  S.reuse_diag = 1;
-  const double inv_radius = 1.0 / S.radius;
-  // L D L^T = H_s + diag/radius  (unit lower L, D = 1/dinv)
+// (A + diag(add)) y = bs by 6x6 LDL^T in registers (fully unrolled; one reciprocal per pivot).  false on failure.
+__device__ inline bool ea_ldlt_solve6(const double (&A)[6][6], const double* add, const double* bs, double* y) {
   double L[6][6], dinv[6], dval[6];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double d = fma(S.diag[j], inv_radius, A[j][j]);
+    double d = A[j][j] + add[j];
     double v[6];
 #pragma unroll
     for (int k = 0; k < j; ++k) { v[k] = L[j][k] * dval[k]; d = fma(-L[j][k], v[k], d); }
@@ -95,7 +82,6 @@ __device__ inline bool ea_lm_compute_step(EaLmState& S, const ea_solve_params& s
     }
   }
   if (!ok) return false;
-  double y[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     double s = bs[i];
@@ -113,18 +99,104 @@ __device__ inline bool ea_lm_compute_step(EaLmState& S, const ea_solve_params& s
     y[i] = s;
     ok = ok && isfinite(s);
   }
-  if (!ok) return false;
-  // step = -y ; model_cost_change = -(step^T b_s + 1/2 step^T H_s step)
+  return ok;
+}
+
+// Trust-region step on the normal equations (H_s = S H S, b_s = S b).  Returns false on an invalid step.
+//   strategy 0: LevenbergMarquardtStrategy::ComputeStep   (H_s + diag/radius) y = b_s, step = -y
+//   strategy 1: DoglegStrategy::ComputeStep, TRADITIONAL_DOGLEG (src/SolveEA.cpp:192): Gauss-Newton / Cauchy interpolation
+//               inside the elliptical region |D step| <= radius
+__device__ inline bool ea_lm_compute_step(EaLmState& S, const ea_solve_params& sp, double* delta) {
+  double A[6][6], bs[6], step[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    bs[a] = S.scale[a] * S.b[a];
+#pragma unroll
+    for (int c = a; c < 6; ++c) { A[a][c] = S.scale[a] * S.H[ea_tri(a, c)] * S.scale[c]; A[c][a] = A[a][c]; }
+  }
+  if (sp.trust_region_strategy == 0) {
+    if (!S.reuse_diag) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) S.diag[j] = fmin(fmax(A[j][j], sp.min_lm_diagonal), sp.max_lm_diagonal);
+    }
+    S.reuse_diag = 1;
+    const double inv_radius = 1.0 / S.radius;
+    double add[6], y[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) add[j] = S.diag[j] * inv_radius;
+    if (!ea_ldlt_solve6(A, add, bs, y)) return false;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) step[j] = -y[j];
+  } else {
+    if (!S.dl_reuse) {
+      S.dl_reuse = 1;
+      double g2 = 0.0, sg[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        S.diag[j] = sqrt(fmin(fmax(A[j][j], sp.min_lm_diagonal), sp.max_lm_diagonal));
+        S.dl_grad[j] = bs[j] / S.diag[j];
+        sg[j] = S.dl_grad[j] / S.diag[j];
+        g2 = fma(S.dl_grad[j], S.dl_grad[j], g2);
+      }
+      double Jg2 = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        double row = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) row = fma(A[a][c], sg[c], row);
+        Jg2 = fma(sg[a], row, Jg2);
+      }
+      S.dl_alpha = g2 / Jg2;
+      bool ok = false;
+      double y[6];
+      while (S.dl_mu < 1.0) {
+        double add[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) add[j] = S.diag[j] * S.diag[j] * S.dl_mu;
+        if (ea_ldlt_solve6(A, add, bs, y)) { ok = true; break; }
+        S.dl_mu *= 10.0;
+      }
+      if (!ok) return false;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) S.dl_gn[j] = -y[j] * S.diag[j];
+    }
+    double gn2 = 0.0, g2 = 0.0, gdotgn = 0.0, ds[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { gn2 = fma(S.dl_gn[j], S.dl_gn[j], gn2); g2 = fma(S.dl_grad[j], S.dl_grad[j], g2); gdotgn = fma(S.dl_grad[j], S.dl_gn[j], gdotgn); }
+    const double gn_norm = sqrt(gn2), g_norm = sqrt(g2);
+    if (gn_norm <= S.radius) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) ds[j] = S.dl_gn[j];
+      S.dl_step_norm = gn_norm;
+    } else if (g_norm * S.dl_alpha >= S.radius) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) ds[j] = -(S.radius / g_norm) * S.dl_grad[j];
+      S.dl_step_norm = S.radius;
+    } else {
+      const double b_dot_a = -S.dl_alpha * gdotgn;
+      const double a2 = (S.dl_alpha * g_norm) * (S.dl_alpha * g_norm);
+      const double bma2 = a2 - 2.0 * b_dot_a + gn2;
+      const double c = b_dot_a - a2;
+      const double d = sqrt(c * c + bma2 * (S.radius * S.radius - a2));
+      const double beta = (c <= 0.0) ? (d - c) / bma2 : (S.radius * S.radius - a2) / (d + c);
+      double nn = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { ds[j] = (-S.dl_alpha * (1.0 - beta)) * S.dl_grad[j] + beta * S.dl_gn[j]; nn = fma(ds[j], ds[j], nn); }
+      S.dl_step_norm = sqrt(nn);
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) step[j] = ds[j] / S.diag[j];
+  }
+  // model_cost_change = -(step^T b_s + 1/2 step^T H_s step)
   double lin = 0.0, quad = 0.0;
 #pragma unroll
   for (int a = 0; a < 6; ++a) {
-    const double sa = -y[a];
-    lin = fma(sa, bs[a], lin);
+    lin = fma(step[a], bs[a], lin);
     double row = 0.0;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) row = fma(A[a][c], -y[c], row);
-    quad = fma(sa, row, quad);
-    delta[a] = sa * S.scale[a];  // undo the Jacobi column scaling
+    for (int c = 0; c < 6; ++c) row = fma(A[a][c], step[c], row);
+    quad = fma(step[a], row, quad);
+    delta[a] = step[a] * S.scale[a];  // undo the Jacobi column scaling
   }
   S.model_cost_change = -(lin + 0.5 * quad);
   return S.model_cost_change > 0.0;
@@ -146,6 +218,7 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
     for (int j = 0; j < 6; ++j) S.scale[j] = sp.jacobi_scaling ? 1.0 / (1.0 + sqrt(S.H[ea_tri(j, j)])) : 1.0;
     if (ea_gradient_converged(S, sp.gradient_tolerance)) { S.term = EA_TERM_CONVERGENCE_GRADIENT; return EA_CMD_DONE; }
     S.radius = sp.initial_trust_region_radius; S.decrease_factor = 2.0; S.reuse_diag = 0;
+    S.dl_mu = 1e-8; S.dl_reuse = 0; S.dl_step_norm = 0.0;
     S.iter = 0; S.phase = 1;
   } else {
     const double cand_cost = fail ? DBL_MAX : sums[28];
@@ -165,12 +238,21 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
 #pragma unroll 1
       for (int k = 0; k < 6; ++k) S.b[k] = sums[21 + k];
       S.cost = cand_cost;
-      const double t = 2.0 * rel - 1.0;
-      S.radius = fmin(sp.max_trust_region_radius, S.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
-      S.decrease_factor = 2.0; S.reuse_diag = 0; S.accepted++;
+      if (sp.trust_region_strategy == 0) {
+        const double t = 2.0 * rel - 1.0;
+        S.radius = fmin(sp.max_trust_region_radius, S.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+        S.decrease_factor = 2.0; S.reuse_diag = 0;
+      } else {   // DoglegStrategy::StepAccepted
+        if (rel < 0.25) S.radius *= 0.5;
+        if (rel > 0.75) S.radius = fmax(S.radius, 3.0 * S.dl_step_norm);
+        S.dl_mu = fmax(1e-8, 2.0 * S.dl_mu / 10.0); S.dl_reuse = 0;
+      }
+      S.accepted++;
       if (ea_gradient_converged(S, sp.gradient_tolerance)) { S.term = EA_TERM_CONVERGENCE_GRADIENT; return EA_CMD_DONE; }
     } else {  // HandleUnsuccessfulStep
-      S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diag = 1; S.rejected++;
+      if (sp.trust_region_strategy == 0) { S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diag = 1; }
+      else { S.radius *= 0.5; S.dl_reuse = 1; }   // DoglegStrategy::StepRejected
+      S.rejected++;
     }
   }
   for (;;) {
@@ -180,7 +262,9 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
     double delta[6];
     if (!ea_lm_compute_step(S, sp, delta)) {  // HandleInvalidStep
       if (++S.invalid_run >= sp.max_consecutive_invalid_steps) { S.term = EA_TERM_FAILURE_INVALID_STEPS; return EA_CMD_DONE; }
-      S.radius *= 0.5; S.reuse_diag = 0; S.rejected++;
+      if (sp.trust_region_strategy == 0) { S.radius *= 0.5; S.reuse_diag = 0; }
+      else { S.dl_mu *= 10.0; S.dl_reuse = 0; }   // DoglegStrategy::StepIsInvalid
+      S.rejected++;
       continue;
     }
     S.invalid_run = 0;

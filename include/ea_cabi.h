@@ -48,6 +48,7 @@ typedef enum ea_status {
 /* ceres::LossFunction attached per residual block (standalone_edge_align.cpp:272 CauchyLoss(1.),
  * :2604 TrivialLoss, src/SolveEA.cpp:144 HuberLoss(0.1)) */
 typedef enum ea_loss { EA_LOSS_TRIVIAL = 0, EA_LOSS_CAUCHY = 1, EA_LOSS_HUBER = 2 } ea_loss;
+typedef enum ea_strategy { EA_STRATEGY_LM = 0, EA_STRATEGY_DOGLEG = 1 } ea_strategy;   /* ceres TrustRegionStrategyType */
 
 /* cv::normalize(NORM_MINMAX) target range: utils.cpp:81 [0,1]; src/SolveEA.cpp:109 [0,255];
  * utils.cpp:142-165 none */
@@ -134,6 +135,8 @@ typedef struct ea_solve_params {
   double min_relative_decrease;       /* 1e-3 */
   double min_lm_diagonal;             /* 1e-6 */
   double max_lm_diagonal;             /* 1e32 */
+  int32_t trust_region_strategy;      /* 0 LEVENBERG_MARQUARDT (Ceres default, standalone); 1 DOGLEG, traditional (src/SolveEA.cpp:192) */
+  int32_t reserved;
 } ea_solve_params;
 
 /* ceres::Solver::Summary, condensed; one per (pair, level) */

@@ -8,9 +8,9 @@
 // Defaults = the literals of src/SolveEA.cpp: half-TUM intrinsics (:12-23), cv::Canny(rgb, 150, 100, 3, true) on the
 // colour image (:46,102), exact Euclidean distance transform of the inverted edge map (:108) normalised to [0,255]
 // (:109), every edge point (:163), NULL loss (:171), 25 iterations (:185), depth in metres as CV_32F with Z==0 -> 1.0
-// (:68-69), start at identity (:130-131).  Two repairs of reference defects: the distance field is sampled
-// as one channel with the standalone's (row == u, col == v) convention, and the trust-region strategy is
-// Levenberg-Marquardt (the reference asks for DOGLEG, :192).  useStandalonePipeline() switches to the edge detector /
+// (:68-69), start at identity (:130-131), TRUST_REGION with traditional DOGLEG (:191-192).  One repair of a reference
+// defect: the distance field is sampled as one channel with the standalone's (row == u, col == v)
+// convention (the reference wraps it in a 2-channel grid, :152).  useStandalonePipeline() switches to the edge detector /
 // DT / loss of standalone/utils.cpp + edge_align_test1.
 #pragma once
 #include "Frame.h"
@@ -28,6 +28,7 @@ class SolveEA {
     fp_.depth_type = EA_DEPTH_F32; fp_.zero_depth_to_one = 1;                             // SolveEA.cpp:27,68-69
     ea_solve_params_default(&sp_);
     sp_.point_stride = 1; sp_.loss_type = EA_LOSS_TRIVIAL; sp_.max_num_iterations = 25;    // SolveEA.cpp:163,171,185
+    sp_.trust_region_strategy = EA_STRATEGY_DOGLEG;                                                      // DOGLEG, SolveEA.cpp:192
     pose_[0] = 1; for (int i = 1; i < 7; ++i) pose_[i] = 0;                               // SolveEA.cpp:130-131
   }
 
@@ -44,6 +45,7 @@ class SolveEA {
   void useStandalonePipeline() {
     fp_.edge_detector = EA_EDGE_LAPLACIAN; fp_.dt_kind = EA_DT_CHAMFER3; fp_.dt_normalize = EA_NORM_01; fp_.use_median = 1;
     sp_.point_stride = 30; sp_.loss_type = EA_LOSS_CAUCHY; sp_.loss_scale = 1.0; sp_.max_num_iterations = 50;
+    sp_.trust_region_strategy = EA_STRATEGY_LM;
     fp_.zero_depth_to_one = 0; fp_.depth_type = EA_DEPTH_U16; dirty_ = true;
   }
 

@@ -506,6 +506,7 @@ struct Options {  // ceres::Solver::Options defaults; SEA:282-284 only sets DENS
   double min_relative_decrease = 1e-3, min_lm_diagonal = 1e-6, max_lm_diagonal = 1e32;
   int jacobi_scaling = 1, max_consecutive_invalid = 5;
   int loss_type = LOSS_CAUCHY; double loss_scale = 1.0;
+  int strategy = 0;   // 0 LEVENBERG_MARQUARDT (Ceres default), 1 DOGLEG / TRADITIONAL_DOGLEG (src/SolveEA.cpp:192)
 };
 
 enum Termination { TERM_CONVERGENCE_GRADIENT = 1, TERM_CONVERGENCE_FUNCTION = 2, TERM_CONVERGENCE_PARAMETER = 3,
@@ -675,29 +676,79 @@ SolveSummary lm_solve(const Problem& p, double x[7], const Options& o, IterRecor
 
   double radius = o.initial_radius, decrease_factor = 2.0, diag[6];
   bool reuse_diagonal = false;
+  bool dl_reuse = false; double dl_mu = 1e-8, dl_alpha = 0, dl_step_norm = 0, dl_grad[6], dl_gn[6];   // DoglegStrategy state
   int invalid_run = 0, iter = 0;
   for (;;) {
     if (iter >= o.max_num_iterations) return finish(TERM_NO_CONVERGENCE);
     if (radius < o.min_radius) return finish(TERM_CONVERGENCE_MIN_RADIUS);
     ++iter;
     S.iterations = iter;
-    // LevenbergMarquardtStrategy::ComputeStep
-    if (!reuse_diagonal)
-      for (int j = 0; j < 6; ++j) {
-        double s = 0; for (int i = 0; i < n; ++i) s += Js[size_t(i) * 6 + j] * Js[size_t(i) * 6 + j];
-        diag[j] = std::min(std::max(s, o.min_lm_diagonal), o.max_lm_diagonal);
-      }
-    A.assign(size_t(n + 6) * 6, 0.0);
-    rhs.assign(n + 6, 0.0);
-    std::copy(Js.begin(), Js.end(), A.begin());
-    std::copy(r.begin(), r.end(), rhs.begin());
-    for (int j = 0; j < 6; ++j) A[size_t(n + j) * 6 + j] = std::sqrt(diag[j] / radius);
     double y[6], step[6];
-    bool ok = householder_lstsq6(A, rhs, n + 6, y);
-    reuse_diagonal = true;
+    bool ok;
+    if (o.strategy == 0) {
+      // LevenbergMarquardtStrategy::ComputeStep
+      if (!reuse_diagonal)
+        for (int j = 0; j < 6; ++j) {
+          double s = 0; for (int i = 0; i < n; ++i) s += Js[size_t(i) * 6 + j] * Js[size_t(i) * 6 + j];
+          diag[j] = std::min(std::max(s, o.min_lm_diagonal), o.max_lm_diagonal);
+        }
+      A.assign(size_t(n + 6) * 6, 0.0);
+      rhs.assign(n + 6, 0.0);
+      std::copy(Js.begin(), Js.end(), A.begin());
+      std::copy(r.begin(), r.end(), rhs.begin());
+      for (int j = 0; j < 6; ++j) A[size_t(n + j) * 6 + j] = std::sqrt(diag[j] / radius);
+      ok = householder_lstsq6(A, rhs, n + 6, y);
+      reuse_diagonal = true;
+      if (ok) for (int j = 0; j < 6; ++j) step[j] = -y[j];
+    } else {
+      // DoglegStrategy::ComputeStep, TRADITIONAL_DOGLEG (ceres/dogleg_strategy.cc)
+      ok = true;
+      if (!dl_reuse) {
+        dl_reuse = true;
+        for (int j = 0; j < 6; ++j) {
+          double s = 0; for (int i = 0; i < n; ++i) s += Js[size_t(i) * 6 + j] * Js[size_t(i) * 6 + j];
+          diag[j] = std::sqrt(std::min(std::max(s, o.min_lm_diagonal), o.max_lm_diagonal));
+        }
+        // gradient_ = (J^T r) / D ; Cauchy step length alpha = |g|^2 / |J (g / D)|^2
+        for (int j = 0; j < 6; ++j) { double gj = 0; for (int i = 0; i < n; ++i) gj += Js[size_t(i) * 6 + j] * r[i]; dl_grad[j] = gj / diag[j]; }
+        double g2 = 0, Jg2 = 0;
+        for (int j = 0; j < 6; ++j) g2 += dl_grad[j] * dl_grad[j];
+        for (int i = 0; i < n; ++i) { double m = 0; for (int j = 0; j < 6; ++j) m += Js[size_t(i) * 6 + j] * (dl_grad[j] / diag[j]); Jg2 += m * m; }
+        dl_alpha = g2 / Jg2;
+        // Gauss-Newton step with a small regularisation mu * D^2, raised until the solve succeeds
+        ok = false;
+        while (dl_mu < 1.0) {
+          A.assign(size_t(n + 6) * 6, 0.0); rhs.assign(n + 6, 0.0);
+          std::copy(Js.begin(), Js.end(), A.begin()); std::copy(r.begin(), r.end(), rhs.begin());
+          for (int j = 0; j < 6; ++j) A[size_t(n + j) * 6 + j] = diag[j] * std::sqrt(dl_mu);
+          if (householder_lstsq6(A, rhs, n + 6, y)) { ok = true; break; }
+          dl_mu *= 10.0;
+        }
+        if (ok) for (int j = 0; j < 6; ++j) dl_gn[j] = -y[j] * diag[j];
+      }
+      if (ok) {
+        double gn_norm = 0, g_norm = 0, gdotgn = 0;
+        for (int j = 0; j < 6; ++j) { gn_norm += dl_gn[j] * dl_gn[j]; g_norm += dl_grad[j] * dl_grad[j]; gdotgn += dl_grad[j] * dl_gn[j]; }
+        gn_norm = std::sqrt(gn_norm); g_norm = std::sqrt(g_norm);
+        double ds[6];
+        if (gn_norm <= radius) { for (int j = 0; j < 6; ++j) ds[j] = dl_gn[j]; dl_step_norm = gn_norm; }
+        else if (g_norm * dl_alpha >= radius) { for (int j = 0; j < 6; ++j) ds[j] = -(radius / g_norm) * dl_grad[j]; dl_step_norm = radius; }
+        else {
+          const double b_dot_a = -dl_alpha * gdotgn;
+          const double a2 = std::pow(dl_alpha * g_norm, 2.0);
+          const double bma2 = a2 - 2 * b_dot_a + gn_norm * gn_norm;
+          const double c = b_dot_a - a2;
+          const double d = std::sqrt(c * c + bma2 * (radius * radius - a2));
+          const double beta = (c <= 0) ? (d - c) / bma2 : (radius * radius - a2) / (d + c);
+          double nn = 0;
+          for (int j = 0; j < 6; ++j) { ds[j] = (-dl_alpha * (1.0 - beta)) * dl_grad[j] + beta * dl_gn[j]; nn += ds[j] * ds[j]; }
+          dl_step_norm = std::sqrt(nn);
+        }
+        for (int j = 0; j < 6; ++j) step[j] = ds[j] / diag[j];
+      }
+    }
     double model_cost_change = 0;
     if (ok) {
-      for (int j = 0; j < 6; ++j) step[j] = -y[j];
       // model_cost_change = -(J step)^T (r + J step / 2)
       for (int i = 0; i < n; ++i) {
         double m = 0; for (int j = 0; j < 6; ++j) m += Js[size_t(i) * 6 + j] * step[j];
@@ -706,7 +757,8 @@ SolveSummary lm_solve(const Problem& p, double x[7], const Options& o, IterRecor
     }
     if (!ok || !(model_cost_change > 0.0)) {  // HandleInvalidStep
       if (++invalid_run >= o.max_consecutive_invalid) return finish(TERM_FAILURE_INVALID_STEPS);
-      radius *= 0.5; reuse_diagonal = false;
+      if (o.strategy == 0) { radius *= 0.5; reuse_diagonal = false; }
+      else { dl_mu *= 10.0; dl_reuse = false; }          // DoglegStrategy::StepIsInvalid
       push({cost, 0, gmax, 0, 0, radius, 0});
       S.rejected++;
       continue;
@@ -736,14 +788,21 @@ SolveSummary lm_solve(const Problem& p, double x[7], const Options& o, IterRecor
       S.jac_evals++;
       gradient(); scale_J();
       gmax = grad_max_norm();
-      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
-      radius = std::min(o.max_radius, radius);
-      decrease_factor = 2.0; reuse_diagonal = false;
+      if (o.strategy == 0) {
+        radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+        radius = std::min(o.max_radius, radius);
+        decrease_factor = 2.0; reuse_diagonal = false;
+      } else {                                             // DoglegStrategy::StepAccepted
+        if (rel < 0.25) radius *= 0.5;
+        if (rel > 0.75) radius = std::max(radius, 3.0 * dl_step_norm);
+        dl_mu = std::max(1e-8, 2.0 * dl_mu / 10.0); dl_reuse = false;
+      }
       S.accepted++;
       push({cost, cost_change, gmax, sn, rel, radius, 1});
       if (gmax <= o.gradient_tolerance) return finish(TERM_CONVERGENCE_GRADIENT);
     } else {  // HandleUnsuccessfulStep
-      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      if (o.strategy == 0) { radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true; }
+      else { radius *= 0.5; dl_reuse = true; }           // DoglegStrategy::StepRejected
       S.rejected++;
       push({cost, cost_change, gmax, sn, rel, radius, 0});
     }
@@ -799,6 +858,7 @@ struct eo_options {
   int max_num_iterations; double function_tolerance, gradient_tolerance, parameter_tolerance;
   double initial_radius, max_radius, min_radius, min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
   int jacobi_scaling, max_consecutive_invalid, loss_type; double loss_scale;
+  int strategy, pad;
 };
 static Options to_opts(const eo_options* e) {
   Options o;
@@ -809,6 +869,7 @@ static Options to_opts(const eo_options* e) {
   o.min_relative_decrease = e->min_relative_decrease; o.min_lm_diagonal = e->min_lm_diagonal;
   o.max_lm_diagonal = e->max_lm_diagonal; o.jacobi_scaling = e->jacobi_scaling;
   o.max_consecutive_invalid = e->max_consecutive_invalid; o.loss_type = e->loss_type; o.loss_scale = e->loss_scale;
+  o.strategy = e->strategy;
   return o;
 }
 void eo_options_default(eo_options* e) {
@@ -819,6 +880,7 @@ void eo_options_default(eo_options* e) {
   e->min_relative_decrease = o.min_relative_decrease; e->min_lm_diagonal = o.min_lm_diagonal;
   e->max_lm_diagonal = o.max_lm_diagonal; e->jacobi_scaling = o.jacobi_scaling;
   e->max_consecutive_invalid = o.max_consecutive_invalid; e->loss_type = o.loss_type; e->loss_scale = o.loss_scale;
+  e->strategy = o.strategy; e->pad = 0;
 }
 
 // ---- image stages (exposed one by one so each can be pinned against cv2) ----

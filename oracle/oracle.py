@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libea_oracle.so")
 
 LOSS_TRIVIAL, LOSS_CAUCHY, LOSS_HUBER = 0, 1, 2
+STRATEGY_LM, STRATEGY_DOGLEG = 0, 1
 TERMINATION = {1: "CONVERGENCE_GRADIENT", 2: "CONVERGENCE_FUNCTION", 3: "CONVERGENCE_PARAMETER",
                4: "CONVERGENCE_MIN_RADIUS", 5: "NO_CONVERGENCE", 6: "FAILURE_EVAL_X0", 7: "FAILURE_INVALID_STEPS"}
 
@@ -24,7 +25,8 @@ class Options(C.Structure):
                 ("initial_radius", C.c_double), ("max_radius", C.c_double), ("min_radius", C.c_double),
                 ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
                 ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int),
-                ("max_consecutive_invalid", C.c_int), ("loss_type", C.c_int), ("loss_scale", C.c_double)]
+                ("max_consecutive_invalid", C.c_int), ("loss_type", C.c_int), ("loss_scale", C.c_double),
+                ("strategy", C.c_int), ("pad", C.c_int)]
 
 
 class Summary(C.Structure):
@@ -73,6 +75,8 @@ def default_options(**kw):
     o = Options()
     lib().eo_options_default(C.byref(o))
     for k, v in kw.items():
+        if not hasattr(type(o), k):
+            raise TypeError('default_options: unknown field %r' % k)
         setattr(o, k, v)
     return o
 

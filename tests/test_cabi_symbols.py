@@ -32,7 +32,7 @@ def test_header_symbols_exported_and_bound():
 def test_struct_layouts_match_header():
     from edge_alignment_b200 import _lib as L
     assert ctypes.sizeof(L.FrameParams) == 8 * 4 + 5 * 8 + 2 * 4 + 2 * 8 + 2 * 4
-    assert ctypes.sizeof(L.SolveParams) == 8 * 4 + 10 * 8
+    assert ctypes.sizeof(L.SolveParams) == 8 * 4 + 10 * 8 + 2 * 4
     assert ctypes.sizeof(L.Summary) == 6 * 4 + 2 * 8
     import edge_alignment_b200 as ea
     fp, sp = ea.frame_params(), ea.solve_params()

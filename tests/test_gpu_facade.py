@@ -44,7 +44,7 @@ def test_cpp_facade_runs_reference_call_sequence(frames, solver_golden, tmp_path
     xyz = np.stack([(us - K[2]) * Z / K[0], (vs - K[3]) * Z / K[1], Z], 1)
     dt = O.normalize_minmax(O.exact_edt(255 - O.canny(frames["bgr"][2], 150, 100, l2=True)), 0, 255)
     op, os_, _ = O.solve(xyz, dt, K, np.array([1.0, 0, 0, 0, 0, 0, 0]), stride=1,
-                         options=O.default_options(loss_type=O.LOSS_TRIVIAL, max_num_iterations=25))
+                         options=O.default_options(loss_type=O.LOSS_TRIVIAL, max_num_iterations=25, strategy=O.STRATEGY_DOGLEG))
     rp = np.array([float(v) for v in rec["rospose"]])
     assert rot_angle_between(rp[:4], op[:4]) < 1e-4 and np.abs(rp[4:] - op[4:]).max() < 1e-4
     assert int(rec["rossummary"][2]) == len(xyz) and abs(int(rec["rossummary"][1]) - os_["iterations"]) <= 2

@@ -291,6 +291,30 @@ def test_solve_edge_cases(ea, ctx, frames):
         fs.close()
 
 
+@pytest.mark.parametrize("radius", [1e4, 1e-2, 1e-3])
+@pytest.mark.parametrize("cluster", [1, 4])
+def test_solve_dogleg_matches_oracle(ea, ctx, fs5, frames, oracle, radius, cluster):
+    """trust_region_strategy = DOGLEG (src/SolveEA.cpp:192) against the oracle's DoglegStrategy restatement; the small
+    radii force the Cauchy-point and interpolated steps, the default one is the Gauss-Newton branch."""
+    O = oracle
+    K = frames["K"]
+    pairs = [(0, 2), (0, 4), (3, 1)]
+    sp = ea.solve_params(point_stride=30, trust_region_strategy=ea.STRATEGY_DOGLEG, initial_trust_region_radius=radius,
+                         max_num_iterations=200, cluster_size=cluster)
+    poses, S = ctx.solve_batch(fs5, [p[0] for p in pairs], fs5, [p[1] for p in pairs], None, sp)
+    opts = O.default_options(strategy=O.STRATEGY_DOGLEG, initial_radius=radius, max_num_iterations=200)
+    for i, (a, b) in enumerate(pairs):
+        xyz, _ = O.get_aX(frames["bgr"][a], frames["depth"][a], K, frames["zscale"])
+        dt, _ = O.get_distance_transform(frames["bgr"][b])
+        op, oS, _ = O.solve(xyz, dt, K, IDENTITY, stride=30, options=opts)
+        assert rot_angle_between(poses[i][:4], op[:4]) < 1e-4 and np.abs(poses[i][4:] - op[4:]).max() < 1e-4
+        assert abs(S[i][0]["iterations"] - oS["iterations"]) <= 2 and S[i][0]["termination"] == oS["termination"]
+        assert abs(S[i][0]["final_cost"] - oS["final_cost"]) <= 1e-5 * oS["final_cost"]
+        assert S[i][0]["rejected"] == oS["rejected"]
+    with pytest.raises(ea.EaError):
+        ctx.solve_batch(fs5, [0], fs5, [1], None, ea.solve_params(trust_region_strategy=2))
+
+
 # ----------------------------------------------------------------------------------------- kernels / tracker
 @pytest.mark.parametrize("kernel", [-1, 1, 2])
 def test_solve_kernel_variants_agree(ea, ctx, fs5, solver_golden, kernel):

@@ -208,3 +208,28 @@ def test_residual_variants_jet_vs_finite_differences(oracle, pair13, frames, num
     np.testing.assert_allclose(e2["sums"], ea_["sums"] + eb_["sums"], rtol=1e-12)
     pose, s = O.solve_views(v2, IDENTITY, O.default_options())
     assert s["termination"] in (1, 2, 3) and s["n_residuals"] == len(e2["raw"])
+
+
+def test_dogleg_strategy(oracle, frames, numpy_pins):
+    """TRUST_REGION + traditional DOGLEG (src/SolveEA.cpp:191-192).  At the Ceres default radius (1e4, in Jacobi-scaled
+    units) both strategies take near Gauss-Newton steps, so they trace the same path; a small starting radius drives the
+    Cauchy-point and interpolation branches, and the solve still lands on scipy's optimum."""
+    O = oracle
+    K = frames["K"]
+    xyz, _ = O.get_aX(frames["bgr"][0], frames["depth"][0], K, frames["zscale"])
+    dt, _ = O.get_distance_transform(frames["bgr"][2])
+    lm, slm, _ = O.solve(xyz, dt, K, IDENTITY, stride=30)
+    dl, sdl, _ = O.solve(xyz, dt, K, IDENTITY, stride=30, options=O.default_options(strategy=O.STRATEGY_DOGLEG))
+    assert sdl["iterations"] == slm["iterations"] and abs(sdl["final_cost"] - slm["final_cost"]) < 1e-7
+    assert rot_angle_between(lm[:4], dl[:4]) < 1e-6 and np.abs(lm[4:] - dl[4:]).max() < 1e-6
+    sp = numpy_pins["scipy_pose_1_3"]
+    for r in (1e-2, 1e-3):
+        p, s, trace = O.solve(xyz, dt, K, IDENTITY, stride=30,
+                              options=O.default_options(strategy=O.STRATEGY_DOGLEG, initial_radius=r, max_num_iterations=200))
+        assert s["termination_name"] == "CONVERGENCE_FUNCTION" and s["iterations"] > slm["iterations"]
+        assert rot_angle_between(p[:4], sp[:4]) < 2e-4 and np.abs(p[4:] - sp[4:]).max() < 2e-4
+        costs = trace[trace[:, 6] > 0, 0]
+        assert np.all(np.diff(costs) <= 0)            # accepted steps only ever decrease the cost
+        assert trace[1, 3] < 0.2 * trace[-1, 5]       # first step was clipped well inside the final region
+    with pytest.raises(TypeError):
+        O.default_options(initial_trust_region_radius=1.0)
