@@ -84,6 +84,7 @@ PROTOTYPES = {
     "ea_frameset_destroy": (_i, [_vp]),
     "ea_frameset_preprocess_host": (_i, [_vp, _i, _i32p, _vp, _vp, _i]),
     "ea_frameset_preprocess_masked": (_i, [_vp, _i, _i32p, _vp, _vp, _vp, _i]),
+    "ea_frameset_preprocess_now_masked": (_i, [_vp, _i, _i32p, _vp, _vp]),
     "ea_frameset_preprocess_device": (_i, [_vp, _i, _i32p, _vp, _vp, _i]),
     "ea_frameset_set_points": (_i, [_vp, _i, _i, _f32p, _i, _i]),
     "ea_frameset_set_dt": (_i, [_vp, _i, _i, _f32p]),

@@ -194,6 +194,13 @@ class FrameSet:
                                                      mask.ctypes.data, roles))
         self.ctx.sync()
 
+    def preprocess_now_masked(self, slots, bgr, mask):
+        """get_distance_transform2_masked[_NoNormalize] (utils.cpp:108-141,166-199): DT of the edges where mask > 1."""
+        slots = np.ascontiguousarray(slots, np.int32)
+        bgr = np.ascontiguousarray(bgr, np.uint8); mask = np.ascontiguousarray(mask, np.uint8)
+        _check(L.lib().ea_frameset_preprocess_now_masked(self._h, len(slots), _ptr(slots, C.c_int32), bgr.ctypes.data, mask.ctypes.data))
+        self.ctx.sync()
+
     def preprocess_device(self, slots, d_bgr, d_depth=0, roles=L.ROLE_BOTH):
         slots = np.ascontiguousarray(slots, np.int32)
         _check(L.lib().ea_frameset_preprocess_device(self._h, len(slots), _ptr(slots, C.c_int32), d_bgr, d_depth or None, roles))

@@ -251,12 +251,12 @@ static int check_slots(ea_frameset* fs, int n, const int32_t* slots) {
 
 }  // extern "C"
 int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const void* d_depth, int roles,
-                       const uint8_t* d_mask) {
+                       const uint8_t* d_mask, const uint8_t* d_now_mask) {
   ea_context* c = fs->ctx;
   EaPrepArgs A;
   std::memset(&A, 0, sizeof A);
   for (int l = 0; l < fs->p.n_levels; ++l) A.lv[l] = fs->lv[l];
-  A.n_levels = fs->p.n_levels; A.slots = d_slots; A.in_bgr = d_bgr; A.in_depth = d_depth; A.in_mask = d_mask;
+  A.n_levels = fs->p.n_levels; A.slots = d_slots; A.in_bgr = d_bgr; A.in_depth = d_depth; A.in_mask = d_mask; A.in_now_mask = d_now_mask;
   A.n_pts = fs->d_npts; A.dt_minmax = fs->d_minmax; A.dt_affine = fs->d_affine; A.overflow = fs->d_overflow;
   A.n = n; A.roles = roles; A.grad_threshold = fs->p.grad_threshold; A.use_median = fs->p.use_median;
   A.dt_normalize = fs->p.dt_normalize;
@@ -313,6 +313,27 @@ int ea_frameset_preprocess_masked(ea_frameset* fs, int n, const int32_t* slots, 
   CU(cudaMemcpyAsync(d_mask, mask, px * n, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(d_slots, slots, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   rc = ea_preprocess_impl(fs, n, d_slots, fs->stage_bgr, fs->stage_depth, roles, d_mask);
+  cudaFreeAsync(d_mask, c->stream);
+  cudaFreeAsync(d_slots, c->stream);
+  return rc;
+}
+
+int ea_frameset_preprocess_now_masked(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr, const uint8_t* mask) {
+  int rc = check_slots(fs, n, slots);
+  if (rc) return rc;
+  if (!bgr || !mask) return ea_fail(EA_ERR_INVALID_ARG, "bgr and mask are required");
+  ea_context* c = fs->ctx;
+  CU(cudaSetDevice(c->device));
+  const size_t px = size_t(fs->p.width) * fs->p.height;
+  if (!fs->stage_bgr) CU(cudaMalloc((void**)&fs->stage_bgr, px * 3 * fs->n_slots));
+  uint8_t* d_mask = nullptr;
+  int32_t* d_slots = nullptr;
+  CU(cudaMallocAsync((void**)&d_mask, px * n, c->stream));
+  CU(cudaMallocAsync((void**)&d_slots, size_t(n) * sizeof(int32_t), c->stream));
+  CU(cudaMemcpyAsync(fs->stage_bgr, bgr, px * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_mask, mask, px * n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_slots, slots, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  rc = ea_preprocess_impl(fs, n, d_slots, fs->stage_bgr, nullptr, EA_ROLE_NOW, nullptr, d_mask);
   cudaFreeAsync(d_mask, c->stream);
   cudaFreeAsync(d_slots, c->stream);
   return rc;

@@ -65,6 +65,7 @@ struct EaPrepArgs {
   const uint8_t* in_bgr;        // [n][h0][w0][3]
   const void* in_depth;         // [n][h0][w0] u16 raw units or f32 metres (depth_type), or null
   const uint8_t* in_mask;       // [n][h0][w0] or null: reference points only where mask > 0 (get_aX_mask, utils.cpp:283-369)
+  const uint8_t* in_now_mask;   // [n][h0][w0] or null: now-frame edges only where mask > 1 (get_distance_transform2_masked, utils.cpp:124-128)
   int* n_pts;                   // [slots][EA_MAX_LEVELS]
   unsigned* dt_minmax;          // [slots][EA_MAX_LEVELS][2]  (min,max of the fixed-point DT)
   float2* dt_affine;            // [slots][EA_MAX_LEVELS]     {scale, shift} of the min-max normalisation
@@ -151,4 +152,4 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
                                    const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries);
 cudaError_t ea_launch_order_by_work(const ea_summary* d_summaries, int n, int n_levels, int32_t* d_order, cudaStream_t stream);
 int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const void* d_depth, int roles,
-                       const uint8_t* d_mask = nullptr);
+                       const uint8_t* d_mask = nullptr, const uint8_t* d_now_mask = nullptr);

@@ -219,9 +219,12 @@ __global__ void __launch_bounds__(E2_TW) k_edge_mask2(const uint8_t* __restrict_
   }
 }
 
-// ---- get_aX_mask (utils.cpp:283-369): keep reference edge points only where mask > 0 (level l samples mask(x<<l, y<<l)) ----
+// ---- masks: keep set bits only where mask > thr (level l samples mask(x<<l, y<<l)) ----------------------------
+//   reference points, get_aX_mask (utils.cpp:335,348): thr 0;  now-frame edges before the DT,
+//   get_distance_transform2_masked[_NoNormalize] (utils.cpp:124-128,182-186: threshold(mask,1,1,BINARY)): thr 1
 __global__ void __launch_bounds__(256) k_mask_ref_bits(uint32_t* __restrict__ ref_bits, const int32_t* __restrict__ dst_slots,
-                                                       const uint8_t* __restrict__ mask, int w0, int h0, int w, int h, int words, int level) {
+                                                       const uint8_t* __restrict__ mask, int w0, int h0, int w, int h, int words, int level,
+                                                       int thr) {
   const int f = blockIdx.y;
   uint32_t* bits = ref_bits + size_t(dst_slots[f]) * h * words;
   const uint8_t* m = mask + size_t(f) * w0 * h0;
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(256) k_mask_ref_bits(uint32_t* __restrict__ re
     unsigned b = bits[i];
     for (unsigned t = b; t; t &= t - 1) {
       const int k = __ffs(t) - 1;
-      if (m[size_t(y << level) * w0 + ((x0 + k) << level)] > 0) keep |= 1u << k;
+      if (m[size_t(y << level) * w0 + ((x0 + k) << level)] > thr) keep |= 1u << k;
     }
     bits[i] = keep;
   }
@@ -587,7 +590,11 @@ static cudaError_t launch_edges_and_points(const EaPrepArgs& A, cudaStream_t str
     }
     ++nl;
     if (want_ref && A.in_mask) {
-      k_mask_ref_bits<<<dim3(unsigned((L.h * L.words + 255) / 256), unsigned(A.n)), 256, 0, stream>>>(L.ref_bits, A.slots, A.in_mask, A.lv[0].w, A.lv[0].h, L.w, L.h, L.words, l);
+      k_mask_ref_bits<<<dim3(unsigned((L.h * L.words + 255) / 256), unsigned(A.n)), 256, 0, stream>>>(L.ref_bits, A.slots, A.in_mask, A.lv[0].w, A.lv[0].h, L.w, L.h, L.words, l, 0);
+      ++nl;
+    }
+    if (A.in_now_mask) {
+      k_mask_ref_bits<<<dim3(unsigned((L.h * L.words + 255) / 256), unsigned(A.n)), 256, 0, stream>>>(L.edge_bits, A.slots, A.in_now_mask, A.lv[0].w, A.lv[0].h, L.w, L.h, L.words, l, 1);
       ++nl;
     }
     if (want_ref) {

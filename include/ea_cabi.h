@@ -187,7 +187,12 @@ int ea_frameset_preprocess_host(ea_frameset* fs, int n, const int32_t* slots, co
 /* get_aX_mask (utils.cpp:283-369): as above from HOST buffers, reference points only where mask [n][h][w] u8 is > 0 */
 int ea_frameset_preprocess_masked(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr,
                                   const void* depth, const uint8_t* mask, int roles);
-/* same, inputs already resident in device memory */
+/* get_distance_transform2_masked[_NoNormalize] (utils.cpp:108-141,166-199): distance transform of the now-frame edges
+ * that lie where mask [n][h][w] u8 is > 1 (the reference's threshold(mask, 1, 1, THRESH_BINARY)); HOST buffers, EA_ROLE_NOW.
+ * With edge_detector = EA_EDGE_CANNY_GRAY (30, 90), dt_kind = EA_DT_CHAMFER3 and dt_normalize = EA_NORM_255 / EA_NORM_NONE
+ * this is the reference's pair of functions; the mask composes with every other detector / DT choice the same way. */
+int ea_frameset_preprocess_now_masked(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr, const uint8_t* mask);
+/* same as ea_frameset_preprocess_host, inputs already resident in device memory */
 int ea_frameset_preprocess_device(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* d_bgr,
                                   const void* d_depth, int roles);
 

@@ -67,9 +67,20 @@ def cv2_stages(bgr, depth):
     cg = cv2.Canny(cv2.cvtColor(out["box3"], cv2.COLOR_RGB2GRAY), 30, 90)
     out["canny_gray_l1"] = cg
     out["dt2_norm"] = cv2.normalize(cv2.distanceTransform(cv2.threshold(cg, 127, 255, cv2.THRESH_BINARY_INV)[1], cv2.DIST_L2, 3), None, 0, 1.0, cv2.NORM_MINMAX)
+    # masked variants (utils.cpp:108-141,166-199): edges * threshold(mask, 1, 1, BINARY), inverted, chamfer DT, [0,255] / raw
+    mb = cv2.threshold(golden_now_mask(), 1, 1, cv2.THRESH_BINARY)[1]
+    dm = cv2.distanceTransform(255 - cv2.multiply(cv2.threshold(cg, 127, 255, cv2.THRESH_BINARY)[1], mb), cv2.DIST_L2, 3)
+    out["dt2_masked_raw"] = dm
+    out["dt2_masked_norm255"] = cv2.normalize(dm, None, 0, 255, cv2.NORM_MINMAX)
     vs2, us2 = np.nonzero((cg > 0) & (depth > 0))
     out["uvd_canny"] = np.stack([us2, vs2, depth[vs2, us2]], 1).astype(np.int32)
     return out
+
+
+def golden_now_mask():
+    """The object mask the masked-DT goldens use (tests/test_gpu_parity.py builds the same one)."""
+    mask = np.zeros((480, 640), np.uint8); mask[60:420, 80:600] = 255; mask[200:260, 300:380] = 1
+    return mask
 
 
 # ---- independent numpy restatement of the residual (not the C++ oracle) ----------

@@ -548,6 +548,31 @@ def test_masked_reference_points(ea, ctx, frames, oracle):
         fs.close()
 
 
+def test_masked_distance_transform(ea, ctx, frames, cv2_stages, oracle):
+    """get_distance_transform2_masked / _masked_NoNormalize (utils.cpp:108-141,166-199): blur -> gray -> Canny(30,90) ->
+    edges * (mask > 1) -> chamfer DT -> [0,255] or raw.  Bit-exact against the oracle stages and the cv2 golden hashes."""
+    O = oracle
+    mask = np.zeros((480, 640), np.uint8); mask[60:420, 80:600] = 255; mask[200:260, 300:380] = 1   # 1 is NOT > 1: masked out
+    for norm, key in ((ea.NORM_255, "dt2_masked_norm255"), (ea.NORM_NONE, "dt2_masked_raw")):
+        fp = ea.frame_params(edge_detector=ea.EDGE_CANNY_GRAY, canny_low=30.0, canny_high=90.0, canny_l2=0, dt_normalize=norm, n_levels=2)
+        fs = ea.FrameSet(ctx, fp, 2)
+        try:
+            fs.preprocess_now_masked([1, 0], frames["bgr"][[0, 2]], np.stack([mask, mask]))
+            for slot, i in ((1, 0), (0, 2)):
+                cg = O.canny(O.rgb2gray(O.box3(frames["bgr"][i])), 30, 90, l2=False)
+                e = np.where(mask > 1, cg, 0).astype(np.uint8)
+                d = O.chamfer3_dt((255 - e).astype(np.uint8))
+                want = O.normalize_minmax(d, 0, 255) if norm == ea.NORM_255 else d
+                np.testing.assert_array_equal(fs.dt(slot), want)
+                assert sha(fs.dt(slot)) == cv2_stages["frames"][i][key]
+                hb = O.half_linear(frames["bgr"][i])
+                c1 = O.canny(O.rgb2gray(O.box3(hb)), 30, 90, l2=False)
+                d1 = O.chamfer3_dt((255 - np.where(mask[::2, ::2] > 1, c1, 0)).astype(np.uint8))
+                np.testing.assert_array_equal(fs.dt(slot, 1), O.normalize_minmax(d1, 0, 255) if norm == ea.NORM_255 else d1)
+        finally:
+            fs.close()
+
+
 def test_float_depth_and_zero_depth_policy(ea, ctx, frames, oracle):
     """SolveEA's depth convention (src/SolveEA.cpp:27,68-69): CV_32F metres, edge pixels without depth kept at Z = 1."""
     O = oracle

@@ -87,6 +87,10 @@ def test_canny_and_exact_edt_bit_exact_vs_cv2(oracle, frames, cv2_stages, i):
     assert sha(cg) == g["canny_gray_l1"]
     inv = np.where(cg > 127, 0, 255).astype(np.uint8)
     assert sha(O.normalize_minmax(O.chamfer3_dt(inv), 0, 1)) == g["dt2_norm"]
+    # masked variants (utils.cpp:108-141,166-199): only edges under mask > 1 seed the distance transform
+    mask = np.zeros((480, 640), np.uint8); mask[60:420, 80:600] = 255; mask[200:260, 300:380] = 1
+    dm = O.chamfer3_dt((255 - np.where(mask > 1, cg, 0)).astype(np.uint8))
+    assert sha(dm) == g["dt2_masked_raw"] and sha(O.normalize_minmax(dm, 0, 255)) == g["dt2_masked_norm255"]
 
 
 def test_exact_edt_edge_cases(oracle):
