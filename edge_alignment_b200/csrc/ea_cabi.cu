@@ -4,8 +4,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
+#include <vector>
 #include <new>
 
 #include "ea_internal.h"
@@ -372,7 +374,19 @@ int ea_frameset_set_points(ea_frameset* fs, int slot, int level, const float* pt
   CU(cudaSetDevice(c->device));
   EaLevelDesc& D = fs->h_desc[size_t(slot) * EA_MAX_LEVELS + level];
   D.pts_mode = mode;
-  if (n > 0) CU(cudaMemcpyAsync(const_cast<float4*>(D.pts), pts4, size_t(n) * 16, cudaMemcpyHostToDevice, c->stream));
+  std::vector<uint2> packed;
+  if (mode == EA_POINTS_PIXEL) {      // the device keeps pixel points as 8 bytes {u | v << 16, raw depth}
+    packed.resize(size_t(n));
+    for (int i = 0; i < n; ++i) {
+      const float u = pts4[4 * i], v = pts4[4 * i + 1];
+      if (!(u >= 0.0f && u <= 65535.0f && v >= 0.0f && v <= 65535.0f) || u != std::floor(u) || v != std::floor(v))
+        return ea_fail(EA_ERR_INVALID_ARG, "EA_POINTS_PIXEL point %d: (%g, %g) is not an integer pixel position (use EA_POINTS_XYZ)", i, u, v);
+      packed[size_t(i)] = ea_pack_pixel_point(unsigned(u), unsigned(v), pts4[4 * i + 2]);
+    }
+    if (n > 0) CU(cudaMemcpyAsync(const_cast<void*>(D.pts), packed.data(), size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
+  } else if (n > 0) {
+    CU(cudaMemcpyAsync(const_cast<void*>(D.pts), pts4, size_t(n) * 16, cudaMemcpyHostToDevice, c->stream));
+  }
   CU(cudaMemcpyAsync(const_cast<int*>(D.n_pts), &n, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(fs->d_desc + size_t(slot) * EA_MAX_LEVELS + level, &D, sizeof D, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -412,8 +426,20 @@ int ea_frameset_get_points(ea_frameset* fs, int slot, int level, float* pts4, in
   const int k = std::min(m, cap);
   if (k > 0 && pts4) {
     ea_context* c = fs->ctx;
-    CU(cudaMemcpyAsync(pts4, fs->lv[level].pts + size_t(slot) * fs->lv[level].cap, size_t(k) * 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    const EaLevelDesc& D = fs->h_desc[size_t(slot) * EA_MAX_LEVELS + level];
+    if (D.pts_mode == EA_POINTS_PIXEL) {
+      std::vector<uint2> packed(static_cast<size_t>(k));
+      CU(cudaMemcpyAsync(packed.data(), D.pts, size_t(k) * 8, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      for (int i = 0; i < k; ++i) {
+        float d; std::memcpy(&d, &packed[size_t(i)].y, 4);
+        pts4[4 * i] = float(packed[size_t(i)].x & 0xffffu); pts4[4 * i + 1] = float(packed[size_t(i)].x >> 16);
+        pts4[4 * i + 2] = d; pts4[4 * i + 3] = 1.0f;
+      }
+    } else {
+      CU(cudaMemcpyAsync(pts4, D.pts, size_t(k) * 16, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
   }
   return rc;
 }

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstring>
+
 #include "ea_cabi.h"
 
 #define EA_WARP 32
@@ -20,7 +22,7 @@
 #define EA_SUMS 29  // reduced totals: [0..20] H upper-tri, [21..26] b, [27] #failed, [28] cost
 
 struct EaLevelDesc {   // one per (slot, level); lives in device memory
-  const float4* pts;   // point stream (EA_POINTS_PIXEL: {u,v,raw depth,1}; EA_POINTS_XYZ: {X,Y,Z,1})
+  const void* pts;     // point stream, see EaPtStream (EA_POINTS_PIXEL: 8 B packed {u | v << 16, raw depth}; EA_POINTS_XYZ: float4 {X,Y,Z,1})
   const int* n_pts;    // device-resident count (written by the compaction kernel)
   const float* dt;     // raw chamfer distance transform [h][w] f32 (pixels)
   const float2* dt_affine;  // {scale, shift} of cv::normalize(MINMAX): sampled value = raw * scale + shift
@@ -114,19 +116,52 @@ __device__ __forceinline__ void ea_floor_frac(double x, int& i, float& frac) {
   frac = float(x - double(i));
 }
 
-// Warp, project, bicubic lookup for one edge point.
+// Point stream element.  Pixel points are 8 bytes: integer pixel coordinates (images up to 65535 px a side) and the raw
+// depth as f32 (exact for u16 and f32 depth maps) -- half the bytes of a float4 per evaluation, and no dead load
+// component for the register allocator to recycle while the prefetch is still in flight.
+template <bool XYZ> struct EaPtStream;
+template <> struct EaPtStream<false> {
+  typedef uint2 T;
+  static __device__ __forceinline__ T load(const void* base, size_t i) { return __ldg(reinterpret_cast<const uint2*>(base) + i); }
+  static __device__ __forceinline__ T pad() { return make_uint2(0u, 0x3f800000u); }
+  static __device__ __forceinline__ void unpack(const T r, double& a0, double& a1, double& a2) {
+    a0 = double(int(r.x & 0xffffu)); a1 = double(int(r.x >> 16)); a2 = double(__uint_as_float(r.y));
+  }
+  static __device__ __forceinline__ float4 as_float4(const T r) {
+    return make_float4(float(r.x & 0xffffu), float(r.x >> 16), __uint_as_float(r.y), 1.0f);
+  }
+};
+template <> struct EaPtStream<true> {
+  typedef float4 T;
+  static __device__ __forceinline__ T load(const void* base, size_t i) { return __ldg(reinterpret_cast<const float4*>(base) + i); }
+  static __device__ __forceinline__ T pad() { return make_float4(0.f, 0.f, 1.f, 0.f); }
+  static __device__ __forceinline__ void unpack(const T r, double& a0, double& a1, double& a2) {
+    a0 = double(r.x); a1 = double(r.y); a2 = double(r.z);
+  }
+  static __device__ __forceinline__ float4 as_float4(const T r) { return r; }
+};
+__host__ __device__ __forceinline__ uint2 ea_pack_pixel_point(unsigned u, unsigned v, float depth) {
+  uint2 r; r.x = (u & 0xffffu) | (v << 16);
+#ifdef __CUDA_ARCH__
+  r.y = __float_as_uint(depth);
+#else
+  memcpy(&r.y, &depth, 4);
+#endif
+  return r;
+}
+
+// Warp, project, bicubic lookup for one edge point (a0, a1, a2) = (u, v, raw depth) or (X, Y, Z).
 template <bool XYZ>
-__device__ __forceinline__ void ea_point_eval(const float4 p, const EaLevelGeom& now, double inv_depth_scale, const EaPose& P,
+__device__ __forceinline__ void ea_point_eval(const double a0, const double a1, const double a2, const EaLevelGeom& now,
+                                              double inv_depth_scale, const EaPose& P,
                                               const float* __restrict__ dt, const float2 affine, EaPointEval& o) {
-  const double a0 = double(p.x), a1 = double(p.y);
   double q0, q1, q2;
   if (XYZ) {
-    const double a2 = double(p.z);
     q0 = fma(P.A[0], a0, fma(P.A[1], a1, fma(P.A[2], a2, P.tt[0])));
     q1 = fma(P.A[3], a0, fma(P.A[4], a1, fma(P.A[5], a2, P.tt[1])));
     q2 = fma(P.A[6], a0, fma(P.A[7], a1, fma(P.A[8], a2, P.tt[2])));
   } else {
-    const double Z = double(p.z) * inv_depth_scale;
+    const double Z = a2 * inv_depth_scale;
     q0 = fma(Z, fma(P.A[0], a0, fma(P.A[1], a1, P.A[2])), P.tt[0]);
     q1 = fma(Z, fma(P.A[3], a0, fma(P.A[4], a1, P.A[5])), P.tt[1]);
     q2 = fma(Z, fma(P.A[6], a0, fma(P.A[7], a1, P.A[8])), P.tt[2]);

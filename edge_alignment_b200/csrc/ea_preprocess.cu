@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const uint32_t* __restri
   const int f = blockIdx.x, slot = dst_slots[f];
   const uint32_t* bits = ref_bits + size_t(slot) * h * words;
   const D* dep = depth + (src_slots ? size_t(src_slots[f]) : size_t(f)) * frame_stride_px;
-  float4* out = pts + size_t(slot) * cap;
+  uint2* out = reinterpret_cast<uint2*>(pts + size_t(slot) * cap);   // 8-byte pixel points at the head of the slot's 16 B x cap area
   const int nw = h * words;
   const int per = (nw + CP_THREADS - 1) / CP_THREADS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const uint32_t* __restri
       if (rank < cap) {
         float dz = float(dep[size_t(y) * w + x]);
         if (zero_to_one && dz == 0.0f) dz = depth_one;               // src/SolveEA.cpp:69
-        out[rank] = make_float4(float(x), float(y), dz, 1.0f);
+        out[rank] = ea_pack_pixel_point(unsigned(x), unsigned(y), dz);
       }
       ++rank;
     }

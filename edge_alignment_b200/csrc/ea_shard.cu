@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(GV_THREADS) k_view_eval_sums(EaLevelDesc rd, E
   for (int base = j0 + warp * 32; base < j1; base += GV_THREADS) {
     const int j = base + lane;
     if (j < j1) {
-      const float4 p = __ldg(rd.pts + size_t(j) * sp.point_stride);
+      const float4 p = EaPtStream<XYZ>::as_float4(EaPtStream<XYZ>::load(rd.pts, size_t(j) * sp.point_stride));
       float f, w, rho0, J[6];
       const bool fail = ea_point_eval_general<XYZ>(p, ng, inv_depth_scale, P, nd.dt, affine, sp.loss_type, float(sp.loss_scale), f, w, rho0, J);
       ea_accumulate(acc, J, f * w);
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) k_view_eval_points(EaLevelDesc rd, EaLeve
   ea_pose_setup_general<XYZ>(pose7, rg, ng, V, P);
   const float2 affine = *nd.dt_affine;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_res; j += gridDim.x * blockDim.x) {
-    const float4 p = __ldg(rd.pts + size_t(j) * sp.point_stride);
+    const float4 p = EaPtStream<XYZ>::as_float4(EaPtStream<XYZ>::load(rd.pts, size_t(j) * sp.point_stride));
     float f, w, rho0, J[6];
     const bool fail = ea_point_eval_general<XYZ>(p, ng, inv_depth_scale, P, nd.dt, affine, sp.loss_type, float(sp.loss_scale), f, w, rho0, J);
     if (raw) raw[j] = double(f);

@@ -29,7 +29,7 @@ namespace cg = cooperative_groups;
 
 struct EaMsg {  // boss -> all threads of the cluster
   double cand[7];
-  const float4* pts;
+  const void* pts;
   const float* dt;
   float2 affine;
   int n_res, level, pts_mode, cmd;
@@ -187,9 +187,12 @@ __global__ void __launch_bounds__(256) ea_k_eval_points(EaLevelDesc rd, EaLevelD
   const int n_round = (n_res + 31) & ~31;   // keep warps converged: the gather's fast path votes with __all_sync
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
     const bool valid = j < n_res;
-    const float4 p = valid ? __ldg(rd.pts + size_t(j) * sp.point_stride) : make_float4(0.f, 0.f, 1.f, 0.f);
+    typedef EaPtStream<XYZ> PS;
+    const typename PS::T p = valid ? PS::load(rd.pts, size_t(j) * sp.point_stride) : PS::pad();
     EaPointEval e;
-    ea_point_eval<XYZ>(p, ng, inv_depth_scale, P, nd.dt, affine, e);
+    double a0, a1, a2;
+    PS::unpack(p, a0, a1, a2);
+    ea_point_eval<XYZ>(a0, a1, a2, ng, inv_depth_scale, P, nd.dt, affine, e);
     float rho0;
     const float w = ea_loss_eval(sp.loss_type, float(sp.loss_scale), e.f, rho0);
     float J[6];

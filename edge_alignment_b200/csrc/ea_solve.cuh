@@ -281,7 +281,7 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
 // Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads and leave per-warp partial
 // sums in S.part / S.cpart (caller synchronises).
 template <bool XYZ, int THREADS>
-__device__ __forceinline__ void ea_eval_slice(const float4* __restrict__ pts, const float* __restrict__ dt, const float2 affine,
+__device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, const float* __restrict__ dt, const float2 affine,
                                               const EaLevelGeom& ng,
                                               double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, int j0,
                                               int j1, double (*part)[EA_NSUM], double* cpart) {
@@ -294,14 +294,17 @@ __device__ __forceinline__ void ea_eval_slice(const float4* __restrict__ pts, co
   double acc64 = 0.0, cost64 = 0.0;
   int since_flush = 0;
   int j = j0 + warp * 32 + lane;
-  float4 p_next = (j < j1) ? __ldg(pts + size_t(j) * stride) : make_float4(0.f, 0.f, 1.f, 0.f);
+  typedef EaPtStream<XYZ> PS;
+  typename PS::T p_next = (j < j1) ? PS::load(pts, size_t(j) * stride) : PS::pad();
   for (int base = j0 + warp * 32; base < j1; base += THREADS) {
-    const float4 p = p_next;
+    const typename PS::T p = p_next;
     const bool valid = j < j1;
     j += THREADS;
-    if (j < j1) p_next = __ldg(pts + size_t(j) * stride);   // prefetch the next point before the gather
+    if (j < j1) p_next = PS::load(pts, size_t(j) * stride);   // prefetch the next point before the gather
     EaPointEval e;
-    ea_point_eval<XYZ>(p, ng, inv_depth_scale, P, dt, affine, e);
+    double a0, a1, a2;
+    PS::unpack(p, a0, a1, a2);
+    ea_point_eval<XYZ>(a0, a1, a2, ng, inv_depth_scale, P, dt, affine, e);
     float rho0;
     float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
     if (!valid) { w = 0.0f; rho0 = 0.0f; e.f = 0.0f; e.fail = false; }

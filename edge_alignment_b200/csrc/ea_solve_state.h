@@ -8,7 +8,7 @@
 struct EaPairState {              // one per pair of the batch
   EaLmState lm;
   double cand[7];                 // candidate pose of the evaluation in flight
-  const float4* pts;
+  const void* pts;
   const float* dt;
   float2 affine;
   int n_res, level, pts_mode, n_chunks;

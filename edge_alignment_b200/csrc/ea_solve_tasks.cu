@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(EA_TASK_THREADS, EA_TASK_MIN_CTAS) ea_k_solve_
     EaPairState* st = A.states + pair;
     // pair state was written by another SM and changes every evaluation: read it around L1
     if (tid < 7) S.cand[tid] = __ldcg(&st->cand[tid]);
-    const float4* pts = reinterpret_cast<const float4*>(__ldcg(reinterpret_cast<const unsigned long long*>(&st->pts)));
+    const void* pts = reinterpret_cast<const void*>(__ldcg(reinterpret_cast<const unsigned long long*>(&st->pts)));
     const float* dt = reinterpret_cast<const float*>(__ldcg(reinterpret_cast<const unsigned long long*>(&st->dt)));
     const float2 affine = __ldcg(&st->affine);
     const int n_res = __ldcg(&st->n_res), level = __ldcg(&st->level), pts_mode = __ldcg(&st->pts_mode), n_chunks = __ldcg(&st->n_chunks);
