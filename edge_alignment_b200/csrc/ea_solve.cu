@@ -13,6 +13,8 @@
 #include <cooperative_groups.h>
 
 #include "ea_internal.h"
+#include <cstdlib>
+
 #include "ea_solve.cuh"
 
 namespace cg = cooperative_groups;
@@ -244,7 +246,9 @@ cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm
   cudaLaunchAttribute attr[1];
   if (cluster_size <= 1) {
     // persistent CTAs (EA_SOLVE_MIN_CTAS per SM) pulling pairs from the work queue
-    const int max_ctas = sm_count * EA_SOLVE_MIN_CTAS;
+    int max_ctas = sm_count * EA_SOLVE_MIN_CTAS;
+    static const int env_ctas = getenv("EA_SOLVE_MAX_CTAS") ? atoi(getenv("EA_SOLVE_MAX_CTAS")) : 0;   // experiment knob
+    if (env_ctas > 0 && env_ctas < max_ctas) max_ctas = env_ctas;
     cfg.gridDim = dim3(unsigned(A.n_pairs < max_ctas ? A.n_pairs : max_ctas));
     cfg.numAttrs = 0;
     return cudaLaunchKernelEx(&cfg, ea_k_solve_batch<EA_SOLVE_THREADS, false>, A);

@@ -275,7 +275,7 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
 
 // ---- slice evaluation shared by every solve kernel ----------------------------------------------------------
 #ifndef EA_FLUSH_EVERY
-#define EA_FLUSH_EVERY 8   // points per thread between fp32 -> fp64 flushes of the normal-equation slots
+#define EA_FLUSH_EVERY 16  // points per thread between fp32 -> fp64 flushes of the normal-equation slots (measured: 8 -> 16 = -1.7 %)
 #endif
 
 // Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads and leave per-warp partial
