@@ -528,6 +528,166 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
   }
 }
 
+// ---- chamfer 3x3 DT, one WARP per (frame, level) ---------------------------------------------------------------------
+// Same recurrence and results as k_chamfer_dt.  Each lane owns a contiguous strip of P pixels of the row, so the
+// horizontal min-plus scan is P register steps plus ONE 5-step warp scan per row: no shared memory, no block barrier, and
+// the per-row overhead is spread over P = 20 pixels at 640 px instead of 4 (the block kernel spends most of its
+// instructions on scan / carry plumbing).  592 frames x 3 levels = 1 776 independent warps keep every scheduler busy
+// without any of them waiting for another.  Used when every level is at most 32 * DTW_PMAX pixels wide.
+#define DTW_PMAX 20
+template <int P, bool BACKWARD>
+__device__ __forceinline__ void dtw_row_scan(int (&d)[P], const int (&cval)[P], const int lane) {
+  // A single warp per scheduler cannot hide latency with other warps, so the row step is arranged for short dependency
+  // chains: with the ramp HV * position taken out, the strip total is a tree minimum (feeds the warp scan at once) and the
+  // strip-local prefix minimum is a two-level scan that overlaps the shuffles.
+  static_assert(P % 4 == 0, "strip length must be a multiple of 4");
+  int e[P];                         // e[kk] = value at scan position kk minus HV * kk
+#pragma unroll
+  for (int kk = 0; kk < P; ++kk) e[kk] = cval[BACKWARD ? (P - 1 - kk) : kk] - DT_HV * kk;
+  int m[P / 4];
+#pragma unroll
+  for (int g = 0; g < P / 4; ++g) m[g] = min(min(e[4 * g], e[4 * g + 1]), min(e[4 * g + 2], e[4 * g + 3]));
+  int mt = m[0];
+#pragma unroll
+  for (int g = 1; g < P / 4; ++g) mt = min(mt, m[g]);
+  const int run = min(mt + DT_HV * (P - 1), DT_INF);          // the strip's last pixel, ignoring upstream strips
+  const int pos = BACKWARD ? (31 - lane) : lane;
+  constexpr int stepP = DT_HV * P;
+  int s = run - stepP * pos;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = BACKWARD ? __shfl_down_sync(0xffffffffu, s, o) : __shfl_up_sync(0xffffffffu, s, o);
+    if (pos >= o) s = min(s, t);
+  }
+  const int out = s + stepP * pos;   // final value of this lane's last pixel along the scan
+  int carry = BACKWARD ? __shfl_down_sync(0xffffffffu, out, 1) : __shfl_up_sync(0xffffffffu, out, 1);
+  if (pos == 0) carry = DT_INF;
+  carry = min(carry, DT_INF);
+  // strip-local prefix minimum (independent of the shuffles above)
+  int gp[P / 4];                    // minimum of all groups before g
+  gp[0] = DT_INF;
+#pragma unroll
+  for (int g = 1; g < P / 4; ++g) gp[g] = min(gp[g - 1], m[g - 1]);
+#pragma unroll
+  for (int g = 0; g < P / 4; ++g) {
+    int pm = gp[g];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = 4 * g + i;
+      pm = min(pm, e[kk]);
+      const int v = min(min(pm, carry + DT_HV) + DT_HV * kk, DT_INF);    // min(local, carry + HV * (kk + 1))
+      d[BACKWARD ? (P - 1 - kk) : kk] = v;
+    }
+  }
+}
+
+template <int P>
+__device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, const int slot, const int lane) {
+  const EaPrepLevel& L = A.lv[level];
+  const int w = L.w, h = L.h, words = L.words;
+  const uint32_t* bits = (A.use_median ? L.med_bits : L.edge_bits) + size_t(slot) * h * words;
+  int* gi = reinterpret_cast<int*>(L.dt + size_t(slot) * w * h);
+  float* gf = L.dt + size_t(slot) * w * h;
+  const int x0 = lane * P;
+  const bool on = x0 < w;
+  const bool vec_ok = (P % 4 == 0) && ((w & 3) == 0);
+  const int wi = x0 >> 5, sh = x0 & 31;
+  const bool two = on && (wi + 1 < words);
+  int d[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) d[k] = DT_INF;
+  // ---------------- forward pass ----------------
+  unsigned b0 = on ? bits[wi] : 0u, b1 = two ? bits[wi + 1] : 0u;
+  for (int y = 0; y < h; ++y) {
+    const unsigned ebits = __funnelshift_r(b0, b1, sh);
+    if (y + 1 < h) {   // prefetch the next row's mask words
+      b0 = on ? bits[size_t(y + 1) * words + wi] : 0u;
+      b1 = two ? bits[size_t(y + 1) * words + wi + 1] : 0u;
+    }
+    int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
+    int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
+    if (lane == 0) pl = DT_INF;
+    if (lane == 31) pr = DT_INF;
+    int cval[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const int a = (k == 0) ? pl : d[k - 1];
+      const int c = (k == P - 1) ? pr : d[k + 1];
+      int v = min(min(a, c) + DT_DG, d[k] + DT_HV);
+      if ((ebits >> k) & 1u) v = 0;
+      if (x0 + k >= w) v = DT_INF;
+      cval[k] = min(v, DT_INF);
+    }
+    dtw_row_scan<P, false>(d, cval, lane);
+#pragma unroll
+    for (int k = 0; k < P; ++k) if (x0 + k >= w) d[k] = DT_INF;
+    if (on) dt_store_row<P, int>(gi + size_t(y) * w, x0, w, d, vec_ok);
+  }
+  // ---------------- backward pass ----------------
+#pragma unroll
+  for (int k = 0; k < P; ++k) d[k] = DT_INF;
+  unsigned vmax = 0, vmin = 0xFFFFFFFFu;
+  int t_next[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) t_next[k] = DT_INF;
+  __syncwarp();   // the forward rows were written by other lanes' neighbours only through registers; own rows are re-read below
+  if (on) dt_load_row<P>(gi + size_t(h - 1) * w, x0, w, t_next, vec_ok);
+  for (int y = h - 1; y >= 0; --y) {
+    int t0[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) t0[k] = t_next[k];
+    if (y > 0 && on) dt_load_row<P>(gi + size_t(y - 1) * w, x0, w, t_next, vec_ok);
+    int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
+    int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
+    if (lane == 0) pl = DT_INF;
+    if (lane == 31) pr = DT_INF;
+    int cval[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const int a = (k == 0) ? pl : d[k - 1];
+      const int c = (k == P - 1) ? pr : d[k + 1];
+      int v = min(t0[k], min(min(a, c) + DT_DG, d[k] + DT_HV));
+      if (x0 + k >= w) v = DT_INF;
+      cval[k] = min(v, DT_INF);
+    }
+    dtw_row_scan<P, true>(d, cval, lane);
+    float outv[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      outv[k] = 0.0f;
+      if (x0 + k >= w) { d[k] = DT_INF; continue; }
+      const unsigned t = (d[k] >= DT_INF) ? DT_DISTMAX : unsigned(d[k]);
+      vmax = max(vmax, t); vmin = min(vmin, t);
+      outv[k] = float(t) * (1.0f / 65536.0f);
+    }
+    if (on) dt_store_row<P, float>(gf + size_t(y) * w, x0, w, outv, vec_ok);
+  }
+  const unsigned mx = __reduce_max_sync(0xffffffffu, vmax);
+  const unsigned mn = __reduce_min_sync(0xffffffffu, vmin);
+  if (lane == 0) {
+    A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2] = mn;
+    A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2 + 1] = mx;
+    // cv::normalize(NORM_MINMAX, alpha = 0, beta): scale = beta / (max - min), shift = -min * scale (double, then float)
+    float2 aff = make_float2(1.0f, 0.0f);
+    if (A.dt_normalize != EA_NORM_NONE) {
+      const double beta = (A.dt_normalize == EA_NORM_255) ? 255.0 : 1.0;
+      const float fmn = float(mn) * (1.0f / 65536.0f), fmx = float(mx) * (1.0f / 65536.0f);
+      const double range = double(fmx) - double(fmn);
+      const double scale = beta * (range > 2.220446049250313e-16 ? 1.0 / range : 0.0);
+      aff = make_float2(float(scale), float(0.0 - double(fmn) * scale));
+    }
+    A.dt_affine[slot * EA_MAX_LEVELS + level] = aff;
+  }
+}
+
+__global__ void __launch_bounds__(32) k_chamfer_dt_warp(const __grid_constant__ EaPrepArgs A) {
+  const int level = blockIdx.y, slot = A.slots[blockIdx.x], lane = threadIdx.x;
+  const int per = (A.lv[level].w + 31) / 32;
+  if (per <= 8) dtw_level<8>(A, level, slot, lane);
+  else if (per <= 12) dtw_level<12>(A, level, slot, lane);
+  else dtw_level<DTW_PMAX>(A, level, slot, lane);
+}
+
 // ---- normalised copy of one DT (read-back for parity tests): dst = raw * scale + shift, exactly as cv::normalize ----
 __global__ void __launch_bounds__(256) k_dt_normalized_copy(const float* __restrict__ raw, const float2* __restrict__ affine, int npx,
                                                             float* __restrict__ out) {
@@ -624,7 +784,14 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
       k_median_bits<<<grid, 256, 0, stream>>>(A);
       ++nl;
     }
-    // every level of every frame in one launch: CTA (frame, level); block sized for level 0
+    static const int env_block = getenv("EA_DT_BLOCK") ? atoi(getenv("EA_DT_BLOCK")) : 0;   // A/B knob: force the block kernel
+    if (L0.w <= 32 * DTW_PMAX && !env_block) {   // one warp per (frame, level); level 0 CTAs are scheduled first
+      k_chamfer_dt_warp<<<dim3(unsigned(A.n), unsigned(A.n_levels)), 32, 0, stream>>>(A);
+      ++nl;
+      if (launches) *launches = nl;
+      return cudaGetLastError();
+    }
+    // wider images: every level of every frame in one launch, CTA (frame, level); block sized for level 0
     int P = (L0.w <= 4096) ? 4 : 8;
     if (const char* e = getenv("EA_DT_P")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v > P) P = v; }   // tuning knob
     const int threads = (((L0.w + P - 1) / P + 31) / 32) * 32;
