@@ -212,6 +212,7 @@ def main():
     fp = ea.frame_params(n_levels=N_LEVELS)
     sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=HUBER_A, cluster_size=args.cluster)
     tracker = ea.Tracker(ctx, fp, sp, S, KEYFRAME_INTERVAL)
+    tracker.set_inputs_ready(True)      # every frame is resident and complete in HBM before the timed region starts
     frame_b = W * H * 3 * S; frame_d = W * H * 2 * S
 
     def run_device(first, last):

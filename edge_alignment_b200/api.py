@@ -280,6 +280,10 @@ class Tracker:
         _check(L.lib().ea_tracker_frame_index(self._h, C.byref(n)))
         return n.value
 
+    def set_inputs_ready(self, ready=True):
+        """Device frames passed to step_device are complete at call time: lets frame t+1's preprocessing overlap frame t's solve."""
+        _check(L.lib().ea_tracker_set_inputs_ready(self._h, 1 if ready else 0))
+
     def step_device(self, d_bgr, d_depth=0):
         _check(L.lib().ea_tracker_step_device(self._h, d_bgr, d_depth or None))
 

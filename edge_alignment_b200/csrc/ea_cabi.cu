@@ -111,7 +111,8 @@ int ea_profile_enable(ea_context* c, int on) {
 }
 int ea_profile_read(ea_context* c, double* pre_ms, int* n_pre, double* solve_ms, int* n_solve) {
   if (!c) return ea_fail(EA_ERR_INVALID_ARG, "null context");
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());        // trackers preprocess on their own stream
   double tot[2] = {0, 0}; int cnt[2] = {0, 0};
   for (int k = 0; k < 2; ++k) {
     for (size_t i = 0; i + 1 < c->ev[k].size(); i += 2) {
@@ -253,8 +254,9 @@ static int check_slots(ea_frameset* fs, int n, const int32_t* slots) {
 
 }  // extern "C"
 int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const void* d_depth, int roles,
-                       const uint8_t* d_mask, const uint8_t* d_now_mask) {
+                       const uint8_t* d_mask, const uint8_t* d_now_mask, cudaStream_t stream) {
   ea_context* c = fs->ctx;
+  if (!stream) stream = c->stream;
   EaPrepArgs A;
   std::memset(&A, 0, sizeof A);
   for (int l = 0; l < fs->p.n_levels; ++l) A.lv[l] = fs->lv[l];
@@ -270,8 +272,8 @@ int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uin
   A.depth_one = fs->p.depth_type == EA_DEPTH_F32 ? 1.0f : float(fs->p.depth_scale);
   if (A.edge_detector != EA_EDGE_LAPLACIAN) A.use_median = 0;   // the Canny pipelines of the reference have no median step
   int nl = 0;
-  EaProfileScope prof(c, 0);
-  cudaError_t e = ea_launch_preprocess(A, c->sm_count, c->stream, &nl);
+  EaProfileScope prof(c, 0, stream);
+  cudaError_t e = ea_launch_preprocess(A, c->sm_count, stream, &nl);
   c->launches += nl;
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "preprocess launch: %s", cudaGetErrorString(e));
   return EA_OK;

@@ -109,13 +109,13 @@ struct ea_context {
   bool profile = false;
   std::vector<cudaEvent_t> ev[2];
 };
-struct EaProfileScope {   // records a start/stop event pair on the context stream when profiling is on
-  ea_context* c; int kind;
-  EaProfileScope(ea_context* c_, int kind_) : c(c_), kind(kind_) {
-    if (c->profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); c->ev[kind].push_back(e); }
+struct EaProfileScope {   // records a start/stop event pair on the launching stream when profiling is on
+  ea_context* c; int kind; cudaStream_t s;
+  EaProfileScope(ea_context* c_, int kind_, cudaStream_t s_ = nullptr) : c(c_), kind(kind_), s(s_ ? s_ : c_->stream) {
+    if (c->profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); c->ev[kind].push_back(e); }
   }
   ~EaProfileScope() {
-    if (c->profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); c->ev[kind].push_back(e); }
+    if (c->profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); c->ev[kind].push_back(e); }
   }
 };
 
@@ -152,4 +152,4 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
                                    const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries);
 cudaError_t ea_launch_order_by_work(const ea_summary* d_summaries, int n, int n_levels, int32_t* d_order, cudaStream_t stream);
 int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const void* d_depth, int roles,
-                       const uint8_t* d_mask = nullptr, const uint8_t* d_now_mask = nullptr);
+                       const uint8_t* d_mask = nullptr, const uint8_t* d_now_mask = nullptr, cudaStream_t stream = nullptr);

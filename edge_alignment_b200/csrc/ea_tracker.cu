@@ -10,12 +10,18 @@
 
 struct ea_tracker {
   ea_context* ctx = nullptr;
-  ea_frameset* fs = nullptr;       // 2 * n_streams slots: stream s owns slots 2s and 2s+1
+  ea_frameset* fs = nullptr;       // 3 * n_streams slots: stream s owns slots 3s, 3s+1, 3s+2 (key frame, frame being aligned, frame being preprocessed)
   ea_solve_params sp;
   int n_streams = 0, interval = 1, n_levels = 1;
   int frame = 0;                   // frames seen so far
-  int key_parity = 0;              // slot parity currently holding the key frames
-  int32_t* d_slots[2] = {nullptr, nullptr};   // [n_streams] slot ids of parity 0 / 1
+  int key_set = 0;                 // slot set currently holding the key frames
+  int prev_key = 0, prev_now = -1; // slot sets the most recently enqueued solve reads
+  int32_t* d_slots[3] = {nullptr, nullptr, nullptr};   // [n_streams] slot ids of set 0 / 1 / 2
+  // frame t+1 is preprocessed on its own stream while frame t is still being aligned: its kernels fill the SMs the
+  // persistent solve kernel releases during its tail
+  cudaStream_t prep_stream = nullptr;
+  cudaEvent_t ev_prep[2] = {nullptr, nullptr}, ev_solved[2] = {nullptr, nullptr};
+  int inputs_ready = 0;            // ea_tracker_set_inputs_ready: device inputs are complete at call time (not stream-ordered)
   double* d_poses = nullptr;       // warm-start table [n_streams][7]
   double* d_result = nullptr;      // poses of the latest step [n_streams][7]
   double* d_identity = nullptr;    // [n_streams][7]
@@ -42,23 +48,27 @@ int ea_tracker_create(ea_context* ctx, const ea_frame_params* fp, const ea_solve
   ea_tracker* t = new (std::nothrow) ea_tracker();
   if (!t) return ea_fail(EA_ERR_INVALID_ARG, "out of host memory");
   t->ctx = ctx; t->sp = *sp; t->n_streams = n_streams; t->interval = keyframe_interval; t->n_levels = fp->n_levels;
-  int rc = ea_frameset_create(ctx, fp, 2 * n_streams, &t->fs);
+  int rc = ea_frameset_create(ctx, fp, 3 * n_streams, &t->fs);
   if (rc) { delete t; return rc; }
-  std::vector<int32_t> s0(n_streams), s1(n_streams);
+  std::vector<int32_t> ss(n_streams);
   std::vector<double> id(size_t(n_streams) * 7, 0.0);
-  for (int i = 0; i < n_streams; ++i) { s0[i] = 2 * i; s1[i] = 2 * i + 1; id[size_t(i) * 7] = 1.0; }
-  CU(cudaMalloc((void**)&t->d_slots[0], n_streams * sizeof(int32_t)));
-  CU(cudaMalloc((void**)&t->d_slots[1], n_streams * sizeof(int32_t)));
+  for (int i = 0; i < n_streams; ++i) id[size_t(i) * 7] = 1.0;
+  for (int k = 0; k < 3; ++k) {
+    for (int i = 0; i < n_streams; ++i) ss[i] = 3 * i + k;
+    CU(cudaMalloc((void**)&t->d_slots[k], n_streams * sizeof(int32_t)));
+    CU(cudaMemcpy(t->d_slots[k], ss.data(), n_streams * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   CU(cudaMalloc((void**)&t->d_poses, id.size() * 8));
   CU(cudaMalloc((void**)&t->d_result, id.size() * 8));
   CU(cudaMalloc((void**)&t->d_identity, id.size() * 8));
   CU(cudaMalloc((void**)&t->d_summaries, size_t(n_streams) * fp->n_levels * sizeof(ea_summary)));
   CU(cudaMalloc((void**)&t->d_order, size_t(n_streams) * sizeof(int32_t)));
-  CU(cudaMemcpy(t->d_slots[0], s0.data(), n_streams * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(t->d_slots[1], s1.data(), n_streams * sizeof(int32_t), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(t->d_identity, id.data(), id.size() * 8, cudaMemcpyHostToDevice));
   CU(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&t->prep_stream, cudaStreamNonBlocking));
   for (int b = 0; b < 2; ++b) {
+    CU(cudaEventCreateWithFlags(&t->ev_prep[b], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&t->ev_solved[b], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&t->ev_copied[b], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&t->ev_consumed[b], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&t->ev_result[b], cudaEventDisableTiming));
@@ -73,7 +83,8 @@ int ea_tracker_destroy(ea_tracker* t) {
   if (!t) return EA_OK;
   cudaSetDevice(t->ctx->device);
   cudaStreamSynchronize(t->ctx->stream);
-  cudaFree(t->d_slots[0]); cudaFree(t->d_slots[1]); cudaFree(t->d_poses); cudaFree(t->d_result);
+  if (t->prep_stream) { cudaStreamSynchronize(t->prep_stream); cudaStreamDestroy(t->prep_stream); }
+  cudaFree(t->d_slots[0]); cudaFree(t->d_slots[1]); cudaFree(t->d_slots[2]); cudaFree(t->d_poses); cudaFree(t->d_result);
   cudaFree(t->d_identity); cudaFree(t->d_summaries); cudaFree(t->d_order);
   if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
   for (int b = 0; b < 2; ++b) {
@@ -81,6 +92,8 @@ int ea_tracker_destroy(ea_tracker* t) {
     if (t->ev_copied[b]) cudaEventDestroy(t->ev_copied[b]);
     if (t->ev_consumed[b]) cudaEventDestroy(t->ev_consumed[b]);
     if (t->ev_result[b]) cudaEventDestroy(t->ev_result[b]);
+    if (t->ev_prep[b]) cudaEventDestroy(t->ev_prep[b]);
+    if (t->ev_solved[b]) cudaEventDestroy(t->ev_solved[b]);
     if (t->h_poses[b]) cudaFreeHost(t->h_poses[b]);
     if (t->h_summaries[b]) cudaFreeHost(t->h_summaries[b]);
   }
@@ -93,30 +106,48 @@ int ea_tracker_reset(ea_tracker* t) {
   if (!t) return ea_fail(EA_ERR_INVALID_ARG, "null tracker");
   cudaStream_t s = t->ctx->stream;
   const size_t pb = size_t(t->n_streams) * 7 * 8;
-  t->frame = 0; t->key_parity = 0; t->result_frame[0] = t->result_frame[1] = -1; t->have_order = false;
+  CU(cudaStreamSynchronize(t->prep_stream));
+  CU(cudaStreamSynchronize(s));
+  t->frame = 0; t->key_set = 0; t->prev_key = 0; t->prev_now = -1; t->result_frame[0] = t->result_frame[1] = -1; t->have_order = false;
   CU(cudaMemcpyAsync(t->d_poses, t->d_identity, pb, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(t->d_result, t->d_identity, pb, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemsetAsync(t->d_summaries, 0, size_t(t->n_streams) * t->n_levels * sizeof(ea_summary), s));
   return EA_OK;
 }
 
-int ea_tracker_step_device(ea_tracker* t, const uint8_t* d_bgr, const void* d_depth) {
-  if (!t || !d_bgr) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
+}  // extern "C"
+
+// input_ready: event after which the frame buffers are complete (host path: the upload); null => the buffers are ordered by
+// the context stream (default) or already complete (inputs_ready).
+static int tracker_step(ea_tracker* t, const uint8_t* d_bgr, const void* d_depth, cudaEvent_t input_ready, cudaEvent_t consumed) {
   ea_context* c = t->ctx;
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   const bool first = (t->frame == 0);
   const bool becomes_key = (t->frame % t->interval) == 0;
   if (becomes_key && !d_depth) return ea_fail(EA_ERR_INVALID_ARG, "frame %d becomes a key frame and needs depth", t->frame);
-  // the new frame lands in the slots NOT holding the key frames
-  const int cur = first ? t->key_parity : (t->key_parity ^ 1);
+  // the new frame lands in the slot set that the solve still in flight (frame - 1) does not read
+  int cur = 0;
+  if (!first) { while (cur == t->prev_key || cur == t->prev_now || cur == t->key_set) ++cur; }
   const int roles = (first ? 0 : EA_ROLE_NOW) | (becomes_key ? EA_ROLE_REF : 0);
-  int rc = ea_preprocess_impl(t->fs, t->n_streams, t->d_slots[cur], d_bgr, d_depth, roles);
+  const int fb = t->frame & 1;
+  cudaStream_t ps = t->prep_stream;
+  if (input_ready) {
+    CU(cudaStreamWaitEvent(ps, input_ready, 0));
+  } else if (!t->inputs_ready) {   // inputs produced by work enqueued on the context stream: keep that order (no overlap)
+    CU(cudaEventRecord(t->ev_prep[fb], s));
+    CU(cudaStreamWaitEvent(ps, t->ev_prep[fb], 0));
+  }
+  if (t->frame >= 3) CU(cudaStreamWaitEvent(ps, t->ev_solved[fb], 0));   // last reader of this slot set: the solve of frame - 2
+  int rc = ea_preprocess_impl(t->fs, t->n_streams, t->d_slots[cur], d_bgr, d_depth, roles, nullptr, nullptr, ps);
   if (rc) return rc;
+  CU(cudaEventRecord(t->ev_prep[fb], ps));
+  if (consumed) CU(cudaEventRecord(consumed, ps));              // the input buffers may be overwritten from here on
+  CU(cudaStreamWaitEvent(s, t->ev_prep[fb], 0));
   const size_t pb = size_t(t->n_streams) * 7 * 8;
   if (!first) {
     // streams that needed the most work last frame go first: hides the launch tail behind the rest of the batch
-    rc = ea_solve_batch_device_ordered(c, t->n_streams, t->fs, t->d_slots[t->key_parity], t->fs, t->d_slots[cur], t->d_poses, nullptr,
+    rc = ea_solve_batch_device_ordered(c, t->n_streams, t->fs, t->d_slots[t->key_set], t->fs, t->d_slots[cur], t->d_poses, nullptr,
                                        t->have_order ? t->d_order : nullptr, &t->sp, t->d_summaries);
     if (rc) return rc;
     if (t->n_streams > 1 && t->n_streams <= 4096) {
@@ -126,12 +157,27 @@ int ea_tracker_step_device(ea_tracker* t, const uint8_t* d_bgr, const void* d_de
       t->have_order = true;
     }
     CU(cudaMemcpyAsync(t->d_result, t->d_poses, pb, cudaMemcpyDeviceToDevice, s));
+    CU(cudaEventRecord(t->ev_solved[fb], s));
+    t->prev_key = t->key_set; t->prev_now = cur;
   }
   if (becomes_key) {
-    t->key_parity = cur;
+    t->key_set = cur;
     CU(cudaMemcpyAsync(t->d_poses, t->d_identity, pb, cudaMemcpyDeviceToDevice, s));  // pose is relative to the new key frame
   }
   t->frame++;
+  return EA_OK;
+}
+
+extern "C" {
+
+int ea_tracker_step_device(ea_tracker* t, const uint8_t* d_bgr, const void* d_depth) {
+  if (!t || !d_bgr) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
+  return tracker_step(t, d_bgr, d_depth, nullptr, nullptr);
+}
+
+int ea_tracker_set_inputs_ready(ea_tracker* t, int ready) {
+  if (!t) return ea_fail(EA_ERR_INVALID_ARG, "null tracker");
+  t->inputs_ready = ready ? 1 : 0;
   return EA_OK;
 }
 
@@ -161,10 +207,8 @@ int ea_tracker_step_host(ea_tracker* t, const uint8_t* bgr, const void* depth, d
   CU(cudaMemcpyAsync(t->stage_bgr[b], bgr, px * 3 * n, cudaMemcpyHostToDevice, t->copy_stream));
   if (becomes_key) CU(cudaMemcpyAsync(t->stage_depth[b], depth, px * fs->depth_elem * n, cudaMemcpyHostToDevice, t->copy_stream));
   CU(cudaEventRecord(t->ev_copied[b], t->copy_stream));
-  CU(cudaStreamWaitEvent(c->stream, t->ev_copied[b], 0));
-  int rc = ea_tracker_step_device(t, t->stage_bgr[b], becomes_key ? t->stage_depth[b] : nullptr);
+  int rc = tracker_step(t, t->stage_bgr[b], becomes_key ? t->stage_depth[b] : nullptr, t->ev_copied[b], t->ev_consumed[b]);
   if (rc) return rc;
-  CU(cudaEventRecord(t->ev_consumed[b], c->stream));
   // results into the pinned ring; the caller reads them now (poses7 given) or later with ea_tracker_wait
   CU(cudaMemcpyAsync(t->h_poses[b], t->d_result, size_t(n) * 7 * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(t->h_summaries[b], t->d_summaries, size_t(n) * t->n_levels * sizeof(ea_summary), cudaMemcpyDeviceToHost, c->stream));

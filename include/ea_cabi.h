@@ -265,6 +265,11 @@ int ea_tracker_step_host(ea_tracker* tr, const uint8_t* bgr, const void* depth, 
  * frame must stay valid until its results have been waited for. */
 int ea_tracker_wait(ea_tracker* tr, int frame, double* poses7, ea_summary* summaries);
 int ea_tracker_step_device(ea_tracker* tr, const uint8_t* d_bgr, const void* d_depth);
+/* By default the device buffers passed to ea_tracker_step_device are ordered by the context stream (work enqueued there
+ * before the call produces them).  ready != 0 declares instead that they are COMPLETE in memory when the call is made; the
+ * tracker then preprocesses frame t+1 on its own stream while frame t is still being aligned (its kernels take over the
+ * SMs the persistent solve kernel releases during its tail).  ea_tracker_step_host always overlaps this way. */
+int ea_tracker_set_inputs_ready(ea_tracker* t, int ready);
 int ea_tracker_get_poses(ea_tracker* tr, double* poses7, ea_summary* summaries); /* syncs */
 int ea_tracker_frame_index(ea_tracker* tr, int* n_frames_seen);
 
