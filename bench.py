@@ -344,7 +344,10 @@ def main():
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                         "kernel": "ea_k_solve_batch", "peak_source": peak_src, "kernel_ms_per_launch": solve_ms_avg,
                         "point_evals_per_launch": pe_per_launch, "bytes_per_point_eval": BYTES_PER_POINT_EVAL,
-                        "kernel_share_of_step": (prof["solve_ms"] / ms) if ms > 0 else None,
+                        # share of the serialised step (comparable with the ncu launch list, which serialises everything);
+                        # live, the kernel is busy for `kernel_busy_fraction_live` of the step while preprocessing overlaps it
+                        "kernel_share_of_step": (iso["kernel_ms_per_launch"] / (iso["kernel_ms_per_launch"] + iso["preprocess_ms_per_step"])) if iso else None,
+                        "kernel_busy_fraction_live": (prof["solve_ms"] / ms) if ms > 0 else None,
                         "preprocess_ms_per_step": prof["preprocess_ms"] / max(1, K),
                         "bytes_per_point_eval_moved": 72.0,
                         "note": "live figures: the next frame's preprocessing kernels run concurrently with this kernel (tracker overlap), which lengthens its launches; `isolated` is the same kernel owning the GPU",
