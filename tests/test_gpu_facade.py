@@ -48,3 +48,33 @@ def test_cpp_facade_runs_reference_call_sequence(frames, solver_golden, tmp_path
     rp = np.array([float(v) for v in rec["rospose"]])
     assert rot_angle_between(rp[:4], op[:4]) < 1e-4 and np.abs(rp[4:] - op[4:]).max() < 1e-4
     assert int(rec["rossummary"][2]) == len(xyz) and abs(int(rec["rossummary"][1]) - os_["iterations"]) <= 2
+
+
+def test_standalone_example_from_png_files(frames, solver_golden, tmp_path):
+    """examples/standalone_edge_align.cpp: the reference's edge_align_test1 flow from files (PNG decode -> C ABI -> printed
+    guess, overlays, .obj), on the bundled pair 1 -> 3."""
+    from edge_alignment_b200 import _lib as L
+    from test_io_formats import write_png
+    exe = str(tmp_path / "standalone_edge_align")
+    lib_dir = os.path.dirname(L.SO_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "standalone_edge_align.cpp"), "-o", exe,
+                           "-L", lib_dir, "-l:libea_b200.so", "-lz", "-Wl,-rpath," + lib_dir, "-Wl,-rpath,/usr/local/cuda/lib64"])
+    write_png(str(tmp_path / "a.png"), np.ascontiguousarray(frames["bgr"][0][:, :, ::-1]), 2, 8)
+    write_png(str(tmp_path / "ad.png"), frames["depth"][0].astype(">u2").view(np.uint8).reshape(480, 640, 2), 0, 16)
+    write_png(str(tmp_path / "b.png"), np.ascontiguousarray(frames["bgr"][2][:, :, ::-1]), 2, 8)
+    out = subprocess.run([exe, str(tmp_path / "a.png"), str(tmp_path / "ad.png"), str(tmp_path / "b.png"), str(tmp_path)],
+                         capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert "44458 pts out of 307200 have a large gradient" in lines[1]
+    import re
+    assert lines[2].startswith("Initial Guess : :YPR=(") and ":TxTyTz=(" in lines[2]
+    assert all(float(v) == 0.0 for v in re.findall(r"-?\d+\.\d+", lines[2]))      # atan2(-0, 1) prints as -0.00, as in the reference
+    assert lines[3].startswith("Residual blocks 1482,")
+    pose = np.array([float(v) for v in [l for l in lines if l.startswith("pose ")][0].split()[1:]])
+    gp = solver_golden["pose_1_3_cauchy"]
+    assert rot_angle_between(pose[:4], gp[:4]) < 1e-4 and np.abs(pose[4:] - gp[4:]).max() < 1e-4
+    assert os.path.getsize(tmp_path / "final.png") > 1000 and os.path.getsize(tmp_path / "initial.png") > 1000
+    obj = open(tmp_path / "sceneEdgeCloud.obj").read().split("\n")
+    assert len(obj) == 44458 and obj[0].startswith("v ")

@@ -23,12 +23,6 @@ def io_bin(tmp_path_factory):
     return out
 
 
-def _paeth(a, b, c):
-    p = a + b - c
-    pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
-    return a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
-
-
 def write_png(path, arr, ctype, bits, palette=None):
     """arr: [h][w][bytes per pixel] uint8 raster exactly as PNG stores it; rows cycle through filter types 0..4."""
     h, w, bpp = arr.shape
@@ -37,15 +31,15 @@ def write_png(path, arr, ctype, bits, palette=None):
     for y in range(h):
         cur = arr[y].reshape(-1).astype(np.int32)
         f = y % 5
-        out = np.zeros_like(cur)
-        for x in range(w * bpp):
-            a = cur[x - bpp] if x >= bpp else 0
-            b = prev[x]
-            c = prev[x - bpp] if x >= bpp else 0
-            pred = [0, a, b, (a + b) >> 1, _paeth(a, b, c)][f]
-            out[x] = (cur[x] - pred) & 255
+        a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        b = prev
+        c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        pp = a + b - c
+        pa, pb, pc = np.abs(pp - a), np.abs(pp - b), np.abs(pp - c)
+        paeth = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, b, c))
+        pred = [np.zeros_like(cur), a, b, (a + b) >> 1, paeth][f]
         raw.append(f)
-        raw += out.astype(np.uint8).tobytes()
+        raw += ((cur - pred) & 255).astype(np.uint8).tobytes()
         prev = cur
 
     def chunk(tag, body):
