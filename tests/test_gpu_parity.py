@@ -121,6 +121,36 @@ def test_preprocess_edge_cases(ea, ctx, oracle):
         fs.close()
 
 
+@pytest.mark.parametrize("w", [8, 33, 100, 255, 256, 257, 383, 384, 385, 510, 639, 640, 641, 700])
+def test_chamfer_dt_widths(ea, ctx, oracle, w):
+    """Every strip-length switch of the warp-per-frame DT kernel (8 / 12 / 20 pixels per lane), partial strips, widths that
+    are not multiples of 4 (scalar row I/O) and the hand-over to the block kernel above 640 px -- sparse and dense edges,
+    two pyramid levels, raw values (no normalisation) bit for bit against the oracle."""
+    O = oracle
+    rng = np.random.default_rng(w)
+    h = 38
+    fp = ea.frame_params(width=w, height=h, fx=50.0, fy=50.0, cx=w / 2.0, cy=h / 2.0, dt_normalize=ea.NORM_NONE, use_median=0,
+                         n_levels=2 if (w >= 16 and w % 2 == 0) else 1)   # pyramid levels need even sizes
+    fs = ea.FrameSet(ctx, fp, 3)
+    try:
+        sparse = np.full((h, w, 3), 70, np.uint8)
+        for _ in range(3):                                       # a few isolated bright blocks: long propagation distances
+            y, x = rng.integers(0, h - 2), rng.integers(0, w - 2)
+            sparse[y:y + 2, x:x + 2] = 255
+        dense = ((rng.integers(0, 4, (h, w, 3)) * 80).astype(np.uint8))
+        one = np.full((h, w, 3), 70, np.uint8); one[h - 1, w - 1] = 255     # a single seed in the last corner
+        bgr = np.stack([sparse, dense, one])
+        fs.preprocess_host([0, 1, 2], bgr, None, ea.ROLE_NOW)
+        for s_ in range(3):
+            odt, _ = O.get_distance_transform(bgr[s_], use_median=False, norm_mode=0)
+            np.testing.assert_array_equal(fs.dt(s_), odt)
+            if fp.n_levels == 2:
+                odt1, _ = O.get_distance_transform(O.half_linear(bgr[s_]), use_median=False, norm_mode=0)
+                np.testing.assert_array_equal(fs.dt(s_, 1), odt1)
+    finally:
+        fs.close()
+
+
 # ------------------------------------------------------------------------------------------------- evaluation
 def _assert_residual_parity(gpu_raw, ref_raw):
     tol = 1e-5 * np.maximum(np.abs(ref_raw), R_FLOOR)
