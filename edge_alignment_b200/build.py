@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc(), "-shared", "-o", SO] + objs + ["-lcudart", "-ldl"]
+    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return SO
 
