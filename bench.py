@@ -137,6 +137,32 @@ def cpu_reference_run(n_streams, steps, warmup, threads, make_frames):
     return n_streams * steps / timed, timed, n_streams * steps
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and allocate its pinned host buffers) on the NUMA node its GPU hangs off: with 8 ranks pushing
+    ~55 GB/s each, uploads that cross the socket interconnect are the first thing to saturate.  Best effort."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        dev = dom[-4:] + ":" + rest
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % dev).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +179,7 @@ def main():
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
     import synth
 
@@ -244,12 +271,22 @@ def main():
     tracker.reset()
     run_device(0, Wm + 1)
     point_evals = 0; iters = 0; n_sum = 0; terms = {}
+    pe_level = [0] * N_LEVELS
     for t in range(Wm + 1, T):
         run_device(t, t + 1)
         _, Ss = tracker.poses()
-        for s in Ss:
+        for i, s in enumerate(Ss):
             point_evals += s.n_residuals * s.evaluations; iters += s.iterations; n_sum += 1
+            pe_level[i % N_LEVELS] += s.n_residuals * s.evaluations
             terms[s.termination] = terms.get(s.termination, 0) + 1
+    # gather roof: stream + project + 16-texel gather only, on the frames and poses of the last step, per pyramid level
+    gather = None
+    try:
+        rates = [tracker.probe_gather(l, 8)[0] for l in range(N_LEVELS)]
+        roof_s = sum(pe_level[l] / rates[l] for l in range(N_LEVELS) if rates[l] > 0) / max(1, K)     # seconds per launch at the roof
+        gather = {"point_gathers_per_s_by_level": rates, "launch_ms_at_roof": roof_s * 1e3}
+    except Exception as ex:        # measurement aid only
+        gather = {"error": str(ex)}
     solve_ms_avg = prof["solve_ms"] / max(1, prof["n_solve"])
     pe_per_launch = point_evals / max(1, K)
     peak, peak_src = measured_peak_hbm()
@@ -342,6 +379,7 @@ def main():
            "config": {"workload": workload_name(S), "streams_per_gpu": S, "cluster_size": args.cluster,
                       "l2": "every step reads %d MB of new frames per GPU (> 126 MB L2): inputs larger than L2" % (frame_b // 2**20),
                       "frames_resident": "%d distinct frames per stream, walked forwards then backwards" % NF,
+                      "numa_node_rank0": numa_node,
                       "point_evals_per_s": world * point_evals / (ms * 1e-3), "mean_lm_iterations_per_level": iters / max(1, n_sum),
                       "terminations": {ea._lib.TERMINATION.get(k, str(k)): v for k, v in terms.items()}},
            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -355,7 +393,12 @@ def main():
                         "preprocess_ms_per_step": prof["preprocess_ms"] / max(1, K),
                         "bytes_per_point_eval_moved": 72.0,
                         "note": "live figures: the next frame's preprocessing kernels run concurrently with this kernel (tracker overlap), which lengthens its launches; `isolated` is the same kernel owning the GPU",
-                        "isolated": iso},
+                        "isolated": iso,
+                        # L1/L2-gather roofline of the same access pattern (ea_k_gather_probe): launch time if the kernel did
+                        # nothing but stream the points, project them and gather the texels, at full occupancy
+                        "gather_roof": (dict(gather, frac_live=(gather["launch_ms_at_roof"] / solve_ms_avg) if solve_ms_avg > 0 else None,
+                                             frac_isolated=(gather["launch_ms_at_roof"] / iso["kernel_ms_per_launch"]) if iso else None)
+                                        if gather and "launch_ms_at_roof" in gather else gather)},
            "cpu_baseline": cpu}
     print(json.dumps(out))
     tracker.close(); ctx.close()

@@ -105,6 +105,7 @@ PROTOTYPES = {
     "ea_tracker_wait": (_i, [_vp, _i, _f64p, C.POINTER(Summary)]),
     "ea_tracker_step_device": (_i, [_vp, _vp, _vp]),
     "ea_tracker_set_inputs_ready": (_i, [_vp, _i]),
+    "ea_tracker_probe_gather": (_i, [_vp, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "ea_tracker_get_poses": (_i, [_vp, _f64p, C.POINTER(Summary)]),
     "ea_tracker_frame_index": (_i, [_vp, _pi]),
     "ea_shard_unique_id": (_i, [_u8p]),

@@ -284,6 +284,12 @@ class Tracker:
         """Device frames passed to step_device are complete at call time: lets frame t+1's preprocessing overlap frame t's solve."""
         _check(L.lib().ea_tracker_set_inputs_ready(self._h, 1 if ready else 0))
 
+    def probe_gather(self, level=0, repeats=8):
+        """Gather-roof probe (measurement only): returns point-gathers per second for the current frames and poses."""
+        ms = C.c_float(); n = C.c_double()
+        _check(L.lib().ea_tracker_probe_gather(self._h, level, repeats, C.byref(ms), C.byref(n)))
+        return n.value / (ms.value * 1e-3), ms.value, n.value
+
     def step_device(self, d_bgr, d_depth=0):
         _check(L.lib().ea_tracker_step_device(self._h, d_bgr, d_depth or None))
 

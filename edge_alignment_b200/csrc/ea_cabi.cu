@@ -594,6 +594,47 @@ int ea_solve_batch_device(ea_context* c, int n, ea_frameset* ref, const int32_t*
 }
 }  // extern "C"
 
+// Gather-roof probe over n pairs (measurement only, see ea_k_gather_probe): device time of `repeats` sweeps over the
+// level's point lists and the number of point-gathers they contain.
+int ea_probe_gather_device(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now, const int32_t* d_now_slots,
+                           const double* d_poses7, int level, int repeats, float* ms, double* point_gathers) {
+  if (!c || !ref || !now || !d_ref_slots || !d_now_slots || !d_poses7 || !ms || !point_gathers) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
+  if (n <= 0 || repeats <= 0) return ea_fail(EA_ERR_INVALID_ARG, "n and repeats must be positive");
+  ea_solve_params sp;
+  ea_solve_params_default(&sp);
+  EaSolveArgs A;
+  int cluster = 0;
+  int rc = fill_solve_args(c, ref, now, &sp, A, &cluster);
+  if (rc) return rc;
+  if (level < 0 || level >= ref->p.n_levels) return ea_fail(EA_ERR_INVALID_ARG, "level %d out of range", level);
+  CU(cudaSetDevice(c->device));
+  A.ref_slots = d_ref_slots; A.now_slots = d_now_slots; A.poses = const_cast<double*>(d_poses7); A.n_pairs = n;
+  const int slices = std::max(1, (c->sm_count * 8 + n - 1) / n);
+  float* d_sink = nullptr;
+  CU(cudaMalloc((void**)&d_sink, size_t(n) * slices * 256 * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  cudaError_t e = ea_launch_gather_probe(A, level, slices, 1, d_sink, c->stream);     // warm-up sweep
+  CU(cudaEventRecord(e0, c->stream));
+  if (e == cudaSuccess) e = ea_launch_gather_probe(A, level, slices, repeats, d_sink, c->stream);
+  CU(cudaEventRecord(e1, c->stream));
+  c->launches += 2;
+  CU(cudaStreamSynchronize(c->stream));
+  if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "gather probe: %s", cudaGetErrorString(e));
+  CU(cudaEventElapsedTime(ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  // point counts of the level (host copy of the device-resident counters)
+  std::vector<int32_t> slots(static_cast<size_t>(n));
+  CU(cudaMemcpy(slots.data(), d_ref_slots, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  std::vector<int> npts(size_t(ref->n_slots) * EA_MAX_LEVELS);
+  CU(cudaMemcpy(npts.data(), ref->d_npts, npts.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  double total = 0.0;
+  for (int i = 0; i < n; ++i) total += std::min(npts[size_t(slots[size_t(i)]) * EA_MAX_LEVELS + level], ref->lv[level].cap);
+  *point_gathers = total * repeats;
+  cudaFree(d_sink);
+  return EA_OK;
+}
+
 int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now,
                                   const int32_t* d_now_slots, double* d_poses7, const int32_t* d_pose_index,
                                   const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries) {

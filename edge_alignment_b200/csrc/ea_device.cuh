@@ -216,6 +216,47 @@ __device__ __forceinline__ void ea_point_eval(const double a0, const double a1, 
   o.pz = float(q2); o.iz = float(iz);
 }
 
+// Projection + gather of ea_point_eval without the interpolation: the sum of the 16 texels (gather-roof probe).
+template <bool XYZ>
+__device__ __forceinline__ float ea_point_gather_sum(const double a0, const double a1, const double a2, const EaLevelGeom& now,
+                                                     double inv_depth_scale, const EaPose& P, const float* __restrict__ dt) {
+  double q0, q1, q2;
+  if (XYZ) {
+    q0 = fma(P.A[0], a0, fma(P.A[1], a1, fma(P.A[2], a2, P.tt[0])));
+    q1 = fma(P.A[3], a0, fma(P.A[4], a1, fma(P.A[5], a2, P.tt[1])));
+    q2 = fma(P.A[6], a0, fma(P.A[7], a1, fma(P.A[8], a2, P.tt[2])));
+  } else {
+    const double Z = a2 * inv_depth_scale;
+    q0 = fma(Z, fma(P.A[0], a0, fma(P.A[1], a1, P.A[2])), P.tt[0]);
+    q1 = fma(Z, fma(P.A[3], a0, fma(P.A[4], a1, P.A[5])), P.tt[1]);
+    q2 = fma(Z, fma(P.A[6], a0, fma(P.A[7], a1, P.A[8])), P.tt[2]);
+  }
+  const double iz = 1.0 / q2;
+  const int W = now.w, H = now.h;
+  int iu, iv;
+  float du, dv;
+  ea_floor_frac(q0 * iz, iu, du);
+  ea_floor_frac(q1 * iz, iv, dv);
+  iu = min(max(iu, -4), W + 4);
+  iv = min(max(iv, -4), H + 4);
+  float s = du + dv;
+  const bool interior = (iu >= 1) && (iu <= W - 3) && (iv >= 1) && (iv <= H - 3);
+  if (__all_sync(0xffffffffu, interior)) {
+    const unsigned o0 = unsigned(iv - 1) * unsigned(W) + unsigned(iu - 1);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s += __ldg(dt + o0 + unsigned(r) * unsigned(W) + unsigned(c));
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        s += __ldg(dt + unsigned(min(max(iv - 1 + r, 0), H - 1)) * unsigned(W) + unsigned(min(max(iu - 1 + c, 0), W - 1)));
+  }
+  return s;
+}
+
 // Loss (ceres/loss_function.cc) + Corrector (rho'' <= 0 for all three => scale by sqrt(rho')) in fp32.
 // Returns sqrt(rho'), writes rho(s).
 __device__ __forceinline__ float ea_loss_eval(int type, float a, float r, float& rho0) {

@@ -34,6 +34,9 @@ struct EaSolveArgs {
 
 cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm_count, cudaStream_t stream);
 cudaError_t ea_launch_solve_tasks(const EaSolveArgs& A, int sm_count, cudaStream_t stream);
+cudaError_t ea_launch_gather_probe(const EaSolveArgs& A, int level, int slices, int repeats, float* d_sink, cudaStream_t stream);
+int ea_probe_gather_device(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now, const int32_t* d_now_slots,
+                           const double* d_poses7, int level, int repeats, float* ms, double* point_gathers);
 cudaError_t ea_launch_eval_points(const EaLevelDesc& rd, const EaLevelDesc& nd, const EaLevelGeom& rg,
                                   const EaLevelGeom& ng, double inv_depth_scale, const ea_solve_params& sp,
                                   const double* d_pose7, int n_res, double* d_raw, double* d_res, double* d_jac,

@@ -235,6 +235,43 @@ __global__ void __launch_bounds__(THREADS) ea_k_eval_sums(EaLevelDesc rd, EaLeve
   }
 }
 
+// ---- memory-side roof of the fused evaluation (measurement only) -----------------------------------------------------
+// The same point stream, the same fp64 projection (it generates the addresses) and the same 16-texel clamp-to-edge gather
+// as ea_eval_slice, and nothing else: no interpolation, no Jacobian, no reduction, no LM, few registers, full occupancy.
+// Its rate is the L1/L2-gather roofline of the access pattern for the frames and poses at hand.
+__global__ void __launch_bounds__(256) ea_k_gather_probe(const __grid_constant__ EaSolveArgs A, int level, int slices, int repeats,
+                                                         float* __restrict__ sink) {
+  const int pair = blockIdx.x / slices, slice = blockIdx.x % slices;
+  if (pair >= A.n_pairs) return;
+  const EaLevelDesc rd = A.ref_desc[size_t(A.ref_slots[pair]) * EA_MAX_LEVELS + level];
+  const EaLevelDesc nd = A.now_desc[size_t(A.now_slots[pair]) * EA_MAX_LEVELS + level];
+  const EaLevelGeom& rg = A.ref_geom[level];
+  const EaLevelGeom& ng = A.now_geom[level];
+  const int n = min(*rd.n_pts, A.ref_cap[level]);
+  const int j0 = int((long long)n * slice / slices), j1 = int((long long)n * (slice + 1) / slices);
+  if (rd.pts_mode != EA_POINTS_PIXEL) return;
+  EaPose P;
+  ea_pose_setup<false>(A.poses + size_t(pair) * 7, rg, ng, P);
+  const float2 affine = make_float2(1.0f, 0.0f);
+  float s = 0.0f;
+  const int n_round = j0 + (((j1 - j0) + 31) & ~31);   // whole warps: the gather votes
+  for (int r = 0; r < repeats; ++r)
+    for (int j = j0 + int(threadIdx.x); j < n_round; j += 256) {
+      typedef EaPtStream<false> PS;
+      const PS::T p = j < j1 ? PS::load(rd.pts, size_t(j)) : PS::pad();
+      double a0, a1, a2;
+      PS::unpack(p, a0, a1, a2);
+      s += ea_point_gather_sum<false>(a0, a1, a2, ng, A.inv_depth_scale, P, nd.dt);
+    }
+  (void)affine;
+  sink[size_t(blockIdx.x) * 256 + threadIdx.x] = s;
+}
+
+cudaError_t ea_launch_gather_probe(const EaSolveArgs& A, int level, int slices, int repeats, float* d_sink, cudaStream_t stream) {
+  ea_k_gather_probe<<<unsigned(A.n_pairs * slices), 256, 0, stream>>>(A, level, slices, repeats, d_sink);
+  return cudaGetLastError();
+}
+
 // ---- host launchers -----------------------------------------------------------------------------------
 cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm_count, cudaStream_t stream) {
   if (A.n_pairs <= 0) return cudaSuccess;

@@ -181,6 +181,15 @@ int ea_tracker_set_inputs_ready(ea_tracker* t, int ready) {
   return EA_OK;
 }
 
+int ea_tracker_probe_gather(ea_tracker* t, int level, int repeats, float* ms, double* point_gathers) {
+  if (!t) return ea_fail(EA_ERR_INVALID_ARG, "null tracker");
+  if (t->prev_now < 0) return ea_fail(EA_ERR_STATE, "the tracker has not aligned a frame yet");
+  CU(cudaStreamSynchronize(t->prep_stream));
+  // the pairs of the most recent alignment: key frames of that solve vs its frames, at the poses it produced
+  return ea_probe_gather_device(t->ctx, t->n_streams, t->fs, t->d_slots[t->prev_key], t->fs, t->d_slots[t->prev_now], t->d_result, level,
+                                repeats, ms, point_gathers);
+}
+
 int ea_tracker_get_poses(ea_tracker* t, double* poses7, ea_summary* summaries) {
   if (!t) return ea_fail(EA_ERR_INVALID_ARG, "null tracker");
   cudaStream_t s = t->ctx->stream;

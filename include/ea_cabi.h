@@ -270,6 +270,10 @@ int ea_tracker_step_device(ea_tracker* tr, const uint8_t* d_bgr, const void* d_d
  * tracker then preprocesses frame t+1 on its own stream while frame t is still being aligned (its kernels take over the
  * SMs the persistent solve kernel releases during its tail).  ea_tracker_step_host always overlaps this way. */
 int ea_tracker_set_inputs_ready(ea_tracker* t, int ready);
+/* Measurement only: the L1/L2-gather roofline of the fused evaluation for the tracker's current frames and poses -- a kernel
+ * that streams the level's point lists, projects them and gathers the 16 distance-transform texels per point, and nothing
+ * else.  ms = device time of `repeats` sweeps, point_gathers = points x repeats (bench.py: roofline.gather_roof). */
+int ea_tracker_probe_gather(ea_tracker* tr, int level, int repeats, float* ms, double* point_gathers);
 int ea_tracker_get_poses(ea_tracker* tr, double* poses7, ea_summary* summaries); /* syncs */
 int ea_tracker_frame_index(ea_tracker* tr, int* n_frames_seen);
 
