@@ -268,7 +268,10 @@ __global__ void __launch_bounds__(256) ea_k_gather_probe(const __grid_constant__
 }
 
 cudaError_t ea_launch_gather_probe(const EaSolveArgs& A, int level, int slices, int repeats, float* d_sink, cudaStream_t stream) {
-  ea_k_gather_probe<<<unsigned(A.n_pairs * slices), 256, 0, stream>>>(A, level, slices, repeats, d_sink);
+  // EA_PROBE_SMEM_KB: occupancy experiment (dynamic shared memory only limits the number of resident CTAs)
+  static const int smem_kb = getenv("EA_PROBE_SMEM_KB") ? atoi(getenv("EA_PROBE_SMEM_KB")) : 0;
+  if (smem_kb > 48) cudaFuncSetAttribute(ea_k_gather_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024);
+  ea_k_gather_probe<<<unsigned(A.n_pairs * slices), 256, size_t(smem_kb) * 1024, stream>>>(A, level, slices, repeats, d_sink);
   return cudaGetLastError();
 }
 
