@@ -497,7 +497,7 @@ static int check_solve_params(const ea_solve_params* sp) {
   if (sp->max_num_iterations < 0) return ea_fail(EA_ERR_INVALID_ARG, "max_num_iterations must be >= 0");
   if (sp->trust_region_strategy < 0 || sp->trust_region_strategy > 1) return ea_fail(EA_ERR_INVALID_ARG, "trust_region_strategy must be 0 (LM) or 1 (DOGLEG)");
   const int cs = sp->cluster_size;
-  if (!(cs == -1 || cs == 0 || cs == 1 || cs == 2 || cs == 4 || cs == 8)) return ea_fail(EA_ERR_INVALID_ARG, "cluster_size must be -1,0,1,2,4 or 8");
+  if (!(cs == -3 || cs == -1 || cs == 0 || cs == 1 || cs == 2 || cs == 4 || cs == 8)) return ea_fail(EA_ERR_INVALID_ARG, "cluster_size must be -3,-1,0,1,2,4 or 8");
   return EA_OK;
 }
 static int check_pairable(ea_frameset* ref, ea_frameset* now) {

@@ -216,6 +216,75 @@ __device__ __forceinline__ void ea_point_eval(const double a0, const double a1, 
   o.pz = float(q2); o.iz = float(iz);
 }
 
+// ea_point_eval in three stages for the warp-specialised kernel (ea_k_solve_ws): gather warps run ea_project + ea_gather,
+// math warps run ea_interp.  Same arithmetic, same operation order.
+struct EaProj {
+  int iu, iv;              // floor(u'), floor(v'), clamped to [-4, W+4] x [-4, H+4]
+  float du, dv;            // fractional offsets (from fp64)
+  float ub, vb, pz, iz;    // u' - cx, v' - cy, z', 1/z'
+  bool fail;               // |z'| < 0.01  (utils.h:70-73)
+};
+template <bool XYZ>
+__device__ __forceinline__ void ea_project(const double a0, const double a1, const double a2, const EaLevelGeom& now,
+                                           double inv_depth_scale, const EaPose& P, EaProj& r) {
+  double q0, q1, q2;
+  if (XYZ) {
+    q0 = fma(P.A[0], a0, fma(P.A[1], a1, fma(P.A[2], a2, P.tt[0])));
+    q1 = fma(P.A[3], a0, fma(P.A[4], a1, fma(P.A[5], a2, P.tt[1])));
+    q2 = fma(P.A[6], a0, fma(P.A[7], a1, fma(P.A[8], a2, P.tt[2])));
+  } else {
+    const double Z = a2 * inv_depth_scale;
+    q0 = fma(Z, fma(P.A[0], a0, fma(P.A[1], a1, P.A[2])), P.tt[0]);
+    q1 = fma(Z, fma(P.A[3], a0, fma(P.A[4], a1, P.A[5])), P.tt[1]);
+    q2 = fma(Z, fma(P.A[6], a0, fma(P.A[7], a1, P.A[8])), P.tt[2]);
+  }
+  r.fail = (q2 < 0.01) && (q2 > -0.01);
+  const double iz = 1.0 / q2;
+  const double u = q0 * iz, v = q1 * iz;
+  int iu, iv;
+  ea_floor_frac(u, iu, r.du);
+  ea_floor_frac(v, iv, r.dv);
+  r.iu = min(max(iu, -4), now.w + 4);
+  r.iv = min(max(iv, -4), now.h + 4);
+  r.ub = float(u - P.cx); r.vb = float(v - P.cy);
+  r.pz = float(q2); r.iz = float(iz);
+}
+// t[4 * row + col] = dt(iv - 1 + row, iu - 1 + col), Grid2D clamp-to-edge.  Warp-collective (vote): all 32 lanes.
+__device__ __forceinline__ void ea_gather(const EaProj& r, const int W, const int H, const float* __restrict__ dt, float (&t)[16]) {
+  const int iu = r.iu, iv = r.iv;
+  const bool interior = (iu >= 1) && (iu <= W - 3) && (iv >= 1) && (iv <= H - 3);
+  if (__all_sync(0xffffffffu, interior)) {
+    const unsigned o0 = unsigned(iv - 1) * unsigned(W) + unsigned(iu - 1);
+    const unsigned o1 = o0 + unsigned(W), o2 = o1 + unsigned(W), o3 = o2 + unsigned(W);
+    t[0] = __ldg(dt + o0); t[1] = __ldg(dt + o0 + 1); t[2] = __ldg(dt + o0 + 2); t[3] = __ldg(dt + o0 + 3);
+    t[4] = __ldg(dt + o1); t[5] = __ldg(dt + o1 + 1); t[6] = __ldg(dt + o1 + 2); t[7] = __ldg(dt + o1 + 3);
+    t[8] = __ldg(dt + o2); t[9] = __ldg(dt + o2 + 1); t[10] = __ldg(dt + o2 + 2); t[11] = __ldg(dt + o2 + 3);
+    t[12] = __ldg(dt + o3); t[13] = __ldg(dt + o3 + 1); t[14] = __ldg(dt + o3 + 2); t[15] = __ldg(dt + o3 + 3);
+  } else {
+    const unsigned x0 = unsigned(min(max(iu - 1, 0), W - 1)), x1 = unsigned(min(max(iu, 0), W - 1)),
+                   x2 = unsigned(min(max(iu + 1, 0), W - 1)), x3 = unsigned(min(max(iu + 2, 0), W - 1));
+    const unsigned r0 = unsigned(min(max(iv - 1, 0), H - 1)) * unsigned(W), r1 = unsigned(min(max(iv, 0), H - 1)) * unsigned(W),
+                   r2 = unsigned(min(max(iv + 1, 0), H - 1)) * unsigned(W), r3 = unsigned(min(max(iv + 2, 0), H - 1)) * unsigned(W);
+    t[0] = __ldg(dt + r0 + x0); t[1] = __ldg(dt + r0 + x1); t[2] = __ldg(dt + r0 + x2); t[3] = __ldg(dt + r0 + x3);
+    t[4] = __ldg(dt + r1 + x0); t[5] = __ldg(dt + r1 + x1); t[6] = __ldg(dt + r1 + x2); t[7] = __ldg(dt + r1 + x3);
+    t[8] = __ldg(dt + r2 + x0); t[9] = __ldg(dt + r2 + x1); t[10] = __ldg(dt + r2 + x2); t[11] = __ldg(dt + r2 + x3);
+    t[12] = __ldg(dt + r3 + x0); t[13] = __ldg(dt + r3 + x1); t[14] = __ldg(dt + r3 + x2); t[15] = __ldg(dt + r3 + x3);
+  }
+}
+__device__ __forceinline__ void ea_interp(const float (&t)[16], const float du, const float dv, const float2 affine, float& f, float& dfdu, float& dfdv) {
+  float f0, f1, f2, f3, d0, d1, d2, d3;
+  const float hv = 0.5f * dv, v15 = 1.5f * dv, hu = 0.5f * du, u15 = 1.5f * du;
+  ea_cubic(t[0], t[4], t[8], t[12], dv, hv, v15, f0, d0);
+  ea_cubic(t[1], t[5], t[9], t[13], dv, hv, v15, f1, d1);
+  ea_cubic(t[2], t[6], t[10], t[14], dv, hv, v15, f2, d2);
+  ea_cubic(t[3], t[7], t[11], t[15], dv, hv, v15, f3, d3);
+  float fr, fdu;
+  ea_cubic(f0, f1, f2, f3, du, hu, u15, fr, fdu);
+  f = fmaf(fr, affine.x, affine.y);
+  dfdu = fdu * affine.x;
+  dfdv = ea_cubic_val(d0, d1, d2, d3, du, hu) * affine.x;
+}
+
 // Projection + gather of ea_point_eval without the interpolation: the sum of the 16 texels (gather-roof probe).
 template <bool XYZ>
 __device__ __forceinline__ float ea_point_gather_sum(const double a0, const double a1, const double a2, const EaLevelGeom& now,

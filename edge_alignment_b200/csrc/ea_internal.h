@@ -9,6 +9,8 @@
 
 #include "ea_solve_state.h"
 
+#define EA_KERNEL_WS (-3)   // ea_solve_params.cluster_size: warp-specialised kernel (ea_k_solve_ws)
+
 struct EaSolveArgs {
   const EaLevelDesc* ref_desc;  // [ref slots][EA_MAX_LEVELS]
   const EaLevelDesc* now_desc;  // [now slots][EA_MAX_LEVELS]

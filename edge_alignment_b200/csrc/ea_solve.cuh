@@ -204,7 +204,7 @@ __device__ inline bool ea_lm_compute_step(EaLmState& S, const ea_solve_params& s
 
 // Advance the minimiser after an evaluation of S.cand produced `sums`.  Returns EA_CMD_EVAL with a
 // new S.cand, or EA_CMD_DONE with S.term set and S.x the final iterate.
-static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sums, const ea_solve_params& sp) {
+static __device__ __forceinline__ int ea_lm_advance_impl(EaLmState& S, const double* sums, const ea_solve_params& sp) {
   const bool fail = sums[27] > 0.0;
   S.evals++;
   if (S.phase == 0) {  // IterationZero
@@ -272,6 +272,10 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
     return EA_CMD_EVAL;
   }
 }
+
+// Out of line for the kernels whose hot loop needs the registers; inlined where calls are not possible (a kernel that uses
+// setmaxnreg cannot contain calls: ptxas C7600).
+static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sums, const ea_solve_params& sp) { return ea_lm_advance_impl(S, sums, sp); }
 
 // ---- slice evaluation shared by every solve kernel ----------------------------------------------------------
 #ifndef EA_FLUSH_EVERY

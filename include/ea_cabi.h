@@ -122,6 +122,7 @@ typedef struct ea_solve_params {
   int32_t max_consecutive_invalid_steps; /* 5 */
   int32_t cluster_size;       /* 1 = one persistent CTA per pair; 2,4,8 = thread-block cluster per pair (DSMEM
                                * reduction); -1 = task-graph kernel ((pair,chunk) tasks through a device queue);
+                               * -3 = warp-specialised kernel (gather / math warps, experimental);
                                * 0 = auto (clusters of 8/4/2 while pairs are fewer than SMs/8, /4, /2; else one CTA per pair) */
   int32_t coarsest_level;     /* first level solved; -1 => n_levels-1 */
   int32_t finest_level;       /* last level solved; 0 */

@@ -346,9 +346,10 @@ def test_solve_dogleg_matches_oracle(ea, ctx, fs5, frames, oracle, radius, clust
 
 
 # ----------------------------------------------------------------------------------------- kernels / tracker
-@pytest.mark.parametrize("kernel", [-1, 1, 2])
+@pytest.mark.parametrize("kernel", [-3, -1, 1, 2])
 def test_solve_kernel_variants_agree(ea, ctx, fs5, solver_golden, kernel):
-    """task-graph (-1), CTA-per-pair (1) and cluster (2) kernels are the same solver: same poses, costs, iterations."""
+    """warp-specialised (-3), task-graph (-1), CTA-per-pair (1) and cluster (2) kernels are the same solver: same poses,
+    costs, iterations."""
     pairs = [(a, b) for a in range(5) for b in range(5) if a != b]
     sp = ea.solve_params(point_stride=3, cluster_size=kernel)
     poses, S = ctx.solve_batch(fs5, [p[0] for p in pairs], fs5, [p[1] for p in pairs], None, sp)
@@ -358,7 +359,7 @@ def test_solve_kernel_variants_agree(ea, ctx, fs5, solver_golden, kernel):
         assert rot_angle_between(poses[i][:4], ref[i][:4]) < 2e-5 and np.abs(poses[i][4:] - ref[i][4:]).max() < 2e-5
         assert abs(S[i][0]["iterations"] - R[i][0]["iterations"]) <= 2
         assert abs(S[i][0]["final_cost"] - R[i][0]["final_cost"]) <= 1e-5 * R[i][0]["final_cost"]
-    if kernel == -1:   # the task-graph reduction order is fixed by chunk index: bitwise reproducible
+    if kernel < 0:   # reduction order fixed by chunk index / by ring slot order: bitwise reproducible
         poses2, _ = ctx.solve_batch(fs5, [p[0] for p in pairs], fs5, [p[1] for p in pairs], None, sp)
         assert np.array_equal(poses, poses2)
 
