@@ -94,7 +94,7 @@ template <bool INL>
 __device__ __forceinline__ void ea_boss_step_impl(const EaSolveArgs& A, EaSolveSmem& S, const double* sums, const EaMsg& cur, EaMsg& out) {
   const int cmd = INL ? ea_lm_advance_impl(S.lm, sums, A.sp) : ea_lm_advance(S.lm, sums, A.sp);
   if (cmd == EA_CMD_EVAL) {
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 7; ++i) out.cand[i] = S.lm.cand[i];
     out.pts = cur.pts; out.dt = cur.dt; out.affine = cur.affine; out.n_res = cur.n_res; out.level = cur.level; out.pts_mode = cur.pts_mode; out.cmd = EA_CMD_EVAL;
     return;

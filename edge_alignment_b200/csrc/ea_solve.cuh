@@ -187,16 +187,18 @@ __device__ inline bool ea_lm_compute_step(EaLmState& S, const ea_solve_params& s
 #pragma unroll
     for (int j = 0; j < 6; ++j) step[j] = ds[j] / S.diag[j];
   }
-  // model_cost_change = -(step^T b_s + 1/2 step^T H_s step)
+  // model_cost_change = -(step^T b_s + 1/2 step^T H_s step) = -(delta^T b + 1/2 delta^T H delta) with delta = S step: taken
+  // from the unscaled sums in shared memory, so that the scaled matrix need not stay in registers across the factorisation
+#pragma unroll
+  for (int a = 0; a < 6; ++a) delta[a] = step[a] * S.scale[a];  // undo the Jacobi column scaling
   double lin = 0.0, quad = 0.0;
 #pragma unroll
   for (int a = 0; a < 6; ++a) {
-    lin = fma(step[a], bs[a], lin);
+    lin = fma(delta[a], S.b[a], lin);
     double row = 0.0;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) row = fma(A[a][c], step[c], row);
-    quad = fma(step[a], row, quad);
-    delta[a] = step[a] * S.scale[a];  // undo the Jacobi column scaling
+    for (int c = 0; c < 6; ++c) row = fma(S.H[a <= c ? ea_tri(a, c) : ea_tri(c, a)], delta[c], row);
+    quad = fma(delta[a], row, quad);
   }
   S.model_cost_change = -(lin + 0.5 * quad);
   return S.model_cost_change > 0.0;
@@ -223,7 +225,7 @@ static __device__ __forceinline__ int ea_lm_advance_impl(EaLmState& S, const dou
   } else {
     const double cand_cost = fail ? DBL_MAX : sums[28];
     double sn = 0.0, xn = 0.0;
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 7; ++i) { const double d = S.x[i] - S.cand[i]; sn += d * d; xn += S.x[i] * S.x[i]; }
     sn = sqrt(sn); xn = sqrt(xn);
     if (sn <= sp.parameter_tolerance * (xn + sp.parameter_tolerance)) { S.term = EA_TERM_CONVERGENCE_PARAMETER; return EA_CMD_DONE; }
@@ -231,11 +233,11 @@ static __device__ __forceinline__ int ea_lm_advance_impl(EaLmState& S, const dou
     if (fabs(cost_change) <= sp.function_tolerance * S.cost) { S.term = EA_TERM_CONVERGENCE_FUNCTION; return EA_CMD_DONE; }
     const double rel = fail ? -DBL_MAX : cost_change / S.model_cost_change;
     if (rel > sp.min_relative_decrease) {  // HandleSuccessfulStep (the fused pass already holds J at x_new)
-#pragma unroll 1
+#pragma unroll
       for (int i = 0; i < 7; ++i) S.x[i] = S.cand[i];
-#pragma unroll 1
+#pragma unroll
       for (int k = 0; k < 21; ++k) S.H[k] = sums[k];
-#pragma unroll 1
+#pragma unroll
       for (int k = 0; k < 6; ++k) S.b[k] = sums[21 + k];
       S.cost = cand_cost;
       if (sp.trust_region_strategy == 0) {

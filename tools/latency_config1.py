@@ -18,7 +18,7 @@ def timeit(fn, n=30):
     ctx.sync(); return (time.perf_counter() - t) / n * 1e3
 out["preprocess_both_frames_ms"] = timeit(lambda: fs.preprocess_host([0, 1], bgr, dep, ea.ROLE_BOTH))
 for stride in (30, 1):
-    for kern, name in ((-1, "task_graph"), (1, "cta_per_pair"), (8, "cluster8")):
+    for kern, name in ((-1, "task_graph"), (1, "cta_per_pair"), (2, "cluster2"), (4, "cluster4"), (8, "cluster8"), (0, "auto")):
         sp = ea.solve_params(point_stride=stride, cluster_size=kern)
         ms = timeit(lambda: ctx.solve_batch(fs, [0], fs, [1], None, sp))
         poses, S = ctx.solve_batch(fs, [0], fs, [1], None, sp)
