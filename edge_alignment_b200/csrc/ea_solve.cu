@@ -35,6 +35,7 @@ struct EaMsg {  // boss -> all threads of the cluster
   const float* dt;
   float2 affine;
   int n_res, level, pts_mode, cmd;
+  int rev, pad;   // sweep direction of this evaluation: alternates per evaluation of the (pair, level), see ea_eval_slice
 };
 
 struct EaSolveSmem {
@@ -82,7 +83,7 @@ __device__ __forceinline__ void ea_boss_next_impl(const EaSolveArgs& A, EaSolveS
     L.phase = 0; L.iter = 0; L.accepted = 0; L.rejected = 0; L.invalid_run = 0; L.evals = 0; L.term = EA_TERM_NONE;
 #pragma unroll 1
     for (int i = 0; i < 7; ++i) { L.cand[i] = L.x[i]; out.cand[i] = L.x[i]; }
-    out.pts = rd.pts; out.dt = nd.dt; out.affine = *nd.dt_affine; out.n_res = n_res; out.level = level; out.pts_mode = rd.pts_mode; out.cmd = EA_CMD_EVAL;
+    out.pts = rd.pts; out.dt = nd.dt; out.affine = *nd.dt_affine; out.n_res = n_res; out.level = level; out.pts_mode = rd.pts_mode; out.cmd = EA_CMD_EVAL; out.rev = 0; out.pad = 0;
     return;
   }
 }
@@ -96,7 +97,7 @@ __device__ __forceinline__ void ea_boss_step_impl(const EaSolveArgs& A, EaSolveS
   if (cmd == EA_CMD_EVAL) {
 #pragma unroll
     for (int i = 0; i < 7; ++i) out.cand[i] = S.lm.cand[i];
-    out.pts = cur.pts; out.dt = cur.dt; out.affine = cur.affine; out.n_res = cur.n_res; out.level = cur.level; out.pts_mode = cur.pts_mode; out.cmd = EA_CMD_EVAL;
+    out.pts = cur.pts; out.dt = cur.dt; out.affine = cur.affine; out.n_res = cur.n_res; out.level = cur.level; out.pts_mode = cur.pts_mode; out.cmd = EA_CMD_EVAL; out.rev = S.lm.evals & 1; out.pad = 0;
     return;
   }
   if (A.summaries) {
@@ -111,6 +112,10 @@ __device__ __forceinline__ void ea_boss_step_impl(const EaSolveArgs& A, EaSolveS
 }
 __device__ __noinline__ void ea_boss_step(const EaSolveArgs& A, EaSolveSmem& S, const double* sums, const EaMsg& cur, EaMsg& out) { ea_boss_step_impl<false>(A, S, sums, cur, out); }
 
+
+#ifndef EA_ALTERNATE_SWEEP
+#define EA_ALTERNATE_SWEEP 1
+#endif
 
 template <int THREADS, bool CLUSTER>
 __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(const __grid_constant__ EaSolveArgs A) {
@@ -143,10 +148,10 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
     EaPose P;
     if (M.pts_mode == EA_POINTS_XYZ) {
       ea_pose_setup<true>(M.cand, rg, ng, P);
-      ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart);
+      ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart, EA_ALTERNATE_SWEEP && M.rev);
     } else {
       ea_pose_setup<false>(M.cand, rg, ng, P);
-      ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart);
+      ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart, EA_ALTERNATE_SWEEP && M.rev);
     }
     __syncthreads();
     if (warp == 0) {

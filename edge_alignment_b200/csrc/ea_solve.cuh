@@ -290,8 +290,11 @@ template <bool XYZ, int THREADS>
 __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, const float* __restrict__ dt, const float2 affine,
                                               const EaLevelGeom& ng,
                                               double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, int j0,
-                                              int j1, double (*part)[EA_NSUM], double* cpart) {
+                                              int j1, double (*part)[EA_NSUM], double* cpart, const bool reverse = false) {
+  // reverse: walk the slice from its end.  Successive evaluations of a pair alternate the direction, so each sweep
+  // starts on the data the previous one touched last (still in L1 / L2) instead of on the data it evicted first.
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int jflip = j0 + j1 - 1;
   const float loss_a = float(sp.loss_scale);
   const int loss_type = sp.loss_type, stride = sp.point_stride;
   float acc[EA_NSUM];
@@ -301,12 +304,12 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
   int since_flush = 0;
   int j = j0 + warp * 32 + lane;
   typedef EaPtStream<XYZ> PS;
-  typename PS::T p_next = (j < j1) ? PS::load(pts, size_t(j) * stride) : PS::pad();
+  typename PS::T p_next = (j < j1) ? PS::load(pts, size_t(reverse ? jflip - j : j) * stride) : PS::pad();
   for (int base = j0 + warp * 32; base < j1; base += THREADS) {
     const typename PS::T p = p_next;
     const bool valid = j < j1;
     j += THREADS;
-    if (j < j1) p_next = PS::load(pts, size_t(j) * stride);   // prefetch the next point before the gather
+    if (j < j1) p_next = PS::load(pts, size_t(reverse ? jflip - j : j) * stride);   // prefetch the next point before the gather
     EaPointEval e;
     double a0, a1, a2;
     PS::unpack(p, a0, a1, a2);
