@@ -279,6 +279,21 @@ int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uin
   return EA_OK;
 }
 
+// The compaction kernel writes packed pixel points: a slot that held caller-supplied 3-D points (ea_frameset_set_points with
+// EA_POINTS_XYZ) goes back to pixel mode when it is preprocessed as a reference frame.
+static int reset_points_mode(ea_frameset* fs, int n, const int32_t* slots) {
+  ea_context* c = fs->ctx;
+  for (int i = 0; i < n; ++i)
+    for (int l = 0; l < fs->p.n_levels; ++l) {
+      EaLevelDesc& D = fs->h_desc[size_t(slots[i]) * EA_MAX_LEVELS + l];
+      if (D.pts_mode == EA_POINTS_PIXEL) continue;
+      D.pts_mode = EA_POINTS_PIXEL;
+      CU(cudaMemcpyAsync(fs->d_desc + size_t(slots[i]) * EA_MAX_LEVELS + l, &D, sizeof D, cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));       // D lives in pageable host memory owned by the frameset
+    }
+  return EA_OK;
+}
+
 extern "C" {
 int ea_frameset_preprocess_device(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* d_bgr, const void* d_depth, int roles) {
   int rc = check_slots(fs, n, slots);
@@ -294,6 +309,7 @@ int ea_frameset_preprocess_device(ea_frameset* fs, int n, const int32_t* slots, 
   CU(cudaMemcpyAsync(d_slots, slots, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   rc = ea_preprocess_impl(fs, n, d_slots, d_bgr, d_depth, roles);
   cudaFreeAsync(d_slots, c->stream);
+  if (rc == EA_OK && (roles & EA_ROLE_REF)) rc = reset_points_mode(fs, n, slots);
   return rc;
 }
 
@@ -319,6 +335,7 @@ int ea_frameset_preprocess_masked(ea_frameset* fs, int n, const int32_t* slots, 
   rc = ea_preprocess_impl(fs, n, d_slots, fs->stage_bgr, fs->stage_depth, roles, d_mask);
   cudaFreeAsync(d_mask, c->stream);
   cudaFreeAsync(d_slots, c->stream);
+  if (rc == EA_OK) rc = reset_points_mode(fs, n, slots);
   return rc;
 }
 

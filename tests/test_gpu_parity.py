@@ -205,6 +205,23 @@ def test_eval_bypass_hooks_and_xyz_mode(ea, ctx, frames, oracle, numpy_pins):
         fs.close()
 
 
+def test_points_mode_returns_to_pixel_after_preprocess(ea, ctx, frames, oracle, numpy_pins):
+    """A slot that held caller-supplied XYZ points is a pixel-point slot again once it is preprocessed as a reference frame."""
+    O = oracle
+    K = frames["K"]
+    fs = ea.FrameSet(ctx, ea.frame_params(), 2)
+    try:
+        fs.preprocess_host([0, 1], frames["bgr"][[0, 2]], frames["depth"][[0, 2]], ea.ROLE_BOTH)
+        want = ctx.eval(fs, 0, fs, 1, numpy_pins["xpert"], ea.solve_params(point_stride=30))["raw"].copy()
+        xyz, _ = O.get_aX(frames["bgr"][0], frames["depth"][0], K)
+        fs.set_points(0, np.concatenate([xyz, np.ones((len(xyz), 1))], 1), mode=ea.POINTS_XYZ)
+        fs.preprocess_host([0], frames["bgr"][:1], frames["depth"][:1], ea.ROLE_REF)
+        got = ctx.eval(fs, 0, fs, 1, numpy_pins["xpert"], ea.solve_params(point_stride=30))["raw"]
+        np.testing.assert_array_equal(got, want)
+    finally:
+        fs.close()
+
+
 def test_eval_out_of_image_and_z_guard(ea, ctx, oracle):
     O = oracle
     rng = np.random.default_rng(5)
