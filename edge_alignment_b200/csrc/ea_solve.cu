@@ -266,6 +266,9 @@ __global__ void __launch_bounds__(THREADS) ea_k_eval_sums(EaLevelDesc rd, EaLeve
 #ifndef EA_WS_GATHER_REGS
 #define EA_WS_GATHER_REGS 64
 #endif
+#ifndef EA_WS_BACKOFF_NS
+#define EA_WS_BACKOFF_NS 0
+#endif
 #define EA_WS_THREADS (32 * EA_WS_MATH * (1 + EA_WS_PROD))
 #define EA_WS_WORDS 24
 #define EA_STR2(x) #x
@@ -290,6 +293,9 @@ __device__ __forceinline__ void ea_mbar_wait(unsigned long long* b, unsigned par
   do {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(done) : "r"(a), "r"(parity) : "memory");
+#if EA_WS_BACKOFF_NS > 0
+    if (!done) __nanosleep(EA_WS_BACKOFF_NS);     // polling warps would otherwise take issue slots from the warps they wait for
+#endif
   } while (!done);
 }
 
