@@ -95,6 +95,7 @@ PROTOTYPES = {
     "ea_frameset_level_geometry": (_i, [_vp, _i, _pi, _pi, _f64p]),
     "ea_eval": (_i, [_vp, _vp, _i, _vp, _i, _i, _f64p, C.POINTER(SolveParams), _pi, _f64p, _f64p, _f64p, _f64p, _pi]),
     "ea_solve_batch": (_i, [_vp, _i, _vp, _i32p, _vp, _i32p, _f64p, C.POINTER(SolveParams), C.POINTER(Summary)]),
+    "ea_solve_traced": (_i, [_vp, _vp, _i, _vp, _i, _f64p, C.POINTER(SolveParams), C.POINTER(Summary), _f64p, _i, _pi]),
     "ea_solve_batch_device": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(SolveParams), _vp]),
     "ea_eval_views": (_i, [_vp, _i, C.POINTER(View), _i, _f64p, C.POINTER(SolveParams), _pi, _f64p, _f64p, _f64p, _f64p, _pi]),
     "ea_solve_views": (_i, [_vp, _i, C.POINTER(View), _i, _f64p, C.POINTER(SolveParams), C.POINTER(Summary)]),

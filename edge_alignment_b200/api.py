@@ -84,6 +84,16 @@ class Context:
         _check(L.lib().ea_profile_read(self._h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
         return dict(preprocess_ms=a.value, n_preprocess=na.value, solve_ms=b.value, n_solve=nb.value)
 
+    def solve_traced(self, ref, ref_slot, now, now_slot, pose7=None, sp=None, cap=512):
+        """One pair with its iteration log: returns (pose7, summaries, trace [n, 6]) -- see ea_solve_traced."""
+        sp = sp or solve_params()
+        pose = np.array(IDENTITY if pose7 is None else pose7, np.float64).copy()
+        S = (L.Summary * ref.params.n_levels)()
+        tr = np.zeros((cap, 6)); n = C.c_int()
+        _check(L.lib().ea_solve_traced(self._h, ref._h, ref_slot, now._h, now_slot, _ptr(pose, C.c_double), C.byref(sp), S,
+                                       _ptr(tr, C.c_double), cap, C.byref(n)))
+        return pose, [s.asdict() for s in S], tr[:min(n.value, cap)]
+
     # ---- evaluation / solve -------------------------------------------------------------------------
     def eval(self, ref, ref_slot, now, now_slot, pose7, sp=None, level=0, want_jac=True):
         sp = sp or solve_params()

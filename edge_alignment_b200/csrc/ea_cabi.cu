@@ -666,6 +666,7 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
   A.summaries = d_summaries; A.n_pairs = n; A.work_counter = c->d_work; A.order = d_order;
   EaProfileScope prof(c, 1);
   cudaError_t e;
+  A.trace = c->d_trace; A.trace_count = c->d_trace_count; A.trace_cap = c->trace_cap;
   // auto (measured): few pairs -> a thread-block cluster per pair so the whole GPU works on them and the
   // per-iteration latency drops (config 1, stride 1: 0.58 ms with clusters of 8 vs 2.4 ms on one CTA); big batches -> one
   // persistent CTA per pair (no scheduling overhead, best L1 locality).  -1 asks for the task-graph kernel explicitly.
@@ -731,6 +732,25 @@ int ea_solve_batch(ea_context* c, int n, ea_frameset* ref, const int32_t* ref_sl
   CU(cudaMemcpy(&ovf, ref->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
   if (ovf) return ea_fail(EA_ERR_CAPACITY, "a reference point list was truncated at max_points; result uses the truncated list");
   return EA_OK;
+}
+
+int ea_solve_traced(ea_context* c, ea_frameset* ref, int ref_slot, ea_frameset* now, int now_slot, double* pose7,
+                    const ea_solve_params* sp, ea_summary* summaries, double* trace, int cap, int* n_records) {
+  if (!c || !trace || cap <= 0 || !n_records) return ea_fail(EA_ERR_INVALID_ARG, "ea_solve_traced: null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMalloc((void**)&c->d_trace, size_t(cap) * EA_TRACE_DOUBLES * sizeof(double)));
+  CU(cudaMalloc((void**)&c->d_trace_count, sizeof(int)));
+  CU(cudaMemsetAsync(c->d_trace_count, 0, sizeof(int), c->stream));
+  c->trace_cap = cap;
+  const int32_t rs = ref_slot, ns = now_slot;
+  int rc = ea_solve_batch(c, 1, ref, &rs, now, &ns, pose7, sp, summaries);
+  int n = 0;
+  cudaMemcpy(&n, c->d_trace_count, sizeof(int), cudaMemcpyDeviceToHost);
+  *n_records = n;
+  cudaMemcpy(trace, c->d_trace, size_t(std::min(n, cap)) * EA_TRACE_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(c->d_trace); cudaFree(c->d_trace_count);
+  c->d_trace = nullptr; c->d_trace_count = nullptr; c->trace_cap = 0;
+  return rc;
 }
 
 }  // extern "C"

@@ -11,6 +11,8 @@
 
 #define EA_KERNEL_WS (-3)   // ea_solve_params.cluster_size: warp-specialised kernel (ea_k_solve_ws)
 
+#define EA_TRACE_DOUBLES 6    // {level, iteration, cost of the accepted iterate, cost at the candidate, radius, decision}
+
 struct EaSolveArgs {
   const EaLevelDesc* ref_desc;  // [ref slots][EA_MAX_LEVELS]
   const EaLevelDesc* now_desc;  // [now slots][EA_MAX_LEVELS]
@@ -26,6 +28,9 @@ struct EaSolveArgs {
   unsigned long long* slots;    // [EA_QUEUE_CAP]
   int window, chunk_points;
   ea_summary* summaries;        // [n_pairs][n_levels] device or null
+  double* trace;                // [trace_cap][EA_TRACE_DOUBLES] device or null: one record per evaluation (single-pair solves only)
+  int* trace_count;             // device counter of records written
+  int trace_cap;
   int n_pairs, n_levels, coarsest, finest;
   double inv_depth_scale;
   EaLevelGeom ref_geom[EA_MAX_LEVELS];
@@ -112,6 +117,7 @@ struct ea_context {
   size_t tmp_cap = 0;
   // optional profiling: event pairs around preprocessing pipelines [0] and solve launches [1]
   bool profile = false;
+  double* d_trace = nullptr; int* d_trace_count = nullptr; int trace_cap = 0;   // ea_solve_traced
   std::vector<cudaEvent_t> ev[2];
 };
 struct EaProfileScope {   // records a start/stop event pair on the launching stream when profiling is on

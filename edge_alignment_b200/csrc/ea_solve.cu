@@ -93,7 +93,16 @@ __device__ __noinline__ void ea_boss_next(const EaSolveArgs& A, EaSolveSmem& S, 
 
 template <bool INL>
 __device__ __forceinline__ void ea_boss_step_impl(const EaSolveArgs& A, EaSolveSmem& S, const double* sums, const EaMsg& cur, EaMsg& out) {
+  const int acc0 = S.lm.accepted, rej0 = S.lm.rejected;
   const int cmd = INL ? ea_lm_advance_impl(S.lm, sums, A.sp) : ea_lm_advance(S.lm, sums, A.sp);
+  if (A.trace) {   // iteration log of a single-pair solve (ea_solve_traced): what Ceres prints with minimizer_progress_to_stdout
+    const int k = (*A.trace_count)++;
+    if (k < A.trace_cap) {
+      double* r = A.trace + size_t(k) * EA_TRACE_DOUBLES;
+      r[0] = cur.level; r[1] = S.lm.accepted + S.lm.rejected; r[2] = S.lm.cost; r[3] = sums[28]; r[4] = S.lm.radius;
+      r[5] = S.lm.accepted > acc0 ? 1.0 : (S.lm.rejected > rej0 ? 0.0 : -1.0);   // accepted / rejected / no decision (first evaluation, termination)
+    }
+  }
   if (cmd == EA_CMD_EVAL) {
 #pragma unroll
     for (int i = 0; i < 7; ++i) out.cand[i] = S.lm.cand[i];

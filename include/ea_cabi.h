@@ -220,6 +220,12 @@ int ea_eval(ea_context* ctx, ea_frameset* ref, int ref_slot, ea_frameset* now, i
  * poses7 [n][7] in/out (HOST); summaries [n][n_levels] (HOST, may be NULL).  Synchronous. */
 int ea_solve_batch(ea_context* ctx, int n, ea_frameset* ref, const int32_t* ref_slots, ea_frameset* now,
                    const int32_t* now_slots, double* poses7, const ea_solve_params* sp, ea_summary* summaries);
+/* One pair with the iteration log Ceres prints under minimizer_progress_to_stdout (standalone_edge_align.cpp:284): one record
+ * of 6 doubles per evaluation, in order, over all pyramid levels: {level, iterations done so far at this level, cost of the
+ * accepted iterate, cost at the evaluated candidate, trust-region radius after the update, decision (1 accepted, 0 rejected,
+ * -1 none: first evaluation of a level or termination)}.  trace [cap][6] (HOST), n_records = evaluations made. */
+int ea_solve_traced(ea_context* ctx, ea_frameset* ref, int ref_slot, ea_frameset* now, int now_slot, double* pose7,
+                    const ea_solve_params* sp, ea_summary* summaries, double* trace, int cap, int* n_records);
 /* Same with DEVICE-resident slot indices / poses / summaries; asynchronous on the context stream.
  * d_pose_index[n] maps pair i to a row of d_poses (in/out) so chained solves need no host round trip. */
 int ea_solve_batch_device(ea_context* ctx, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now,

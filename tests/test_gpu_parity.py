@@ -362,6 +362,30 @@ def test_solve_dogleg_matches_oracle(ea, ctx, fs5, frames, oracle, radius, clust
         ctx.solve_batch(fs5, [0], fs5, [1], None, ea.solve_params(trust_region_strategy=2))
 
 
+@pytest.mark.parametrize("strategy,radius", [(0, 1e4), (0, 1e-2), (1, 1e-2)])
+def test_iteration_log_matches_oracle(ea, ctx, fs5, frames, oracle, strategy, radius):
+    """ea_solve_traced: the per-iteration log (cost of the accepted iterate, trust-region radius, accept / reject) follows the
+    oracle's iteration by iteration -- a much stronger statement than agreeing at the optimum.  Small starting radii make
+    the radius sequence non-trivial (LM damping, dogleg Cauchy / interpolated steps)."""
+    O = oracle
+    K = frames["K"]
+    for a, b in ((0, 2), (0, 4)):
+        xyz, _ = O.get_aX(frames["bgr"][a], frames["depth"][a], K, frames["zscale"])
+        dt, _ = O.get_distance_transform(frames["bgr"][b])
+        opts = O.default_options(strategy=strategy, initial_radius=radius, max_num_iterations=200)
+        op, oS, otr = O.solve(xyz, dt, K, IDENTITY, stride=30, options=opts)
+        sp = ea.solve_params(point_stride=30, trust_region_strategy=strategy, initial_trust_region_radius=radius, max_num_iterations=200)
+        pose, S, tr = ctx.solve_traced(fs5, a, fs5, b, None, sp)
+        assert rot_angle_between(pose[:4], op[:4]) < 1e-4 and np.abs(pose[4:] - op[4:]).max() < 1e-4
+        n = min(len(tr), len(otr)) - 1                      # the last record is the terminating evaluation on both sides
+        assert n >= 10 and abs(len(tr) - len(otr)) <= 2
+        assert tr[0][5] == -1 and abs(tr[0][2] - otr[0][0]) <= 1e-6 * otr[0][0] and tr[0][4] == radius
+        np.testing.assert_allclose(tr[1:n, 2], otr[1:n, 0], rtol=2e-6)          # cost after every iteration
+        np.testing.assert_array_equal(tr[1:n, 5], otr[1:n, 6])                   # same accept / reject decisions
+        np.testing.assert_allclose(tr[1:n, 4], otr[1:n, 5], rtol=1e-3)          # same trust-region radius sequence
+        assert np.all(tr[:, 0] == 0) and np.array_equal(tr[1:n, 1], np.arange(1, n))
+
+
 # ----------------------------------------------------------------------------------------- kernels / tracker
 @pytest.mark.parametrize("kernel", [-3, -1, 1, 2])
 def test_solve_kernel_variants_agree(ea, ctx, fs5, solver_golden, kernel):
