@@ -615,10 +615,11 @@ __device__ __forceinline__ void dtw_row_scan(int (&d)[P], const int (&cval)[P], 
   }
 }
 
-template <int P>
+// FULL: every lane's strip lies inside the image (w == 32 * P, e.g. 640 px at P = 20): the per-pixel bound checks drop out.
+template <int P, bool FULL>
 __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, const int slot, const int lane) {
   const EaPrepLevel& L = A.lv[level];
-  const int w = L.w, h = L.h, words = L.words;
+  const int w = FULL ? 32 * P : L.w, h = L.h, words = L.words;   // FULL: a compile-time width folds every bound check
   const uint32_t* bits = (A.use_median ? L.med_bits : L.edge_bits) + size_t(slot) * h * words;
   int* gi = reinterpret_cast<int*>(L.dt + size_t(slot) * w * h);
   float* gf = L.dt + size_t(slot) * w * h;
@@ -649,12 +650,12 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
       const int c = (k == P - 1) ? pr : d[k + 1];
       int v = min(min(a, c) + DT_DG, d[k] + DT_HV);
       if ((ebits >> k) & 1u) v = 0;
-      if (x0 + k >= w) v = DT_INF;
+      if (!FULL && x0 + k >= w) v = DT_INF;
       cval[k] = min(v, DT_INF);
     }
     dtw_row_scan<P, false>(d, cval, lane);
 #pragma unroll
-    for (int k = 0; k < P; ++k) if (x0 + k >= w) d[k] = DT_INF;
+    for (int k = 0; k < P; ++k) if (!FULL && x0 + k >= w) d[k] = DT_INF;
     if (on) dt_store_row<P, int>(gi + size_t(y) * w, x0, w, d, vec_ok);
   }
   // ---------------- backward pass ----------------
@@ -681,7 +682,7 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
       const int a = (k == 0) ? pl : d[k - 1];
       const int c = (k == P - 1) ? pr : d[k + 1];
       int v = min(t0[k], min(min(a, c) + DT_DG, d[k] + DT_HV));
-      if (x0 + k >= w) v = DT_INF;
+      if (!FULL && x0 + k >= w) v = DT_INF;
       cval[k] = min(v, DT_INF);
     }
     dtw_row_scan<P, true>(d, cval, lane);
@@ -689,7 +690,7 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       outv[k] = 0.0f;
-      if (x0 + k >= w) { d[k] = DT_INF; continue; }
+      if (!FULL && x0 + k >= w) { d[k] = DT_INF; continue; }
       const unsigned t = (d[k] >= DT_INF) ? DT_DISTMAX : unsigned(d[k]);
       vmax = max(vmax, t); vmin = min(vmin, t);
       outv[k] = float(t) * (1.0f / 65536.0f);
@@ -717,9 +718,10 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
 __global__ void __launch_bounds__(32) k_chamfer_dt_warp(const __grid_constant__ EaPrepArgs A) {
   const int level = blockIdx.y, slot = A.slots[blockIdx.x], lane = threadIdx.x;
   const int per = (A.lv[level].w + 31) / 32;
-  if (per <= 8) dtw_level<8>(A, level, slot, lane);
-  else if (per <= 12) dtw_level<12>(A, level, slot, lane);
-  else dtw_level<DTW_PMAX>(A, level, slot, lane);
+  const int w = A.lv[level].w;
+  if (per <= 8) { if (w == 256) dtw_level<8, true>(A, level, slot, lane); else dtw_level<8, false>(A, level, slot, lane); }
+  else if (per <= 12) { if (w == 384) dtw_level<12, true>(A, level, slot, lane); else dtw_level<12, false>(A, level, slot, lane); }
+  else { if (w == 32 * DTW_PMAX) dtw_level<DTW_PMAX, true>(A, level, slot, lane); else dtw_level<DTW_PMAX, false>(A, level, slot, lane); }
 }
 
 // ---- normalised copy of one DT (read-back for parity tests): dst = raw * scale + shift, exactly as cv::normalize ----
