@@ -609,7 +609,7 @@ __device__ __forceinline__ void dtw_row_scan(int (&d)[P], const int (&cval)[P], 
     for (int i = 0; i < 4; ++i) {
       const int kk = 4 * g + i;
       pm = min(pm, e[kk]);
-      const int v = min(min(pm, carry + DT_HV) + DT_HV * kk, DT_INF);    // min(local, carry + HV * (kk + 1))
+      const int v = min(pm, carry + DT_HV) + DT_HV * kk;                 // min(local, carry + HV * (kk + 1)); >= DT_INF means no seed yet
       d[BACKWARD ? (P - 1 - kk) : kk] = v;
     }
   }
@@ -651,7 +651,7 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
       int v = min(min(a, c) + DT_DG, d[k] + DT_HV);
       if ((ebits >> k) & 1u) v = 0;
       if (!FULL && x0 + k >= w) v = DT_INF;
-      cval[k] = min(v, DT_INF);
+      cval[k] = v;     // "infinite" values stay >= DT_INF and bounded by DT_INF + DG + HV * P (the carry below is clamped every row)
     }
     dtw_row_scan<P, false>(d, cval, lane);
 #pragma unroll
@@ -683,7 +683,7 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
       const int c = (k == P - 1) ? pr : d[k + 1];
       int v = min(t0[k], min(min(a, c) + DT_DG, d[k] + DT_HV));
       if (!FULL && x0 + k >= w) v = DT_INF;
-      cval[k] = min(v, DT_INF);
+      cval[k] = v;     // "infinite" values stay >= DT_INF and bounded by DT_INF + DG + HV * P (the carry below is clamped every row)
     }
     dtw_row_scan<P, true>(d, cval, lane);
     float outv[P];
