@@ -616,6 +616,9 @@ __device__ __forceinline__ void dtw_row_scan(int (&d)[P], const int (&cval)[P], 
 }
 
 // FULL: every lane's strip lies inside the image (w == 32 * P, e.g. 640 px at P = 20): the per-pixel bound checks drop out.
+#ifndef DTW_L2_AHEAD
+#define DTW_L2_AHEAD 4      // rows of L2 prefetch distance (measured: see profiles)
+#endif
 template <int P, bool FULL>
 __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, const int slot, const int lane) {
   const EaPrepLevel& L = A.lv[level];
@@ -635,6 +638,7 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
   unsigned b0 = on ? bits[wi] : 0u, b1 = two ? bits[wi + 1] : 0u;
   for (int y = 0; y < h; ++y) {
     const unsigned ebits = __funnelshift_r(b0, b1, sh);
+    if (y + DTW_L2_AHEAD < h && lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(bits + size_t(y + DTW_L2_AHEAD) * words));
     if (y + 1 < h) {   // prefetch the next row's mask words
       b0 = on ? bits[size_t(y + 1) * words + wi] : 0u;
       b1 = two ? bits[size_t(y + 1) * words + wi + 1] : 0u;
@@ -672,6 +676,10 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
 #pragma unroll
     for (int k = 0; k < P; ++k) t0[k] = t_next[k];
     if (y > 0 && on) dt_load_row<P>(gi + size_t(y - 1) * w, x0, w, t_next, vec_ok);
+    // the forward rows were written ~1 ms ago and have left the L2: the register prefetch one row ahead does not cover a
+    // DRAM round trip (ncu: 31 % of the kernel's samples waited here), so rows further up are pulled into L2 early
+    if (y >= DTW_L2_AHEAD && lane * 32 < w)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + size_t(y - DTW_L2_AHEAD) * w + lane * 32));
     int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
     int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
     if (lane == 0) pl = DT_INF;
