@@ -134,9 +134,7 @@ __global__ void __launch_bounds__(256) k_edge_mask(const uint8_t* __restrict__ b
 // Same arithmetic as k_edge_mask (bit exact); ~3x fewer instructions per pixel.  Needs w % 4 == 0 (32-bit row loads).
 #define E2_TW 128
 #define E2_TH 32
-#define E2_PW (E2_TW + 8)   // packed tile: image columns x0-4 .. x0+131
 #define E2_PH (E2_TH + 4)   // image rows y0-2 .. y0+33 (through REFLECT_101)
-#define E2_GW (E2_TW + 4)   // gray tile: columns x0-1 .. x0+128 (+2 pad)
 
 // packed pixel p = B | G<<8 | R<<16  ->  16-bit lanes {B, G} and {R}
 __device__ __forceinline__ void e2_expand(unsigned p, unsigned& bg, unsigned& r) {
@@ -151,22 +149,26 @@ __device__ __forceinline__ unsigned e2_gray(unsigned v_bg, unsigned v_r) {
   return (B * 9798u + G * 19235u + b_r * 3735u + 16384u) >> 15;
 }
 
-template <typename D>
-__global__ void __launch_bounds__(E2_TW) k_edge_mask2(const uint8_t* __restrict__ bgr, const D* __restrict__ depth,
+// TW = tile width = threads per CTA (128; 64 for levels whose width is a multiple of 64 but not of 128, where a 128-wide
+// last tile would be half empty)
+template <typename D, int TW>
+__global__ void __launch_bounds__(TW) k_edge_mask2(const uint8_t* __restrict__ bgr, const D* __restrict__ depth,
                                                       size_t frame_stride_px, const int32_t* __restrict__ src_slots,
                                                       const int32_t* __restrict__ dst_slots, uint32_t* __restrict__ edge_bits,
                                                       uint32_t* __restrict__ ref_bits, int w, int h, int words, int thresh, int zero_to_one) {
-  __shared__ unsigned tile[E2_PH][E2_PW];
-  __shared__ uint8_t gray[E2_TH + 2][E2_GW];
+  constexpr int PW = TW + 8;   // packed tile: image columns x0-4 .. x0+TW+3
+  constexpr int GW = TW + 4;   // gray tile: columns x0-1 .. x0+TW (+2 pad)
+  __shared__ unsigned tile[E2_PH][PW];
+  __shared__ uint8_t gray[E2_TH + 2][GW];
   const int f = blockIdx.z;
   const size_t sbase = (src_slots ? size_t(src_slots[f]) : size_t(f)) * frame_stride_px;
-  const int x0 = blockIdx.x * E2_TW, y0 = blockIdx.y * E2_TH;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * E2_TH;
   const int t = threadIdx.x;
   const unsigned* img = reinterpret_cast<const unsigned*>(bgr + sbase * 3);
   const int row_words = (w * 3) >> 2;
   // ---- phase 1: 32-bit row loads, 3 words -> 4 packed pixels ----
-  for (int i = t; i < E2_PH * (E2_PW / 4); i += E2_TW) {
-    const int r = i / (E2_PW / 4), g = i % (E2_PW / 4);
+  for (int i = t; i < E2_PH * (PW / 4); i += TW) {
+    const int r = i / (PW / 4), g = i % (PW / 4);
     const int col = x0 - 4 + 4 * g;                      // first image column of the group (multiple of 4)
     if (col < 0 || col + 3 >= w) continue;                // outside the image: never read (REFLECT_101 maps inside)
     const int ry = reflect101(y0 - 2 + r, h);
@@ -197,12 +199,12 @@ __global__ void __launch_bounds__(E2_TW) k_edge_mask2(const uint8_t* __restrict_
     }
   }
   // the two halo gray columns (x0-1 and x0+128): 2 x 34 values, computed directly
-  if (t < 2 * (E2_TH + 2)) {
-    const int which = t / (E2_TH + 2), gy = t % (E2_TH + 2);
-    const int hx = which ? x0 + E2_TW : x0 - 1;
+  for (int q = t; q < 2 * (E2_TH + 2); q += TW) {
+    const int which = q / (E2_TH + 2), gy = q % (E2_TH + 2);
+    const int hx = which ? x0 + TW : x0 - 1;
     if (which == 0 || hx <= w) {                          // column w itself is still needed (reflect of w is w-2 ...)
       const int cl = reflect101(hx - 1, w) - x0 + 4, cc = reflect101(hx, w) - x0 + 4, cr = reflect101(hx + 1, w) - x0 + 4;
-      if (cl >= 0 && cl < E2_PW && cc >= 0 && cc < E2_PW && cr >= 0 && cr < E2_PW) {
+      if (cl >= 0 && cl < PW && cc >= 0 && cc < PW && cr >= 0 && cr < PW) {
         unsigned vbg = 0, vr = 0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(E2_TW) k_edge_mask2(const uint8_t* __restrict_
           vbg += (lbg + rbg + (cbg << 1)) << m;
           vr += (lr + rr + (crr << 1)) << m;
         }
-        gray[gy][which ? E2_TW + 1 : 0] = uint8_t(e2_gray(vbg, vr));
+        gray[gy][which ? TW + 1 : 0] = uint8_t(e2_gray(vbg, vr));
       }
     }
   }
@@ -792,8 +794,13 @@ static cudaError_t launch_edges_and_points(const EaPrepArgs& A, cudaStream_t str
       nl += k - 1;
       if (ce != cudaSuccess) return ce;
     } else if ((L.w & 3) == 0 && L.w >= 8 && L.h >= 4) {
-      dim3 grid(unsigned((L.w + E2_TW - 1) / E2_TW), unsigned((L.h + E2_TH - 1) / E2_TH), unsigned(A.n));
-      k_edge_mask2<D><<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
+      if ((L.w % 128) != 0 && (L.w % 128) <= 64) {   // the last 128-wide tile would be at most half full: 64-wide tiles
+        dim3 grid(unsigned((L.w + 63) / 64), unsigned((L.h + E2_TH - 1) / E2_TH), unsigned(A.n));
+        k_edge_mask2<D, 64><<<grid, 64, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
+      } else {
+        dim3 grid(unsigned((L.w + E2_TW - 1) / E2_TW), unsigned((L.h + E2_TH - 1) / E2_TH), unsigned(A.n));
+        k_edge_mask2<D, E2_TW><<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
+      }
     } else {   // generic byte path (any width)
       dim3 grid(unsigned((L.w + ET_W - 1) / ET_W), unsigned((L.h + ET_H - 1) / ET_H), unsigned(A.n));
       k_edge_mask<D><<<grid, dim3(ET_W, ET_H), 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
