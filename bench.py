@@ -355,7 +355,7 @@ def main():
         # depth only travels for frames that become key frames (1 in KEYFRAME_INTERVAL)
         n_key = sum(1 for t in range(Wm + 1, T) if t % KEYFRAME_INTERVAL == 0)
         h2d = (frame_b * K + frame_d * n_key) / K
-        d2h = S * (7 * 8 + N_LEVELS * 40)
+        d2h = S * (7 * 8 + N_LEVELS * 48)
         e2e = {"value": world * S * K / (ms_e * 1e-3), "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / K}
         del hb, hd

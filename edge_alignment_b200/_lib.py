@@ -47,7 +47,7 @@ class SolveParams(C.Structure):
 class Summary(C.Structure):
     _fields_ = [("termination", C.c_int32), ("iterations", C.c_int32), ("accepted", C.c_int32),
                 ("rejected", C.c_int32), ("n_residuals", C.c_int32), ("evaluations", C.c_int32),
-                ("initial_cost", C.c_double), ("final_cost", C.c_double)]
+                ("initial_cost", C.c_double), ("final_cost", C.c_double), ("truncated", C.c_int32), ("reserved", C.c_int32)]
 
     def asdict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

@@ -56,8 +56,6 @@ int ea_create(int device, ea_context** out) {
   CU(cudaMalloc(&c->d_pose, 7 * sizeof(double)));
   CU(cudaMalloc(&c->d_failed, sizeof(int)));
   CU(cudaMalloc(&c->d_work, sizeof(int)));
-  CU(cudaMalloc(&c->d_queue, sizeof(EaQueue)));
-  CU(cudaMalloc(&c->d_slots, size_t(EA_QUEUE_CAP) * sizeof(unsigned long long)));
   CU(cudaMalloc(&c->d_sums, size_t(1024) * EA_SUMS * sizeof(double)));
   *out = c;
   return EA_OK;
@@ -66,7 +64,7 @@ int ea_destroy(ea_context* c) {
   if (!c) return EA_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_work); cudaFree(c->d_queue); cudaFree(c->d_slots); cudaFree(c->d_states); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
+  cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_work); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return EA_OK;
@@ -188,7 +186,9 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
     if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.edge_bits, size_t(L.h) * L.words * 4 * n_slots);
     if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.ref_bits, size_t(L.h) * L.words * 4 * n_slots);
     if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.med_bits, size_t(L.h) * L.words * 4 * n_slots);
-    if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.dt, px * 4 * n_slots);
+    // replicate-padded rows (EA_DT_PAD); + one row of slack so that vector accesses of a row's tail stay inside the pool
+    L.dt_pitch = ea_dt_pitch(L.w); L.dt_slot = ea_dt_slot_floats(L.w, L.h);
+    if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.dt, (L.dt_slot * n_slots + L.dt_pitch) * 4);
     if (rc == EA_OK) rc = fs_alloc(fs, (void**)&L.pts, size_t(L.cap) * 16 * n_slots);
     const double s = 1.0 / double(1 << l);
     EaLevelGeom& G = fs->geom[l];
@@ -206,12 +206,12 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
   }
   if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_npts, size_t(n_slots) * EA_MAX_LEVELS * sizeof(int));
   if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_minmax, size_t(n_slots) * EA_MAX_LEVELS * 2 * sizeof(unsigned));
-  if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_overflow, sizeof(int));
+  if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_overflow, size_t(n_slots) * EA_MAX_LEVELS * sizeof(int));
   if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_affine, size_t(n_slots) * EA_MAX_LEVELS * sizeof(float2));
   if (rc == EA_OK) rc = fs_alloc(fs, (void**)&fs->d_desc, size_t(n_slots) * EA_MAX_LEVELS * sizeof(EaLevelDesc));
   if (rc != EA_OK) { ea_frameset_destroy(fs); return rc; }
   cudaMemsetAsync(fs->d_npts, 0, size_t(n_slots) * EA_MAX_LEVELS * sizeof(int), ctx->stream);
-  cudaMemsetAsync(fs->d_overflow, 0, sizeof(int), ctx->stream);
+  cudaMemsetAsync(fs->d_overflow, 0, size_t(n_slots) * EA_MAX_LEVELS * sizeof(int), ctx->stream);
   {
     std::vector<float2> ones(size_t(n_slots) * EA_MAX_LEVELS, make_float2(1.0f, 0.0f));
     cudaMemcpy(fs->d_affine, ones.data(), ones.size() * sizeof(float2), cudaMemcpyHostToDevice);
@@ -223,9 +223,10 @@ int ea_frameset_create(ea_context* ctx, const ea_frame_params* p, int n_slots, e
       const EaPrepLevel& L = fs->lv[l];
       D.pts = L.pts + size_t(s) * L.cap;
       D.n_pts = fs->d_npts + size_t(s) * EA_MAX_LEVELS + l;
-      D.dt = L.dt + size_t(s) * L.w * L.h;
+      D.dt = ea_dt_origin(L, s);
       D.dt_affine = fs->d_affine + size_t(s) * EA_MAX_LEVELS + l;
-      D.w = L.w; D.h = L.h; D.pts_mode = EA_POINTS_PIXEL; D.pad = 0;
+      D.w = L.w; D.h = L.h; D.pts_mode = EA_POINTS_PIXEL; D.dt_pitch = L.dt_pitch;
+      D.truncated = fs->d_overflow + size_t(s) * EA_MAX_LEVELS + l;
     }
   CU(cudaMemcpyAsync(fs->d_desc, fs->h_desc.data(), fs->h_desc.size() * sizeof(EaLevelDesc), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -392,7 +393,6 @@ int ea_frameset_set_points(ea_frameset* fs, int slot, int level, const float* pt
   ea_context* c = fs->ctx;
   CU(cudaSetDevice(c->device));
   EaLevelDesc& D = fs->h_desc[size_t(slot) * EA_MAX_LEVELS + level];
-  D.pts_mode = mode;
   std::vector<uint2> packed;
   if (mode == EA_POINTS_PIXEL) {      // the device keeps pixel points as 8 bytes {u | v << 16, raw depth}
     packed.resize(size_t(n));
@@ -402,11 +402,16 @@ int ea_frameset_set_points(ea_frameset* fs, int slot, int level, const float* pt
         return ea_fail(EA_ERR_INVALID_ARG, "EA_POINTS_PIXEL point %d: (%g, %g) is not an integer pixel position (use EA_POINTS_XYZ)", i, u, v);
       packed[size_t(i)] = ea_pack_pixel_point(unsigned(u), unsigned(v), pts4[4 * i + 2]);
     }
+    D.pts_mode = mode;     // only now: a rejected list leaves the host and device descriptors untouched
     if (n > 0) CU(cudaMemcpyAsync(const_cast<void*>(D.pts), packed.data(), size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
-  } else if (n > 0) {
+  } else {
+    D.pts_mode = mode;
+  }
+  if (mode == EA_POINTS_XYZ && n > 0) {
     CU(cudaMemcpyAsync(const_cast<void*>(D.pts), pts4, size_t(n) * 16, cudaMemcpyHostToDevice, c->stream));
   }
   CU(cudaMemcpyAsync(const_cast<int*>(D.n_pts), &n, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(fs->d_overflow + size_t(slot) * EA_MAX_LEVELS + level, 0, sizeof(int), c->stream));   // a complete caller-supplied list
   CU(cudaMemcpyAsync(fs->d_desc + size_t(slot) * EA_MAX_LEVELS + level, &D, sizeof D, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return EA_OK;
@@ -418,7 +423,12 @@ int ea_frameset_set_dt(ea_frameset* fs, int slot, int level, const float* dt) {
   const EaPrepLevel& L = fs->lv[level];
   ea_context* c = fs->ctx;
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(L.dt + size_t(slot) * L.w * L.h, dt, size_t(L.w) * L.h * 4, cudaMemcpyHostToDevice, c->stream));
+  rc = ea_ensure_tmp(c, size_t(L.w) * L.h * 4);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(c->d_tmp, dt, size_t(L.w) * L.h * 4, cudaMemcpyHostToDevice, c->stream));
+  cudaError_t e = ea_launch_dt_import((const float*)c->d_tmp, ea_dt_origin(L, slot), L.w, L.h, L.dt_pitch, c->stream);   // interior + replicated border
+  c->launches++;
+  if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "dt import: %s", cudaGetErrorString(e));
   const float2 one = make_float2(1.0f, 0.0f);   // the caller's DT is used as is
   CU(cudaMemcpyAsync(fs->d_affine + size_t(slot) * EA_MAX_LEVELS + level, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -432,9 +442,9 @@ int ea_frameset_get_num_points(ea_frameset* fs, int slot, int level, int* n) {
   CU(cudaSetDevice(c->device));
   int ovf = 0;
   CU(cudaMemcpyAsync(n, fs->d_npts + size_t(slot) * EA_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(&ovf, fs->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&ovf, fs->d_overflow + size_t(slot) * EA_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (ovf) return ea_fail(EA_ERR_CAPACITY, "a point list was truncated at max_points; raise ea_frame_params.max_points");
+  if (ovf) return ea_fail(EA_ERR_CAPACITY, "the point list of slot %d level %d was truncated at max_points; raise ea_frame_params.max_points", slot, level);
   return EA_OK;
 }
 int ea_frameset_get_points(ea_frameset* fs, int slot, int level, float* pts4, int cap, int* n) {
@@ -472,8 +482,8 @@ int ea_frameset_get_dt(ea_frameset* fs, int slot, int level, float* dt) {
   // the device keeps the raw chamfer DT plus the normalisation {scale, shift}; hand back the normalised image
   rc = ea_ensure_tmp(c, size_t(L.w) * L.h * 4);
   if (rc) return rc;
-  cudaError_t e = ea_launch_dt_normalized_copy(L.dt + size_t(slot) * L.w * L.h, fs->d_affine + size_t(slot) * EA_MAX_LEVELS + level,
-                                              L.w * L.h, (float*)c->d_tmp, c->stream);
+  cudaError_t e = ea_launch_dt_normalized_copy(ea_dt_origin(L, slot), L.dt_pitch, fs->d_affine + size_t(slot) * EA_MAX_LEVELS + level,
+                                              L.w, L.h, (float*)c->d_tmp, c->stream);
   c->launches++;
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "dt copy: %s", cudaGetErrorString(e));
   CU(cudaMemcpyAsync(dt, c->d_tmp, size_t(L.w) * L.h * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -514,7 +524,7 @@ static int check_solve_params(const ea_solve_params* sp) {
   if (sp->max_num_iterations < 0) return ea_fail(EA_ERR_INVALID_ARG, "max_num_iterations must be >= 0");
   if (sp->trust_region_strategy < 0 || sp->trust_region_strategy > 1) return ea_fail(EA_ERR_INVALID_ARG, "trust_region_strategy must be 0 (LM) or 1 (DOGLEG)");
   const int cs = sp->cluster_size;
-  if (!(cs == -3 || cs == -1 || cs == 0 || cs == 1 || cs == 2 || cs == 4 || cs == 8)) return ea_fail(EA_ERR_INVALID_ARG, "cluster_size must be -3,-1,0,1,2,4 or 8");
+  if (!(cs == 0 || cs == 1 || cs == 2 || cs == 4 || cs == 8)) return ea_fail(EA_ERR_INVALID_ARG, "cluster_size must be 0,1,2,4 or 8");
   return EA_OK;
 }
 static int check_pairable(ea_frameset* ref, ea_frameset* now) {
@@ -669,26 +679,9 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
   A.trace = c->d_trace; A.trace_count = c->d_trace_count; A.trace_cap = c->trace_cap;
   // auto (measured): few pairs -> a thread-block cluster per pair so the whole GPU works on them and the
   // per-iteration latency drops (config 1, stride 1: 0.58 ms with clusters of 8 vs 2.4 ms on one CTA); big batches -> one
-  // persistent CTA per pair (no scheduling overhead, best L1 locality).  -1 asks for the task-graph kernel explicitly.
+  // persistent CTA per pair (no scheduling overhead, best L1 locality).
   if (cluster == 0) cluster = auto_cluster(c, n, 0);
-  if (cluster == -1) {
-    if (c->states_cap < size_t(n)) {
-      CU(cudaStreamSynchronize(c->stream));
-      if (c->d_states) cudaFree(c->d_states);
-      c->d_states = nullptr; c->states_cap = 0;
-      const size_t cap = std::max<size_t>(size_t(n), 64);
-      CU(cudaMalloc((void**)&c->d_states, cap * sizeof(EaPairState)));
-      c->states_cap = cap;
-    }
-    A.states = c->d_states; A.queue = c->d_queue; A.slots = c->d_slots;
-    static const int env_window = getenv("EA_SOLVE_WINDOW") ? atoi(getenv("EA_SOLVE_WINDOW")) : 0;     // tuning knobs
-    static const int env_chunk = getenv("EA_SOLVE_CHUNK") ? atoi(getenv("EA_SOLVE_CHUNK")) : 0;
-    A.window = env_window;
-    A.chunk_points = env_chunk > 0 ? env_chunk : 4096;
-    e = ea_launch_solve_tasks(A, c->sm_count, c->stream);
-  } else {
-    e = ea_launch_solve_batch(A, cluster, c->sm_count, c->stream);
-  }
+  e = ea_launch_solve_batch(A, cluster, c->sm_count, c->stream);
   c->launches++;
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "solve launch: %s", cudaGetErrorString(e));
   return EA_OK;
@@ -728,9 +721,15 @@ int ea_solve_batch(ea_context* c, int n, ea_frameset* ref, const int32_t* ref_sl
   CU(cudaMemcpyAsync(poses7, d_poses, size_t(n) * 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (summaries) CU(cudaMemcpyAsync(summaries, d_sum, size_t(n) * L * sizeof(ea_summary), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  int ovf = 0;
-  CU(cudaMemcpy(&ovf, ref->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
-  if (ovf) return ea_fail(EA_ERR_CAPACITY, "a reference point list was truncated at max_points; result uses the truncated list");
+  {   // truncated point lists among the reference slots this call used
+    std::vector<int> ovf(size_t(ref->n_slots) * EA_MAX_LEVELS);
+    CU(cudaMemcpy(ovf.data(), ref->d_overflow, ovf.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    const int lc = sp->coarsest_level < 0 ? L - 1 : sp->coarsest_level;
+    for (int i = 0; i < n; ++i)
+      for (int l = sp->finest_level; l <= lc; ++l)
+        if (ovf[size_t(ref_slots[i]) * EA_MAX_LEVELS + l])
+          return ea_fail(EA_ERR_CAPACITY, "pair %d: the reference point list (slot %d, level %d) was truncated at max_points; result uses the truncated list", i, ref_slots[i], l);
+  }
   return EA_OK;
 }
 

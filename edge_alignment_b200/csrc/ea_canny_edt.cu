@@ -161,10 +161,10 @@ __global__ void __launch_bounds__(256) k_edt_cols(const uint32_t* __restrict__ e
 }
 
 __global__ void __launch_bounds__(256) k_edt_rows(const int* __restrict__ g, size_t scratch_stride_px, const int32_t* __restrict__ dst_slots,
-                                                  float* __restrict__ dt, unsigned* __restrict__ fminmax, int level, int w, int h) {
+                                                  float* __restrict__ dt, size_t dt_slot, int pitch, unsigned* __restrict__ fminmax, int level, int w, int h) {
   const int f = blockIdx.y, slot = dst_slots[f];
   const int* G = g + size_t(f) * scratch_stride_px;
-  float* D = dt + size_t(slot) * w * h;
+  float* D = dt + size_t(slot) * dt_slot + size_t(EA_DT_PAD) * pitch + EA_DT_PAD;   // pixel (0,0) of the padded image
   unsigned lmin = 0x7F800000u, lmax = 0u;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * h; i += gridDim.x * blockDim.x) {
     const int q = i % w;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) k_edt_rows(const int* __restrict__ g, siz
       if (q + k < w) { const int a = row[q + k]; if (a < EDT_INF) { const long long v = kk + (long long)a * a; if (best < 0 || v < best) best = v; } }
     }
     const float r = best < 0 ? 65536.0f : __fsqrt_rn(float(best));
-    D[i] = r;
+    D[size_t(i / w) * pitch + q] = r;
     const unsigned bits = __float_as_uint(r);
     lmin = min(lmin, bits); lmax = max(lmax, bits);
   }
@@ -249,8 +249,9 @@ cudaError_t ea_launch_exact_edt_level(const EaPrepArgs& A, int l, const EaScratc
   const int npx = L.w * L.h;
   k_edt_minmax_init<<<(A.n + 255) / 256, 256, 0, stream>>>(A.dt_minmax, A.slots, l, A.n);
   k_edt_cols<<<dim3(unsigned((L.w + 255) / 256), unsigned(A.n)), 256, 0, stream>>>(L.edge_bits, A.slots, S.mag, S.stride, L.w, L.h, L.words);
-  k_edt_rows<<<dim3(unsigned(std::min((npx + 255) / 256, 4096)), unsigned(A.n)), 256, 0, stream>>>(S.mag, S.stride, A.slots, L.dt, A.dt_minmax, l, L.w, L.h);
+  k_edt_rows<<<dim3(unsigned(std::min((npx + 255) / 256, 4096)), unsigned(A.n)), 256, 0, stream>>>(S.mag, S.stride, A.slots, L.dt, L.dt_slot, L.dt_pitch, A.dt_minmax, l, L.w, L.h);
   k_edt_affine<<<(A.n + 255) / 256, 256, 0, stream>>>(A.dt_minmax, A.slots, l, A.n, A.dt_normalize, A.dt_affine);
-  *launches += 4;
+  ea_launch_dt_fill_pad(L, A.slots, A.n, stream);
+  *launches += 5;
   return cudaGetLastError();
 }

@@ -24,11 +24,22 @@
 struct EaLevelDesc {   // one per (slot, level); lives in device memory
   const void* pts;     // point stream, see EaPtStream (EA_POINTS_PIXEL: 8 B packed {u | v << 16, raw depth}; EA_POINTS_XYZ: float4 {X,Y,Z,1})
   const int* n_pts;    // device-resident count (written by the compaction kernel)
-  const float* dt;     // raw chamfer distance transform [h][w] f32 (pixels)
+  const float* dt;     // raw distance transform (pixels), f32: pixel (0,0) of a replicate-padded image, see EA_DT_PAD
   const float2* dt_affine;  // {scale, shift} of cv::normalize(MINMAX): sampled value = raw * scale + shift
   int w, h;
-  int pts_mode, pad;
+  int pts_mode, dt_pitch;   // dt_pitch = ea_dt_pitch(w), floats per padded row
+  const int* truncated;     // device flag: the point list was cut at its capacity (written by the compaction kernel)
 };
+
+// Distance transforms live in HBM with a replicated border of EA_DT_PAD pixels on every side: rows -4 .. h+3 and
+// columns -4 .. w+3 hold the value of the nearest image pixel, which IS ceres::Grid2D::GetValue's clamp-to-edge.  With
+// floor(u'), floor(v') clamped to [-3, w+1] x [-3, h+1] the 4x4 footprint of BiCubicInterpolator::Evaluate always lies
+// inside the padded image and reads exactly the values the clamped reference would read (a footprint further out sees
+// one constant either way) -- no per-texel clamps, no border path in the gather.
+#define EA_DT_PAD 4
+__host__ __device__ __forceinline__ int ea_dt_pitch(int w) { return (w + 2 * EA_DT_PAD + 3) & ~3; }
+__host__ __device__ __forceinline__ size_t ea_dt_slot_floats(int w, int h) { return size_t(ea_dt_pitch(w)) * size_t(h + 2 * EA_DT_PAD); }
+__host__ __device__ __forceinline__ size_t ea_dt_origin_offset(int w) { return size_t(EA_DT_PAD) * ea_dt_pitch(w) + EA_DT_PAD; }
 
 struct EaLevelGeom {   // per level, identical for every slot of a frameset (kernel parameter => constant bank)
   double fx, fy, cx, cy;
@@ -150,82 +161,16 @@ __host__ __device__ __forceinline__ uint2 ea_pack_pixel_point(unsigned u, unsign
   return r;
 }
 
-// Warp, project, bicubic lookup for one edge point (a0, a1, a2) = (u, v, raw depth) or (X, Y, Z).
-template <bool XYZ>
-__device__ __forceinline__ void ea_point_eval(const double a0, const double a1, const double a2, const EaLevelGeom& now,
-                                              double inv_depth_scale, const EaPose& P,
-                                              const float* __restrict__ dt, const float2 affine, EaPointEval& o) {
-  double q0, q1, q2;
-  if (XYZ) {
-    q0 = fma(P.A[0], a0, fma(P.A[1], a1, fma(P.A[2], a2, P.tt[0])));
-    q1 = fma(P.A[3], a0, fma(P.A[4], a1, fma(P.A[5], a2, P.tt[1])));
-    q2 = fma(P.A[6], a0, fma(P.A[7], a1, fma(P.A[8], a2, P.tt[2])));
-  } else {
-    const double Z = a2 * inv_depth_scale;
-    q0 = fma(Z, fma(P.A[0], a0, fma(P.A[1], a1, P.A[2])), P.tt[0]);
-    q1 = fma(Z, fma(P.A[3], a0, fma(P.A[4], a1, P.A[5])), P.tt[1]);
-    q2 = fma(Z, fma(P.A[6], a0, fma(P.A[7], a1, P.A[8])), P.tt[2]);
-  }
-  o.fail = (q2 < 0.01) && (q2 > -0.01);
-  const double iz = 1.0 / q2;
-  const double u = q0 * iz, v = q1 * iz;
-  const int W = now.w, H = now.h;
-  int iu, iv;
-  float du, dv;
-  ea_floor_frac(u, iu, du);
-  ea_floor_frac(v, iv, dv);
-  // the conversion saturates, so the 4x4 footprint arithmetic below cannot wrap for any input
-  iu = min(max(iu, -4), W + 4);
-  iv = min(max(iv, -4), H + 4);
-  float p00, p01, p02, p03, p10, p11, p12, p13, p20, p21, p22, p23, p30, p31, p32, p33;
-  const bool interior = (iu >= 1) && (iu <= W - 3) && (iv >= 1) && (iv <= H - 3);
-  if (__all_sync(0xffffffffu, interior)) {
-    // fast path: 4 contiguous texels per row, one 32-bit offset per row
-    const unsigned o0 = unsigned(iv - 1) * unsigned(W) + unsigned(iu - 1);
-    const unsigned o1 = o0 + unsigned(W), o2 = o1 + unsigned(W), o3 = o2 + unsigned(W);
-    p00 = __ldg(dt + o0); p01 = __ldg(dt + o0 + 1); p02 = __ldg(dt + o0 + 2); p03 = __ldg(dt + o0 + 3);
-    p10 = __ldg(dt + o1); p11 = __ldg(dt + o1 + 1); p12 = __ldg(dt + o1 + 2); p13 = __ldg(dt + o1 + 3);
-    p20 = __ldg(dt + o2); p21 = __ldg(dt + o2 + 1); p22 = __ldg(dt + o2 + 2); p23 = __ldg(dt + o2 + 3);
-    p30 = __ldg(dt + o3); p31 = __ldg(dt + o3 + 1); p32 = __ldg(dt + o3 + 2); p33 = __ldg(dt + o3 + 3);
-  } else {
-    // Grid2D::GetValue clamp-to-edge
-    const unsigned x0 = unsigned(min(max(iu - 1, 0), W - 1)), x1 = unsigned(min(max(iu, 0), W - 1)),
-                   x2 = unsigned(min(max(iu + 1, 0), W - 1)), x3 = unsigned(min(max(iu + 2, 0), W - 1));
-    const unsigned r0 = unsigned(min(max(iv - 1, 0), H - 1)) * unsigned(W), r1 = unsigned(min(max(iv, 0), H - 1)) * unsigned(W),
-                   r2 = unsigned(min(max(iv + 1, 0), H - 1)) * unsigned(W), r3 = unsigned(min(max(iv + 2, 0), H - 1)) * unsigned(W);
-    p00 = __ldg(dt + r0 + x0); p01 = __ldg(dt + r0 + x1); p02 = __ldg(dt + r0 + x2); p03 = __ldg(dt + r0 + x3);
-    p10 = __ldg(dt + r1 + x0); p11 = __ldg(dt + r1 + x1); p12 = __ldg(dt + r1 + x2); p13 = __ldg(dt + r1 + x3);
-    p20 = __ldg(dt + r2 + x0); p21 = __ldg(dt + r2 + x1); p22 = __ldg(dt + r2 + x2); p23 = __ldg(dt + r2 + x3);
-    p30 = __ldg(dt + r3 + x0); p31 = __ldg(dt + r3 + x1); p32 = __ldg(dt + r3 + x2); p33 = __ldg(dt + r3 + x3);
-  }
-  // BiCubicInterpolator::Evaluate: for each grid row (== image column x_k) spline along c (== image y),
-  // then spline the four results along r (== image x).
-  float f0, f1, f2, f3, d0, d1, d2, d3;
-  const float hv = 0.5f * dv, v15 = 1.5f * dv, hu = 0.5f * du, u15 = 1.5f * du;
-  ea_cubic(p00, p10, p20, p30, dv, hv, v15, f0, d0);
-  ea_cubic(p01, p11, p21, p31, dv, hv, v15, f1, d1);
-  ea_cubic(p02, p12, p22, p32, dv, hv, v15, f2, d2);
-  ea_cubic(p03, p13, p23, p33, dv, hv, v15, f3, d3);
-  float fr, fdu;
-  ea_cubic(f0, f1, f2, f3, du, hu, u15, fr, fdu);
-  // cv::normalize(NORM_MINMAX) folded into the sampler: the interpolant is linear in the texels
-  o.f = fmaf(fr, affine.x, affine.y);
-  o.dfdu = fdu * affine.x;
-  o.dfdv = ea_cubic_val(d0, d1, d2, d3, du, hu) * affine.x;
-  o.ub = float(u - P.cx); o.vb = float(v - P.cy);
-  o.pz = float(q2); o.iz = float(iz);
-}
-
-// ea_point_eval in three stages for the warp-specialised kernel (ea_k_solve_ws): gather warps run ea_project + ea_gather,
-// math warps run ea_interp.  Same arithmetic, same operation order.
+// ---- one edge point in three stages: project (fp64) -> gather (16 texels) -> interpolate (fp32) ----------------------
 struct EaProj {
-  int iu, iv;              // floor(u'), floor(v'), clamped to [-4, W+4] x [-4, H+4]
+  unsigned off;            // element offset of texel (floor(v') - 1, floor(u') - 1) from the padded image's first element
   float du, dv;            // fractional offsets (from fp64)
   float ub, vb, pz, iz;    // u' - cx, v' - cy, z', 1/z'
   bool fail;               // |z'| < 0.01  (utils.h:70-73)
 };
+// (a0, a1, a2) = (u, v, raw depth) or (X, Y, Z)
 template <bool XYZ>
-__device__ __forceinline__ void ea_project(const double a0, const double a1, const double a2, const EaLevelGeom& now,
+__device__ __forceinline__ void ea_project(const double a0, const double a1, const double a2, const int W, const int H, const int pitch,
                                            double inv_depth_scale, const EaPose& P, EaProj& r) {
   double q0, q1, q2;
   if (XYZ) {
@@ -244,33 +189,26 @@ __device__ __forceinline__ void ea_project(const double a0, const double a1, con
   int iu, iv;
   ea_floor_frac(u, iu, r.du);
   ea_floor_frac(v, iv, r.dv);
-  r.iu = min(max(iu, -4), now.w + 4);
-  r.iv = min(max(iv, -4), now.h + 4);
+  // the conversion saturates; the clamp keeps the 4x4 footprint inside the padded image for any input (NaN -> 0)
+  iu = min(max(iu, 1 - EA_DT_PAD), W + 1);
+  iv = min(max(iv, 1 - EA_DT_PAD), H + 1);
+  r.off = unsigned(iv + (EA_DT_PAD - 1)) * unsigned(pitch) + unsigned(iu + (EA_DT_PAD - 1));
   r.ub = float(u - P.cx); r.vb = float(v - P.cy);
   r.pz = float(q2); r.iz = float(iz);
 }
-// t[4 * row + col] = dt(iv - 1 + row, iu - 1 + col), Grid2D clamp-to-edge.  Warp-collective (vote): all 32 lanes.
-__device__ __forceinline__ void ea_gather(const EaProj& r, const int W, const int H, const float* __restrict__ dt, float (&t)[16]) {
-  const int iu = r.iu, iv = r.iv;
-  const bool interior = (iu >= 1) && (iu <= W - 3) && (iv >= 1) && (iv <= H - 3);
-  if (__all_sync(0xffffffffu, interior)) {
-    const unsigned o0 = unsigned(iv - 1) * unsigned(W) + unsigned(iu - 1);
-    const unsigned o1 = o0 + unsigned(W), o2 = o1 + unsigned(W), o3 = o2 + unsigned(W);
-    t[0] = __ldg(dt + o0); t[1] = __ldg(dt + o0 + 1); t[2] = __ldg(dt + o0 + 2); t[3] = __ldg(dt + o0 + 3);
-    t[4] = __ldg(dt + o1); t[5] = __ldg(dt + o1 + 1); t[6] = __ldg(dt + o1 + 2); t[7] = __ldg(dt + o1 + 3);
-    t[8] = __ldg(dt + o2); t[9] = __ldg(dt + o2 + 1); t[10] = __ldg(dt + o2 + 2); t[11] = __ldg(dt + o2 + 3);
-    t[12] = __ldg(dt + o3); t[13] = __ldg(dt + o3 + 1); t[14] = __ldg(dt + o3 + 2); t[15] = __ldg(dt + o3 + 3);
-  } else {
-    const unsigned x0 = unsigned(min(max(iu - 1, 0), W - 1)), x1 = unsigned(min(max(iu, 0), W - 1)),
-                   x2 = unsigned(min(max(iu + 1, 0), W - 1)), x3 = unsigned(min(max(iu + 2, 0), W - 1));
-    const unsigned r0 = unsigned(min(max(iv - 1, 0), H - 1)) * unsigned(W), r1 = unsigned(min(max(iv, 0), H - 1)) * unsigned(W),
-                   r2 = unsigned(min(max(iv + 1, 0), H - 1)) * unsigned(W), r3 = unsigned(min(max(iv + 2, 0), H - 1)) * unsigned(W);
-    t[0] = __ldg(dt + r0 + x0); t[1] = __ldg(dt + r0 + x1); t[2] = __ldg(dt + r0 + x2); t[3] = __ldg(dt + r0 + x3);
-    t[4] = __ldg(dt + r1 + x0); t[5] = __ldg(dt + r1 + x1); t[6] = __ldg(dt + r1 + x2); t[7] = __ldg(dt + r1 + x3);
-    t[8] = __ldg(dt + r2 + x0); t[9] = __ldg(dt + r2 + x1); t[10] = __ldg(dt + r2 + x2); t[11] = __ldg(dt + r2 + x3);
-    t[12] = __ldg(dt + r3 + x0); t[13] = __ldg(dt + r3 + x1); t[14] = __ldg(dt + r3 + x2); t[15] = __ldg(dt + r3 + x3);
-  }
+// t[4 * row + col] = dt(floor(v') - 1 + row, floor(u') - 1 + col) with Grid2D clamp-to-edge (through the padding)
+__device__ __forceinline__ void ea_gather(const float* __restrict__ dt_pad, const unsigned off, const unsigned pitch, float (&t)[16]) {
+  const float* p0 = dt_pad + off;
+  const float* p1 = p0 + pitch;
+  const float* p2 = p1 + pitch;
+  const float* p3 = p2 + pitch;
+  t[0] = __ldg(p0); t[1] = __ldg(p0 + 1); t[2] = __ldg(p0 + 2); t[3] = __ldg(p0 + 3);
+  t[4] = __ldg(p1); t[5] = __ldg(p1 + 1); t[6] = __ldg(p1 + 2); t[7] = __ldg(p1 + 3);
+  t[8] = __ldg(p2); t[9] = __ldg(p2 + 1); t[10] = __ldg(p2 + 2); t[11] = __ldg(p2 + 3);
+  t[12] = __ldg(p3); t[13] = __ldg(p3 + 1); t[14] = __ldg(p3 + 2); t[15] = __ldg(p3 + 3);
 }
+// BiCubicInterpolator::Evaluate: for each grid row (== image column x_k) spline along c (== image y), then spline the
+// four results along r (== image x).  cv::normalize(NORM_MINMAX) is folded in: the interpolant is linear in the texels.
 __device__ __forceinline__ void ea_interp(const float (&t)[16], const float du, const float dv, const float2 affine, float& f, float& dfdu, float& dfdv) {
   float f0, f1, f2, f3, d0, d1, d2, d3;
   const float hv = 0.5f * dv, v15 = 1.5f * dv, hu = 0.5f * du, u15 = 1.5f * du;
@@ -285,45 +223,18 @@ __device__ __forceinline__ void ea_interp(const float (&t)[16], const float du, 
   dfdv = ea_cubic_val(d0, d1, d2, d3, du, hu) * affine.x;
 }
 
-// Projection + gather of ea_point_eval without the interpolation: the sum of the 16 texels (gather-roof probe).
+// Warp, project, bicubic lookup for one edge point.  dt = pixel (0,0) of the padded distance transform.
 template <bool XYZ>
-__device__ __forceinline__ float ea_point_gather_sum(const double a0, const double a1, const double a2, const EaLevelGeom& now,
-                                                     double inv_depth_scale, const EaPose& P, const float* __restrict__ dt) {
-  double q0, q1, q2;
-  if (XYZ) {
-    q0 = fma(P.A[0], a0, fma(P.A[1], a1, fma(P.A[2], a2, P.tt[0])));
-    q1 = fma(P.A[3], a0, fma(P.A[4], a1, fma(P.A[5], a2, P.tt[1])));
-    q2 = fma(P.A[6], a0, fma(P.A[7], a1, fma(P.A[8], a2, P.tt[2])));
-  } else {
-    const double Z = a2 * inv_depth_scale;
-    q0 = fma(Z, fma(P.A[0], a0, fma(P.A[1], a1, P.A[2])), P.tt[0]);
-    q1 = fma(Z, fma(P.A[3], a0, fma(P.A[4], a1, P.A[5])), P.tt[1]);
-    q2 = fma(Z, fma(P.A[6], a0, fma(P.A[7], a1, P.A[8])), P.tt[2]);
-  }
-  const double iz = 1.0 / q2;
-  const int W = now.w, H = now.h;
-  int iu, iv;
-  float du, dv;
-  ea_floor_frac(q0 * iz, iu, du);
-  ea_floor_frac(q1 * iz, iv, dv);
-  iu = min(max(iu, -4), W + 4);
-  iv = min(max(iv, -4), H + 4);
-  float s = du + dv;
-  const bool interior = (iu >= 1) && (iu <= W - 3) && (iv >= 1) && (iv <= H - 3);
-  if (__all_sync(0xffffffffu, interior)) {
-    const unsigned o0 = unsigned(iv - 1) * unsigned(W) + unsigned(iu - 1);
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) s += __ldg(dt + o0 + unsigned(r) * unsigned(W) + unsigned(c));
-  } else {
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        s += __ldg(dt + unsigned(min(max(iv - 1 + r, 0), H - 1)) * unsigned(W) + unsigned(min(max(iu - 1 + c, 0), W - 1)));
-  }
-  return s;
+__device__ __forceinline__ void ea_point_eval(const double a0, const double a1, const double a2, const EaLevelGeom& now,
+                                              double inv_depth_scale, const EaPose& P,
+                                              const float* __restrict__ dt, const float2 affine, EaPointEval& o) {
+  const int pitch = ea_dt_pitch(now.w);
+  EaProj r;
+  ea_project<XYZ>(a0, a1, a2, now.w, now.h, pitch, inv_depth_scale, P, r);
+  float t[16];
+  ea_gather(dt - ea_dt_origin_offset(now.w), r.off, unsigned(pitch), t);
+  ea_interp(t, r.du, r.dv, affine, o.f, o.dfdu, o.dfdv);
+  o.ub = r.ub; o.vb = r.vb; o.pz = r.pz; o.iz = r.iz; o.fail = r.fail;
 }
 
 // Loss (ceres/loss_function.cc) + Corrector (rho'' <= 0 for all three => scale by sqrt(rho')) in fp32.
@@ -517,19 +428,14 @@ __device__ __forceinline__ bool ea_point_eval_general(const float4 p, const EaLe
     u = q0 * iz; v = q1 * iz;
     xn = float((u - P.cx)) * P.inv_fx; yn = float((v - P.cy)) * P.inv_fy;
   }
-  const int W = now.w, H = now.h;
+  const int W = now.w, H = now.h, pitch = ea_dt_pitch(W);
   int iu, iv;
   float du, dv;
   ea_floor_frac(u, iu, du);
   ea_floor_frac(v, iv, dv);
-  iu = min(max(iu, -4), W + 4); iv = min(max(iv, -4), H + 4);
+  iu = min(max(iu, 1 - EA_DT_PAD), W + 1); iv = min(max(iv, 1 - EA_DT_PAD), H + 1);
   float tex[16];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const unsigned row = unsigned(min(max(iv - 1 + r, 0), H - 1)) * unsigned(W);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tex[4 * r + c] = __ldg(dt + row + unsigned(min(max(iu - 1 + c, 0), W - 1)));
-  }
+  ea_gather(dt - ea_dt_origin_offset(W), unsigned(iv + (EA_DT_PAD - 1)) * unsigned(pitch) + unsigned(iu + (EA_DT_PAD - 1)), unsigned(pitch), tex);
   float f0, f1, f2, f3, d0, d1, d2, d3, fr, fdu;
   const float hv = 0.5f * dv, v15 = 1.5f * dv, hu = 0.5f * du, u15 = 1.5f * du;
   ea_cubic(tex[0], tex[4], tex[8], tex[12], dv, hv, v15, f0, d0);

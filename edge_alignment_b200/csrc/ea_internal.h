@@ -7,9 +7,7 @@
 
 #include "ea_device.cuh"
 
-#include "ea_solve_state.h"
-
-#define EA_KERNEL_WS (-3)   // ea_solve_params.cluster_size: warp-specialised kernel (ea_k_solve_ws)
+#include "ea_solve.cuh"
 
 #define EA_TRACE_DOUBLES 6    // {level, iteration, cost of the accepted iterate, cost at the candidate, radius, decision}
 
@@ -22,11 +20,6 @@ struct EaSolveArgs {
   const int32_t* order;         // [n_pairs] device or null: processing order of the work queue (longest first)
   double* poses;                // [*][7] device, in/out
   int* work_counter;            // device: next pair index of the dynamic work queue (zeroed per launch)
-  // task-graph kernel (ea_solve_tasks.cu)
-  EaPairState* states;          // [n_pairs]
-  EaQueue* queue;
-  unsigned long long* slots;    // [EA_QUEUE_CAP]
-  int window, chunk_points;
   ea_summary* summaries;        // [n_pairs][n_levels] device or null
   double* trace;                // [trace_cap][EA_TRACE_DOUBLES] device or null: one record per evaluation (single-pair solves only)
   int* trace_count;             // device counter of records written
@@ -40,7 +33,6 @@ struct EaSolveArgs {
 };
 
 cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm_count, cudaStream_t stream);
-cudaError_t ea_launch_solve_tasks(const EaSolveArgs& A, int sm_count, cudaStream_t stream);
 cudaError_t ea_launch_gather_probe(const EaSolveArgs& A, int level, int slices, int repeats, float* d_sink, cudaStream_t stream);
 int ea_probe_gather_device(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now, const int32_t* d_now_slots,
                            const double* d_poses7, int level, int repeats, float* ms, double* point_gathers);
@@ -60,7 +52,8 @@ struct EaPrepLevel {            // device pointers of one pyramid level, slot-ma
   uint32_t* edge_bits;          // [slots][h][words]  raw Laplacian>threshold mask, 1 bit / pixel
   uint32_t* ref_bits;           // [slots][h][words]  edge & depth>0
   uint32_t* med_bits;           // [slots][h][words]  3x3 median of edge_bits
-  float* dt;                    // [slots][h][w]
+  float* dt;                    // [slots][h + 2 PAD][dt_pitch] replicate-padded (EA_DT_PAD, ea_device.cuh)
+  int dt_pitch; size_t dt_slot; // floats per padded row / per slot
   float4* pts;                  // [slots][cap]
   int w, h, words, cap;
 };
@@ -79,7 +72,7 @@ struct EaPrepArgs {
   int* n_pts;                   // [slots][EA_MAX_LEVELS]
   unsigned* dt_minmax;          // [slots][EA_MAX_LEVELS][2]  (min,max of the fixed-point DT)
   float2* dt_affine;            // [slots][EA_MAX_LEVELS]     {scale, shift} of the min-max normalisation
-  int* overflow;                // single flag: some point list was truncated
+  int* overflow;                // [slots][EA_MAX_LEVELS]: that point list was truncated at cap (rewritten by every compaction)
   int n, roles, grad_threshold, use_median, dt_normalize;
   int edge_detector, dt_kind;
   int depth_type;               // 0 = u16 raw units, 1 = f32 metres
@@ -90,7 +83,12 @@ struct EaPrepArgs {
 };
 // enqueue the whole preprocessing pipeline for n frames; returns number of kernel launches via *launches
 cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches);
-cudaError_t ea_launch_dt_normalized_copy(const float* raw, const float2* affine, int npx, float* out, cudaStream_t stream);
+__host__ __device__ inline float* ea_dt_origin(const EaPrepLevel& L, int slot) {   // pixel (0,0) of a slot's padded DT
+  return L.dt + size_t(slot) * L.dt_slot + size_t(EA_DT_PAD) * L.dt_pitch + EA_DT_PAD;
+}
+cudaError_t ea_launch_dt_normalized_copy(const float* origin, int pitch, const float2* affine, int w, int h, float* out, cudaStream_t stream);
+cudaError_t ea_launch_dt_import(const float* src, float* origin, int w, int h, int pitch, cudaStream_t stream);
+cudaError_t ea_launch_dt_fill_pad(const EaPrepLevel& L, const int32_t* d_slots, int n, cudaStream_t stream);
 cudaError_t ea_launch_canny_level(const EaPrepArgs& A, int l, const uint8_t* bgr, const void* depth, size_t frame_stride_px,
                                   bool slot_indexed, const EaCannyCfg& cfg, const EaScratch& S, cudaStream_t stream, int* launches);
 cudaError_t ea_launch_exact_edt_level(const EaPrepArgs& A, int l, const EaScratch& S, cudaStream_t stream, int* launches);
@@ -107,9 +105,6 @@ struct ea_context {
   double* d_pose = nullptr;      // [7]
   int* d_failed = nullptr;
   int* d_work = nullptr;         // work-queue counter of the batched solve
-  EaPairState* d_states = nullptr; size_t states_cap = 0;   // task-graph solve: per-pair state
-  EaQueue* d_queue = nullptr;
-  unsigned long long* d_slots = nullptr;
   double* d_sums = nullptr;      // [max blocks][EA_SUMS]
   int32_t* d_idx = nullptr;      // scratch slot indices
   size_t idx_cap = 0;

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const uint32_t* __restri
   }
   if (tid == 0) {
     n_pts[slot * EA_MAX_LEVELS + level] = min(total_s, cap);
-    if (total_s > cap) atomicExch(overflow, 1);
+    overflow[slot * EA_MAX_LEVELS + level] = total_s > cap ? 1 : 0;   // describes the list just written, not the frameset's history
   }
 }
 
@@ -465,8 +465,9 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
   const int w = L.w, h = L.h, words = L.words;
   const int slot = A.slots[blockIdx.x];
   const uint32_t* bits = (A.use_median ? L.med_bits : L.edge_bits) + size_t(slot) * h * words;
-  int* gi = reinterpret_cast<int*>(L.dt + size_t(slot) * w * h);
-  float* gf = L.dt + size_t(slot) * w * h;
+  float* gf = ea_dt_origin(L, slot);                 // pixel (0,0) of the padded image; rows are pitch apart
+  int* gi = reinterpret_cast<int*>(gf);
+  const int pitch = L.dt_pitch;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_warps = ((w + P - 1) / P + 31) / 32;          // warps that own pixels at this level
   const bool warp_on = warp < n_warps;
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
     dt_row_scan<P, false>(d, cval, lane, warp, n_warps, par, tot, first, left_bnd, right_bnd);
 #pragma unroll
     for (int k = 0; k < P; ++k) if (x0 + k >= w) d[k] = DT_INF;
-    if (x0 < w) dt_store_row<P, int>(gi + size_t(y) * w, x0, w, d, vec_ok);
+    if (x0 < w) dt_store_row<P, int>(gi + size_t(y) * pitch, x0, w, d, vec_ok);
   }
   // ---------------- backward pass: rows bottom -> top, scan right -> left ----------------
 #pragma unroll
@@ -510,13 +511,13 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
   int t_next[P];
 #pragma unroll
   for (int k = 0; k < P; ++k) t_next[k] = DT_INF;
-  if (warp_on && x0 < w) dt_load_row<P>(gi + size_t(h - 1) * w, x0, w, t_next, vec_ok);
+  if (warp_on && x0 < w) dt_load_row<P>(gi + size_t(h - 1) * pitch, x0, w, t_next, vec_ok);
   for (int y = h - 1; y >= 0; --y, par ^= 1) {
     if (!warp_on) { __syncthreads(); continue; }
     int t0[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) t0[k] = t_next[k];
-    if (y > 0 && x0 < w) dt_load_row<P>(gi + size_t(y - 1) * w, x0, w, t_next, vec_ok);   // prefetch the next row up
+    if (y > 0 && x0 < w) dt_load_row<P>(gi + size_t(y - 1) * pitch, x0, w, t_next, vec_ok);   // prefetch the next row up
     int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
     int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
     if (lane == 0) pl = left_bnd;
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
       vmax = max(vmax, t); vmin = min(vmin, t);
       outv[k] = float(t) * (1.0f / 65536.0f);
     }
-    if (x0 < w) dt_store_row<P, float>(gf + size_t(y) * w, x0, w, outv, vec_ok);
+    if (x0 < w) dt_store_row<P, float>(gf + size_t(y) * pitch, x0, w, outv, vec_ok);
   }
   vmax = __reduce_max_sync(0xffffffffu, vmax);
   vmin = __reduce_min_sync(0xffffffffu, vmin);
@@ -626,8 +627,9 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
   const EaPrepLevel& L = A.lv[level];
   const int w = FULL ? 32 * P : L.w, h = L.h, words = L.words;   // FULL: a compile-time width folds every bound check
   const uint32_t* bits = (A.use_median ? L.med_bits : L.edge_bits) + size_t(slot) * h * words;
-  int* gi = reinterpret_cast<int*>(L.dt + size_t(slot) * w * h);
-  float* gf = L.dt + size_t(slot) * w * h;
+  float* gf = ea_dt_origin(L, slot);                 // pixel (0,0) of the padded image; rows are pitch apart
+  int* gi = reinterpret_cast<int*>(gf);
+  const int pitch = L.dt_pitch;
   const int x0 = lane * P;
   const bool on = x0 < w;
   const bool vec_ok = (P % 4 == 0) && ((w & 3) == 0);
@@ -662,7 +664,7 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
     dtw_row_scan<P, false>(d, cval, lane);
 #pragma unroll
     for (int k = 0; k < P; ++k) if (!FULL && x0 + k >= w) d[k] = DT_INF;
-    if (on) dt_store_row<P, int>(gi + size_t(y) * w, x0, w, d, vec_ok);
+    if (on) dt_store_row<P, int>(gi + size_t(y) * pitch, x0, w, d, vec_ok);
   }
   // ---------------- backward pass ----------------
 #pragma unroll
@@ -672,16 +674,16 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
 #pragma unroll
   for (int k = 0; k < P; ++k) t_next[k] = DT_INF;
   __syncwarp();   // the forward rows were written by other lanes' neighbours only through registers; own rows are re-read below
-  if (on) dt_load_row<P>(gi + size_t(h - 1) * w, x0, w, t_next, vec_ok);
+  if (on) dt_load_row<P>(gi + size_t(h - 1) * pitch, x0, w, t_next, vec_ok);
   for (int y = h - 1; y >= 0; --y) {
     int t0[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) t0[k] = t_next[k];
-    if (y > 0 && on) dt_load_row<P>(gi + size_t(y - 1) * w, x0, w, t_next, vec_ok);
+    if (y > 0 && on) dt_load_row<P>(gi + size_t(y - 1) * pitch, x0, w, t_next, vec_ok);
     // the forward rows were written ~1 ms ago and have left the L2: the register prefetch one row ahead does not cover a
     // DRAM round trip (ncu: 31 % of the kernel's samples waited here), so rows further up are pulled into L2 early
     if (y >= DTW_L2_AHEAD && lane * 32 < w)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + size_t(y - DTW_L2_AHEAD) * w + lane * 32));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + size_t(y - DTW_L2_AHEAD) * pitch + lane * 32));
     int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
     int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
     if (lane == 0) pl = DT_INF;
@@ -705,7 +707,30 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
       vmax = max(vmax, t); vmin = min(vmin, t);
       outv[k] = float(t) * (1.0f / 65536.0f);
     }
-    if (on) dt_store_row<P, float>(gf + size_t(y) * w, x0, w, outv, vec_ok);
+    // the finished row plus its share of the replicated border (EA_DT_PAD): the left / right 4 columns, and the 4 rows
+    // above the first / below the last image row
+    const int copies = (y == 0 || y == h - 1) ? 1 + EA_DT_PAD : 1;
+    const int ystep = (y == 0) ? -1 : 1;
+    const bool last_strip = on && (x0 + P >= w);
+    float edge_r = 0.0f;
+    if (last_strip) {
+#pragma unroll
+      for (int k = 0; k < P; ++k) if (x0 + k == w - 1) edge_r = outv[k];
+    }
+    for (int c = 0; c < copies; ++c) {
+      float* row = gf + (ptrdiff_t(y) + ptrdiff_t(c) * ystep) * pitch;
+      if (on) dt_store_row<P, float>(row, x0, w, outv, vec_ok);
+      if (lane == 0) *reinterpret_cast<float4*>(row - EA_DT_PAD) = make_float4(outv[0], outv[0], outv[0], outv[0]);
+      if (last_strip) for (int x = w; x < pitch - EA_DT_PAD; ++x) row[x] = edge_r;
+    }
+    if (h == 1 && y == 0) {   // a single image row is both first and last: the rows below it as well
+      for (int c = 1; c <= EA_DT_PAD; ++c) {
+        float* row = gf + ptrdiff_t(c) * pitch;
+        if (on) dt_store_row<P, float>(row, x0, w, outv, vec_ok);
+        if (lane == 0) *reinterpret_cast<float4*>(row - EA_DT_PAD) = make_float4(outv[0], outv[0], outv[0], outv[0]);
+        if (last_strip) for (int x = w; x < pitch - EA_DT_PAD; ++x) row[x] = edge_r;
+      }
+    }
   }
   const unsigned mx = __reduce_max_sync(0xffffffffu, vmax);
   const unsigned mn = __reduce_min_sync(0xffffffffu, vmin);
@@ -735,10 +760,31 @@ __global__ void __launch_bounds__(32) k_chamfer_dt_warp(const __grid_constant__ 
 }
 
 // ---- normalised copy of one DT (read-back for parity tests): dst = raw * scale + shift, exactly as cv::normalize ----
-__global__ void __launch_bounds__(256) k_dt_normalized_copy(const float* __restrict__ raw, const float2* __restrict__ affine, int npx,
-                                                            float* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_dt_normalized_copy(const float* __restrict__ origin, int pitch, const float2* __restrict__ affine,
+                                                            int w, int h, float* __restrict__ out) {
   const float2 a = *affine;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) out[i] = __fadd_rn(__fmul_rn(raw[i], a.x), a.y);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * h; i += gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(__fmul_rn(origin[size_t(i / w) * pitch + (i % w)], a.x), a.y);
+}
+
+// ---- padded layout helpers (EA_DT_PAD): every element of the padded image = the nearest image pixel --------------------
+// import: from a dense [h][w] source (ea_frameset_set_dt);  fill_pad: border only, from the interior already in place
+__global__ void __launch_bounds__(256) k_dt_import(const float* __restrict__ src, float* __restrict__ origin, int w, int h, int pitch) {
+  const int n = pitch * (h + 2 * EA_DT_PAD);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int py = i / pitch - EA_DT_PAD, px = i % pitch - EA_DT_PAD;
+    origin[ptrdiff_t(py) * pitch + px] = src[size_t(min(max(py, 0), h - 1)) * w + min(max(px, 0), w - 1)];
+  }
+}
+__global__ void __launch_bounds__(256) k_dt_fill_pad(float* __restrict__ pool, size_t slot_floats, const int32_t* __restrict__ slots,
+                                                     int w, int h, int pitch) {
+  float* origin = pool + size_t(slots[blockIdx.y]) * slot_floats + size_t(EA_DT_PAD) * pitch + EA_DT_PAD;
+  const int n = pitch * (h + 2 * EA_DT_PAD);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int py = i / pitch - EA_DT_PAD, px = i % pitch - EA_DT_PAD;
+    if (py >= 0 && py < h && px >= 0 && px < w) continue;
+    origin[ptrdiff_t(py) * pitch + px] = origin[size_t(min(max(py, 0), h - 1)) * pitch + min(max(px, 0), w - 1)];
+  }
 }
 
 __global__ void __launch_bounds__(256) k_unpack_mask(const uint32_t* __restrict__ bits, int w, int h, int words, int median,
@@ -858,13 +904,24 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
     else if (P == 4) k_chamfer_dt<4><<<grid, threads, 0, stream>>>(A);
     else k_chamfer_dt<8><<<grid, threads, 0, stream>>>(A);
     ++nl;
+    for (int l = 0; l < A.n_levels; ++l) { ea_launch_dt_fill_pad(A.lv[l], A.slots, A.n, stream); ++nl; }
   }
   if (launches) *launches = nl;
   return cudaGetLastError();
 }
 
-cudaError_t ea_launch_dt_normalized_copy(const float* raw, const float2* affine, int npx, float* out, cudaStream_t stream) {
-  k_dt_normalized_copy<<<(npx + 255) / 256, 256, 0, stream>>>(raw, affine, npx, out);
+cudaError_t ea_launch_dt_normalized_copy(const float* origin, int pitch, const float2* affine, int w, int h, float* out, cudaStream_t stream) {
+  k_dt_normalized_copy<<<(w * h + 255) / 256, 256, 0, stream>>>(origin, pitch, affine, w, h, out);
+  return cudaGetLastError();
+}
+cudaError_t ea_launch_dt_import(const float* src, float* origin, int w, int h, int pitch, cudaStream_t stream) {
+  const int n = pitch * (h + 2 * EA_DT_PAD);
+  k_dt_import<<<(n + 255) / 256, 256, 0, stream>>>(src, origin, w, h, pitch);
+  return cudaGetLastError();
+}
+cudaError_t ea_launch_dt_fill_pad(const EaPrepLevel& L, const int32_t* d_slots, int n, cudaStream_t stream) {
+  const int tot = L.dt_pitch * (L.h + 2 * EA_DT_PAD);
+  k_dt_fill_pad<<<dim3(unsigned(std::min((tot + 255) / 256, 1024)), unsigned(n)), 256, 0, stream>>>(L.dt, L.dt_slot, d_slots, L.w, L.h, L.dt_pitch);
   return cudaGetLastError();
 }
 

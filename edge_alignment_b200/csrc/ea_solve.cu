@@ -45,7 +45,7 @@ struct EaSolveSmem {
   double sums[EA_SUMS + 3];                 // CTA totals
   double cluster_sums[8][EA_SUMS + 3];      // rank 0 only: one row per cluster rank
   EaLmState lm;                             // boss only
-  int pair, level;                          // boss only
+  int pair, level, truncated;               // boss only
 };
 
 // Boss: move to the next (pair, level) that has points and publish its first evaluation, or EXIT.
@@ -74,6 +74,7 @@ __device__ __forceinline__ void ea_boss_next_impl(const EaSolveArgs& A, EaSolveS
     const EaLevelDesc nd = A.now_desc[size_t(A.now_slots[pair]) * EA_MAX_LEVELS + level];
     const int n_pts = min(*rd.n_pts, A.ref_cap[level]);
     const int n_res = (n_pts + A.sp.point_stride - 1) / A.sp.point_stride;
+    S.truncated = *rd.truncated;
     if (n_res == 0) {
       if (A.summaries) { ea_summary z = {}; z.termination = EA_TERM_SKIPPED_NO_POINTS; A.summaries[size_t(pair) * A.n_levels + level] = z; }
       S.level = level - 1;
@@ -114,6 +115,7 @@ __device__ __forceinline__ void ea_boss_step_impl(const EaSolveArgs& A, EaSolveS
     ea_summary z;
     z.termination = L.term; z.iterations = L.iter; z.accepted = L.accepted; z.rejected = L.rejected;
     z.n_residuals = cur.n_res; z.evaluations = L.evals; z.initial_cost = L.initial_cost; z.final_cost = L.cost;
+    z.truncated = S.truncated; z.reserved = 0;
     A.summaries[size_t(S.pair) * A.n_levels + cur.level] = z;
   }
   S.level = cur.level - 1;
@@ -255,220 +257,6 @@ __global__ void __launch_bounds__(THREADS) ea_k_eval_sums(EaLevelDesc rd, EaLeve
   }
 }
 
-// ---- warp-specialised solve kernel -------------------------------------------------------------------------------------
-// tools/probe_occupancy.sh: the memory side of an evaluation (point stream, projection, 16-texel gather) is latency-bound
-// and scales with resident warps (2.2 / 3.6 / 5.2 ms per launch at 32 / 16 / 8 warps per SM); the fused loop needs 128
-// registers and therefore runs 16.  Here the CTA has 24 warps: warpgroup 0 (4 "math" warps, 160 registers after
-// setmaxnreg) and warpgroups 1..5 (20 "gather" warps, 64 registers).  Gather warp (p, m) projects the points of
-// warp-iterations k = 4 q + m, gathers their texels and hands {16 texels, du, dv, ub, vb, z', 1/z', flags} per point to math
-// warp m through a 5-slot shared-memory ring (one slot per producer, mbarrier full/empty pairs); the math warp
-// interpolates, builds the Jacobian and accumulates in a fixed order (k ascending), so the sums stay reproducible.
-#ifndef EA_WS_MATH
-#define EA_WS_MATH 4          // math warps (a multiple of 4: setmaxnreg works on warpgroups)
-#endif
-#ifndef EA_WS_PROD
-#define EA_WS_PROD 5          // gather warps per math warp
-#endif
-#ifndef EA_WS_MATH_REGS
-#define EA_WS_MATH_REGS 160
-#endif
-#ifndef EA_WS_GATHER_REGS
-#define EA_WS_GATHER_REGS 64
-#endif
-#ifndef EA_WS_BACKOFF_NS
-#define EA_WS_BACKOFF_NS 0
-#endif
-#define EA_WS_THREADS (32 * EA_WS_MATH * (1 + EA_WS_PROD))
-#define EA_WS_WORDS 24
-#define EA_STR2(x) #x
-#define EA_STR(x) EA_STR2(x)
-
-struct EaWsRing {
-  unsigned long long full[EA_WS_MATH][EA_WS_PROD];
-  unsigned long long empty[EA_WS_MATH][EA_WS_PROD];
-  float slot[EA_WS_MATH][EA_WS_PROD][EA_WS_WORDS][32];
-};
-
-__device__ __forceinline__ unsigned ea_smem_u32(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void ea_mbar_init(unsigned long long* b, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ea_smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void ea_mbar_arrive(unsigned long long* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ea_smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void ea_mbar_wait(unsigned long long* b, unsigned parity) {
-  const unsigned a = ea_smem_u32(b);
-  unsigned done;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
-#if EA_WS_BACKOFF_NS > 0
-    if (!done) __nanosleep(EA_WS_BACKOFF_NS);     // polling warps would otherwise take issue slots from the warps they wait for
-#endif
-  } while (!done);
-}
-
-// warp-iterations of an evaluation that belong to math warp m: k = 4 q + m, q in [0, Qm)
-__device__ __forceinline__ int ea_ws_count(int n_res, int m) {
-  const int K = (n_res + 31) >> 5;
-  return K > m ? (K - m + EA_WS_MATH - 1) / EA_WS_MATH : 0;
-}
-
-template <bool XYZ>
-__device__ __forceinline__ void ea_ws_produce(const void* __restrict__ pts, const float* __restrict__ dt, const int n_res, const int stride,
-                                              const EaLevelGeom& ng, const double inv_depth_scale, const EaPose& P, EaWsRing& R,
-                                              const int m, const int p, const int lane, unsigned& seq) {
-  typedef EaPtStream<XYZ> PS;
-  const int Qm = ea_ws_count(n_res, m);
-  const unsigned n0 = seq;
-  seq = n0 + unsigned(Qm);
-  int q = int((unsigned(p) + EA_WS_PROD - (n0 % EA_WS_PROD)) % EA_WS_PROD);   // first q with (n0 + q) % 5 == p
-  if (q >= Qm) return;
-  int j = ((q * EA_WS_MATH + m) << 5) + lane;
-  typename PS::T p_next = j < n_res ? PS::load(pts, size_t(j) * stride) : PS::pad();
-  float* const s = &R.slot[m][p][0][lane];
-  for (; q < Qm; q += EA_WS_PROD) {
-    const unsigned n = n0 + unsigned(q);
-    const typename PS::T pt = p_next;
-    const bool valid = j < n_res;
-    j += EA_WS_PROD * EA_WS_MATH * 32;
-    if (j < n_res) p_next = PS::load(pts, size_t(j) * stride);
-    double a0, a1, a2;
-    PS::unpack(pt, a0, a1, a2);
-    EaProj r;
-    ea_project<XYZ>(a0, a1, a2, ng, inv_depth_scale, P, r);
-    float t[16];
-    ea_gather(r, ng.w, ng.h, dt, t);
-    ea_mbar_wait(&R.empty[m][p], ((n / EA_WS_PROD) & 1u) ^ 1u);     // the math warp is done with this slot's previous content
-#pragma unroll
-    for (int k = 0; k < 16; ++k) s[k * 32] = t[k];
-    s[16 * 32] = r.du; s[17 * 32] = r.dv; s[18 * 32] = r.ub; s[19 * 32] = r.vb; s[20 * 32] = r.pz; s[21 * 32] = r.iz;
-    s[22 * 32] = __int_as_float((valid ? 1 : 0) | (r.fail ? 2 : 0));
-    __syncwarp();
-    if (lane == 0) ea_mbar_arrive(&R.full[m][p]);
-  }
-}
-
-__device__ __forceinline__ void ea_ws_consume(const int n_res, const float2 affine, const ea_solve_params& sp, const EaPose& P, EaWsRing& R,
-                                              const int m, const int lane, unsigned& seq, double (*part)[EA_NSUM], double* cpart) {
-  const int Qm = ea_ws_count(n_res, m);
-  const unsigned n0 = seq;
-  seq = n0 + unsigned(Qm);
-  const float loss_a = float(sp.loss_scale);
-  const int loss_type = sp.loss_type;
-  float acc[EA_NSUM];
-#pragma unroll
-  for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
-  double acc64 = 0.0, cost64 = 0.0;
-  int since_flush = 0;
-  for (int q = 0; q < Qm; ++q) {
-    const unsigned n = n0 + unsigned(q);
-    const unsigned slot = n % EA_WS_PROD;
-    ea_mbar_wait(&R.full[m][slot], (n / EA_WS_PROD) & 1u);
-    const float* const s = &R.slot[m][slot][0][lane];
-    float t[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) t[k] = s[k * 32];
-    EaPointEval e;
-    const float du = s[16 * 32], dv = s[17 * 32];
-    e.ub = s[18 * 32]; e.vb = s[19 * 32]; e.pz = s[20 * 32]; e.iz = s[21 * 32];
-    const int flags = __float_as_int(s[22 * 32]);
-    ea_interp(t, du, dv, affine, e.f, e.dfdu, e.dfdv);
-    const bool valid = (flags & 1) != 0;
-    e.fail = (flags & 2) != 0;
-    float rho0;
-    float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
-    if (!valid) { w = 0.0f; rho0 = 0.0f; e.f = 0.0f; e.fail = false; }
-    float J[6];
-    ea_jacobian(e, P, w, J);
-    if (!valid) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) J[k] = 0.0f;
-    }
-    __syncwarp();                                           // every lane has consumed what it read from the slot
-    if (lane == 0) ea_mbar_arrive(&R.empty[m][slot]);
-    ea_accumulate(acc, J, e.f * w);
-    acc[27] += e.fail ? 1.0f : 0.0f;
-    cost64 += double(0.5f * rho0);
-    if (++since_flush == EA_FLUSH_EVERY) {
-      acc64 += double(ea_warp_transpose_reduce(acc, lane));
-#pragma unroll
-      for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
-      since_flush = 0;
-    }
-  }
-  if (since_flush) acc64 += double(ea_warp_transpose_reduce(acc, lane));
-  cost64 = ea_warp_sum(cost64);
-  part[m][lane] = acc64;
-  if (lane == 0) cpart[m] = cost64;
-}
-
-__global__ void __launch_bounds__(EA_WS_THREADS, 1) ea_k_solve_ws(const __grid_constant__ EaSolveArgs A) {
-  __shared__ EaSolveSmem S;
-  extern __shared__ __align__(16) unsigned char ea_ws_raw[];
-  EaWsRing& R = *reinterpret_cast<EaWsRing*>(ea_ws_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < EA_WS_MATH * EA_WS_PROD) {
-    ea_mbar_init(&R.full[tid / EA_WS_PROD][tid % EA_WS_PROD], 1);
-    ea_mbar_init(&R.empty[tid / EA_WS_PROD][tid % EA_WS_PROD], 1);
-  }
-  if (tid == 0) {
-    EaMsg m0;
-    ea_boss_next_impl<true>(A, S, m0, true);
-    S.msg[0] = m0;
-  }
-  __syncthreads();
-  // Two separate code paths from here on (each with its own loop and the same sequence of CTA barriers): ptxas gives every
-  // region the register budget of the setmaxnreg that dominates it, code shared by both would have to live in 64.
-  if (warp < EA_WS_MATH) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 " EA_STR(EA_WS_MATH_REGS) ";");
-    unsigned seq = 0;                                  // warp-iterations this math warp has consumed so far
-    for (unsigned g = 0;; ++g) {
-      const EaMsg& M = S.msg[g & 1];
-      if (M.cmd == EA_CMD_EXIT) break;
-      const EaLevelGeom& rg = A.ref_geom[M.level];
-      const EaLevelGeom& ng = A.now_geom[M.level];
-      EaPose P;
-      if (M.pts_mode == EA_POINTS_XYZ) ea_pose_setup<true>(M.cand, rg, ng, P);
-      else ea_pose_setup<false>(M.cand, rg, ng, P);
-      ea_ws_consume(M.n_res, M.affine, A.sp, P, R, warp, lane, seq, S.part, S.cpart);
-      asm volatile("bar.sync 0;" ::: "memory");
-      if (warp == 0) {
-        const double tot = ea_cta_total<EA_WS_MATH>(S.part, S.cpart, lane);
-        if (lane < EA_SUMS) S.sums[lane] = tot;
-        __syncwarp();
-        if (lane == 0) {
-          EaMsg mn;
-          ea_boss_step_impl<true>(A, S, S.sums, M, mn);
-          S.msg[(g + 1) & 1] = mn;
-        }
-      }
-      asm volatile("bar.sync 0;" ::: "memory");
-    }
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 " EA_STR(EA_WS_GATHER_REGS) ";");
-    const int mw = (warp - EA_WS_MATH) % EA_WS_MATH;   // the math warp this gather warp feeds
-    const int pw = (warp - EA_WS_MATH) / EA_WS_MATH;   // its index among that math warp's five producers
-    unsigned seq = 0;
-    for (unsigned g = 0;; ++g) {
-      const EaMsg& M = S.msg[g & 1];
-      if (M.cmd == EA_CMD_EXIT) break;
-      const EaLevelGeom& rg = A.ref_geom[M.level];
-      const EaLevelGeom& ng = A.now_geom[M.level];
-      EaPose P;
-      if (M.pts_mode == EA_POINTS_XYZ) {
-        ea_pose_setup<true>(M.cand, rg, ng, P);
-        ea_ws_produce<true>(M.pts, M.dt, M.n_res, A.sp.point_stride, ng, A.inv_depth_scale, P, R, mw, pw, lane, seq);
-      } else {
-        ea_pose_setup<false>(M.cand, rg, ng, P);
-        ea_ws_produce<false>(M.pts, M.dt, M.n_res, A.sp.point_stride, ng, A.inv_depth_scale, P, R, mw, pw, lane, seq);
-      }
-      asm volatile("bar.sync 0;" ::: "memory");
-      asm volatile("bar.sync 0;" ::: "memory");         // the boss' LM step happens between the two
-    }
-  }
-}
-
 // ---- memory-side roof of the fused evaluation (measurement only) -----------------------------------------------------
 // The same point stream, the same fp64 projection (it generates the addresses) and the same 16-texel clamp-to-edge gather
 // as ea_eval_slice, and nothing else: no interpolation, no Jacobian, no reduction, no LM, few registers, full occupancy.
@@ -486,18 +274,24 @@ __global__ void __launch_bounds__(256) ea_k_gather_probe(const __grid_constant__
   if (rd.pts_mode != EA_POINTS_PIXEL) return;
   EaPose P;
   ea_pose_setup<false>(A.poses + size_t(pair) * 7, rg, ng, P);
-  const float2 affine = make_float2(1.0f, 0.0f);
   float s = 0.0f;
-  const int n_round = j0 + (((j1 - j0) + 31) & ~31);   // whole warps: the gather votes
+  const int pitch = ea_dt_pitch(ng.w);
+  const float* dt_pad = nd.dt - ea_dt_origin_offset(ng.w);
   for (int r = 0; r < repeats; ++r)
-    for (int j = j0 + int(threadIdx.x); j < n_round; j += 256) {
+    for (int j = j0 + int(threadIdx.x); j < j1; j += 256) {
       typedef EaPtStream<false> PS;
-      const PS::T p = j < j1 ? PS::load(rd.pts, size_t(j)) : PS::pad();
+      const PS::T p = PS::load(rd.pts, size_t(j));
       double a0, a1, a2;
       PS::unpack(p, a0, a1, a2);
-      s += ea_point_gather_sum<false>(a0, a1, a2, ng, A.inv_depth_scale, P, nd.dt);
+      EaProj pr;
+      ea_project<false>(a0, a1, a2, ng.w, ng.h, pitch, A.inv_depth_scale, P, pr);
+      float t[16];
+      ea_gather(dt_pad, pr.off, unsigned(pitch), t);
+      float ts = pr.du + pr.dv;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) ts += t[k];
+      s += ts;
     }
-  (void)affine;
   sink[size_t(blockIdx.x) * 256 + threadIdx.x] = s;
 }
 
@@ -518,19 +312,6 @@ cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm
   cfg.blockDim = dim3(EA_SOLVE_THREADS);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  if (cluster_size == EA_KERNEL_WS) {
-    static bool ws_attr = false;
-    if (!ws_attr) {
-      e = cudaFuncSetAttribute(ea_k_solve_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(EaWsRing)));
-      if (e != cudaSuccess) return e;
-      ws_attr = true;
-    }
-    cfg.blockDim = dim3(EA_WS_THREADS);
-    cfg.dynamicSmemBytes = sizeof(EaWsRing);
-    cfg.gridDim = dim3(unsigned(A.n_pairs < sm_count ? A.n_pairs : sm_count));
-    cfg.numAttrs = 0;
-    return cudaLaunchKernelEx(&cfg, ea_k_solve_ws, A);
-  }
   if (cluster_size <= 1) {
     // persistent CTAs (EA_SOLVE_MIN_CTAS per SM) pulling pairs from the work queue
     int max_ctas = sm_count * EA_SOLVE_MIN_CTAS;

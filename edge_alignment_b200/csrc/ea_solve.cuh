@@ -283,10 +283,19 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
 #ifndef EA_FLUSH_EVERY
 #define EA_FLUSH_EVERY 16  // points per thread between fp32 -> fp64 flushes of the normal-equation slots (measured: 8 -> 16 = -1.7 %)
 #endif
+#ifndef EA_EVAL_UNROLL
+#define EA_EVAL_UNROLL 2   // points per thread in flight (U): their projections, then all 16 U gathers, then the arithmetic
+#endif
 
 // Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads and leave per-warp partial
-// sums in S.part / S.cpart (caller synchronises).
-template <bool XYZ, int THREADS>
+// sums in part / cpart (caller synchronises).  dt = pixel (0,0) of the padded distance transform.
+//
+// The memory side of an evaluation (point stream -> fp64 projection -> 16-texel gather) is latency-bound and scales with
+// the number of gathers in flight per SM (profiles/r1_kernels_v3.md: 2.2 / 3.6 / 5.2 ms at 32 / 16 / 8 warps); the register
+// file caps the warps at 16, so each thread keeps U independent points in flight instead: one CTA iteration covers
+// THREADS * U consecutive points, thread t owning points base + u * THREADS + t (a warp load still covers 32 consecutive
+// points, the CTA still walks the list -- and the DT rows under it -- front to back).
+template <bool XYZ, int THREADS, int U = EA_EVAL_UNROLL>
 __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, const float* __restrict__ dt, const float2 affine,
                                               const EaLevelGeom& ng,
                                               double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, int j0,
@@ -297,36 +306,62 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
   const int jflip = j0 + j1 - 1;
   const float loss_a = float(sp.loss_scale);
   const int loss_type = sp.loss_type, stride = sp.point_stride;
+  const int W = ng.w, H = ng.h, pitch = ea_dt_pitch(W);
+  const float* __restrict__ dt_pad = dt - ea_dt_origin_offset(W);
   float acc[EA_NSUM];
 #pragma unroll
   for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
   double acc64 = 0.0, cost64 = 0.0;
   int since_flush = 0;
-  int j = j0 + warp * 32 + lane;
   typedef EaPtStream<XYZ> PS;
-  typename PS::T p_next = (j < j1) ? PS::load(pts, size_t(reverse ? jflip - j : j) * stride) : PS::pad();
-  for (int base = j0 + warp * 32; base < j1; base += THREADS) {
-    const typename PS::T p = p_next;
-    const bool valid = j < j1;
-    j += THREADS;
-    if (j < j1) p_next = PS::load(pts, size_t(reverse ? jflip - j : j) * stride);   // prefetch the next point before the gather
-    EaPointEval e;
-    double a0, a1, a2;
-    PS::unpack(p, a0, a1, a2);
-    ea_point_eval<XYZ>(a0, a1, a2, ng, inv_depth_scale, P, dt, affine, e);
-    float rho0;
-    float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
-    if (!valid) { w = 0.0f; rho0 = 0.0f; e.f = 0.0f; e.fail = false; }
-    float J[6];
-    ea_jacobian(e, P, w, J);
-    if (!valid) {   // padding lanes of the last iteration: the dummy point may project to inf/NaN
+  typename PS::T p_next[U];
+  int j = j0 + tid;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) J[k] = 0.0f;
+  for (int u = 0; u < U; ++u) {
+    const int jj = j + u * THREADS;
+    p_next[u] = (jj < j1) ? PS::load(pts, size_t(reverse ? jflip - jj : jj) * stride) : PS::pad();
+  }
+  for (int base = j0; base < j1; base += THREADS * U) {
+    typename PS::T p[U];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { p[u] = p_next[u]; valid[u] = (j + u * THREADS) < j1; }
+    j += THREADS * U;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {   // prefetch the next iteration's points before the gathers
+      const int jj = j + u * THREADS;
+      if (jj < j1) p_next[u] = PS::load(pts, size_t(reverse ? jflip - jj : jj) * stride);
     }
-    ea_accumulate(acc, J, e.f * w);
-    acc[27] += e.fail ? 1.0f : 0.0f;
-    cost64 += double(0.5f * rho0);
-    if (++since_flush == EA_FLUSH_EVERY) {
+    EaProj r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double a0, a1, a2;
+      PS::unpack(p[u], a0, a1, a2);
+      ea_project<XYZ>(a0, a1, a2, W, H, pitch, inv_depth_scale, P, r[u]);
+    }
+    float t[U][16];
+#pragma unroll
+    for (int u = 0; u < U; ++u) ea_gather(dt_pad, r[u].off, unsigned(pitch), t[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      EaPointEval e;
+      ea_interp(t[u], r[u].du, r[u].dv, affine, e.f, e.dfdu, e.dfdv);
+      e.ub = r[u].ub; e.vb = r[u].vb; e.pz = r[u].pz; e.iz = r[u].iz; e.fail = r[u].fail;
+      float rho0;
+      float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
+      if (!valid[u]) { w = 0.0f; rho0 = 0.0f; e.f = 0.0f; e.fail = false; }
+      float J[6];
+      ea_jacobian(e, P, w, J);
+      if (!valid[u]) {   // padding lanes of the last iteration: the dummy point may project to inf/NaN
+#pragma unroll
+        for (int k = 0; k < 6; ++k) J[k] = 0.0f;
+      }
+      ea_accumulate(acc, J, e.f * w);
+      acc[27] += e.fail ? 1.0f : 0.0f;
+      cost64 += double(0.5f * rho0);
+    }
+    since_flush += U;
+    if (since_flush >= EA_FLUSH_EVERY) {
       acc64 += double(ea_warp_transpose_reduce(acc, lane));
 #pragma unroll
       for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;

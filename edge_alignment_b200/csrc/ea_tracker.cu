@@ -8,6 +8,16 @@
 
 #include "ea_internal.h"
 
+// a key frame whose point list was cut at max_points is reported with the results that used it (EA_ERR_CAPACITY; the
+// poses and summaries are still delivered)
+static int tracker_check_truncated(const ea_summary* s, int n_streams, int n_levels) {
+  for (int i = 0; i < n_streams * n_levels; ++i)
+    if (s[i].truncated)
+      return ea_fail(EA_ERR_CAPACITY, "stream %d level %d: the key frame's point list was truncated at max_points; raise ea_frame_params.max_points",
+                     i / n_levels, i % n_levels);
+  return EA_OK;
+}
+
 struct ea_tracker {
   ea_context* ctx = nullptr;
   ea_frameset* fs = nullptr;       // 3 * n_streams slots: stream s owns slots 3s, 3s+1, 3s+2 (key frame, frame being aligned, frame being preprocessed)
@@ -193,10 +203,12 @@ int ea_tracker_probe_gather(ea_tracker* t, int level, int repeats, float* ms, do
 int ea_tracker_get_poses(ea_tracker* t, double* poses7, ea_summary* summaries) {
   if (!t) return ea_fail(EA_ERR_INVALID_ARG, "null tracker");
   cudaStream_t s = t->ctx->stream;
+  std::vector<ea_summary> tmp;
+  if (!summaries) { tmp.resize(size_t(t->n_streams) * t->n_levels); summaries = tmp.data(); }
   if (poses7) CU(cudaMemcpyAsync(poses7, t->d_result, size_t(t->n_streams) * 7 * 8, cudaMemcpyDeviceToHost, s));
-  if (summaries) CU(cudaMemcpyAsync(summaries, t->d_summaries, size_t(t->n_streams) * t->n_levels * sizeof(ea_summary), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(summaries, t->d_summaries, size_t(t->n_streams) * t->n_levels * sizeof(ea_summary), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  return EA_OK;
+  return tracker_check_truncated(summaries, t->n_streams, t->n_levels);
 }
 
 int ea_tracker_step_host(ea_tracker* t, const uint8_t* bgr, const void* depth, double* poses7, ea_summary* summaries) {
@@ -234,7 +246,7 @@ int ea_tracker_wait(ea_tracker* t, int frame, double* poses7, ea_summary* summar
   CU(cudaEventSynchronize(t->ev_result[b]));
   if (poses7) std::memcpy(poses7, t->h_poses[b], size_t(t->n_streams) * 7 * 8);
   if (summaries) std::memcpy(summaries, t->h_summaries[b], size_t(t->n_streams) * t->n_levels * sizeof(ea_summary));
-  return EA_OK;
+  return tracker_check_truncated(t->h_summaries[b], t->n_streams, t->n_levels);
 }
 
 int ea_tracker_frame_index(ea_tracker* t, int* n) {

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define EA_ABI_VERSION 1
+#define EA_ABI_VERSION 2
 #define EA_MAX_LEVELS 4
 
 typedef struct ea_context ea_context;   /* one per (host thread, CUDA device, stream) */
@@ -121,9 +121,8 @@ typedef struct ea_solve_params {
   int32_t jacobi_scaling;     /* 1 */
   int32_t max_consecutive_invalid_steps; /* 5 */
   int32_t cluster_size;       /* 1 = one persistent CTA per pair; 2,4,8 = thread-block cluster per pair (DSMEM
-                               * reduction); -1 = task-graph kernel ((pair,chunk) tasks through a device queue);
-                               * -3 = warp-specialised kernel (gather / math warps, experimental);
-                               * 0 = auto (clusters of 8/4/2 while pairs are fewer than SMs/8, /4, /2; else one CTA per pair) */
+                               * reduction); 0 = auto (clusters of 8/4/2 while pairs are fewer than SMs/8, /4, /2;
+                               * else one CTA per pair) */
   int32_t coarsest_level;     /* first level solved; -1 => n_levels-1 */
   int32_t finest_level;       /* last level solved; 0 */
   double loss_scale;          /* 1.0 */
@@ -148,6 +147,8 @@ typedef struct ea_summary {
   int32_t n_residuals;  /* residual blocks = ceil(N/stride) */
   int32_t evaluations;  /* fused residual+Jacobian passes over the n_residuals points */
   double initial_cost, final_cost;
+  int32_t truncated;    /* 1: the reference point list was cut at ea_frame_params.max_points (result uses the cut list) */
+  int32_t reserved;
 } ea_summary;
 
 /* ---- library / context ------------------------------------------------------ */

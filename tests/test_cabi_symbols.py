@@ -26,14 +26,14 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, s), "libea_b200.so does not export %s" % s
         assert s in L.PROTOTYPES, "python binding lacks %s" % s
     assert sorted(L.PROTOTYPES) == syms
-    assert L.lib().ea_abi_version() == 1
+    assert L.lib().ea_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     from edge_alignment_b200 import _lib as L
     assert ctypes.sizeof(L.FrameParams) == 8 * 4 + 5 * 8 + 2 * 4 + 2 * 8 + 2 * 4
     assert ctypes.sizeof(L.SolveParams) == 8 * 4 + 10 * 8 + 2 * 4
-    assert ctypes.sizeof(L.Summary) == 6 * 4 + 2 * 8
+    assert ctypes.sizeof(L.Summary) == 6 * 4 + 2 * 8 + 2 * 4
     import edge_alignment_b200 as ea
     fp, sp = ea.frame_params(), ea.solve_params()
     # defaults reproduce edge_align_test1 (standalone_edge_align.cpp:152,160,267,272; utils.cpp:65,75,81)

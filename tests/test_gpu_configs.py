@@ -98,7 +98,7 @@ def test_config4_dense_1280x720_coarse_to_fine(ea, oracle):
         sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=0.1)
         cfg = O.pair_cfg(w, h, K, n_levels=4, stride=1)
         op, oS = O.align_pair(hb[0], hd[0], hb[2], cfg, IDENTITY, O.default_options(loss_type=O.LOSS_HUBER, loss_scale=0.1))
-        for kernel in (0, -1, 1):    # auto (cluster of 8 for a single pair), task graph, CTA per pair
+        for kernel in (0, 1):    # auto (cluster of 8 for a single pair), CTA per pair
             sp.cluster_size = kernel
             poses, S = ctx.solve_batch(fs, [0], fs, [1], None, sp)
             assert rot_angle_between(poses[0][:4], op[:4]) < 1e-4 and np.abs(poses[0][4:] - op[4:]).max() < 1e-4
