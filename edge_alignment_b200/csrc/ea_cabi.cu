@@ -57,6 +57,10 @@ int ea_create(int device, ea_context** out) {
   CU(cudaMalloc(&c->d_failed, sizeof(int)));
   CU(cudaMalloc(&c->d_work, sizeof(int)));
   CU(cudaMalloc(&c->d_sums, size_t(1024) * EA_SUMS * sizeof(double)));
+  if (getenv("EA_SOLVE_DEBUG")) {
+    CU(cudaMalloc(&c->d_debug, size_t(1024) * 6 * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_debug, 0, size_t(1024) * 6 * sizeof(unsigned long long)));
+  }
   *out = c;
   return EA_OK;
 }
@@ -64,6 +68,12 @@ int ea_destroy(ea_context* c) {
   if (!c) return EA_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->d_debug && c->debug_launches > 0) {
+    const double n = double(c->debug_launches);
+    fprintf(stderr, "[EA_SOLVE_DEBUG] %ld launches; per launch, mean over CTAs, kcycles of thread 0: eval %.1f  wait+totals %.1f  LM %.1f  wait2 %.1f  lifetime %.1f; evaluations %.1f\n",
+            c->debug_launches, c->debug_sum[0] / n / 1e3, c->debug_sum[1] / n / 1e3, c->debug_sum[2] / n / 1e3, c->debug_sum[3] / n / 1e3, c->debug_sum[5] / n / 1e3, c->debug_sum[4] / n);
+  }
+  cudaFree(c->d_debug);
   cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_work); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -681,7 +691,16 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
   // per-iteration latency drops (config 1, stride 1: 0.58 ms with clusters of 8 vs 2.4 ms on one CTA); big batches -> one
   // persistent CTA per pair (no scheduling overhead, best L1 locality).
   if (cluster == 0) cluster = auto_cluster(c, n, 0);
+  A.debug = c->d_debug;
   e = ea_launch_solve_batch(A, cluster, c->sm_count, c->stream);
+  if (c->d_debug && e == cudaSuccess) {   // development aid: synchronous read-back of the cycle counters
+    const int grid = std::min(n, c->sm_count);
+    std::vector<unsigned long long> h(size_t(grid) * 6);
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(h.data(), c->d_debug, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    for (int k = 0; k < 6; ++k) { double sum = 0; for (int b = 0; b < grid; ++b) sum += double(h[size_t(b) * 6 + k]); c->debug_sum[k] += sum / grid; }
+    c->debug_launches++;
+  }
   c->launches++;
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "solve launch: %s", cudaGetErrorString(e));
   return EA_OK;

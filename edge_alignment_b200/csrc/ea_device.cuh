@@ -55,7 +55,7 @@ struct EaPose {  // per-evaluation uniform transform, fp64
   double tt[3];
   float t[3];        // translation, for y = p' - t in the Jacobian
   float fx, fy, inv_fx, inv_fy;   // now-level intrinsics in fp32 (Jacobian)
-  double cx, cy;     // now-level principal point
+  float cx, cy;      // now-level principal point (only the Jacobian's lever arm u' - cx uses it: fp32)
 };
 
 // Eigen::Quaternion::toRotationMatrix(), as called at standalone/utils.h:51-53 (no normalisation), folded with the
@@ -92,7 +92,7 @@ __device__ __forceinline__ void ea_pose_setup(const double* x7, const EaLevelGeo
   P.tt[2] = x7[6];
   P.t[0] = float(x7[4]); P.t[1] = float(x7[5]); P.t[2] = float(x7[6]);
   P.fx = float(now.fx); P.fy = float(now.fy); P.inv_fx = float(now.inv_fx); P.inv_fy = float(now.inv_fy);
-  P.cx = now.cx; P.cy = now.cy;
+  P.cx = float(now.cx); P.cy = float(now.cy);
 }
 
 struct EaPointEval {
@@ -193,15 +193,18 @@ __device__ __forceinline__ void ea_project(const double a0, const double a1, con
   iu = min(max(iu, 1 - EA_DT_PAD), W + 1);
   iv = min(max(iv, 1 - EA_DT_PAD), H + 1);
   r.off = unsigned(iv + (EA_DT_PAD - 1)) * unsigned(pitch) + unsigned(iu + (EA_DT_PAD - 1));
-  r.ub = float(u - P.cx); r.vb = float(v - P.cy);
+  r.ub = float(u) - P.cx; r.vb = float(v) - P.cy;
   r.pz = float(q2); r.iz = float(iz);
 }
 // t[4 * row + col] = dt(floor(v') - 1 + row, floor(u') - 1 + col) with Grid2D clamp-to-edge (through the padding)
 __device__ __forceinline__ void ea_gather(const float* __restrict__ dt_pad, const unsigned off, const unsigned pitch, float (&t)[16]) {
+  // one 32-bit element offset per footprint row, widened against the single 64-bit base (IMAD.WIDE.U32), the four columns
+  // as immediates: 7 integer instructions for the 16 addresses
+  const unsigned o1 = off + pitch, o2 = o1 + pitch, o3 = o2 + pitch;
   const float* p0 = dt_pad + off;
-  const float* p1 = p0 + pitch;
-  const float* p2 = p1 + pitch;
-  const float* p3 = p2 + pitch;
+  const float* p1 = dt_pad + o1;
+  const float* p2 = dt_pad + o2;
+  const float* p3 = dt_pad + o3;
   t[0] = __ldg(p0); t[1] = __ldg(p0 + 1); t[2] = __ldg(p0 + 2); t[3] = __ldg(p0 + 3);
   t[4] = __ldg(p1); t[5] = __ldg(p1 + 1); t[6] = __ldg(p1 + 2); t[7] = __ldg(p1 + 3);
   t[8] = __ldg(p2); t[9] = __ldg(p2 + 1); t[10] = __ldg(p2 + 2); t[11] = __ldg(p2 + 3);
@@ -249,9 +252,14 @@ __device__ __forceinline__ float ea_loss_eval(int type, float a, float r, float&
   } else if (type == EA_LOSS_HUBER) {
     const float b = a * a;
     if (s > b) {
+      // rho = 2 a |r| - a^2, sqrt(rho') = sqrt(a / |r|) = rsqrt(|r| / a): MUFU.RSQ plus one Newton step (<= 1 ulp) instead of an
+      // IEEE division and square root (25 instructions with their slow-path calls, paid by every warp that holds one outlier)
       const float ar = fabsf(r);
       rho0 = 2.0f * a * ar - b;
-      return sqrtf(a / ar);
+      const float x = ar * (1.0f / a);
+      float y = rsqrtf(x);
+      y = y * fmaf(-0.5f * x, y * y, 1.5f);
+      return y;
     }
     rho0 = s;
     return 1.0f;

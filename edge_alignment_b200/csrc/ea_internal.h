@@ -20,6 +20,7 @@ struct EaSolveArgs {
   const int32_t* order;         // [n_pairs] device or null: processing order of the work queue (longest first)
   double* poses;                // [*][7] device, in/out
   int* work_counter;            // device: next pair index of the dynamic work queue (zeroed per launch)
+  unsigned long long* debug;    // null, or [grid][6] cycle counters of each CTA's thread 0 (EA_SOLVE_DEBUG=1, development aid)
   ea_summary* summaries;        // [n_pairs][n_levels] device or null
   double* trace;                // [trace_cap][EA_TRACE_DOUBLES] device or null: one record per evaluation (single-pair solves only)
   int* trace_count;             // device counter of records written
@@ -105,6 +106,7 @@ struct ea_context {
   double* d_pose = nullptr;      // [7]
   int* d_failed = nullptr;
   int* d_work = nullptr;         // work-queue counter of the batched solve
+  unsigned long long* d_debug = nullptr; double debug_sum[6] = {0, 0, 0, 0, 0, 0}; long debug_launches = 0;   // EA_SOLVE_DEBUG=1
   double* d_sums = nullptr;      // [max blocks][EA_SUMS]
   int32_t* d_idx = nullptr;      // scratch slot indices
   size_t idx_cap = 0;

@@ -30,12 +30,13 @@ namespace cg = cooperative_groups;
 #define EA_CMD_EXIT 2
 
 struct EaMsg {  // boss -> all threads of the cluster
-  double cand[7];
+  EaPose P;       // the candidate pose folded with the level's intrinsics (ea_pose_setup): computed once, by the boss
   const void* pts;
-  const float* dt;
+  const float* dt;     // first element of the padded distance transform (pixel (-PAD, -PAD)): offsets from it are unsigned
   float2 affine;
   int n_res, level, pts_mode, cmd;
-  int rev, pad;   // sweep direction of this evaluation: alternates per evaluation of the (pair, level), see ea_eval_slice
+  int rev;        // sweep direction of this evaluation: alternates per evaluation of the (pair, level), see ea_eval_slice
+  int same;       // this evaluation continues the previous one's (pair, level): the points prefetched before the barrier are its first
 };
 
 struct EaSolveSmem {
@@ -46,6 +47,7 @@ struct EaSolveSmem {
   double cluster_sums[8][EA_SUMS + 3];      // rank 0 only: one row per cluster rank
   EaLmState lm;                             // boss only
   int pair, level, truncated;               // boss only
+  long long dbg[6], dbg_t, dbg_t0;          // EA_SOLVE_DEBUG cycle counters (thread 0)
 };
 
 // Boss: move to the next (pair, level) that has points and publish its first evaluation, or EXIT.
@@ -83,8 +85,10 @@ __device__ __forceinline__ void ea_boss_next_impl(const EaSolveArgs& A, EaSolveS
     EaLmState& L = S.lm;
     L.phase = 0; L.iter = 0; L.accepted = 0; L.rejected = 0; L.invalid_run = 0; L.evals = 0; L.term = EA_TERM_NONE;
 #pragma unroll 1
-    for (int i = 0; i < 7; ++i) { L.cand[i] = L.x[i]; out.cand[i] = L.x[i]; }
-    out.pts = rd.pts; out.dt = nd.dt; out.affine = *nd.dt_affine; out.n_res = n_res; out.level = level; out.pts_mode = rd.pts_mode; out.cmd = EA_CMD_EVAL; out.rev = 0; out.pad = 0;
+    for (int i = 0; i < 7; ++i) L.cand[i] = L.x[i];
+    if (rd.pts_mode == EA_POINTS_XYZ) ea_pose_setup<true>(L.cand, A.ref_geom[level], A.now_geom[level], out.P);
+    else ea_pose_setup<false>(L.cand, A.ref_geom[level], A.now_geom[level], out.P);
+    out.pts = rd.pts; out.dt = nd.dt - ea_dt_origin_offset(nd.w); out.affine = *nd.dt_affine; out.n_res = n_res; out.level = level; out.pts_mode = rd.pts_mode; out.cmd = EA_CMD_EVAL; out.rev = 0; out.same = 0;
     return;
   }
 }
@@ -105,9 +109,10 @@ __device__ __forceinline__ void ea_boss_step_impl(const EaSolveArgs& A, EaSolveS
     }
   }
   if (cmd == EA_CMD_EVAL) {
-#pragma unroll
-    for (int i = 0; i < 7; ++i) out.cand[i] = S.lm.cand[i];
-    out.pts = cur.pts; out.dt = cur.dt; out.affine = cur.affine; out.n_res = cur.n_res; out.level = cur.level; out.pts_mode = cur.pts_mode; out.cmd = EA_CMD_EVAL; out.rev = S.lm.evals & 1; out.pad = 0;
+    if (cur.pts_mode == EA_POINTS_XYZ) ea_pose_setup<true>(S.lm.cand, A.ref_geom[cur.level], A.now_geom[cur.level], out.P);
+    else ea_pose_setup<false>(S.lm.cand, A.ref_geom[cur.level], A.now_geom[cur.level], out.P);
+    out.pts = cur.pts; out.dt = cur.dt; out.affine = cur.affine; out.n_res = cur.n_res; out.level = cur.level; out.pts_mode = cur.pts_mode; out.cmd = EA_CMD_EVAL;
+    out.rev = S.lm.evals & 1; out.same = 1;
     return;
   }
   if (A.summaries) {
@@ -123,10 +128,6 @@ __device__ __forceinline__ void ea_boss_step_impl(const EaSolveArgs& A, EaSolveS
 }
 __device__ __noinline__ void ea_boss_step(const EaSolveArgs& A, EaSolveSmem& S, const double* sums, const EaMsg& cur, EaMsg& out) { ea_boss_step_impl<false>(A, S, sums, cur, out); }
 
-
-#ifndef EA_ALTERNATE_SWEEP
-#define EA_ALTERNATE_SWEEP 1
-#endif
 
 template <int THREADS, bool CLUSTER>
 __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(const __grid_constant__ EaSolveArgs A) {
@@ -150,20 +151,27 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
     publish(m, 0);
   }
   sync_all();
+  // EA_SOLVE_DEBUG=1: where the boss thread's cycles go {evaluation, wait + totals, LM step, second wait, evaluations, lifetime}
+  // (counters live in shared memory: the evaluation loop has no registers to spare)
+  const bool dbg_on = A.debug != nullptr && tid == 0;
+  if (dbg_on) { for (int k = 0; k < 6; ++k) S.dbg[k] = 0; S.dbg_t0 = clock64(); S.dbg_t = S.dbg_t0; }
+  auto lap = [&](int k) { if (dbg_on) { const long long t = clock64(); S.dbg[k] += t - S.dbg_t; S.dbg_t = t; } };
+  EaPtStream<false>::T pre[EA_EVAL_UNROLL];   // first points of the NEXT evaluation, requested before the barrier (pixel points only)
+#pragma unroll
+  for (int u = 0; u < EA_EVAL_UNROLL; ++u) pre[u] = EaPtStream<false>::pad();
   for (;;) {
     const EaMsg& M = S.msg[g & 1];
     if (M.cmd == EA_CMD_EXIT) break;
-    const EaLevelGeom& rg = A.ref_geom[M.level];
     const EaLevelGeom& ng = A.now_geom[M.level];
     const int j0 = int((long long)M.n_res * crank / csize), j1 = int((long long)M.n_res * (crank + 1) / csize);
-    EaPose P;
+    const EaPose P = M.P;
     if (M.pts_mode == EA_POINTS_XYZ) {
-      ea_pose_setup<true>(M.cand, rg, ng, P);
       ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart, EA_ALTERNATE_SWEEP && M.rev);
     } else {
-      ea_pose_setup<false>(M.cand, rg, ng, P);
-      ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart, EA_ALTERNATE_SWEEP && M.rev);
+      ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart, EA_ALTERNATE_SWEEP && M.rev,
+                                    pre, M.same != 0);
     }
+    lap(0);
     __syncthreads();
     if (warp == 0) {
       const double tot = ea_cta_total<THREADS / 32>(S.part, S.cpart, lane);
@@ -173,11 +181,13 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
       } else {
         if (lane < EA_SUMS) S.sums[lane] = tot;
         __syncwarp();
+        lap(1);
         if (lane == 0) {
           EaMsg m;
           ea_boss_step(A, S, S.sums, M, m);
           S.msg[(g + 1) & 1] = m;
         }
+        lap(2);
       }
     }
     if (CLUSTER) {
@@ -195,7 +205,13 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
       }
     }
     sync_all();
+    lap(3);
+    if (dbg_on) S.dbg[4] += 1;
     g += 1;
+  }
+  if (dbg_on) {
+    S.dbg[5] = clock64() - S.dbg_t0;
+    for (int k = 0; k < 6; ++k) A.debug[size_t(blockIdx.x) * 6 + k] = (unsigned long long)S.dbg[k];
   }
   if (CLUSTER) cluster.sync();  // no CTA may exit while a peer can still touch its shared memory
 }
@@ -208,7 +224,7 @@ __global__ void __launch_bounds__(256) ea_k_eval_points(EaLevelDesc rd, EaLevelD
   EaPose P;
   ea_pose_setup<XYZ>(pose7, rg, ng, P);
   const float2 affine = *nd.dt_affine;
-  const int n_round = (n_res + 31) & ~31;   // keep warps converged: the gather's fast path votes with __all_sync
+  const int n_round = (n_res + 31) & ~31;   // whole warps
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
     const bool valid = j < n_res;
     typedef EaPtStream<XYZ> PS;
@@ -245,10 +261,10 @@ __global__ void __launch_bounds__(THREADS) ea_k_eval_sums(EaLevelDesc rd, EaLeve
   EaPose P;
   if (rd.pts_mode == EA_POINTS_XYZ) {
     ea_pose_setup<true>(pose7, rg, ng, P);
-    ea_eval_slice<true, THREADS>(rd.pts, nd.dt, *nd.dt_affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
+    ea_eval_slice<true, THREADS>(rd.pts, nd.dt - ea_dt_origin_offset(nd.w), *nd.dt_affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
   } else {
     ea_pose_setup<false>(pose7, rg, ng, P);
-    ea_eval_slice<false, THREADS>(rd.pts, nd.dt, *nd.dt_affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
+    ea_eval_slice<false, THREADS>(rd.pts, nd.dt - ea_dt_origin_offset(nd.w), *nd.dt_affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
   }
   __syncthreads();
   if (threadIdx.x < 32) {

@@ -24,10 +24,20 @@ struct EaLmState {
 };
 
 __device__ inline void ea_quat_plus(const double* x, const double* d, double* out) {
-  // ceres::QuaternionParameterization::Plus -- delta is a half-angle vector, left multiplication
-  const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-  if (n > 0.0) {
-    const double s = sin(n) / n, c = cos(n);
+  // ceres::QuaternionParameterization::Plus -- delta is a half-angle vector, left multiplication:
+  //   q+ = (cos|d|, sin|d| / |d| * d) (x) q.   Both factors are even in |d|: for |d| < 0.1 (every LM step of a tracker) they
+  // are taken from their Maclaurin series in |d|^2 (truncation < 1e-20, i.e. correct to the last bit or two) -- no sqrt, no
+  // libm range reduction on the serial section between two evaluations.  Larger steps take the textbook form.
+  const double n2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  if (n2 > 0.0) {
+    double s, c;
+    if (n2 < 0.01) {
+      c = fma(n2, fma(n2, fma(n2, fma(n2, fma(n2, fma(n2, 1.0 / 479001600.0, -1.0 / 3628800.0), 1.0 / 40320.0), -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
+      s = fma(n2, fma(n2, fma(n2, fma(n2, fma(n2, fma(n2, 1.0 / 6227020800.0, -1.0 / 39916800.0), 1.0 / 362880.0), -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
+    } else {
+      const double n = sqrt(n2);
+      s = sin(n) / n; c = cos(n);
+    }
     const double q0 = c, q1 = s * d[0], q2 = s * d[1], q3 = s * d[2];
     out[0] = q0 * x[0] - q1 * x[1] - q2 * x[2] - q3 * x[3];
     out[1] = q0 * x[1] + q1 * x[0] + q2 * x[3] - q3 * x[2];
@@ -227,8 +237,12 @@ static __device__ __forceinline__ int ea_lm_advance_impl(EaLmState& S, const dou
     double sn = 0.0, xn = 0.0;
 #pragma unroll
     for (int i = 0; i < 7; ++i) { const double d = S.x[i] - S.cand[i]; sn += d * d; xn += S.x[i] * S.x[i]; }
-    sn = sqrt(sn); xn = sqrt(xn);
-    if (sn <= sp.parameter_tolerance * (xn + sp.parameter_tolerance)) { S.term = EA_TERM_CONVERGENCE_PARAMETER; return EA_CMD_DONE; }
+    // |step| <= ptol (|x| + ptol).  (a + b)^2 <= 2 a^2 + 2 b^2, so a squared step above that bound cannot pass: the two square
+    // roots are only taken when the step is within a factor sqrt(2) of the tolerance (same decisions either way)
+    const double pt2 = sp.parameter_tolerance * sp.parameter_tolerance;
+    if (sn <= 2.0 * pt2 * (xn + pt2)) {
+      if (sqrt(sn) <= sp.parameter_tolerance * (sqrt(xn) + sp.parameter_tolerance)) { S.term = EA_TERM_CONVERGENCE_PARAMETER; return EA_CMD_DONE; }
+    }
     const double cost_change = S.cost - cand_cost;
     if (fabs(cost_change) <= sp.function_tolerance * S.cost) { S.term = EA_TERM_CONVERGENCE_FUNCTION; return EA_CMD_DONE; }
     const double rel = fail ? -DBL_MAX : cost_change / S.model_cost_change;
@@ -283,12 +297,15 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
 #ifndef EA_FLUSH_EVERY
 #define EA_FLUSH_EVERY 16  // points per thread between fp32 -> fp64 flushes of the normal-equation slots (measured: 8 -> 16 = -1.7 %)
 #endif
+#ifndef EA_ALTERNATE_SWEEP
+#define EA_ALTERNATE_SWEEP 1
+#endif
 #ifndef EA_EVAL_UNROLL
-#define EA_EVAL_UNROLL 2   // points per thread in flight (U): their projections, then all 16 U gathers, then the arithmetic
+#define EA_EVAL_UNROLL 1   // points per thread in flight (U): their projections, then all 16 U gathers, then the arithmetic
 #endif
 
 // Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads and leave per-warp partial
-// sums in part / cpart (caller synchronises).  dt = pixel (0,0) of the padded distance transform.
+// sums in part / cpart (caller synchronises).  dt_pad = FIRST element of the padded distance transform (pixel (-PAD,-PAD)).
 //
 // The memory side of an evaluation (point stream -> fp64 projection -> 16-texel gather) is latency-bound and scales with
 // the number of gathers in flight per SM (profiles/r1_kernels_v3.md: 2.2 / 3.6 / 5.2 ms at 32 / 16 / 8 warps); the register
@@ -296,10 +313,14 @@ static __device__ __noinline__ int ea_lm_advance(EaLmState& S, const double* sum
 // THREADS * U consecutive points, thread t owning points base + u * THREADS + t (a warp load still covers 32 consecutive
 // points, the CTA still walks the list -- and the DT rows under it -- front to back).
 template <bool XYZ, int THREADS, int U = EA_EVAL_UNROLL>
-__device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, const float* __restrict__ dt, const float2 affine,
+__device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, const float* __restrict__ dt_pad, const float2 affine,
                                               const EaLevelGeom& ng,
                                               double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, int j0,
-                                              int j1, double (*part)[EA_NSUM], double* cpart, const bool reverse = false) {
+                                              int j1, double (*part)[EA_NSUM], double* cpart, const bool reverse = false,
+                                              typename EaPtStream<XYZ>::T* pre = nullptr, const bool pre_valid = false) {
+  // pre (optional, U entries): in -- this thread's first points, already requested by the previous evaluation of the same
+  // (pair, level) when pre_valid; out -- the first points of the NEXT evaluation of this slice (opposite direction), requested
+  // before the final reduction so that their latency hides behind it, the CTA barrier and the serial LM step.
   // reverse: walk the slice from its end.  Successive evaluations of a pair alternate the direction, so each sweep
   // starts on the data the previous one touched last (still in L1 / L2) instead of on the data it evicted first.
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -307,7 +328,6 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
   const float loss_a = float(sp.loss_scale);
   const int loss_type = sp.loss_type, stride = sp.point_stride;
   const int W = ng.w, H = ng.h, pitch = ea_dt_pitch(W);
-  const float* __restrict__ dt_pad = dt - ea_dt_origin_offset(W);
   float acc[EA_NSUM];
 #pragma unroll
   for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
@@ -319,7 +339,8 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int jj = j + u * THREADS;
-    p_next[u] = (jj < j1) ? PS::load(pts, size_t(reverse ? jflip - jj : jj) * stride) : PS::pad();
+    if (pre && pre_valid) p_next[u] = pre[u];
+    else p_next[u] = (jj < j1) ? PS::load(pts, size_t(reverse ? jflip - jj : jj) * stride) : PS::pad();
   }
   for (int base = j0; base < j1; base += THREADS * U) {
     typename PS::T p[U];
@@ -366,6 +387,14 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
 #pragma unroll
       for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
       since_flush = 0;
+    }
+  }
+  if (pre) {   // the next evaluation of this (pair, level) sweeps the other way (EA_ALTERNATE_SWEEP) or the same way
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int jj = j0 + tid + u * THREADS;
+      const bool rn = EA_ALTERNATE_SWEEP ? !reverse : reverse;
+      pre[u] = (jj < j1) ? PS::load(pts, size_t(rn ? jflip - jj : jj) * stride) : PS::pad();
     }
   }
   if (since_flush) acc64 += double(ea_warp_transpose_reduce(acc, lane));
