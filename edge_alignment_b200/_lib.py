@@ -22,7 +22,7 @@ DEPTH_U16, DEPTH_F32 = 0, 1
 POINTS_PIXEL, POINTS_XYZ = 0, 1
 TERMINATION = {0: "NONE", 1: "CONVERGENCE_GRADIENT", 2: "CONVERGENCE_FUNCTION", 3: "CONVERGENCE_PARAMETER",
                4: "CONVERGENCE_MIN_RADIUS", 5: "NO_CONVERGENCE", 6: "FAILURE_EVAL_X0", 7: "FAILURE_INVALID_STEPS",
-               8: "SKIPPED_NO_POINTS"}
+               8: "SKIPPED_NO_POINTS", 9: "FAILURE_PEER"}
 
 
 class FrameParams(C.Structure):
@@ -113,6 +113,7 @@ PROTOTYPES = {
     "ea_shard_create": (_i, [_vp, _u8p, _i, _i, C.POINTER(_vp)]),
     "ea_shard_destroy": (_i, [_vp]),
     "ea_shard_solve": (_i, [_vp, _vp, _i, _vp, _i, _i, _f64p, C.POINTER(SolveParams), C.POINTER(Summary)]),
+    "ea_shard_profile": (_i, [_vp, _f64p]),
 }
 
 _lib = None

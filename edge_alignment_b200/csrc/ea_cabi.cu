@@ -526,7 +526,7 @@ int ea_frameset_level_geometry(ea_frameset* fs, int level, int* w, int* h, doubl
 }
 
 // ---- evaluation / solve -------------------------------------------------------------------------------------
-static int check_solve_params(const ea_solve_params* sp) {
+int ea_check_solve_params(const ea_solve_params* sp) {
   if (!sp) return ea_fail(EA_ERR_INVALID_ARG, "solve params are null");
   if (sp->point_stride < 1) return ea_fail(EA_ERR_INVALID_ARG, "point_stride must be >= 1");
   if (sp->loss_type < EA_LOSS_TRIVIAL || sp->loss_type > EA_LOSS_HUBER) return ea_fail(EA_ERR_INVALID_ARG, "unknown loss type");
@@ -548,7 +548,7 @@ static int check_pairable(ea_frameset* ref, ea_frameset* now) {
 int ea_eval(ea_context* c, ea_frameset* ref, int ref_slot, ea_frameset* now, int now_slot, int level, const double* pose7,
             const ea_solve_params* sp, int* n_residuals, double* raw, double* residuals, double* jac, double* sums28, int* failed) {
   if (!c || !pose7) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
-  int rc = check_solve_params(sp);
+  int rc = ea_check_solve_params(sp);
   if (!rc) rc = check_pairable(ref, now);
   if (!rc) rc = check_slot_level(ref, ref_slot, level);
   if (!rc) rc = check_slot_level(now, now_slot, level);
@@ -598,7 +598,7 @@ int ea_eval(ea_context* c, ea_frameset* ref, int ref_slot, ea_frameset* now, int
 }
 
 static int fill_solve_args(ea_context* c, ea_frameset* ref, ea_frameset* now, const ea_solve_params* sp, EaSolveArgs& A, int* cluster) {
-  int rc = check_solve_params(sp);
+  int rc = ea_check_solve_params(sp);
   if (!rc) rc = check_pairable(ref, now);
   if (rc) return rc;
   std::memset(&A, 0, sizeof A);

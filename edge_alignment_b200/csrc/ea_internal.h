@@ -155,6 +155,7 @@ int ea_fail(int code, const char* fmt, ...);
     if (e_ != cudaSuccess) return ea_fail(EA_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
   } while (0)
 int ea_ensure_tmp(ea_context* c, size_t bytes);
+extern "C" int ea_check_solve_params(const ea_solve_params* sp);   // shared argument validation of every solve entry point
 int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now,
                                    const int32_t* d_now_slots, double* d_poses7, const int32_t* d_pose_index,
                                    const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries);

@@ -25,6 +25,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -38,9 +39,10 @@ int load_nccl() {
   g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
     return ea_fail(EA_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
   g_nccl.handle = h;
   return EA_OK;
@@ -137,6 +139,202 @@ __global__ void k_shard_lm(ShardState* st, const double* sums, ea_solve_params s
   else st->done = 1;
 }
 
+// =====================================================================================================================
+// One persistent cooperative kernel per rank for the whole solve of one (pair, level): no host round trip, no kernel
+// launch and no NCCL call per LM evaluation.
+//
+//   every CTA      evaluates its slice of this rank's point range (ea_eval_slice, the production loop) -> 29 CTA totals
+//   grid reduce    totals to global memory, one atomic ticket per CTA; the CTA that draws the last ticket adds the
+//                  per-CTA totals in a fixed order (bitwise reproducible)
+//   all-reduce     that CTA stores the rank's 29 doubles straight into every peer's exchange buffer over NVLink (peer-mapped
+//                  cudaIpc memory), fences, raises a per-source epoch flag there, waits for the world's flags in its own
+//                  buffer and adds the world's contributions in rank order: every rank obtains bit-identical sums, so all
+//                  ranks take identical LM decisions with no broadcast.  Data slots are double-buffered by evaluation parity
+//                  (a rank can be at most one evaluation ahead of a peer).
+//   LM             one thread advances the Ceres-equivalent trust-region state machine (ea_lm_advance), publishes the next
+//                  candidate pose and releases the grid through an epoch word the other CTAs poll
+// Every wait is bounded (EA_SHARD_SPIN_LIMIT polls): a lost peer ends the solve with EA_TERM_FAILURE_PEER instead of hanging
+// the GPU.
+#define EA_SHARD_MAX_WORLD 8
+#define EA_SHARD_SPIN_LIMIT (1ll << 22)   // ~3 s of polling
+struct ShardXchg {                                  // lives in cudaIpc-shared device memory, one per rank
+  double data[2][EA_SHARD_MAX_WORLD][32];           // [evaluation parity][source rank][29 sums]
+  unsigned long long flag[2][EA_SHARD_MAX_WORLD];   // epoch of the evaluation whose data the slot holds
+};
+struct ShardPeers { ShardXchg* p[EA_SHARD_MAX_WORLD]; };
+struct ShardCtl {                                   // per-rank control block (device memory)
+  EaLmState lm;
+  EaPose P;                                         // candidate pose folded with the intrinsics, for the evaluation in flight
+  unsigned long long go;                            // evaluation epoch released to the grid
+  unsigned long long ticket;                        // CTAs that have delivered their totals (monotonic over the solve)
+  int done, error;
+  long long prof[6];                                // cycles: {evaluation (CTA 0), grid reduce, all-reduce, LM} of the CTA that did them, evaluations
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLevelDesc nd, EaLevelGeom rg, EaLevelGeom ng,
+                                                            double inv_depth_scale, ea_solve_params sp, ShardCtl* ctl,
+                                                            double* partials /*[grid][32]*/, ShardPeers peers, int rank, int world,
+                                                            unsigned long long epoch0, int j_begin, int j_end) {
+  __shared__ double part[THREADS / 32][EA_NSUM];
+  __shared__ double cpart[THREADS / 32];
+  __shared__ double wsum[THREADS / 32][32];
+  __shared__ unsigned long long s_ticket;
+  __shared__ int s_stop;
+  __shared__ EaLmState s_lm;      // the LM state of the CTA that drew the last ticket (global memory between evaluations)
+  static_assert(sizeof(EaLmState) % 8 == 0, "EaLmState is copied as 8-byte words");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = j_end - j_begin;
+  const int j0 = j_begin + int((long long)n * blockIdx.x / gridDim.x), j1 = j_begin + int((long long)n * (blockIdx.x + 1) / gridDim.x);
+  const float2 affine = *nd.dt_affine;
+  const float* dt_pad = nd.dt - ea_dt_origin_offset(nd.w);
+  const bool xyz = rd.pts_mode == EA_POINTS_XYZ;
+  for (unsigned long long e = 1;; ++e) {
+    // ---- wait for the release of evaluation e (e == 1 is released by the host-side initialisation) ----
+    if (tid == 0) {
+      long long spins = 0;
+      int stop = 0;
+      while (ld_acquire_gpu(&ctl->go) < e) {
+        if (++spins > EA_SHARD_SPIN_LIMIT) { stop = 2; break; }
+        __nanosleep(20);
+      }
+      if (!stop) stop = *reinterpret_cast<volatile int*>(&ctl->done);
+      s_stop = stop;
+    }
+    __syncthreads();
+    if (s_stop) break;
+    long long t0 = 0;
+    if (blockIdx.x == 0 && tid == 0) t0 = clock64();
+    EaPose P;
+    {   // the candidate's folded pose, written by the LM thread of the previous round (L2: bypass the non-coherent L1)
+      const double* src = reinterpret_cast<const double*>(&ctl->P);
+      double* dst = reinterpret_cast<double*>(&P);
+#pragma unroll
+      for (int i = 0; i < int(sizeof(EaPose) / 8); ++i) dst[i] = __ldcg(src + i);
+    }
+    if (xyz) ea_eval_slice<true, THREADS>(rd.pts, dt_pad, affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart, EA_ALTERNATE_SWEEP && !(e & 1));
+    else ea_eval_slice<false, THREADS>(rd.pts, dt_pad, affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart, EA_ALTERNATE_SWEEP && !(e & 1));
+    __syncthreads();
+    if (warp == 0) {
+      const double tot = ea_cta_total<THREADS / 32>(part, cpart, lane);
+      __stcg(&partials[size_t(blockIdx.x) * 32 + lane], lane < EA_SUMS ? tot : 0.0);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->prof[0]), (unsigned long long)(clock64() - t0));
+        s_ticket = atomicAdd(&ctl->ticket, 1ull);
+      }
+    }
+    __syncthreads();
+    if (s_ticket != e * gridDim.x - 1) continue;          // not the last CTA of this evaluation: wait for the next release
+    // ---- last CTA: grid reduce (fixed order: warp w adds CTAs w, w + W, ...; then the warps in order) ----
+    __threadfence();
+    long long t1 = clock64();
+    {
+      double s_ = 0.0;
+      for (unsigned b = warp; b < gridDim.x; b += THREADS / 32) s_ += __ldcg(&partials[size_t(b) * 32 + lane]);
+      wsum[warp][lane] = s_;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w2 = 0; w2 < THREADS / 32; ++w2) tot += wsum[w2][lane];
+      long long t2 = clock64();
+      int err = 0;
+      // ---- all-reduce over NVLink peer memory ----
+      if (world > 1) {
+        const int par = int(e & 1);
+        const unsigned long long epoch = epoch0 + e;
+        for (int r = 0; r < world; ++r) peers.p[r]->data[par][rank][lane] = tot;       // 32 lanes x 8 B = one 256 B burst per peer
+        __threadfence_system();
+        __syncwarp();
+        if (lane < world) st_release_sys(&peers.p[lane]->flag[par][rank], epoch);
+        if (lane < world) {
+          long long spins = 0;
+          while (ld_acquire_sys(&peers.p[rank]->flag[par][lane]) != epoch) {
+            if (++spins > EA_SHARD_SPIN_LIMIT) { err = 1; break; }
+          }
+        }
+        err = __any_sync(0xffffffffu, err);
+        __syncwarp();
+        __threadfence_system();
+        double g = 0.0;
+        for (int r = 0; r < world; ++r) g += *reinterpret_cast<volatile double*>(&peers.p[rank]->data[par][r][lane]);   // rank order: identical everywhere
+        tot = g;
+      }
+      long long t3 = clock64();
+      wsum[0][lane] = tot;
+      {   // LM state: global -> shared (the state machine touches it a few hundred times)
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&ctl->lm);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_lm);
+        for (int i = lane; i < int(sizeof(EaLmState) / 8); i += 32) dst[i] = __ldcg(src + i);
+      }
+      __syncwarp();
+      int done = 0;
+      if (lane == 0) {
+        if (err) { s_lm.term = EA_TERM_FAILURE_PEER; ctl->error = 1; done = 1; }
+        else {
+          const int cmd = ea_lm_advance(s_lm, wsum[0], sp);
+          if (cmd == EA_CMD_EVAL) {
+            EaPose Pn;
+            if (xyz) ea_pose_setup<true>(s_lm.cand, rg, ng, Pn); else ea_pose_setup<false>(s_lm.cand, rg, ng, Pn);
+            ctl->P = Pn;
+          } else done = 1;
+        }
+      }
+      __syncwarp();
+      {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_lm);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&ctl->lm);
+        for (int i = lane; i < int(sizeof(EaLmState) / 8); i += 32) __stcg(dst + i, src[i]);
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        ctl->done = done;
+        const long long t4 = clock64();
+        ctl->prof[1] += t2 - t1; ctl->prof[2] += t3 - t2; ctl->prof[3] += t4 - t3; ctl->prof[4] += 1;
+        __threadfence();
+        st_release_gpu(&ctl->go, e + 1);
+      }
+    }
+  }
+  if (s_stop == 2 && tid == 0) ctl->error = 2;   // the release never came (a CTA of this grid or a peer rank is gone)
+}
+
+// first evaluation's control block: LM state at the initial pose, its folded pose, evaluation 1 released
+__global__ void k_shard_ctl_init(ShardCtl* ctl, const double* pose7, EaLevelGeom rg, EaLevelGeom ng, int xyz) {
+  EaLmState& L = ctl->lm;
+  L.phase = 0; L.iter = 0; L.accepted = 0; L.rejected = 0; L.invalid_run = 0; L.evals = 0; L.term = EA_TERM_NONE;
+  L.cost = 0.0; L.initial_cost = 0.0;
+  for (int i = 0; i < 7; ++i) { L.x[i] = pose7[i]; L.cand[i] = pose7[i]; }
+  EaPose P;
+  if (xyz) ea_pose_setup<true>(L.cand, rg, ng, P); else ea_pose_setup<false>(L.cand, rg, ng, P);
+  ctl->P = P;
+  ctl->ticket = 0; ctl->done = 0; ctl->error = 0;
+  for (int k = 0; k < 6; ++k) ctl->prof[k] = 0;
+  __threadfence();
+  ctl->go = 1;
+}
+
 __global__ void k_shard_init(ShardState* st, const double* pose7) {
   EaLmState& L = st->lm;
   L.phase = 0; L.iter = 0; L.accepted = 0; L.rejected = 0; L.invalid_run = 0; L.evals = 0; L.term = EA_TERM_NONE;
@@ -151,12 +349,24 @@ struct ea_shard {
   ea_context* ctx = nullptr;
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  // host-driven path (EA_SHARD_MODE=nccl, or no peer access): one launch triple + ncclAllReduce per evaluation
   ShardState* d_state = nullptr;
   double* d_partials = nullptr;
   double* d_sums = nullptr;
   double* d_pose = nullptr;
   int n_blocks = 0;
   int* h_done = nullptr;  // pinned
+  // persistent path: one cooperative kernel per solve, all-reduce through peer-mapped exchange buffers
+  bool in_kernel = false;
+  ShardCtl* d_ctl = nullptr;
+  double* d_cta_sums = nullptr;                 // [sm_count][32]
+  ShardXchg* xchg = nullptr;                    // this rank's buffer (cudaMalloc; exported with cudaIpcGetMemHandle)
+  ShardPeers peers{};                           // every rank's buffer as seen from this device
+  bool peer_open[EA_SHARD_MAX_WORLD] = {};
+  unsigned long long epoch = 1;                 // advances identically on every rank (same evaluation counts)
+  bool poisoned = false;                        // a peer was lost: epochs may have diverged
+  double clock_khz = 1.0;
+  double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};    // last solve: see ea_shard_profile
 };
 
 extern "C" {
@@ -172,6 +382,64 @@ int ea_shard_unique_id(uint8_t id128[128]) {
   return EA_OK;
 }
 
+int ea_shard_destroy(ea_shard* s) {
+  if (!s) return EA_OK;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  for (int r = 0; r < EA_SHARD_MAX_WORLD; ++r)
+    if (s->peer_open[r]) cudaIpcCloseMemHandle(s->peers.p[r]);
+  if (s->comm) g_nccl.CommDestroy(s->comm);
+  cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_sums); cudaFree(s->d_pose);
+  cudaFree(s->d_ctl); cudaFree(s->d_cta_sums); cudaFree(s->xchg);
+  if (s->h_done) cudaFreeHost(s->h_done);
+  delete s;
+  return EA_OK;
+}
+
+// Exchange buffers: every rank exports its own with cudaIpc, the 64-byte handles travel once through ncclAllGather (the
+// only NCCL traffic of the persistent path), every rank maps its peers' buffers.  Returns EA_OK with in_kernel == false
+// when the devices cannot reach each other (the host-driven NCCL path then serves).
+static int shard_open_peers(ea_shard* s) {
+  cudaStream_t st = s->ctx->stream;
+  CU(cudaMalloc((void**)&s->xchg, sizeof(ShardXchg)));
+  CU(cudaMemset(s->xchg, 0, sizeof(ShardXchg)));
+  for (int r = 0; r < EA_SHARD_MAX_WORLD; ++r) s->peers.p[r] = s->xchg;
+  if (s->world == 1) { s->in_kernel = true; return EA_OK; }
+  if (s->world > EA_SHARD_MAX_WORLD) return EA_OK;
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, s->xchg) != cudaSuccess) { cudaGetLastError(); return EA_OK; }
+  unsigned char* d_all = nullptr;
+  CU(cudaMalloc((void**)&d_all, size_t(s->world) * sizeof(mine)));
+  CU(cudaMemcpyAsync(d_all + size_t(s->rank) * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  ncclResult_t nr = g_nccl.AllGather(d_all + size_t(s->rank) * sizeof(mine), d_all, sizeof(mine), ncclChar, s->comm, st);
+  if (nr != ncclSuccess) { cudaFree(d_all); return ea_fail(EA_ERR_NCCL, "ncclAllGather(ipc handles) -> %s", g_nccl.GetErrorString(nr)); }
+  std::vector<cudaIpcMemHandle_t> all(static_cast<size_t>(s->world));
+  cudaError_t ce = cudaMemcpyAsync(all.data(), d_all, size_t(s->world) * sizeof(mine), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  cudaFree(d_all);
+  if (ce != cudaSuccess) return ea_fail(EA_ERR_CUDA, "ipc handle exchange: %s", cudaGetErrorString(ce));
+  bool ok = true;
+  for (int r = 0; r < s->world && ok; ++r) {
+    if (r == s->rank) continue;
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[size_t(r)], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    s->peers.p[r] = static_cast<ShardXchg*>(p);
+    s->peer_open[r] = true;
+  }
+  // all ranks must agree on the path: one that cannot map its peers sends everyone to the NCCL path
+  int* d_ok = nullptr;
+  CU(cudaMalloc((void**)&d_ok, sizeof(int)));
+  const int mine_ok = ok ? 1 : 0;
+  CU(cudaMemcpyAsync(d_ok, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, st));
+  nr = g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, s->comm, st);
+  int all_ok = 0;
+  if (nr == ncclSuccess) { cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); }
+  cudaFree(d_ok);
+  if (nr != ncclSuccess) return ea_fail(EA_ERR_NCCL, "ncclAllReduce(path agreement) -> %s", g_nccl.GetErrorString(nr));
+  s->in_kernel = all_ok == 1;
+  return EA_OK;
+}
+
 int ea_shard_create(ea_context* ctx, const uint8_t id128[128], int rank, int world, ea_shard** out) {
   if (!ctx || !out) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
   *out = nullptr;
@@ -180,33 +448,94 @@ int ea_shard_create(ea_context* ctx, const uint8_t id128[128], int rank, int wor
   ea_shard* s = new (std::nothrow) ea_shard();
   if (!s) return ea_fail(EA_ERR_INVALID_ARG, "out of host memory");
   s->ctx = ctx; s->rank = rank; s->world = world;
+  int rc = EA_OK;
   if (world > 1) {
-    if (!id128) { delete s; return ea_fail(EA_ERR_INVALID_ARG, "world > 1 needs the NCCL unique id"); }
-    int rc = load_nccl();
-    if (rc) { delete s; return rc; }
-    ncclUniqueId id;
-    std::memcpy(&id, id128, 128);
-    ncclResult_t r = g_nccl.CommInitRank(&s->comm, world, id, rank);
-    if (r != ncclSuccess) { delete s; return ea_fail(EA_ERR_NCCL, "ncclCommInitRank -> %s", g_nccl.GetErrorString(r)); }
+    if (!id128) rc = ea_fail(EA_ERR_INVALID_ARG, "world > 1 needs the NCCL unique id");
+    if (!rc) rc = load_nccl();
+    if (!rc) {
+      ncclUniqueId id;
+      std::memcpy(&id, id128, 128);
+      ncclResult_t r = g_nccl.CommInitRank(&s->comm, world, id, rank);
+      if (r != ncclSuccess) rc = ea_fail(EA_ERR_NCCL, "ncclCommInitRank -> %s", g_nccl.GetErrorString(r));
+    }
   }
   s->n_blocks = ctx->sm_count * 2;
-  CU(cudaMalloc((void**)&s->d_state, sizeof(ShardState)));
-  CU(cudaMalloc((void**)&s->d_partials, size_t(s->n_blocks) * EA_SUMS * 8));
-  CU(cudaMalloc((void**)&s->d_sums, EA_SUMS * 8));
-  CU(cudaMalloc((void**)&s->d_pose, 7 * 8));
-  CU(cudaHostAlloc((void**)&s->h_done, sizeof(int), cudaHostAllocDefault));
+  auto alloc = [&](void** p, size_t bytes) { if (!rc && cudaMalloc(p, bytes) != cudaSuccess) rc = ea_fail(EA_ERR_CUDA, "ea_shard_create: cudaMalloc(%zu) failed", bytes); };
+  alloc((void**)&s->d_state, sizeof(ShardState));
+  alloc((void**)&s->d_partials, size_t(s->n_blocks) * EA_SUMS * 8);
+  alloc((void**)&s->d_sums, EA_SUMS * 8);
+  alloc((void**)&s->d_pose, 7 * 8);
+  alloc((void**)&s->d_ctl, sizeof(ShardCtl));
+  alloc((void**)&s->d_cta_sums, size_t(ctx->sm_count) * 32 * 8);
+  if (!rc && cudaHostAlloc((void**)&s->h_done, sizeof(int), cudaHostAllocDefault) != cudaSuccess) rc = ea_fail(EA_ERR_CUDA, "ea_shard_create: cudaHostAlloc failed");
+  if (!rc) rc = shard_open_peers(s);
+  if (!rc) {
+    const char* mode = getenv("EA_SHARD_MODE");      // "nccl": force the host-driven path (A/B measurements)
+    if (mode && !strcmp(mode, "nccl")) s->in_kernel = false;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    s->clock_khz = khz > 0 ? double(khz) : 1.0;
+  }
+  if (rc) { ea_shard_destroy(s); return rc; }     // nothing allocated above outlives a failed create
   *out = s;
   return EA_OK;
 }
 
-int ea_shard_destroy(ea_shard* s) {
-  if (!s) return EA_OK;
-  cudaSetDevice(s->ctx->device);
-  cudaStreamSynchronize(s->ctx->stream);
-  if (s->comm) g_nccl.CommDestroy(s->comm);
-  cudaFree(s->d_state); cudaFree(s->d_partials); cudaFree(s->d_sums); cudaFree(s->d_pose);
-  if (s->h_done) cudaFreeHost(s->h_done);
-  delete s;
+// Last solve of this shard: out[0] evaluations, out[1] device ms of the whole solve, out[2..5] microseconds per evaluation
+// spent in {evaluation of the slice (CTA 0's view), grid reduce, cross-rank all-reduce, LM step}, out[6] 1 if the persistent
+// in-kernel path ran (0: host-driven launches + ncclAllReduce), out[7] kernel launches of the solve.
+int ea_shard_profile(ea_shard* s, double out[8]) {
+  if (!s || !out) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
+  for (int i = 0; i < 8; ++i) out[i] = s->prof[i];
+  return EA_OK;
+}
+
+static int shard_solve_persistent(ea_shard* s, ea_frameset* ref, int ref_slot, ea_frameset* now, int now_slot, int level, double* pose7,
+                                  const ea_solve_params* sp, ea_summary* summary, int n_res, int j0, int j1) {
+  ea_context* c = s->ctx;
+  cudaStream_t st = c->stream;
+  if (s->poisoned) return ea_fail(EA_ERR_STATE, "this shard lost a peer in an earlier solve; create a new one");
+  EaLevelDesc rd = ref->h_desc[size_t(ref_slot) * EA_MAX_LEVELS + level];
+  EaLevelDesc nd = now->h_desc[size_t(now_slot) * EA_MAX_LEVELS + level];
+  EaLevelGeom rg = ref->geom[level], ng = now->geom[level];
+  double ids = ref->inv_depth_unit;
+  ea_solve_params spv = *sp;
+  // one CTA per SM at most, at least ~2 iterations of the evaluation loop per CTA; every rank sizes its grid for its own slice
+  int grid = std::max(1, std::min(c->sm_count, (j1 - j0 + 1023) / 1024));
+  CU(cudaMemcpyAsync(s->d_pose, pose7, 56, cudaMemcpyHostToDevice, st));
+  k_shard_ctl_init<<<1, 1, 0, st>>>(s->d_ctl, s->d_pose, rg, ng, rd.pts_mode == EA_POINTS_XYZ ? 1 : 0);
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, st));
+  ShardCtl* ctl = s->d_ctl; double* cta = s->d_cta_sums; ShardPeers peers = s->peers; int rank = s->rank, world = s->world;
+  unsigned long long epoch0 = s->epoch;
+  void* args[] = {&rd, &nd, &rg, &ng, &ids, &spv, &ctl, &cta, &peers, &rank, &world, &epoch0, &j0, &j1};
+  cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_shard_solve<EA_SOLVE_THREADS>, dim3(unsigned(grid)), dim3(EA_SOLVE_THREADS), args, 0, st);
+  cudaEventRecord(e1, st);
+  c->launches += 2;
+  if (le != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return ea_fail(EA_ERR_CUDA, "shard solve launch: %s", cudaGetErrorString(le)); }
+  ShardCtl h;
+  cudaError_t ce = cudaMemcpyAsync(&h, s->d_ctl, sizeof h, cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  if (ce == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (ce != cudaSuccess) return ea_fail(EA_ERR_CUDA, "shard solve: %s", cudaGetErrorString(ce));
+  s->epoch += (unsigned long long)h.lm.evals + 1;
+  const double ev = std::max(1, h.lm.evals), us = 1e3 / s->clock_khz;
+  s->prof[0] = h.lm.evals; s->prof[1] = ms;
+  s->prof[2] = double(h.prof[0]) * us / ev; s->prof[3] = double(h.prof[1]) * us / ev; s->prof[4] = double(h.prof[2]) * us / ev; s->prof[5] = double(h.prof[3]) * us / ev;
+  s->prof[6] = 1.0; s->prof[7] = 2.0;
+  for (int i = 0; i < 7; ++i) pose7[i] = h.lm.x[i];
+  if (summary) {
+    summary->termination = h.lm.term; summary->iterations = h.lm.iter; summary->accepted = h.lm.accepted; summary->rejected = h.lm.rejected;
+    summary->n_residuals = n_res; summary->evaluations = h.lm.evals;
+    summary->initial_cost = h.lm.initial_cost; summary->final_cost = h.lm.cost; summary->truncated = 0; summary->reserved = 0;
+  }
+  if (h.error) {
+    s->poisoned = true;
+    return ea_fail(EA_ERR_NCCL, "point-sharded solve: %s", h.error == 1 ? "a peer rank stopped answering the in-kernel all-reduce" : "the grid was never released (a CTA or peer is gone)");
+  }
   return EA_OK;
 }
 
@@ -215,16 +544,22 @@ int ea_shard_solve(ea_shard* s, ea_frameset* ref, int ref_slot, ea_frameset* now
   if (!s || !ref || !now || !pose7 || !sp) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
   if (level < 0 || level >= ref->p.n_levels || level >= now->p.n_levels) return ea_fail(EA_ERR_INVALID_ARG, "bad level");
   if (ref_slot < 0 || ref_slot >= ref->n_slots || now_slot < 0 || now_slot >= now->n_slots) return ea_fail(EA_ERR_INVALID_ARG, "bad slot");
-  if (sp->point_stride < 1) return ea_fail(EA_ERR_INVALID_ARG, "point_stride must be >= 1");
+  int rc = ea_check_solve_params(sp);
+  if (rc) return rc;
   ea_context* c = s->ctx;
   CU(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   int n_pts = 0;
-  int rc = ea_frameset_get_num_points(ref, ref_slot, level, &n_pts);
+  rc = ea_frameset_get_num_points(ref, ref_slot, level, &n_pts);
   if (rc) return rc;
   const int n_res = (n_pts + sp->point_stride - 1) / sp->point_stride;
   // this rank's contiguous slice of the ordered residual list
   const int j0 = int((long long)n_res * s->rank / s->world), j1 = int((long long)n_res * (s->rank + 1) / s->world);
+  if (s->in_kernel) return shard_solve_persistent(s, ref, ref_slot, now, now_slot, level, pose7, sp, summary, n_res, j0, j1);
+  cudaEvent_t pe0, pe1;
+  CU(cudaEventCreate(&pe0)); CU(cudaEventCreate(&pe1));
+  CU(cudaEventRecord(pe0, st));
+  const int64_t launches0 = c->launches;
   const EaLevelDesc& rd = ref->h_desc[size_t(ref_slot) * EA_MAX_LEVELS + level];
   const EaLevelDesc& nd = now->h_desc[size_t(now_slot) * EA_MAX_LEVELS + level];
   const double ids = ref->inv_depth_unit;
@@ -251,14 +586,20 @@ int ea_shard_solve(ea_shard* s, ea_frameset* ref, int ref_slot, ea_frameset* now
     CU(cudaMemcpyAsync(s->h_done, &s->d_state->done, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
   }
+  cudaEventRecord(pe1, st);
   ShardState h;
   CU(cudaMemcpy(&h, s->d_state, sizeof h, cudaMemcpyDeviceToHost));
+  float pms = 0.f;
+  cudaEventSynchronize(pe1); cudaEventElapsedTime(&pms, pe0, pe1);
+  cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+  for (int i = 0; i < 8; ++i) s->prof[i] = 0.0;
+  s->prof[0] = h.lm.evals; s->prof[1] = pms; s->prof[7] = double(c->launches - launches0);
   for (int i = 0; i < 7; ++i) pose7[i] = h.lm.x[i];
   if (summary) {
     summary->termination = h.done ? h.lm.term : EA_TERM_NO_CONVERGENCE;
     summary->iterations = h.lm.iter; summary->accepted = h.lm.accepted; summary->rejected = h.lm.rejected;
     summary->n_residuals = n_res; summary->evaluations = h.lm.evals;
-    summary->initial_cost = h.lm.initial_cost; summary->final_cost = h.lm.cost;
+    summary->initial_cost = h.lm.initial_cost; summary->final_cost = h.lm.cost; summary->truncated = 0; summary->reserved = 0;
   }
   return EA_OK;
 }
@@ -286,7 +627,7 @@ static int check_view(const ea_view& v, int level) {
 int ea_eval_views(ea_context* c, int n_views, const ea_view* views, int level, const double* pose7, const ea_solve_params* sp,
                   int* n_residuals, double* raw, double* residuals, double* jac, double* sums28, int* failed) {
   if (!c || !views || n_views < 1 || !pose7 || !sp) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
-  if (sp->point_stride < 1) return ea_fail(EA_ERR_INVALID_ARG, "point_stride must be >= 1");
+  { const int prc = ea_check_solve_params(sp); if (prc) return prc; }
   CU(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   std::vector<int> nres(n_views);
@@ -350,7 +691,7 @@ int ea_eval_views(ea_context* c, int n_views, const ea_view* views, int level, c
 int ea_solve_views(ea_context* c, int n_views, const ea_view* views, int level, double* pose7, const ea_solve_params* sp,
                    ea_summary* summary) {
   if (!c || !views || n_views < 1 || !pose7 || !sp) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
-  if (sp->point_stride < 1) return ea_fail(EA_ERR_INVALID_ARG, "point_stride must be >= 1");
+  { const int prc = ea_check_solve_params(sp); if (prc) return prc; }
   CU(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   std::vector<int> nres(n_views), nb(n_views);

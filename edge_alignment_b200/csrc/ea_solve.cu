@@ -19,9 +19,6 @@
 
 namespace cg = cooperative_groups;
 
-#ifndef EA_SOLVE_THREADS
-#define EA_SOLVE_THREADS 512
-#endif
 #define EA_SOLVE_WARPS (EA_SOLVE_THREADS / 32)
 #ifndef EA_SOLVE_MIN_CTAS
 #define EA_SOLVE_MIN_CTAS 1

@@ -8,6 +8,10 @@
 
 #include "ea_device.cuh"
 
+#ifndef EA_SOLVE_THREADS
+#define EA_SOLVE_THREADS 512   // threads per CTA of every kernel built on ea_eval_slice (128 registers each: one CTA fills an SM)
+#endif
+
 #define EA_CMD_EVAL 0
 #define EA_CMD_DONE 1
 

@@ -27,6 +27,11 @@ int main(int argc, char** argv) {
     ea::io::Image imB = ea::io::imread(argv[3]);                                   // SEA:122
     if (imA_depth.type != ea::U16C1 || imA.type != ea::U8C3 || imB.type != ea::U8C3) { std::fprintf(stderr, "unexpected image types\n"); return 1; }
     std::printf("imA %dx%d, imA_depth %dx%d (16 bit), imB %dx%d\n", imA.cols, imA.rows, imA_depth.cols, imA_depth.rows, imB.cols, imB.rows);
+    // the uploads below read width x height pixels from every buffer: all three images must have that size
+    if (imA_depth.cols != imA.cols || imA_depth.rows != imA.rows || imB.cols != imA.cols || imB.rows != imA.rows) {
+      std::fprintf(stderr, "the depth image and image B must have image A's size (%dx%d)\n", imA.cols, imA.rows);
+      return 1;
+    }
 
     ea_context* ctx = nullptr;
     CHECK(ea_create(0, &ctx));

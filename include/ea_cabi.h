@@ -89,7 +89,8 @@ typedef enum ea_termination {
   EA_TERM_NO_CONVERGENCE = 5,
   EA_TERM_FAILURE_EVAL_X0 = 6, /* functor returned false at x0 (utils.h:70-73) */
   EA_TERM_FAILURE_INVALID_STEPS = 7,
-  EA_TERM_SKIPPED_NO_POINTS = 8
+  EA_TERM_SKIPPED_NO_POINTS = 8,
+  EA_TERM_FAILURE_PEER = 9      /* point-sharded solve: a peer rank stopped answering the all-reduce */
 } ea_termination;
 
 /* Preprocessing configuration: every literal of utils.cpp:38-83,201-281 and
@@ -285,7 +286,9 @@ int ea_tracker_probe_gather(ea_tracker* tr, int level, int repeats, float* ms, d
 int ea_tracker_get_poses(ea_tracker* tr, double* poses7, ea_summary* summaries); /* syncs */
 int ea_tracker_frame_index(ea_tracker* tr, int* n_frames_seen);
 
-/* ---- point-sharded single pair across ranks (NCCL all-reduce of the normal equations) ---- */
+/* ---- point-sharded single pair across ranks: one persistent cooperative kernel per rank, the 29 normal-equation sums
+ * all-reduced inside the kernel through peer-mapped NVLink memory (NCCL only bootstraps the exchange of the cudaIpc
+ * handles; EA_SHARD_MODE=nccl or devices without peer access fall back to launches + ncclAllReduce per evaluation) ---- */
 int ea_shard_unique_id(uint8_t id128[128]);
 int ea_shard_create(ea_context* ctx, const uint8_t id128[128], int rank, int world, ea_shard** out);
 int ea_shard_destroy(ea_shard* sh);
@@ -293,6 +296,10 @@ int ea_shard_destroy(ea_shard* sh);
  * (slot's point list is sliced [rank*n/world, (rank+1)*n/world)); pose7 in/out identical on all ranks */
 int ea_shard_solve(ea_shard* sh, ea_frameset* ref, int ref_slot, ea_frameset* now, int now_slot, int level,
                    double* pose7, const ea_solve_params* sp, ea_summary* summary);
+/* Measurement: the last solve of this shard.  out[0] evaluations, out[1] device ms of the whole solve, out[2..5] microseconds
+ * per evaluation in {slice evaluation, grid reduce, cross-rank all-reduce, LM step}, out[6] 1 = persistent in-kernel path,
+ * out[7] kernel launches */
+int ea_shard_profile(ea_shard* sh, double out[8]);
 
 #ifdef __cplusplus
 }

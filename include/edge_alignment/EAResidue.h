@@ -3,7 +3,14 @@
 // and the same operator()(q, t, residue) contract (returns false when |z'| < 0.01, utils.h:70-73).  The Ceres
 // BiCubicInterpolator argument becomes a Frame holding the now-frame's distance transform; the evaluation runs the
 // production device function on a one-point list.  Meant for tests and for probing single points, not for speed.
+//
+// The projection uses the now Frame's own intrinsics (that is where the distance field lives); the constructor's
+// fx, fy, cx, cy must therefore equal them -- as they do at every call site of the reference (one K per problem,
+// standalone_edge_align.cpp:152,271) -- and the constructor throws std::invalid_argument otherwise instead of silently
+// evaluating for the wrong camera.
 #pragma once
+#include <cmath>
+
 #include "Frame.h"
 
 class EAResidue {
@@ -11,12 +18,21 @@ class EAResidue {
   EAResidue(double fx, double fy, double cx, double cy, double a_Xx, double a_Xy, double a_Xz, const Frame& now_frame)
       : X_(a_Xx), Y_(a_Xy), Z_(a_Xz), now_(&now_frame) {
     ea_frame_params p = now_frame.params();
+    auto differs = [](double a, double b) { return std::abs(a - b) > 1e-9 * (1.0 + std::abs(b)); };
+    if (differs(fx, p.fx) || differs(fy, p.fy) || differs(cx, p.cx) || differs(cy, p.cy))
+      throw std::invalid_argument("EAResidue: fx, fy, cx, cy differ from the now Frame's intrinsics (the Frame's K is the one used)");
     p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.max_points = 64;
     pt_.init(p, now_frame.context());
     const float p4[4] = {float(a_Xx), float(a_Xy), float(a_Xz), 1.0f};
     ea::check(ea_frameset_set_points(pt_.handle(), 0, 0, p4, 1, EA_POINTS_XYZ), "set_points");
     ea_solve_params_default(&sp_);
     sp_.point_stride = 1; sp_.loss_type = EA_LOSS_TRIVIAL;
+  }
+  // standalone/utils.h:82-92: the reference returns a ceres::CostFunction* owning a new EAResidue (AutoDiff<EAResidue,1,4,3>);
+  // without Ceres the functor itself is the cost function: caller owns the returned object.
+  static EAResidue* Create(const double fx, const double fy, const double cx, const double cy, const double a_Xx,
+                           const double a_Xy, const double a_Xz, const Frame& now_frame) {
+    return new EAResidue(fx, fy, cx, cy, a_Xx, a_Xy, a_Xz, now_frame);
   }
   // residue[0] = DT(u, v); optional jacobian[6] = d residue / d (half-angle rotation, translation)
   bool operator()(const double* quat_wxyz, const double* t, double* residue, double* jacobian6 = nullptr) const {

@@ -107,6 +107,8 @@ inline void decode_png(const std::vector<unsigned char>& file, Image& out, int f
     pos += 12 + len;
   }
   if (w <= 0 || h <= 0 || interlace) throw std::runtime_error("unsupported PNG (size / interlace)");
+  if (w > 32768 || h > 32768) throw std::runtime_error("PNG dimensions above 32768 are refused (unchecked IHDR sizes would size the buffers)");
+  if (ctype < 0 || idat.empty()) throw std::runtime_error("PNG without IHDR / IDAT");
   int channels;
   switch (ctype) { case 0: channels = 1; break; case 2: channels = 3; break; case 3: channels = 1; break; case 6: channels = 4; break;
                    default: throw std::runtime_error("unsupported PNG colour type"); }
@@ -156,8 +158,12 @@ inline void decode_bmp(const std::vector<unsigned char>& file, Image& out, int f
   if (top_down) h = -h;
   if (w <= 0 || h <= 0 || (comp != 0 && !(comp == 3 && bpp == 32)) || !(bpp == 24 || bpp == 32 || bpp == 8)) throw std::runtime_error("unsupported BMP");
   const size_t row = ((size_t(w) * bpp + 31) / 32) * 4;
-  if (off + row * h > file.size()) throw std::runtime_error("truncated BMP");
-  const unsigned char* pal = &file[14 + hdr];
+  if (w > 32768 || h > 32768) throw std::runtime_error("BMP dimensions above 32768 are refused");
+  if (size_t(off) > file.size() || size_t(off) + row * size_t(h) > file.size()) throw std::runtime_error("truncated BMP");
+  // 8-bit files index a 256-entry BGRA palette that sits between the headers and the pixel data: all of it must be there
+  if (bpp == 8 && (size_t(hdr) < 12 || size_t(14) + hdr + 4 * 256 > size_t(off) || size_t(14) + hdr + 4 * 256 > file.size()))
+    throw std::runtime_error("BMP palette is missing or truncated");
+  const unsigned char* pal = file.data() + (bpp == 8 ? 14 + size_t(hdr) : 0);
   std::vector<unsigned char> rgb(size_t(w) * h * 3);
   bool gray_palette = (bpp == 8);
   for (int y = 0; y < h; ++y) {

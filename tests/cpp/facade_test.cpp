@@ -2,6 +2,7 @@
 // C++ facade and prints the pose so the Python test can compare it with the C-ABI / oracle result.
 #include <cstdio>
 #include <cstdlib>
+#include <stdexcept>
 #include <vector>
 
 #include "edge_alignment/EAResidue.h"
@@ -45,6 +46,30 @@ int main(int argc, char** argv) {
     double r = -1, J[6];
     const bool ok = res(qi, ti, &r, J);
     printf("residue %d %.9g %.9g %.9g\n", int(ok), r, J[3], J[4]);
+    // standalone/utils.h:82-92: EAResidue::Create(...) -- same evaluation through the factory; caller owns the object
+    {
+      EAResidue* made = EAResidue::Create(525.0, 525.0, 319.5, 239.5, X, Y, Z, ea->nowFrame());
+      double r2 = -2;
+      const bool ok2 = (*made)(qi, ti, &r2);
+      printf("created %d %.9g\n", int(ok2), r2);
+      delete made;
+      bool threw = false;
+      try { EAResidue wrong(500.0, 525.0, 319.5, 239.5, X, Y, Z, ea->nowFrame()); } catch (const std::invalid_argument&) { threw = true; }
+      printf("wrongK %d\n", int(threw));
+    }
+    // a second setAsCERESProblem starts from identity again (src/SolveEA.cpp:130-131), not from the first result
+    {
+      ea->setAsCERESProblem();
+      double q2[4], t2[3];
+      ea->getPose(q2, t2);
+      bool same = ea->getSummary()[0].iterations == s.iterations;   // (s aliases the refreshed summary: compare poses too)
+      for (int i = 0; i < 4; ++i) same = same && q2[i] == q[i];
+      for (int i = 0; i < 3; ++i) same = same && t2[i] == t[i];
+      printf("restart %d\n", int(same));
+    }
+    // include/SolveEA.h:47 / src/SolveEA.cpp:218-272: the solver self-check
+    ea->_sampleCERESProblem();
+    printf("sample %d\n", int(ea->sampleProblemOk()));
     // the reference's own (ROS) flavour: Canny colour + exact DT [0,255] + every point + no loss + 25 iterations
     {
       SolveEA ros;

@@ -34,6 +34,12 @@ def test_cpp_facade_runs_reference_call_sequence(frames, solver_golden, tmp_path
     # EAResidue probe at identity: first point's residual == SURVEY A.6 anchor (0.1514616 with the portable DT)
     ok, r = int(rec["residue"][0]), float(rec["residue"][1])
     assert ok == 1 and abs(r - 0.15146105) < 2e-6
+    # EAResidue::Create (standalone/utils.h:82-92) evaluates the same; intrinsics that contradict the Frame's are refused
+    assert int(rec["created"][0]) == 1 and float(rec["created"][1]) == r and int(rec["wrongK"][0]) == 1
+    # every setAsCERESProblem call starts from identity (src/SolveEA.cpp:130-131): identical result the second time
+    assert int(rec["restart"][0]) == 1
+    # SolveEA::_sampleCERESProblem (include/SolveEA.h:47): the solver self-check passes and prints the reference's fields
+    assert int(rec["sample"][0]) == 1 and "NumResidualBlocks" in out.stdout and "x_final" in out.stdout
     assert "checked" in out.stdout.splitlines()[-1]
     # ROS-flavour defaults (src/SolveEA.cpp literals) against the oracle fed with the same stages
     from oracle import oracle as O

@@ -136,6 +136,21 @@ def test_png_and_bmp_decoders(io_bin, tmp_path, frames):
     # errors are reported, not crashes
     open(p, "wb").write(b"not an image")
     assert subprocess.run([io_bin, "img", p, "0", o], capture_output=True).returncode == 1
+    # malformed headers are refused before they index or size anything: an 8-bit BMP whose header size points the palette
+    # past the end of the file, one whose palette overlaps the pixel data, and a PNG announcing absurd dimensions
+    write_bmp8(b, mask)
+    good = bytearray(open(b, "rb").read())
+    bad = bytearray(good); bad[14:18] = (0x7fffff00).to_bytes(4, "little")
+    open(b, "wb").write(bad)
+    assert subprocess.run([io_bin, "img", b, str(READ_GRAYSCALE), o], capture_output=True).returncode == 1
+    bad = bytearray(good); bad[10:14] = (54 + 16).to_bytes(4, "little")          # pixel data starts inside the palette
+    open(b, "wb").write(bad)
+    assert subprocess.run([io_bin, "img", b, str(READ_GRAYSCALE), o], capture_output=True).returncode == 1
+    write_png(p, gray, 0, 8)
+    png = bytearray(open(p, "rb").read())
+    png[16:20] = (0x40000000).to_bytes(4, "big")                                 # IHDR width (the CRC is not checked)
+    open(p, "wb").write(png)
+    assert subprocess.run([io_bin, "img", p, "0", o], capture_output=True).returncode == 1
 
 
 def test_ply_obj_pose_overlay(io_bin, tmp_path):
