@@ -130,13 +130,22 @@ __global__ void k_shard_reduce(const ShardState* st, const double* partials, int
   }
 }
 
-__global__ void k_shard_lm(ShardState* st, const double* sums, ea_solve_params sp) {
+__global__ void __launch_bounds__(32) k_shard_lm(ShardState* st, const double* sums, ea_solve_params sp) {   // one warp
   if (st->done) return;
-  double local[EA_SUMS];
-  for (int k = 0; k < EA_SUMS; ++k) local[k] = sums[k];
-  const int cmd = ea_lm_advance(st->lm, local, sp);
-  if (cmd == EA_CMD_EVAL) { for (int i = 0; i < 7; ++i) st->cand[i] = st->lm.cand[i]; }
-  else st->done = 1;
+  __shared__ double local[32];
+  __shared__ EaLmState lm;
+  const int lane = threadIdx.x;
+  local[lane] = lane < EA_SUMS ? sums[lane] : 0.0;
+  for (int i = lane; i < int(sizeof(EaLmState) / 8); i += 32) reinterpret_cast<unsigned long long*>(&lm)[i] = reinterpret_cast<const unsigned long long*>(&st->lm)[i];
+  __syncwarp();
+  double cand[7];
+  const int cmd = ea_lm_advance_warp(lm, local, sp, lane, cand);
+  __syncwarp();
+  for (int i = lane; i < int(sizeof(EaLmState) / 8); i += 32) reinterpret_cast<unsigned long long*>(&st->lm)[i] = reinterpret_cast<const unsigned long long*>(&lm)[i];
+  if (lane == 0) {
+    if (cmd == EA_CMD_EVAL) { for (int i = 0; i < 7; ++i) st->cand[i] = cand[i]; }
+    else st->done = 1;
+  }
 }
 
 // =====================================================================================================================
@@ -289,16 +298,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
       }
       __syncwarp();
       int done = 0;
-      if (lane == 0) {
-        if (err) { s_lm.term = EA_TERM_FAILURE_PEER; ctl->error = 1; done = 1; }
-        else {
-          const int cmd = ea_lm_advance(s_lm, wsum[0], sp);
-          if (cmd == EA_CMD_EVAL) {
-            EaPose Pn;
-            if (xyz) ea_pose_setup<true>(s_lm.cand, rg, ng, Pn); else ea_pose_setup<false>(s_lm.cand, rg, ng, Pn);
-            ctl->P = Pn;
-          } else done = 1;
-        }
+      if (err) { if (lane == 0) { s_lm.term = EA_TERM_FAILURE_PEER; ctl->error = 1; } done = 1; }
+      else {
+        double cand[7];
+        const int cmd = ea_lm_advance_warp(s_lm, wsum[0], sp, lane, cand);      // all 32 lanes: warp-cooperative LM step
+        if (cmd == EA_CMD_EVAL) {
+          EaPose Pn;
+          if (xyz) ea_pose_setup<true>(cand, rg, ng, Pn); else ea_pose_setup<false>(cand, rg, ng, Pn);
+          if (lane == 0) ctl->P = Pn;
+        } else done = 1;
       }
       __syncwarp();
       {
@@ -579,7 +587,7 @@ int ea_shard_solve(ea_shard* s, ea_frameset* ref, int ref_slot, ea_frameset* now
       if (le != cudaSuccess) return ea_fail(EA_ERR_CUDA, "shard eval launch: %s", cudaGetErrorString(le));
       k_shard_reduce<<<1, 32, 0, st>>>(s->d_state, s->d_partials, nb, s->d_sums);
       if (s->world > 1) NC(g_nccl.AllReduce(s->d_sums, s->d_sums, EA_SUMS, ncclDouble, ncclSum, s->comm, st));
-      k_shard_lm<<<1, 1, 0, st>>>(s->d_state, s->d_sums, *sp);
+      k_shard_lm<<<1, 32, 0, st>>>(s->d_state, s->d_sums, *sp);
       c->launches += 3;
     }
     evals += chunk;
@@ -738,7 +746,7 @@ int ea_solve_views(ea_context* c, int n_views, const ea_view* views, int level, 
         c->launches++;
       }
       k_shard_reduce<<<1, 32, 0, st>>>(d_state, d_partials, nb_total, d_sums);
-      k_shard_lm<<<1, 1, 0, st>>>(d_state, d_sums, *sp);
+      k_shard_lm<<<1, 32, 0, st>>>(d_state, d_sums, *sp);
       c->launches += 2;
     }
     evals += chunk;

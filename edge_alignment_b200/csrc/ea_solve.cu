@@ -27,14 +27,18 @@ namespace cg = cooperative_groups;
 #define EA_CMD_EXIT 2
 
 struct EaMsg {  // boss -> all threads of the cluster
-  EaPose P;       // the candidate pose folded with the level's intrinsics (ea_pose_setup): computed once, by the boss
+  // -- constant over the evaluations of one (pair, level): 5 eight-byte words
   const void* pts;
   const float* dt;     // first element of the padded distance transform (pixel (-PAD, -PAD)): offsets from it are unsigned
   float2 affine;
   int n_res, level, pts_mode, cmd;
+  // -- per evaluation
   int rev;        // sweep direction of this evaluation: alternates per evaluation of the (pair, level), see ea_eval_slice
   int same;       // this evaluation continues the previous one's (pair, level): the points prefetched before the barrier are its first
+  EaPose P;       // the candidate pose folded with the level's intrinsics (ea_pose_setup): computed once, by the boss
 };
+#define EA_MSG_FIXED_WORDS 5
+static_assert(sizeof(EaMsg) % 8 == 0, "EaMsg is copied as 8-byte words");
 
 struct EaSolveSmem {
   EaMsg msg[2];
@@ -93,37 +97,46 @@ __device__ __forceinline__ void ea_boss_next_impl(const EaSolveArgs& A, EaSolveS
 // Boss: consume the sums of one evaluation; fills `out` with the next message.
 __device__ __noinline__ void ea_boss_next(const EaSolveArgs& A, EaSolveSmem& S, EaMsg& out, bool new_pair_needed) { ea_boss_next_impl<false>(A, S, out, new_pair_needed); }
 
-template <bool INL>
-__device__ __forceinline__ void ea_boss_step_impl(const EaSolveArgs& A, EaSolveSmem& S, const double* sums, const EaMsg& cur, EaMsg& out) {
+// Boss warp (all 32 lanes): consume the sums of one evaluation (S.sums) and write the next message into `out` (shared
+// memory).  The LM step itself is warp-cooperative (ea_lm_advance_warp); level / pair changes stay on lane 0.
+__device__ __noinline__ void ea_boss_step_warp(const EaSolveArgs& A, EaSolveSmem& S, const EaMsg& cur, EaMsg& out, const int lane) {
   const int acc0 = S.lm.accepted, rej0 = S.lm.rejected;
-  const int cmd = INL ? ea_lm_advance_impl(S.lm, sums, A.sp) : ea_lm_advance(S.lm, sums, A.sp);
-  if (A.trace) {   // iteration log of a single-pair solve (ea_solve_traced): what Ceres prints with minimizer_progress_to_stdout
+  double cand[7];
+  const int cmd = ea_lm_advance_warp(S.lm, S.sums, A.sp, lane, cand);
+  if (A.trace && lane == 0) {   // iteration log of a single-pair solve (ea_solve_traced): what Ceres prints with minimizer_progress_to_stdout
     const int k = (*A.trace_count)++;
     if (k < A.trace_cap) {
       double* r = A.trace + size_t(k) * EA_TRACE_DOUBLES;
-      r[0] = cur.level; r[1] = S.lm.accepted + S.lm.rejected; r[2] = S.lm.cost; r[3] = sums[28]; r[4] = S.lm.radius;
+      r[0] = cur.level; r[1] = S.lm.accepted + S.lm.rejected; r[2] = S.lm.cost; r[3] = S.sums[28]; r[4] = S.lm.radius;
       r[5] = S.lm.accepted > acc0 ? 1.0 : (S.lm.rejected > rej0 ? 0.0 : -1.0);   // accepted / rejected / no decision (first evaluation, termination)
     }
   }
   if (cmd == EA_CMD_EVAL) {
-    if (cur.pts_mode == EA_POINTS_XYZ) ea_pose_setup<true>(S.lm.cand, A.ref_geom[cur.level], A.now_geom[cur.level], out.P);
-    else ea_pose_setup<false>(S.lm.cand, A.ref_geom[cur.level], A.now_geom[cur.level], out.P);
-    out.pts = cur.pts; out.dt = cur.dt; out.affine = cur.affine; out.n_res = cur.n_res; out.level = cur.level; out.pts_mode = cur.pts_mode; out.cmd = EA_CMD_EVAL;
-    out.rev = S.lm.evals & 1; out.same = 1;
+    // the same (pair, level) again at the new candidate: the fixed words are copied by lanes 0..4, every lane folds the pose
+    // (no divergence), lane 0 stores it
+    EaPose P;
+    if (cur.pts_mode == EA_POINTS_XYZ) ea_pose_setup<true>(cand, A.ref_geom[cur.level], A.now_geom[cur.level], P);
+    else ea_pose_setup<false>(cand, A.ref_geom[cur.level], A.now_geom[cur.level], P);
+    if (lane < EA_MSG_FIXED_WORDS) reinterpret_cast<unsigned long long*>(&out)[lane] = reinterpret_cast<const unsigned long long*>(&cur)[lane];
+    if (lane == 5) { out.rev = S.lm.evals & 1; out.same = 1; }
+    if (lane == 0) out.P = P;
+    __syncwarp();
     return;
   }
-  if (A.summaries) {
-    const EaLmState& L = S.lm;
-    ea_summary z;
-    z.termination = L.term; z.iterations = L.iter; z.accepted = L.accepted; z.rejected = L.rejected;
-    z.n_residuals = cur.n_res; z.evaluations = L.evals; z.initial_cost = L.initial_cost; z.final_cost = L.cost;
-    z.truncated = S.truncated; z.reserved = 0;
-    A.summaries[size_t(S.pair) * A.n_levels + cur.level] = z;
+  if (lane == 0) {
+    if (A.summaries) {
+      const EaLmState& L = S.lm;
+      ea_summary z;
+      z.termination = L.term; z.iterations = L.iter; z.accepted = L.accepted; z.rejected = L.rejected;
+      z.n_residuals = cur.n_res; z.evaluations = L.evals; z.initial_cost = L.initial_cost; z.final_cost = L.cost;
+      z.truncated = S.truncated; z.reserved = 0;
+      A.summaries[size_t(S.pair) * A.n_levels + cur.level] = z;
+    }
+    S.level = cur.level - 1;
+    ea_boss_next(A, S, out, false);
   }
-  S.level = cur.level - 1;
-  if (INL) ea_boss_next_impl<true>(A, S, out, false); else ea_boss_next(A, S, out, false);
+  __syncwarp();
 }
-__device__ __noinline__ void ea_boss_step(const EaSolveArgs& A, EaSolveSmem& S, const double* sums, const EaMsg& cur, EaMsg& out) { ea_boss_step_impl<false>(A, S, sums, cur, out); }
 
 
 template <int THREADS, bool CLUSTER>
@@ -179,11 +192,7 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
         if (lane < EA_SUMS) S.sums[lane] = tot;
         __syncwarp();
         lap(1);
-        if (lane == 0) {
-          EaMsg m;
-          ea_boss_step(A, S, S.sums, M, m);
-          S.msg[(g + 1) & 1] = m;
-        }
+        ea_boss_step_warp(A, S, M, S.msg[(g + 1) & 1], lane);
         lap(2);
       }
     }
@@ -194,10 +203,11 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
         if (lane < EA_SUMS) for (unsigned r = 0; r < csize; ++r) s += S.cluster_sums[r][lane];
         if (lane < EA_SUMS) S.sums[lane] = s;
         __syncwarp();
-        if (lane == 0) {
-          EaMsg m;
-          ea_boss_step(A, S, S.sums, M, m);
-          publish(m, (g + 1) & 1);
+        EaMsg& nm = S.msg[(g + 1) & 1];
+        ea_boss_step_warp(A, S, M, nm, lane);
+        for (unsigned r = 1; r < csize; ++r) {      // the other ranks' copies, word by word over DSMEM
+          unsigned long long* dst = reinterpret_cast<unsigned long long*>(&cluster.map_shared_rank(&S, r)->msg[(g + 1) & 1]);
+          for (int i = lane; i < int(sizeof(EaMsg) / 8); i += 32) dst[i] = reinterpret_cast<const unsigned long long*>(&nm)[i];
         }
       }
     }

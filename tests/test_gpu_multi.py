@@ -66,7 +66,7 @@ def test_point_sharded_solve_single_rank(frames, solver_golden, mode, monkeypatc
         assert np.array_equal(got[0][0], got[1][0]) and got[0][1:] == got[1][1:]
         # invalid solve parameters are refused here as everywhere else
         bad = ea.solve_params(point_stride=1); bad.loss_scale = 0.0
-        assert L.lib().ea_shard_solve(sh, fs._h, 0, fs._h, 1, 0, pose.ctypes.data_as(C.POINTER(C.c_double)), C.byref(bad), C.byref(s)) == 2
+        assert L.lib().ea_shard_solve(sh, fs._h, 0, fs._h, 1, 0, pose.ctypes.data_as(C.POINTER(C.c_double)), C.byref(bad), C.byref(s)) == 1      # EA_ERR_INVALID_ARG
         L.lib().ea_shard_destroy(sh)
     finally:
         fs.close(); ctx.close()
