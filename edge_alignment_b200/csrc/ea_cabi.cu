@@ -57,6 +57,13 @@ int ea_create(int device, ea_context** out) {
   CU(cudaMalloc(&c->d_failed, sizeof(int)));
   CU(cudaMalloc(&c->d_work, sizeof(int)));
   CU(cudaMalloc(&c->d_sums, size_t(1024) * EA_SUMS * sizeof(double)));
+  {
+    const char* h = getenv("EA_SOLVE_HELPERS");       // "0": no tail helpers (A/B measurements)
+    if (!(h && h[0] == '0')) {
+      c->boards_bytes = ea_help_boards_bytes(c->sm_count);
+      CU(cudaMalloc(&c->d_boards, c->boards_bytes));
+    }
+  }
   if (getenv("EA_SOLVE_DEBUG")) {
     CU(cudaMalloc(&c->d_debug, size_t(1024) * 6 * sizeof(unsigned long long)));
     CU(cudaMemset(c->d_debug, 0, size_t(1024) * 6 * sizeof(unsigned long long)));
@@ -73,7 +80,7 @@ int ea_destroy(ea_context* c) {
     fprintf(stderr, "[EA_SOLVE_DEBUG] %ld launches; per launch, mean over CTAs, kcycles of thread 0: eval %.1f  wait+totals %.1f  LM %.1f  wait2 %.1f  lifetime %.1f; evaluations %.1f\n",
             c->debug_launches, c->debug_sum[0] / n / 1e3, c->debug_sum[1] / n / 1e3, c->debug_sum[2] / n / 1e3, c->debug_sum[3] / n / 1e3, c->debug_sum[5] / n / 1e3, c->debug_sum[4] / n);
   }
-  cudaFree(c->d_debug);
+  cudaFree(c->d_debug); cudaFree(c->d_boards);
   cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_work); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -692,6 +699,7 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
   // persistent CTA per pair (no scheduling overhead, best L1 locality).
   if (cluster == 0) cluster = auto_cluster(c, n, 0);
   A.debug = c->d_debug;
+  A.boards = static_cast<EaHelpBoard*>(c->d_boards);
   e = ea_launch_solve_batch(A, cluster, c->sm_count, c->stream);
   if (c->d_debug && e == cudaSuccess) {   // development aid: synchronous read-back of the cycle counters
     const int grid = std::min(n, c->sm_count);

@@ -20,6 +20,7 @@ struct EaSolveArgs {
   const int32_t* order;         // [n_pairs] device or null: processing order of the work queue (longest first)
   double* poses;                // [*][7] device, in/out
   int* work_counter;            // device: next pair index of the dynamic work queue (zeroed per launch)
+  struct EaHelpBoard* boards;   // [grid] tail-helper boards of the persistent kernel (zeroed per launch), or null: no helpers
   unsigned long long* debug;    // null, or [grid][6] cycle counters of each CTA's thread 0 (EA_SOLVE_DEBUG=1, development aid)
   ea_summary* summaries;        // [n_pairs][n_levels] device or null
   double* trace;                // [trace_cap][EA_TRACE_DOUBLES] device or null: one record per evaluation (single-pair solves only)
@@ -34,6 +35,7 @@ struct EaSolveArgs {
 };
 
 cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm_count, cudaStream_t stream);
+size_t ea_help_boards_bytes(int sm_count);
 cudaError_t ea_launch_gather_probe(const EaSolveArgs& A, int level, int slices, int repeats, float* d_sink, cudaStream_t stream);
 int ea_probe_gather_device(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now, const int32_t* d_now_slots,
                            const double* d_poses7, int level, int repeats, float* ms, double* point_gathers);
@@ -106,6 +108,7 @@ struct ea_context {
   double* d_pose = nullptr;      // [7]
   int* d_failed = nullptr;
   int* d_work = nullptr;         // work-queue counter of the batched solve
+  void* d_boards = nullptr; size_t boards_bytes = 0;        // tail-helper boards of the persistent solve kernel
   unsigned long long* d_debug = nullptr; double debug_sum[6] = {0, 0, 0, 0, 0, 0}; long debug_launches = 0;   // EA_SOLVE_DEBUG=1
   double* d_sums = nullptr;      // [max blocks][EA_SUMS]
   int32_t* d_idx = nullptr;      // scratch slot indices

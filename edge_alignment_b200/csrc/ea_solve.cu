@@ -34,20 +34,42 @@ struct EaMsg {  // boss -> all threads of the cluster
   int n_res, level, pts_mode, cmd;
   // -- per evaluation
   int rev;        // sweep direction of this evaluation: alternates per evaluation of the (pair, level), see ea_eval_slice
-  int same;       // this evaluation continues the previous one's (pair, level): the points prefetched before the barrier are its first
+  int same;       // this evaluation continues the previous one's (pair, level) with the same chunk range: the points prefetched before the barrier are its first
+  int nh, pad;    // tail helpers sharing this evaluation (0: the owner evaluates every chunk)
   EaPose P;       // the candidate pose folded with the level's intrinsics (ea_pose_setup): computed once, by the boss
 };
 #define EA_MSG_FIXED_WORDS 5
 static_assert(sizeof(EaMsg) % 8 == 0, "EaMsg is copied as 8-byte words");
 
+// ---- tail helpers -------------------------------------------------------------------------------------------------------
+// One pair per persistent CTA leaves the SMs idle once the work queue is empty while the last, longest pairs finish (measured:
+// 29 % of the launch; a single pair that runs to the iteration limit can outweigh a CTA's whole mean load).  A CTA that finds
+// the queue empty therefore becomes a HELPER: it registers on the board of a CTA that still owns a pair and from then on
+// evaluates a share of the chunks of every evaluation the owner publishes there, delivering chunk totals the owner adds in
+// chunk order -- the sums are the same whoever computed them (ea_chunking).  Owner and helpers talk through global memory
+// only: release / acquire on an epoch word, bounded spins.
+#define EA_MAX_HELPERS (EA_MAX_CHUNKS - 1)
+#define EA_BOARD_EXIT (~0ull)
+#define EA_BOARD_SPIN_LIMIT (1ll << 22)
+struct EaHelpBoard {                          // one per persistent CTA; zeroed by the host before every launch
+  unsigned long long word;                    // (epoch << 8) | helpers sharing that evaluation; EA_BOARD_EXIT: the owner is done
+  int n_helpers;                              // registered helpers (atomicAdd by the helpers)
+  int busy;                                   // the CTA owns a pair
+  unsigned long long done[EA_MAX_HELPERS];    // per helper: epoch of the evaluation it last delivered
+  double chunk[EA_MAX_CHUNKS][32];            // chunk totals written by the helpers
+  EaMsg msg;                                  // the evaluation being shared
+};
+
 struct EaSolveSmem {
   EaMsg msg[2];
-  double part[EA_SOLVE_WARPS][EA_NSUM];     // per-warp lane-slot sums
-  double cpart[EA_SOLVE_WARPS];             // per-warp cost
-  double sums[EA_SUMS + 3];                 // CTA totals
+  double part[EA_MAX_CHUNKS][EA_SOLVE_WARPS][EA_NSUM];     // per chunk, per warp: lane-slot sums
+  double cpart[EA_MAX_CHUNKS][EA_SOLVE_WARPS];             // per chunk, per warp: cost
+  double sums[EA_SUMS + 3];                 // evaluation totals
   double cluster_sums[8][EA_SUMS + 3];      // rank 0 only: one row per cluster rank
   EaLmState lm;                             // boss only
   int pair, level, truncated;               // boss only
+  unsigned long long help_epoch;            // owner: evaluations published on its board so far
+  int help_owner, help_index, help_fail;    // helper: the board it serves and its slot there (1-based); owner: a helper went missing
   long long dbg[6], dbg_t, dbg_t0;          // EA_SOLVE_DEBUG cycle counters (thread 0)
 };
 
@@ -89,7 +111,7 @@ __device__ __forceinline__ void ea_boss_next_impl(const EaSolveArgs& A, EaSolveS
     for (int i = 0; i < 7; ++i) L.cand[i] = L.x[i];
     if (rd.pts_mode == EA_POINTS_XYZ) ea_pose_setup<true>(L.cand, A.ref_geom[level], A.now_geom[level], out.P);
     else ea_pose_setup<false>(L.cand, A.ref_geom[level], A.now_geom[level], out.P);
-    out.pts = rd.pts; out.dt = nd.dt - ea_dt_origin_offset(nd.w); out.affine = *nd.dt_affine; out.n_res = n_res; out.level = level; out.pts_mode = rd.pts_mode; out.cmd = EA_CMD_EVAL; out.rev = 0; out.same = 0;
+    out.pts = rd.pts; out.dt = nd.dt - ea_dt_origin_offset(nd.w); out.affine = *nd.dt_affine; out.n_res = n_res; out.level = level; out.pts_mode = rd.pts_mode; out.cmd = EA_CMD_EVAL; out.rev = 0; out.same = 0; out.nh = 0; out.pad = 0;
     return;
   }
 }
@@ -102,7 +124,15 @@ __device__ __noinline__ void ea_boss_next(const EaSolveArgs& A, EaSolveSmem& S, 
 __device__ __noinline__ void ea_boss_step_warp(const EaSolveArgs& A, EaSolveSmem& S, const EaMsg& cur, EaMsg& out, const int lane) {
   const int acc0 = S.lm.accepted, rej0 = S.lm.rejected;
   double cand[7];
+#ifdef EA_LM_PROFILE
+  const long long t_in = clock64();
+#endif
   const int cmd = ea_lm_advance_warp(S.lm, S.sums, A.sp, lane, cand);
+#ifdef EA_LM_PROFILE
+  __syncwarp();
+  if (lane == 0) { S.lm.prof[6] += clock64() - t_in; S.lm.prof[7] += 1; }
+  __syncwarp();
+#endif
   if (A.trace && lane == 0) {   // iteration log of a single-pair solve (ea_solve_traced): what Ceres prints with minimizer_progress_to_stdout
     const int k = (*A.trace_count)++;
     if (k < A.trace_cap) {
@@ -118,7 +148,7 @@ __device__ __noinline__ void ea_boss_step_warp(const EaSolveArgs& A, EaSolveSmem
     if (cur.pts_mode == EA_POINTS_XYZ) ea_pose_setup<true>(cand, A.ref_geom[cur.level], A.now_geom[cur.level], P);
     else ea_pose_setup<false>(cand, A.ref_geom[cur.level], A.now_geom[cur.level], P);
     if (lane < EA_MSG_FIXED_WORDS) reinterpret_cast<unsigned long long*>(&out)[lane] = reinterpret_cast<const unsigned long long*>(&cur)[lane];
-    if (lane == 5) { out.rev = S.lm.evals & 1; out.same = 1; }
+    if (lane == 5) { out.rev = S.lm.evals & 1; out.same = 1; out.nh = 0; out.pad = 0; }
     if (lane == 0) out.P = P;
     __syncwarp();
     return;
@@ -139,6 +169,39 @@ __device__ __noinline__ void ea_boss_step_warp(const EaSolveArgs& A, EaSolveSmem
 }
 
 
+__device__ __forceinline__ unsigned long long ea_ld_acquire(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ea_st_release(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// One worker's share of an evaluation: chunks [cb, ce) of M, walked in M's direction; per-chunk partials into S.part / S.cpart.
+// next_*: what this CTA will evaluate after this call returns (the first chunk of the next evaluation), for the point prefetch.
+template <int THREADS>
+__device__ __forceinline__ void ea_eval_chunks(const EaSolveArgs& A, EaSolveSmem& S, const EaMsg& M, const EaPose& P, const int cb, const int ce,
+                                               const int chunk, EaPtStream<false>::T* pre, bool pre_valid, const bool chain_next_eval) {
+  const EaLevelGeom& ng = A.now_geom[M.level];
+  const bool rev = EA_ALTERNATE_SWEEP && M.rev;
+  for (int i = 0; i < ce - cb; ++i) {
+    const int c = rev ? ce - 1 - i : cb + i;
+    const int lo = c * chunk, hi = min(lo + chunk, M.n_res);
+    // the range evaluated next: the following chunk of this evaluation, or (same pair and level continuing) the first chunk
+    // of the next evaluation, which sweeps the other way
+    int nlo = -1, nhi = 0;
+    bool nrev = rev;
+    if (i + 1 < ce - cb) { const int cn = rev ? ce - 2 - i : cb + i + 1; nlo = cn * chunk; nhi = min(nlo + chunk, M.n_res); }
+    else if (chain_next_eval) { nrev = EA_ALTERNATE_SWEEP ? !rev : rev; const int cn = nrev ? ce - 1 : cb; nlo = cn * chunk; nhi = min(nlo + chunk, M.n_res); }
+    if (M.pts_mode == EA_POINTS_XYZ)
+      ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[c], S.cpart[c], rev);
+    else
+      ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[c], S.cpart[c], rev, pre, pre_valid, nlo, nhi, nrev);
+    pre_valid = true;      // the call above requested the next range's first points
+  }
+}
+
 template <int THREADS, bool CLUSTER>
 __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(const __grid_constant__ EaSolveArgs A) {
   __shared__ EaSolveSmem S;
@@ -147,6 +210,8 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
   const unsigned csize = CLUSTER ? cluster.num_blocks() : 1u;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool boss = (crank == 0 && tid == 0);
+  const bool helpers_on = !CLUSTER && A.boards != nullptr;
+  EaHelpBoard* const my_board = helpers_on ? A.boards + blockIdx.x : nullptr;
   auto sync_all = [&]() { if (CLUSTER) cluster.sync(); else __syncthreads(); };
   auto publish = [&](const EaMsg& m, unsigned slot) {
     for (unsigned r = 0; r < csize; ++r) {
@@ -157,7 +222,9 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
   unsigned g = 0;
   if (boss) {
     EaMsg m;
+    S.help_epoch = 0; S.help_fail = 0;
     ea_boss_next(A, S, m, true);
+    if (helpers_on && m.cmd != EA_CMD_EXIT) { *reinterpret_cast<volatile int*>(&my_board->busy) = 1; __threadfence(); }
     publish(m, 0);
   }
   sync_all();
@@ -165,34 +232,88 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
   // (counters live in shared memory: the evaluation loop has no registers to spare)
   const bool dbg_on = A.debug != nullptr && tid == 0;
   if (dbg_on) { for (int k = 0; k < 6; ++k) S.dbg[k] = 0; S.dbg_t0 = clock64(); S.dbg_t = S.dbg_t0; }
+#ifdef EA_LM_PROFILE
+  if (tid == 0) for (int k = 0; k < 8; ++k) S.lm.prof[k] = 0;
+#endif
   auto lap = [&](int k) { if (dbg_on) { const long long t = clock64(); S.dbg[k] += t - S.dbg_t; S.dbg_t = t; } };
-  EaPtStream<false>::T pre[EA_EVAL_UNROLL];   // first points of the NEXT evaluation, requested before the barrier (pixel points only)
+  EaPtStream<false>::T pre[EA_EVAL_UNROLL];   // first points of the NEXT range, requested before the barrier (pixel points only)
 #pragma unroll
   for (int u = 0; u < EA_EVAL_UNROLL; ++u) pre[u] = EaPtStream<false>::pad();
+  // ================================================= owner loop =================================================
   for (;;) {
     const EaMsg& M = S.msg[g & 1];
     if (M.cmd == EA_CMD_EXIT) break;
-    const EaLevelGeom& ng = A.now_geom[M.level];
-    const int j0 = int((long long)M.n_res * crank / csize), j1 = int((long long)M.n_res * (crank + 1) / csize);
     const EaPose P = M.P;
-    if (M.pts_mode == EA_POINTS_XYZ) {
-      ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart, EA_ALTERNATE_SWEEP && M.rev);
+    int chunk = 0, K = 1, cb = 0;
+    if (CLUSTER) {
+      // a cluster shares the evaluation by rank: one slice, one partial per CTA
+      const int j0 = int((long long)M.n_res * crank / csize), j1 = int((long long)M.n_res * (crank + 1) / csize);
+      const EaLevelGeom& ng = A.now_geom[M.level];
+      const bool rev = EA_ALTERNATE_SWEEP && M.rev, nrev = EA_ALTERNATE_SWEEP ? !rev : rev;
+      if (M.pts_mode == EA_POINTS_XYZ) ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part[0], S.cpart[0], rev);
+      else ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part[0], S.cpart[0], rev, pre, M.same != 0, j0, j1, nrev);
     } else {
-      ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part, S.cpart, EA_ALTERNATE_SWEEP && M.rev,
-                                    pre, M.same != 0);
+      K = ea_chunking(M.n_res, THREADS, chunk);
+      cb = (K * M.nh) / (M.nh + 1);             // the owner is the last of nh + 1 workers: chunks [cb, K)
+      ea_eval_chunks<THREADS>(A, S, M, P, cb, K, chunk, pre, M.same != 0, true);
     }
     lap(0);
     __syncthreads();
     if (warp == 0) {
-      const double tot = ea_cta_total<THREADS / 32>(S.part, S.cpart, lane);
       if (CLUSTER) {
+        const double tot = ea_cta_total<THREADS / 32>(S.part[0], S.cpart[0], lane);
         EaSolveSmem* S0 = cluster.map_shared_rank(&S, 0);
         if (lane < EA_SUMS) S0->cluster_sums[crank][lane] = tot;
       } else {
+        // chunk totals in chunk order: the helpers' from the board (once each has delivered this epoch), the owner's from
+        // shared memory
+        double tot = 0.0;
+        if (M.nh > 0) {
+          int ok = 1;
+          if (lane < M.nh) {
+            long long spins = 0;
+            while (ea_ld_acquire(&my_board->done[lane]) != S.help_epoch) {
+              if (++spins > EA_BOARD_SPIN_LIMIT) { ok = 0; break; }
+            }
+          }
+          ok = __all_sync(0xffffffffu, ok);
+          __threadfence();
+          if (!ok && lane == 0) S.help_fail = 1;
+          for (int c = 0; c < cb; ++c) tot += __ldcg(&my_board->chunk[c][lane]);
+        }
+        for (int c = cb; c < K; ++c) tot += ea_cta_total<THREADS / 32>(S.part[c], S.cpart[c], lane);
         if (lane < EA_SUMS) S.sums[lane] = tot;
+        if (lane == 27 && S.help_fail) S.sums[27] = 1.0;      // a helper went missing: the evaluation counts as failed
         __syncwarp();
         lap(1);
-        ea_boss_step_warp(A, S, M, S.msg[(g + 1) & 1], lane);
+        EaMsg& nm = S.msg[(g + 1) & 1];
+        // (the number of registered helpers is read early: its latency hides behind the LM step)
+        int reg = 0;
+        if (helpers_on && lane == 31) reg = *reinterpret_cast<volatile int*>(&my_board->n_helpers);
+        ea_boss_step_warp(A, S, M, nm, lane);
+        reg = __shfl_sync(0xffffffffu, reg, 31);
+        if (helpers_on) {
+          // share the next evaluation with the registered helpers when it has chunks to give away
+          int nh = 0;
+          if (nm.cmd == EA_CMD_EVAL && reg > 0) {
+            int ch2; const int K2 = ea_chunking(nm.n_res, THREADS, ch2);
+            nh = min(min(reg, EA_MAX_HELPERS), K2 - 1);
+          }
+          if (lane == 0) { nm.nh = nh; if (nh != M.nh) nm.same = 0; }
+          __syncwarp();
+          if (nh > 0) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(&my_board->msg);
+            for (int i = lane; i < int(sizeof(EaMsg) / 8); i += 32) __stcg(dst + i, reinterpret_cast<const unsigned long long*>(&nm)[i]);
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) { S.help_epoch += 1; ea_st_release(&my_board->word, (S.help_epoch << 8) | (unsigned long long)nh); }
+          }
+          if (nm.cmd == EA_CMD_EXIT && lane == 0) {        // this CTA owns nothing any more: release its helpers
+            *reinterpret_cast<volatile int*>(&my_board->busy) = 0;
+            __threadfence();
+            ea_st_release(&my_board->word, EA_BOARD_EXIT);
+          }
+        }
         lap(2);
       }
     }
@@ -216,11 +337,92 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
     if (dbg_on) S.dbg[4] += 1;
     g += 1;
   }
+#ifdef EA_LM_PROFILE
+  if (dbg_on && blockIdx.x == 0 && S.dbg[4] > 0)
+    printf("[EA_LM_PROFILE] CTA 0, %lld evaluations; cycles per evaluation: tests %lld, update %lld, build %lld, LDLT %lld, model %lld, plus+stores %lld | advance_warp mean %lld\n",
+           S.dbg[4], S.lm.prof[0] / S.dbg[4], S.lm.prof[1] / S.dbg[4], S.lm.prof[2] / S.dbg[4], S.lm.prof[3] / S.dbg[4], S.lm.prof[4] / S.dbg[4], S.lm.prof[5] / S.dbg[4], S.lm.prof[6] / S.dbg[4]);
+#endif
   if (dbg_on) {
     S.dbg[5] = clock64() - S.dbg_t0;
     for (int k = 0; k < 6; ++k) A.debug[size_t(blockIdx.x) * 6 + k] = (unsigned long long)S.dbg[k];
   }
-  if (CLUSTER) cluster.sync();  // no CTA may exit while a peer can still touch its shared memory
+  if (CLUSTER) { cluster.sync(); return; }  // no CTA may exit while a peer can still touch its shared memory
+  if (!helpers_on) return;
+  // ================================================= helper loop ================================================
+  // The queue is empty (tickets only grow, so no CTA will ever own a new pair): serve the CTAs that still own one.
+  for (;;) {
+    // ---- pick the busy owner with the fewest helpers and register there ----
+    if (tid == 0) {
+      int best = -1, best_n = EA_MAX_HELPERS, any_busy = 0;
+      const int G = int(gridDim.x);
+      for (int k = 1; k < G; ++k) {
+        const int o = (int(blockIdx.x) + k) % G;
+        if (!*reinterpret_cast<volatile int*>(&A.boards[o].busy)) continue;
+        any_busy = 1;
+        const int nreg = *reinterpret_cast<volatile int*>(&A.boards[o].n_helpers);
+        if (nreg < best_n) { best_n = nreg; best = o; }
+      }
+      int idx = 0;
+      if (best >= 0) {
+        idx = atomicAdd(&A.boards[best].n_helpers, 1) + 1;
+        if (idx > EA_MAX_HELPERS) { atomicSub(&A.boards[best].n_helpers, 1); best = -2; }      // lost the race for the last slot: look again
+      }
+      S.help_owner = best >= 0 ? best : (any_busy || best == -2 ? -2 : -1);
+      S.help_index = idx;
+    }
+    __syncthreads();
+    const int owner = S.help_owner, index = S.help_index;
+    __syncthreads();
+    if (owner == -1) break;                         // nobody owns a pair any more
+    if (owner == -2) { __nanosleep(2000); continue; }  // every busy owner has its helpers: wait for one to finish
+    EaHelpBoard* const B = A.boards + owner;
+    unsigned long long seen = 0;
+    for (;;) {
+      // ---- wait for an evaluation that includes this helper, or for the owner to finish ----
+      if (tid == 0) {
+        unsigned long long w;
+        long long spins = 0;
+        for (;;) {
+          w = ea_ld_acquire(&B->word);
+          if (w == EA_BOARD_EXIT) break;
+          if ((w >> 8) != seen && int(w & 0xff) >= index) break;
+          if ((w >> 8) != seen) seen = w >> 8;      // an evaluation this helper is not part of yet
+          if (++spins > EA_BOARD_SPIN_LIMIT) { w = EA_BOARD_EXIT; break; }
+          __nanosleep(100);
+        }
+        S.help_epoch = w;
+      }
+      __syncthreads();
+      const unsigned long long w = S.help_epoch;
+      if (w == EA_BOARD_EXIT) { __syncthreads(); break; }
+      seen = w >> 8;
+      const int nh = int(w & 0xff);
+      // ---- the shared evaluation's message, then this helper's chunks (worker index - 1 of nh + 1) ----
+      if (warp == 0) {
+        __threadfence();
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&B->msg);
+        for (int i = lane; i < int(sizeof(EaMsg) / 8); i += 32) reinterpret_cast<unsigned long long*>(&S.msg[0])[i] = __ldcg(src + i);
+      }
+      __syncthreads();
+      const EaMsg& M = S.msg[0];
+      const EaPose P = M.P;
+      int chunk;
+      const int K = ea_chunking(M.n_res, THREADS, chunk);
+      const int cb = (K * (index - 1)) / (nh + 1), ce = (K * index) / (nh + 1);
+      ea_eval_chunks<THREADS>(A, S, M, P, cb, ce, chunk, pre, false, false);
+      __syncthreads();
+      if (warp == 0) {
+        for (int c = cb; c < ce; ++c) {
+          const double tot = ea_cta_total<THREADS / 32>(S.part[c], S.cpart[c], lane);
+          __stcg(&B->chunk[c][lane], lane < EA_SUMS ? tot : 0.0);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) ea_st_release(&B->done[index - 1], seen);
+      }
+      __syncthreads();
+    }
+  }
 }
 
 // Per-point outputs for ea_eval (parity tests / EAResidue facade): same device functions as the solve.
@@ -327,10 +529,16 @@ cudaError_t ea_launch_gather_probe(const EaSolveArgs& A, int level, int slices, 
 }
 
 // ---- host launchers -----------------------------------------------------------------------------------
+size_t ea_help_boards_bytes(int sm_count) { return size_t(sm_count) * EA_SOLVE_MIN_CTAS * sizeof(EaHelpBoard); }
+
 cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm_count, cudaStream_t stream) {
   if (A.n_pairs <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(A.work_counter, 0, sizeof(int), stream);
   if (e != cudaSuccess) return e;
+  if (A.boards && cluster_size <= 1) {
+    e = cudaMemsetAsync(A.boards, 0, ea_help_boards_bytes(sm_count), stream);
+    if (e != cudaSuccess) return e;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(EA_SOLVE_THREADS);
   cfg.stream = stream;

@@ -25,7 +25,15 @@ struct EaLmState {
   double dl_mu, dl_alpha, dl_step_norm, dl_grad[6], dl_gn[6];   // DoglegStrategy state (trust_region_strategy == 1)
   int phase, iter, accepted, rejected, invalid_run, reuse_diag, evals, term;
   int dl_reuse, pad;
+#ifdef EA_LM_PROFILE
+  long long prof[8];   // cycles per section of ea_lm_advance_warp's fast track (development aid)
+#endif
 };
+#ifdef EA_LM_PROFILE
+#define EA_LM_LAP(k) do { const long long t_ = clock64(); if (lane == 0) S.prof[k] += t_ - lm_t_; lm_t_ = t_; } while (0)
+#else
+#define EA_LM_LAP(k) do { } while (0)
+#endif
 
 __device__ inline void ea_quat_plus(const double* x, const double* d, double* out) {
   // ceres::QuaternionParameterization::Plus -- delta is a half-angle vector, left multiplication:
@@ -356,18 +364,31 @@ __device__ __forceinline__ bool ea_ldlt_solve6_packed(double (&U)[21], const dou
 
 static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double* sums, const ea_solve_params& sp, const int lane, double (&out_cand)[7]) {
   const unsigned full = 0xffffffffu;
-  bool fast = (S.phase == 1) && (sp.trust_region_strategy == 0) && !(sums[27] > 0.0);
-  double xc[7], rel = 0.0;
+#ifdef EA_LM_PROFILE
+  long long lm_t_ = clock64();
+#endif
+  // the serial state machine serves: the dogleg strategy, failed evaluations, rejected steps, near-tolerance decisions
+  bool fast = (sp.trust_region_strategy == 0) && !(sums[27] > 0.0);
+  const int phase = S.phase;
+  double xc[7], rel = 0.0, radius = 0.0;
   const double cand_cost = sums[28];
-  if (fast) {
+  int iter = 0;
+  if (fast && phase == 1) {
     double sn = 0.0, xn = 0.0;
 #pragma unroll
     for (int i = 0; i < 7; ++i) { const double xo = S.x[i]; xc[i] = S.cand[i]; const double d = xo - xc[i]; sn += d * d; xn += xo * xo; }
     const double pt2 = sp.parameter_tolerance * sp.parameter_tolerance;
     if (sn <= 2.0 * pt2 * (xn + pt2)) fast = false;                    // near the parameter tolerance: the exact test decides
     const double cost_change = S.cost - cand_cost;
-    if (fabs(cost_change) <= sp.function_tolerance * S.cost) fast = false;
-    else { rel = cost_change / S.model_cost_change; if (!(rel > sp.min_relative_decrease)) fast = false; }
+    if (fabs(cost_change) <= sp.function_tolerance * S.cost) {
+      // CONVERGENCE_FUNCTION (what nearly every level ends with): decided here, the iterate stays where it is
+      if (fast) {
+        __syncwarp();
+        if (lane == 0) { S.evals++; S.term = EA_TERM_CONVERGENCE_FUNCTION; }
+        __syncwarp();
+        return EA_CMD_DONE;
+      }
+    } else { rel = cost_change / S.model_cost_change; if (!(rel > sp.min_relative_decrease)) fast = false; }
   }
   if (!fast) {
     int cmd = 0;
@@ -380,17 +401,37 @@ static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double
     }
     return cmd;
   }
-  // ---- HandleSuccessfulStep ----
-  const double t = 2.0 * rel - 1.0;
-  const double radius = fmin(sp.max_trust_region_radius, S.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
-  const int iter = S.iter;
+  EA_LM_LAP(0);
   double sc[6];
+  if (phase == 0) {
+    // ---- IterationZero: the state at x0, Jacobi scaling from the first Jacobian (one sqrt + one division per lane) ----
 #pragma unroll
-  for (int j = 0; j < 6; ++j) sc[j] = S.scale[j];
-  __syncwarp();                                  // every lane has read the old state
-  if (lane < 7) S.x[lane] = S.cand[lane];
-  if (lane < 21) S.H[lane] = sums[lane]; else if (lane < 27) S.b[lane - 21] = sums[lane];
-  if (lane == 27) { S.cost = cand_cost; S.radius = radius; S.decrease_factor = 2.0; S.accepted++; S.evals++; S.invalid_run = 0; }
+    for (int i = 0; i < 7; ++i) xc[i] = S.x[i];
+    double mine = 1.0;
+    if (lane < 6 && sp.jacobi_scaling) mine = 1.0 / (1.0 + sqrt(sums[ea_tri(lane, lane)]));
+#pragma unroll
+    for (int j = 0; j < 6; ++j) sc[j] = __shfl_sync(full, mine, j);
+    radius = sp.initial_trust_region_radius;
+    iter = 0;
+    __syncwarp();
+    if (lane < 6) S.scale[lane] = mine;
+    if (lane < 21) S.H[lane] = sums[lane]; else if (lane < 27) S.b[lane - 21] = sums[lane];
+    if (lane == 27) {
+      S.cost = cand_cost; S.initial_cost = cand_cost; S.radius = radius; S.decrease_factor = 2.0; S.evals++;
+      S.dl_mu = 1e-8; S.dl_reuse = 0; S.dl_step_norm = 0.0; S.phase = 1; S.invalid_run = 0;
+    }
+  } else {
+    // ---- HandleSuccessfulStep ----
+    const double t = 2.0 * rel - 1.0;
+    radius = fmin(sp.max_trust_region_radius, S.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+    iter = S.iter;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) sc[j] = S.scale[j];
+    __syncwarp();                                  // every lane has read the old state
+    if (lane < 7) S.x[lane] = S.cand[lane];
+    if (lane < 21) S.H[lane] = sums[lane]; else if (lane < 27) S.b[lane - 21] = sums[lane];
+    if (lane == 27) { S.cost = cand_cost; S.radius = radius; S.decrease_factor = 2.0; S.accepted++; S.evals++; S.invalid_run = 0; }
+  }
   // gradient tolerance (same shortcut as ea_gradient_converged: the translation block of Plus is a plain addition)
   {
     const double gt = fmax(fabs(sums[24]), fmax(fabs(sums[25]), fabs(sums[26])));
@@ -399,12 +440,13 @@ static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double
       __syncwarp();
       int conv = 0;
       if (lane == 0) { conv = ea_gradient_converged(S, sp.gradient_tolerance) ? 1 : 0; if (conv) S.term = EA_TERM_CONVERGENCE_GRADIENT; }
-      if (__shfl_sync(full, conv, 0)) { __syncwarp(); return EA_CMD_DONE; }
+      if (__shfl_sync(full, conv, 0)) { if (lane == 0) { S.iter = iter; S.reuse_diag = 0; } __syncwarp(); return EA_CMD_DONE; }
     }
   }
   // ---- loop head of the next iteration ----
-  if (iter >= sp.max_num_iterations) { if (lane == 0) { S.term = EA_TERM_NO_CONVERGENCE; S.reuse_diag = 0; } __syncwarp(); return EA_CMD_DONE; }
-  if (radius < sp.min_trust_region_radius) { if (lane == 0) { S.term = EA_TERM_CONVERGENCE_MIN_RADIUS; S.reuse_diag = 0; } __syncwarp(); return EA_CMD_DONE; }
+  if (iter >= sp.max_num_iterations) { if (lane == 0) { S.term = EA_TERM_NO_CONVERGENCE; S.iter = iter; S.reuse_diag = 0; } __syncwarp(); return EA_CMD_DONE; }
+  if (radius < sp.min_trust_region_radius) { if (lane == 0) { S.term = EA_TERM_CONVERGENCE_MIN_RADIUS; S.iter = iter; S.reuse_diag = 0; } __syncwarp(); return EA_CMD_DONE; }
+  EA_LM_LAP(1);
   // ---- LevenbergMarquardtStrategy::ComputeStep on (S H S + diag / radius) y = S b ----
   double U[21], bs[6], y[6], delta[6];
   const double inv_radius = 1.0 / radius;
@@ -420,9 +462,11 @@ static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double
     if (lane == j) S.diag[j] = dg;
     U[ea_tri(j, j)] += dg * inv_radius;
   }
+  EA_LM_LAP(2);
   bool ok = ea_ldlt_solve6_packed(U, bs, y);
 #pragma unroll
   for (int a = 0; a < 6; ++a) delta[a] = -y[a] * sc[a];
+  EA_LM_LAP(3);
   // model_cost_change = -(delta^T b + 1/2 delta^T H delta): the serial code's order, as six independent row chains
   double lin = 0.0, quad = 0.0;
 #pragma unroll
@@ -435,10 +479,11 @@ static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double
   }
   const double model = -(lin + 0.5 * quad);
   ok = ok && (model > 0.0);
+  EA_LM_LAP(4);
   if (!ok) {     // HandleInvalidStep: rare; the serial loop recomputes this step, finds it invalid and carries on from there
     __syncwarp();
     int cmd = 0;
-    if (lane == 0) { S.reuse_diag = 0; cmd = ea_lm_propose(S, sp); }
+    if (lane == 0) { S.iter = iter; S.reuse_diag = 0; cmd = ea_lm_propose(S, sp); }
     cmd = __shfl_sync(full, cmd, 0);
     __syncwarp();
     if (cmd == EA_CMD_EVAL) {
@@ -455,6 +500,7 @@ static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double
     for (int i = 0; i < 7; ++i) S.cand[i] = out_cand[i];
   }
   __syncwarp();
+  EA_LM_LAP(5);
   return EA_CMD_EVAL;
 }
 
@@ -482,10 +528,12 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
                                               const EaLevelGeom& ng,
                                               double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, int j0,
                                               int j1, double (*part)[EA_NSUM], double* cpart, const bool reverse = false,
-                                              typename EaPtStream<XYZ>::T* pre = nullptr, const bool pre_valid = false) {
-  // pre (optional, U entries): in -- this thread's first points, already requested by the previous evaluation of the same
-  // (pair, level) when pre_valid; out -- the first points of the NEXT evaluation of this slice (opposite direction), requested
-  // before the final reduction so that their latency hides behind it, the CTA barrier and the serial LM step.
+                                              typename EaPtStream<XYZ>::T* pre = nullptr, const bool pre_valid = false,
+                                              const int nj0 = -1, const int nj1 = 0, const bool nrev = false) {
+  // pre (optional, U entries): in -- this thread's first points, already requested by the previous call when pre_valid;
+  // out -- the first points of the NEXT range this CTA will evaluate, [nj0, nj1) walked in direction nrev (the next chunk of
+  // this evaluation, or the first chunk of the next evaluation of the same (pair, level)), requested before the final
+  // reduction so that their latency hides behind it, the CTA barrier and the serial LM step.  nj0 < 0: nothing to prefetch.
   // reverse: walk the slice from its end.  Successive evaluations of a pair alternate the direction, so each sweep
   // starts on the data the previous one touched last (still in L1 / L2) instead of on the data it evicted first.
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -554,18 +602,30 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
       since_flush = 0;
     }
   }
-  if (pre) {   // the next evaluation of this (pair, level) sweeps the other way (EA_ALTERNATE_SWEEP) or the same way
+  if (pre && nj0 >= 0) {
+    const int nflip = nj0 + nj1 - 1;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int jj = j0 + tid + u * THREADS;
-      const bool rn = EA_ALTERNATE_SWEEP ? !reverse : reverse;
-      pre[u] = (jj < j1) ? PS::load(pts, size_t(rn ? jflip - jj : jj) * stride) : PS::pad();
+      const int jj = nj0 + tid + u * THREADS;
+      pre[u] = (jj < nj1) ? PS::load(pts, size_t(nrev ? nflip - jj : jj) * stride) : PS::pad();
     }
   }
   if (since_flush) acc64 += double(ea_warp_transpose_reduce(acc, lane));
   cost64 = ea_warp_sum(cost64);
   part[warp][lane] = acc64;
   if (lane == 0) cpart[warp] = cost64;
+}
+
+// An evaluation of n_res residuals is cut into at most EA_MAX_CHUNKS chunks of `size` residuals (a multiple of
+// THREADS * EA_FLUSH_EVERY, so chunk ends coincide with the fp32 -> fp64 flushes).  Every chunk is reduced on its own, in a
+// fixed order, by whichever CTA evaluates it, and the chunk totals are added in chunk order: the sums do not depend on how
+// many CTAs shared the evaluation (tail helpers, ea_solve.cu).
+#define EA_MAX_CHUNKS 4
+__device__ __forceinline__ int ea_chunking(const int n_res, const int threads, int& size) {
+  const int unit = threads * EA_FLUSH_EVERY;
+  const int nb = (n_res + unit - 1) / unit;
+  size = ((nb + EA_MAX_CHUNKS - 1) / EA_MAX_CHUNKS) * unit;
+  return n_res > 0 ? (n_res + size - 1) / size : 1;
 }
 
 // CTA totals from the per-warp partials: lane k of the calling warp returns slot k (k < EA_SUMS), fixed order.
