@@ -179,27 +179,19 @@ __device__ __forceinline__ void ea_st_release(unsigned long long* p, unsigned lo
 }
 
 // One worker's share of an evaluation: chunks [cb, ce) of M, walked in M's direction; per-chunk partials into S.part / S.cpart.
-// next_*: what this CTA will evaluate after this call returns (the first chunk of the next evaluation), for the point prefetch.
+// chain_next_eval: the same CTA evaluates the same chunks of the next evaluation of this (pair, level): prefetch its first point.
 template <int THREADS>
 __device__ __forceinline__ void ea_eval_chunks(const EaSolveArgs& A, EaSolveSmem& S, const EaMsg& M, const EaPose& P, const int cb, const int ce,
-                                               const int chunk, EaPtStream<false>::T* pre, bool pre_valid, const bool chain_next_eval) {
+                                               const int chunk, EaPtStream<false>::T* pre, const bool pre_valid, const bool chain_next_eval) {
   const EaLevelGeom& ng = A.now_geom[M.level];
-  const bool rev = EA_ALTERNATE_SWEEP && M.rev;
-  for (int i = 0; i < ce - cb; ++i) {
-    const int c = rev ? ce - 1 - i : cb + i;
-    const int lo = c * chunk, hi = min(lo + chunk, M.n_res);
-    // the range evaluated next: the following chunk of this evaluation, or (same pair and level continuing) the first chunk
-    // of the next evaluation, which sweeps the other way
-    int nlo = -1, nhi = 0;
-    bool nrev = rev;
-    if (i + 1 < ce - cb) { const int cn = rev ? ce - 2 - i : cb + i + 1; nlo = cn * chunk; nhi = min(nlo + chunk, M.n_res); }
-    else if (chain_next_eval) { nrev = EA_ALTERNATE_SWEEP ? !rev : rev; const int cn = nrev ? ce - 1 : cb; nlo = cn * chunk; nhi = min(nlo + chunk, M.n_res); }
-    if (M.pts_mode == EA_POINTS_XYZ)
-      ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[c], S.cpart[c], rev);
-    else
-      ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[c], S.cpart[c], rev, pre, pre_valid, nlo, nhi, nrev);
-    pre_valid = true;      // the call above requested the next range's first points
-  }
+  const bool rev = EA_ALTERNATE_SWEEP && M.rev, nrev = EA_ALTERNATE_SWEEP ? !rev : rev;
+  const int lo = cb * chunk, hi = min(ce * chunk, M.n_res);
+  if (M.pts_mode == EA_POINTS_XYZ)
+    ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[cb], S.cpart[cb], rev, nullptr, false, false, false,
+                                 chunk / THREADS, THREADS / 32);
+  else
+    ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[cb], S.cpart[cb], rev, pre, pre_valid, chain_next_eval, nrev,
+                                  chunk / THREADS, THREADS / 32);
 }
 
 template <int THREADS, bool CLUSTER>
@@ -236,9 +228,8 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
   if (tid == 0) for (int k = 0; k < 8; ++k) S.lm.prof[k] = 0;
 #endif
   auto lap = [&](int k) { if (dbg_on) { const long long t = clock64(); S.dbg[k] += t - S.dbg_t; S.dbg_t = t; } };
-  EaPtStream<false>::T pre[EA_EVAL_UNROLL];   // first points of the NEXT range, requested before the barrier (pixel points only)
-#pragma unroll
-  for (int u = 0; u < EA_EVAL_UNROLL; ++u) pre[u] = EaPtStream<false>::pad();
+  EaPtStream<false>::T pre[1];   // first point of the NEXT evaluation, requested before the barrier (pixel points only)
+  pre[0] = EaPtStream<false>::pad();
   // ================================================= owner loop =================================================
   for (;;) {
     const EaMsg& M = S.msg[g & 1];
@@ -251,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
       const EaLevelGeom& ng = A.now_geom[M.level];
       const bool rev = EA_ALTERNATE_SWEEP && M.rev, nrev = EA_ALTERNATE_SWEEP ? !rev : rev;
       if (M.pts_mode == EA_POINTS_XYZ) ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part[0], S.cpart[0], rev);
-      else ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part[0], S.cpart[0], rev, pre, M.same != 0, j0, j1, nrev);
+      else ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part[0], S.cpart[0], rev, pre, M.same != 0, true, nrev);
     } else {
       K = ea_chunking(M.n_res, THREADS, chunk);
       cb = (K * M.nh) / (M.nh + 1);             // the owner is the last of nh + 1 workers: chunks [cb, K)

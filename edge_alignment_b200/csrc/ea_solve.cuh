@@ -511,109 +511,109 @@ static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double
 #ifndef EA_ALTERNATE_SWEEP
 #define EA_ALTERNATE_SWEEP 1
 #endif
-#ifndef EA_EVAL_UNROLL
-#define EA_EVAL_UNROLL 1   // points per thread in flight (U): their projections, then all 16 U gathers, then the arithmetic
-#endif
 
-// Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads and leave per-warp partial
-// sums in part / cpart (caller synchronises).  dt_pad = FIRST element of the padded distance transform (pixel (-PAD,-PAD)).
+// Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads and leave per-warp partial sums in
+// part / cpart (caller synchronises).  dt_pad = FIRST element of the padded distance transform (pixel (-PAD,-PAD)).
 //
-// The memory side of an evaluation (point stream -> fp64 projection -> 16-texel gather) is latency-bound and scales with
-// the number of gathers in flight per SM (profiles/r1_kernels_v3.md: 2.2 / 3.6 / 5.2 ms at 32 / 16 / 8 warps); the register
-// file caps the warps at 16, so each thread keeps U independent points in flight instead: one CTA iteration covers
-// THREADS * U consecutive points, thread t owning points base + u * THREADS + t (a warp load still covers 32 consecutive
-// points, the CTA still walks the list -- and the DT rows under it -- front to back).
-template <bool XYZ, int THREADS, int U = EA_EVAL_UNROLL>
+// One CTA iteration covers THREADS consecutive residuals (a warp load covers 32 consecutive points; the CTA walks the list --
+// and the DT rows under it -- front to back, or back to front when `reverse`: successive evaluations of a pair alternate the
+// direction, so each sweep starts on the data the previous one touched last, still in L1 / L2, instead of on the data it
+// evicted first).  Keeping more than one point per thread in flight was measured and lost (the evaluation phase is issue-
+// bound at 16 warps, profiles/r2_kernels.md).
+//
+// Chunks (chunk_iters > 0, a multiple of EA_FLUSH_EVERY): [j0, j1) starts on a chunk boundary and is cut every
+// chunk_iters * THREADS residuals; chunk k of the range leaves its partials in part[k * part_stride ...] / cpart[k * ...]
+// (k counted from the range's LOW end in both directions).  A chunk's partials depend only on the chunk, not on the range it
+// was evaluated in: iterations are aligned to the chunk grid from the low end (forward) or from the virtual high end `vend`
+// (reverse; vend = j0 + n_chunks * chunk, the ragged part of the last chunk sits in the first iterations).  Chunk ends
+// coincide with the fp32 -> fp64 flushes, so the bookkeeping lives in the flush branch, not in the loop body.
+//
+// pre (optional): in -- this thread's first point, requested by the previous call when pre_valid; out, when prefetch_next --
+// the first point of the NEXT evaluation of the same range (direction next_reverse), requested before the final reduction so
+// that its latency hides behind the reduction, the CTA barrier and the serial LM step.
+template <bool XYZ, int THREADS>
 __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, const float* __restrict__ dt_pad, const float2 affine,
                                               const EaLevelGeom& ng,
-                                              double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, int j0,
-                                              int j1, double (*part)[EA_NSUM], double* cpart, const bool reverse = false,
+                                              double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, const int j0,
+                                              const int j1, double (*part)[EA_NSUM], double* cpart, const bool reverse = false,
                                               typename EaPtStream<XYZ>::T* pre = nullptr, const bool pre_valid = false,
-                                              const int nj0 = -1, const int nj1 = 0, const bool nrev = false) {
-  // pre (optional, U entries): in -- this thread's first points, already requested by the previous call when pre_valid;
-  // out -- the first points of the NEXT range this CTA will evaluate, [nj0, nj1) walked in direction nrev (the next chunk of
-  // this evaluation, or the first chunk of the next evaluation of the same (pair, level)), requested before the final
-  // reduction so that their latency hides behind it, the CTA barrier and the serial LM step.  nj0 < 0: nothing to prefetch.
-  // reverse: walk the slice from its end.  Successive evaluations of a pair alternate the direction, so each sweep
-  // starts on the data the previous one touched last (still in L1 / L2) instead of on the data it evicted first.
+                                              const bool prefetch_next = false, const bool next_reverse = false,
+                                              const int chunk_iters = 0, const int part_stride = 0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int jflip = j0 + j1 - 1;
   const float loss_a = float(sp.loss_scale);
   const int loss_type = sp.loss_type, stride = sp.point_stride;
   const int W = ng.w, H = ng.h, pitch = ea_dt_pitch(W);
+  typedef EaPtStream<XYZ> PS;
+  // virtual iteration space: residual of (iteration it, thread t) = j0 + it * THREADS + t   (forward)
+  //                                                                 vend - 1 - (it * THREADS + t)   (reverse)
+  const int n = j1 - j0;
+  const int n_it = (n + THREADS - 1) / THREADS;
+  const int cspan = chunk_iters > 0 ? chunk_iters * THREADS : 0;
+  const int n_chunks = cspan > 0 ? (n + cspan - 1) / cspan : 1;
+  const int vend = cspan > 0 ? j0 + n_chunks * cspan : j1;
+  const int it_first_rev = (vend - j1) / THREADS;             // reverse: whole iterations of padding above j1 are skipped
+  auto residual_of = [&](const int it, const bool rev) { return rev ? vend - 1 - (it * THREADS + tid) : j0 + it * THREADS + tid; };
+  const int it0 = reverse ? it_first_rev : 0;
+  const int it1 = reverse ? (vend - j0 + THREADS - 1) / THREADS : n_it;
   float acc[EA_NSUM];
 #pragma unroll
   for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
   double acc64 = 0.0, cost64 = 0.0;
-  int since_flush = 0;
-  typedef EaPtStream<XYZ> PS;
-  typename PS::T p_next[U];
-  int j = j0 + tid;
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int jj = j + u * THREADS;
-    if (pre && pre_valid) p_next[u] = pre[u];
-    else p_next[u] = (jj < j1) ? PS::load(pts, size_t(reverse ? jflip - jj : jj) * stride) : PS::pad();
-  }
-  for (int base = j0; base < j1; base += THREADS * U) {
-    typename PS::T p[U];
-    bool valid[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) { p[u] = p_next[u]; valid[u] = (j + u * THREADS) < j1; }
-    j += THREADS * U;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {   // prefetch the next iteration's points before the gathers
-      const int jj = j + u * THREADS;
-      if (jj < j1) p_next[u] = PS::load(pts, size_t(reverse ? jflip - jj : jj) * stride);
-    }
-    EaProj r[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
+  int k_chunk = reverse ? n_chunks - 1 : 0;                    // chunk being accumulated (from the range's low end)
+  typename PS::T p_next;
+  int rj = residual_of(it0, reverse);                          // this thread's residual in the current iteration
+  const int dr = reverse ? -THREADS : THREADS;
+  if (pre && pre_valid) p_next = pre[0];
+  else p_next = (unsigned(rj - j0) < unsigned(n)) ? PS::load(pts, size_t(rj) * stride) : PS::pad();
+  for (int it = it0; it < it1; ++it) {
+    const typename PS::T p = p_next;
+    const bool valid = unsigned(rj - j0) < unsigned(n);
+    rj += dr;
+    if (unsigned(rj - j0) < unsigned(n)) p_next = PS::load(pts, size_t(rj) * stride);   // prefetch the next iteration's point before the gather
+    EaProj r;
+    {
       double a0, a1, a2;
-      PS::unpack(p[u], a0, a1, a2);
-      ea_project<XYZ>(a0, a1, a2, W, H, pitch, inv_depth_scale, P, r[u]);
+      PS::unpack(p, a0, a1, a2);
+      ea_project<XYZ>(a0, a1, a2, W, H, pitch, inv_depth_scale, P, r);
     }
-    float t[U][16];
+    float t[16];
+    ea_gather(dt_pad, r.off, unsigned(pitch), t);
+    EaPointEval e;
+    ea_interp(t, r.du, r.dv, affine, e.f, e.dfdu, e.dfdv);
+    e.ub = r.ub; e.vb = r.vb; e.pz = r.pz; e.iz = r.iz; e.fail = r.fail;
+    float rho0;
+    float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
+    if (!valid) { w = 0.0f; rho0 = 0.0f; e.f = 0.0f; e.fail = false; }
+    float J[6];
+    ea_jacobian(e, P, w, J);
+    if (!valid) {   // padding lanes of a ragged iteration: the dummy point may project to inf/NaN
 #pragma unroll
-    for (int u = 0; u < U; ++u) ea_gather(dt_pad, r[u].off, unsigned(pitch), t[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      EaPointEval e;
-      ea_interp(t[u], r[u].du, r[u].dv, affine, e.f, e.dfdu, e.dfdv);
-      e.ub = r[u].ub; e.vb = r[u].vb; e.pz = r[u].pz; e.iz = r[u].iz; e.fail = r[u].fail;
-      float rho0;
-      float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
-      if (!valid[u]) { w = 0.0f; rho0 = 0.0f; e.f = 0.0f; e.fail = false; }
-      float J[6];
-      ea_jacobian(e, P, w, J);
-      if (!valid[u]) {   // padding lanes of the last iteration: the dummy point may project to inf/NaN
-#pragma unroll
-        for (int k = 0; k < 6; ++k) J[k] = 0.0f;
-      }
-      ea_accumulate(acc, J, e.f * w);
-      acc[27] += e.fail ? 1.0f : 0.0f;
-      cost64 += double(0.5f * rho0);
+      for (int k = 0; k < 6; ++k) J[k] = 0.0f;
     }
-    since_flush += U;
-    if (since_flush >= EA_FLUSH_EVERY) {
+    ea_accumulate(acc, J, e.f * w);
+    acc[27] += e.fail ? 1.0f : 0.0f;
+    cost64 += double(0.5f * rho0);
+    if (((it + 1) & (EA_FLUSH_EVERY - 1)) == 0) {              // flush cadence on the virtual iteration grid
       acc64 += double(ea_warp_transpose_reduce(acc, lane));
 #pragma unroll
       for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
-      since_flush = 0;
+      if (chunk_iters > 0 && (it + 1) % chunk_iters == 0 && it + 1 < it1) {   // a chunk is complete: park its partials
+        const double c64 = ea_warp_sum(cost64);
+        part[size_t(k_chunk) * part_stride + warp][lane] = acc64;
+        if (lane == 0) cpart[size_t(k_chunk) * part_stride + warp] = c64;
+        acc64 = 0.0; cost64 = 0.0;
+        k_chunk += reverse ? -1 : 1;
+      }
     }
   }
-  if (pre && nj0 >= 0) {
-    const int nflip = nj0 + nj1 - 1;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int jj = nj0 + tid + u * THREADS;
-      pre[u] = (jj < nj1) ? PS::load(pts, size_t(nrev ? nflip - jj : jj) * stride) : PS::pad();
-    }
+  if (pre && prefetch_next) {
+    const int rn = residual_of(next_reverse ? it_first_rev : 0, next_reverse);
+    pre[0] = (rn >= j0 && rn < j1) ? PS::load(pts, size_t(rn) * stride) : PS::pad();
   }
-  if (since_flush) acc64 += double(ea_warp_transpose_reduce(acc, lane));
+  if (((it1 - it0) > 0) && (it1 & (EA_FLUSH_EVERY - 1)) != 0) acc64 += double(ea_warp_transpose_reduce(acc, lane));
   cost64 = ea_warp_sum(cost64);
-  part[warp][lane] = acc64;
-  if (lane == 0) cpart[warp] = cost64;
+  part[size_t(k_chunk) * part_stride + warp][lane] = acc64;
+  if (lane == 0) cpart[size_t(k_chunk) * part_stride + warp] = cost64;
 }
 
 // An evaluation of n_res residuals is cut into at most EA_MAX_CHUNKS chunks of `size` residuals (a multiple of
