@@ -310,6 +310,45 @@ class Tracker:
         return poses, S
 
 
+class Shard:
+    """One huge pair solved by all ranks together (BASELINE configs[4]): every rank holds the full distance transform and a
+    contiguous slice of the ordered point list; the 29 normal-equation sums are all-reduced inside the solve kernel over
+    peer-mapped NVLink memory (ea_shard_*).  id128: the 128-byte NCCL id from Shard.unique_id() on rank 0, passed around by the
+    caller (e.g. torch.distributed broadcast); None for world == 1."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        _check(L.lib().ea_shard_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, ctx, id128=None, rank=0, world=1):
+        self.ctx = ctx; self.rank = rank; self.world = world
+        self._h = C.c_void_p()
+        idbuf = (C.c_uint8 * 128)(*id128) if id128 is not None else None
+        _check(L.lib().ea_shard_create(ctx._h, idbuf, rank, world, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            L.lib().ea_shard_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def solve(self, ref, ref_slot, now, now_slot, pose7=None, sp=None, level=0):
+        pose = np.array(IDENTITY if pose7 is None else pose7, dtype=np.float64)
+        s = L.Summary()
+        _check(L.lib().ea_shard_solve(self._h, ref._h, ref_slot, now._h, now_slot, level, _ptr(pose, C.c_double),
+                                      C.byref(sp if sp is not None else solve_params()), C.byref(s)))
+        return pose, s.asdict()
+
+    def profile(self):
+        """The last solve: evaluations, device ms, microseconds per evaluation {slice evaluation, grid reduce, cross-rank
+        all-reduce, LM step}, in-kernel path?, kernel launches."""
+        p = (C.c_double * 8)()
+        _check(L.lib().ea_shard_profile(self._h, p))
+        return {"evaluations": int(p[0]), "solve_ms": p[1], "eval_us": p[2], "grid_reduce_us": p[3], "allreduce_us": p[4],
+                "lm_us": p[5], "in_kernel": bool(p[6]), "launches": int(p[7])}
+
+
 def pixel_points(uvd):
     """[N,3] integer (u, v, raw depth) -> float4 rows of the EA_POINTS_PIXEL stream."""
     uvd = np.asarray(uvd)

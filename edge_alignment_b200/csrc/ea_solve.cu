@@ -68,6 +68,7 @@ struct EaSolveSmem {
   double cluster_sums[8][EA_SUMS + 3];      // rank 0 only: one row per cluster rank
   EaLmState lm;                             // boss only
   int pair, level, truncated;               // boss only
+  uint2 stage[2][EA_SOLVE_THREADS];         // cp.async staging of the point stream (ea_eval_slice)
   unsigned long long help_epoch;            // owner: evaluations published on its board so far
   int help_owner, help_index, help_fail;    // helper: the board it serves and its slot there (1-based); owner: a helper went missing
   long long dbg[6], dbg_t, dbg_t0;          // EA_SOLVE_DEBUG cycle counters (thread 0)
@@ -182,7 +183,7 @@ __device__ __forceinline__ void ea_st_release(unsigned long long* p, unsigned lo
 // chain_next_eval: the same CTA evaluates the same chunks of the next evaluation of this (pair, level): prefetch its first point.
 template <int THREADS>
 __device__ __forceinline__ void ea_eval_chunks(const EaSolveArgs& A, EaSolveSmem& S, const EaMsg& M, const EaPose& P, const int cb, const int ce,
-                                               const int chunk, EaPtStream<false>::T* pre, const bool pre_valid, const bool chain_next_eval) {
+                                               const int chunk, const bool pre_valid, const bool chain_next_eval) {
   const EaLevelGeom& ng = A.now_geom[M.level];
   const bool rev = EA_ALTERNATE_SWEEP && M.rev, nrev = EA_ALTERNATE_SWEEP ? !rev : rev;
   const int lo = cb * chunk, hi = min(ce * chunk, M.n_res);
@@ -190,7 +191,7 @@ __device__ __forceinline__ void ea_eval_chunks(const EaSolveArgs& A, EaSolveSmem
     ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[cb], S.cpart[cb], rev, nullptr, false, false, false,
                                  chunk / THREADS, THREADS / 32);
   else
-    ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[cb], S.cpart[cb], rev, pre, pre_valid, chain_next_eval, nrev,
+    ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[cb], S.cpart[cb], rev, &S.stage[0][0], pre_valid, chain_next_eval, nrev,
                                   chunk / THREADS, THREADS / 32);
 }
 
@@ -228,8 +229,6 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
   if (tid == 0) for (int k = 0; k < 8; ++k) S.lm.prof[k] = 0;
 #endif
   auto lap = [&](int k) { if (dbg_on) { const long long t = clock64(); S.dbg[k] += t - S.dbg_t; S.dbg_t = t; } };
-  EaPtStream<false>::T pre[1];   // first point of the NEXT evaluation, requested before the barrier (pixel points only)
-  pre[0] = EaPtStream<false>::pad();
   // ================================================= owner loop =================================================
   for (;;) {
     const EaMsg& M = S.msg[g & 1];
@@ -242,11 +241,11 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
       const EaLevelGeom& ng = A.now_geom[M.level];
       const bool rev = EA_ALTERNATE_SWEEP && M.rev, nrev = EA_ALTERNATE_SWEEP ? !rev : rev;
       if (M.pts_mode == EA_POINTS_XYZ) ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part[0], S.cpart[0], rev);
-      else ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part[0], S.cpart[0], rev, pre, M.same != 0, true, nrev);
+      else ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part[0], S.cpart[0], rev, &S.stage[0][0], M.same != 0, true, nrev);
     } else {
       K = ea_chunking(M.n_res, THREADS, chunk);
       cb = (K * M.nh) / (M.nh + 1);             // the owner is the last of nh + 1 workers: chunks [cb, K)
-      ea_eval_chunks<THREADS>(A, S, M, P, cb, K, chunk, pre, M.same != 0, true);
+      ea_eval_chunks<THREADS>(A, S, M, P, cb, K, chunk, M.same != 0, true);
     }
     lap(0);
     __syncthreads();
@@ -400,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
       int chunk;
       const int K = ea_chunking(M.n_res, THREADS, chunk);
       const int cb = (K * (index - 1)) / (nh + 1), ce = (K * index) / (nh + 1);
-      ea_eval_chunks<THREADS>(A, S, M, P, cb, ce, chunk, pre, false, false);
+      ea_eval_chunks<THREADS>(A, S, M, P, cb, ce, chunk, false, false);
       __syncthreads();
       if (warp == 0) {
         for (int c = cb; c < ce; ++c) {

@@ -504,6 +504,18 @@ static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double
   return EA_CMD_EVAL;
 }
 
+// ---- asynchronous point staging (cp.async: global -> shared without a register in between) -----------------------------
+__device__ __forceinline__ void ea_cp_async8(const unsigned saddr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void ea_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ea_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint2 ea_lds_u2(const unsigned saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
+  return v;
+}
+
 // ---- slice evaluation shared by every solve kernel ----------------------------------------------------------
 #ifndef EA_FLUSH_EVERY
 #define EA_FLUSH_EVERY 16  // points per thread between fp32 -> fp64 flushes of the normal-equation slots (measured: 8 -> 16 = -1.7 %)
@@ -528,15 +540,19 @@ static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double
 // (reverse; vend = j0 + n_chunks * chunk, the ragged part of the last chunk sits in the first iterations).  Chunk ends
 // coincide with the fp32 -> fp64 flushes, so the bookkeeping lives in the flush branch, not in the loop body.
 //
-// pre (optional): in -- this thread's first point, requested by the previous call when pre_valid; out, when prefetch_next --
-// the first point of the NEXT evaluation of the same range (direction next_reverse), requested before the final reduction so
-// that its latency hides behind the reduction, the CTA barrier and the serial LM step.
+// stage (optional, pixel points only): shared memory, uint2 [2][THREADS].  The point of iteration i + 1 is requested at the top
+// of iteration i with cp.async straight into the thread's staging slot and read back (LDS) at the top of iteration i + 1: it
+// never occupies registers across the loop body.  (As a register prefetch it did, the loop sits at the 128-register limit, and
+// ptxas parked it in local memory right behind the load -- exposing the load latency in every iteration, +27 % evaluation time.)
+// pre_valid: slot 0 already holds (or is about to receive) this call's first point, requested by the previous call;
+// prefetch_next: request the first point of the NEXT evaluation of the same range (direction next_reverse) into slot 0 before
+// returning, so that its latency hides behind the CTA barrier and the serial LM step.
 template <bool XYZ, int THREADS>
 __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, const float* __restrict__ dt_pad, const float2 affine,
                                               const EaLevelGeom& ng,
                                               double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, const int j0,
                                               const int j1, double (*part)[EA_NSUM], double* cpart, const bool reverse = false,
-                                              typename EaPtStream<XYZ>::T* pre = nullptr, const bool pre_valid = false,
+                                              uint2* stage = nullptr, const bool pre_valid = false,
                                               const bool prefetch_next = false, const bool next_reverse = false,
                                               const int chunk_iters = 0, const int part_stride = 0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -558,18 +574,34 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
   float acc[EA_NSUM];
 #pragma unroll
   for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
-  double acc64 = 0.0, cost64 = 0.0;
-  int k_chunk = reverse ? n_chunks - 1 : 0;                    // chunk being accumulated (from the range's low end)
-  typename PS::T p_next;
+  // The fp64 accumulators of the 32 slots live in shared memory (part itself): they are touched once per flush, and the
+  // registers they would hold across the loop body are what keeps the prefetched point out of local memory.
+  double cost64 = 0.0;
+  for (int k = 0; k < n_chunks; ++k) part[size_t(k) * part_stride + warp][lane] = 0.0;
+  typename PS::T p_next = PS::pad();
   int rj = residual_of(it0, reverse);                          // this thread's residual in the current iteration
-  const int dr = reverse ? -THREADS : THREADS;
-  if (pre && pre_valid) p_next = pre[0];
-  else p_next = (unsigned(rj - j0) < unsigned(n)) ? PS::load(pts, size_t(rj) * stride) : PS::pad();
+  bool any_fail = false;                                       // slot 27 only says "some point failed": a predicate, not an accumulator
+  const bool staged = !XYZ && stage != nullptr;
+  const unsigned st0 = staged ? unsigned(__cvta_generic_to_shared(stage + tid)) : 0u;   // this thread's slot 0; slot 1 is THREADS * 8 bytes further
+  unsigned st_cur = st0;
+  if (staged) {
+    if (!pre_valid) { if (unsigned(rj - j0) < unsigned(n)) ea_cp_async8(st0, reinterpret_cast<const uint2*>(pts) + size_t(rj) * stride); ea_cp_async_commit(); }
+  } else {
+    if (unsigned(rj - j0) < unsigned(n)) p_next = PS::load(pts, size_t(rj) * stride);
+  }
   for (int it = it0; it < it1; ++it) {
-    const typename PS::T p = p_next;
     const bool valid = unsigned(rj - j0) < unsigned(n);
-    rj += dr;
-    if (unsigned(rj - j0) < unsigned(n)) p_next = PS::load(pts, size_t(rj) * stride);   // prefetch the next iteration's point before the gather
+    typename PS::T p = p_next;
+    if (reverse) rj -= THREADS; else rj += THREADS;
+    if (staged) {
+      ea_cp_async_wait_all();
+      if constexpr (!XYZ) { p = valid ? ea_lds_u2(st_cur) : PS::pad(); }
+      st_cur = (2u * st0 + unsigned(THREADS * 8)) - st_cur;                     // the other slot
+      if (unsigned(rj - j0) < unsigned(n)) ea_cp_async8(st_cur, reinterpret_cast<const uint2*>(pts) + size_t(rj) * stride);
+      ea_cp_async_commit();
+    } else {
+      if (unsigned(rj - j0) < unsigned(n)) p_next = PS::load(pts, size_t(rj) * stride);   // register prefetch (XYZ points, callers without staging)
+    }
     EaProj r;
     {
       double a0, a1, a2;
@@ -591,29 +623,30 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
       for (int k = 0; k < 6; ++k) J[k] = 0.0f;
     }
     ea_accumulate(acc, J, e.f * w);
-    acc[27] += e.fail ? 1.0f : 0.0f;
+    any_fail = any_fail || e.fail;
     cost64 += double(0.5f * rho0);
-    if (((it + 1) & (EA_FLUSH_EVERY - 1)) == 0) {              // flush cadence on the virtual iteration grid
-      acc64 += double(ea_warp_transpose_reduce(acc, lane));
+    if (((it + 1) & (EA_FLUSH_EVERY - 1)) == 0 || it + 1 == it1) {   // flush cadence on the virtual iteration grid, and at the end
+      acc[27] = any_fail ? 1.0f : 0.0f;
+      any_fail = false;
+      const int kc = chunk_iters > 0 ? (reverse ? n_chunks - 1 - it / chunk_iters : it / chunk_iters) : 0;   // chunk, from the range's low end
+      double* slot = &part[size_t(kc) * part_stride + warp][lane];
+      *slot += double(ea_warp_transpose_reduce(acc, lane));
 #pragma unroll
       for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
-      if (chunk_iters > 0 && (it + 1) % chunk_iters == 0 && it + 1 < it1) {   // a chunk is complete: park its partials
+      if (it + 1 == it1 || (chunk_iters > 0 && (it + 1) % chunk_iters == 0)) {   // the chunk is complete: its cost
         const double c64 = ea_warp_sum(cost64);
-        part[size_t(k_chunk) * part_stride + warp][lane] = acc64;
-        if (lane == 0) cpart[size_t(k_chunk) * part_stride + warp] = c64;
-        acc64 = 0.0; cost64 = 0.0;
-        k_chunk += reverse ? -1 : 1;
+        if (lane == 0) cpart[size_t(kc) * part_stride + warp] = c64;
+        cost64 = 0.0;
       }
     }
   }
-  if (pre && prefetch_next) {
+  if (it1 <= it0) { if (lane == 0) cpart[warp] = 0.0; }        // empty range
+  if (staged && prefetch_next) {
     const int rn = residual_of(next_reverse ? it_first_rev : 0, next_reverse);
-    pre[0] = (rn >= j0 && rn < j1) ? PS::load(pts, size_t(rn) * stride) : PS::pad();
+    ea_cp_async_wait_all();                                      // (nothing of this call is still reading or filling slot 0)
+    if (rn >= j0 && rn < j1) ea_cp_async8(st0, reinterpret_cast<const uint2*>(pts) + size_t(rn) * stride);
+    ea_cp_async_commit();
   }
-  if (((it1 - it0) > 0) && (it1 & (EA_FLUSH_EVERY - 1)) != 0) acc64 += double(ea_warp_transpose_reduce(acc, lane));
-  cost64 = ea_warp_sum(cost64);
-  part[size_t(k_chunk) * part_stride + warp][lane] = acc64;
-  if (lane == 0) cpart[size_t(k_chunk) * part_stride + warp] = cost64;
 }
 
 // An evaluation of n_res residuals is cut into at most EA_MAX_CHUNKS chunks of `size` residuals (a multiple of

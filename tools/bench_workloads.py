@@ -1,0 +1,465 @@
+"""bench.py --workload config1 | config3 | config4 | config5: the other BASELINE.json configurations, each printed as one
+JSON line with the same keys as the default line (configs[1], `--workload config2`, lives in bench.py itself).
+
+  config1  configs[0]  the bundled standalone/rgb-d pair 1 -> 3, single level, Cauchy(1), Ceres defaults
+                       (standalone_edge_align.cpp:109-305): latency of ONE pair, stride 30 (the reference's) and stride 1
+  config3  configs[2]  4096 independent synthetic 640x480 pairs in one batch, strong-scaled over the ranks
+  config4  configs[3]  synthetic 1280x720 sequences with dense edges (~300 k edge points per frame), 4-level coarse-to-fine LM
+  config5  configs[4]  one synthetic 3840x2160 pair with > 1.5 M edge points, point-sharded over the ranks with the in-kernel
+                       all-reduce of the normal equations (ea_shard_solve)
+
+A step is one pass of the workload's hot path over its batch; `value` has the inputs resident in HBM, `e2e` goes through the
+host entry points with host buffers.  `cpu_baseline` is the oracle (CPU restatement of the reference) on a bounded sample, on one
+thread (what the reference runs: standalone/README.md:44) and on all host threads.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BYTES_PER_POINT_EVAL = 80.0
+
+
+def _events(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def _roofline(point_evals_per_launch, solve_ms, peak, peak_src, kernel, launches_per_step=1, extra=None):
+    ach = point_evals_per_launch * BYTES_PER_POINT_EVAL / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+    r = {"bound": "l1_gather_latency", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+         "kernel": kernel, "peak_source": peak_src, "kernel_ms_per_launch": solve_ms, "point_evals_per_launch": point_evals_per_launch,
+         "bytes_per_point_eval": BYTES_PER_POINT_EVAL, "launches_per_step": launches_per_step,
+         "note": "HBM-equivalent of SURVEY 8d's 80 B per point-evaluation against the measured copy bandwidth; the gather is "
+                 "L1/L2-served, the binding resources are issue slots and gather latency (DESIGN.md 8)"}
+    if extra:
+        r.update(extra)
+    return r
+
+
+def _cpu_pairs(O, bgr, depth, pairs, cfg, opts, threads):
+    """Oracle over a list of (ref frame, now frame) index pairs: (alignments/s pair-total, alignments/s solve-only)."""
+    flat_b = bgr.reshape((-1,) + bgr.shape[-3:]); flat_d = depth.reshape((-1,) + depth.shape[-2:])
+    ref = [p[0] for p in pairs]; now = [p[1] for p in pairs]
+    ident = np.tile(np.array([1.0, 0, 0, 0, 0, 0, 0]), (len(pairs), 1))
+    _, _, sec_total = O.align_batch(flat_b, flat_d, ref, now, cfg, ident, opts, n_threads=threads, include_preprocess=True)
+    _, _, sec_solve = O.align_batch(flat_b, flat_d, ref, now, cfg, ident, opts, n_threads=threads, include_preprocess=False)
+    return len(pairs) / sec_total, len(pairs) / sec_solve, sec_total + sec_solve
+
+
+def _finish(out, tracker_like=None):
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------ config 1
+def config1(args, env):
+    torch, ea, dist, dev, rank, world = env["torch"], env["ea"], env["dist"], env["dev"], env["rank"], env["world"]
+    z = np.load(os.path.join(ROOT, "tests", "golden", "frames.npz"))
+    bgr = np.ascontiguousarray(z["bgr"][[0, 2]]); dep = np.ascontiguousarray(z["depth"][[0, 2]])
+    K, Wm = args.steps, args.warmup
+    ctx = ea.Context(env["local_rank"]); stream = torch.cuda.current_stream(); ctx.set_stream(stream.cuda_stream)
+    fs = ea.FrameSet(ctx, ea.frame_params(), 2)
+    d_b = torch.from_numpy(bgr).to(dev); d_d = torch.from_numpy(dep).to(dev)
+    hb = torch.from_numpy(bgr).pin_memory(); hd = torch.from_numpy(dep).pin_memory()
+    slots = np.array([0, 1], np.int32)
+    res = {}
+    sp30 = ea.solve_params(point_stride=30); sp1 = ea.solve_params(point_stride=1)
+
+    def timed(fn, n):
+        for _ in range(max(3, Wm)):
+            fn()
+        env["barrier"]()
+        e0, e1 = _events(torch)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        env["barrier"]()
+        return e0.elapsed_time(e1) / n
+
+    def pair_total(sp):
+        fs.preprocess_device(slots, d_b.data_ptr(), d_d.data_ptr(), ea.ROLE_BOTH)
+        return ctx.solve_batch(fs, [0], fs, [1], None, sp)
+
+    env["sampler"].begin()
+    l0 = ctx.launch_count()
+    ms_total30 = timed(lambda: pair_total(sp30), K)
+    launches = (ctx.launch_count() - l0) // (K + max(3, Wm))
+    clocks = env["sampler"].stop()
+    res["pair_total_ms_stride30"] = ms_total30
+    res["pair_total_ms_stride1"] = timed(lambda: pair_total(sp1), K)
+    res["preprocess_both_frames_ms"] = timed(lambda: fs.preprocess_device(slots, d_b.data_ptr(), d_d.data_ptr(), ea.ROLE_BOTH), K)
+    for stride, sp in ((30, sp30), (1, sp1)):
+        for kern, name in ((0, "auto_cluster8"), (1, "one_cta")):
+            spk = ea.solve_params(point_stride=stride, cluster_size=kern)
+            res["solve_only_ms_stride%d_%s" % (stride, name)] = timed(lambda: ctx.solve_batch(fs, [0], fs, [1], None, spk), K)
+    # solve kernel alone (events around the launch) for the roofline line: stride 1, every edge point
+    ctx.profile_enable(True); ctx.profile_read()
+    poses, S = ctx.solve_batch(fs, [0], fs, [1], None, sp1)
+    prof = ctx.profile_read(); ctx.profile_enable(False)
+    pe = S[0][0]["n_residuals"] * S[0][0]["evaluations"]
+    # e2e: host frames in, pose out, through the host entry points
+    def e2e_fn():
+        fs.preprocess_host(slots, hb.numpy(), hd.numpy(), ea.ROLE_BOTH)
+        return ctx.solve_batch(fs, [0], fs, [1], None, sp30)
+    ms_e = timed(e2e_fn, K)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        Kt = tuple(float(v) for v in z["K"])
+        t = time.perf_counter(); xyz, _ = O.get_aX(z["bgr"][0], z["depth"][0], Kt); dt, _ = O.get_distance_transform(z["bgr"][2]); t_pre = time.perf_counter() - t
+        tt = {}
+        for stride in (30, 1):
+            t = time.perf_counter(); O.solve(xyz, dt, Kt, ea.IDENTITY, stride=stride); tt[stride] = time.perf_counter() - t
+        cv2_ms = None
+        try:
+            import cv2
+            cv2.setNumThreads(1)
+            t = time.perf_counter()
+            for im in (z["bgr"][0], z["bgr"][2]):
+                g = cv2.cvtColor(cv2.GaussianBlur(im, (3, 3), 0, 0), cv2.COLOR_RGB2GRAY)
+                lap = cv2.convertScaleAbs(cv2.Laplacian(g, cv2.CV_16S, ksize=3))
+                B = np.where(lap > 35, 0, 255).astype(np.uint8)
+                cv2.normalize(cv2.distanceTransform(cv2.medianBlur(B, 3), cv2.DIST_L2, 3), None, 0, 1.0, cv2.NORM_MINMAX)
+            cv2_ms = (time.perf_counter() - t) * 1e3
+        except Exception:
+            pass
+        cpu = {"value": 1.0 / (t_pre + tt[30]), "unit": "alignments/s", "cores": 1, "kind": "port",
+               "sample": "the bundled pair once: oracle preprocessing %.1f ms, solve stride 30 %.1f ms, stride 1 %.1f ms" % (t_pre * 1e3, tt[30] * 1e3, tt[1] * 1e3),
+               "solve_only_alignments_per_s_stride30": 1.0 / tt[30], "solve_only_alignments_per_s_stride1": 1.0 / tt[1],
+               "cv2_preprocessing_ms_both_frames_1_thread": cv2_ms,
+               "reference_published": "standalone/README.md:21-66: ~60 ms per pair (solve 55.7 ms), 1482 residuals, 30 iterations, unstated CPU"}
+    peak, peak_src = env["peak"]
+    out = {"metric": "frame-pair alignments/sec at 640x480", "value": 1e3 / ms_total30, "unit": "alignments/s", "n_gpus": world, "steps": K, "warmup": Wm,
+           "ms_per_step": ms_total30, "higher_is_better": True, "scaling": "replicas", "vs_baseline": None, "dtype": "f32+f64", "data": "bundled TUM pair (tests/golden/frames.npz)",
+           "config": dict(res, workload="configs[0]: bundled standalone/rgb-d pair 1 -> 3, 640x480, single level, Cauchy(1), stride 30, Ceres-default LM; one pair at a time (latency)",
+                          iterations_stride1=S[0][0]["iterations"], l2="one pair: inputs (1.5 MB) are L2-resident by construction; this line is a latency, not a bandwidth, measurement"),
+           "e2e": {"value": 1e3 / ms_e, "unit": "alignments/s", "h2d_bytes_per_step": int(bgr.nbytes + dep.nbytes), "d2h_bytes_per_step": 7 * 8 + 48, "ms_per_step": ms_e},
+           "gpu_launches": int(launches), "clocks": clocks,
+           "roofline": _roofline(pe, prof["solve_ms"] / max(1, prof["n_solve"]), peak, peak_src, "ea_k_solve_batch<512,cluster 8> (stride 1)"),
+           "cpu_baseline": cpu}
+    fs.close(); ctx.close()
+    return _finish(out) if rank == 0 else 0
+
+
+# ------------------------------------------------------------------------------------------------------------ config 3
+def config3(args, env):
+    torch, ea, dist, dev, rank, world = env["torch"], env["ea"], env["dist"], env["dev"], env["rank"], env["world"]
+    import synth
+    from edge_alignment_b200 import sharding
+    N_TOTAL = args.pairs or 4096
+    b, e = sharding.shard_range(N_TOTAL, rank, world)
+    n = e - b
+    K, Wm = args.steps, args.warmup
+    # pair p = frames 0 and 1 of the 2-frame sequence with seed p (every pair has its own scene and motion)
+    bgr = torch.empty((2, n, 480, 640, 3), dtype=torch.uint8, device=dev); dep = torch.empty((2, n, 480, 640), dtype=torch.uint16, device=dev)
+    gt = []
+    for i in range(n):
+        Rw, tw = synth.trajectory(2, 77000 + b + i, max_rot_deg=2.5, max_trans=0.05)
+        bb, dd = synth.render(Rw, tw, 77000 + b + i, device=dev)
+        bgr[:, i] = bb; dep[:, i] = dd
+        gt.append(synth.relative_pose(Rw, tw, 0, 1))
+    torch.cuda.synchronize()
+    ctx = ea.Context(env["local_rank"]); stream = torch.cuda.current_stream(); ctx.set_stream(stream.cuda_stream)
+    fs = ea.FrameSet(ctx, ea.frame_params(n_levels=3), 2 * n)
+    sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=0.1)
+    ref_slots = np.arange(n, dtype=np.int32); now_slots = np.arange(n, 2 * n, dtype=np.int32)
+
+    def step():
+        fs.preprocess_device(ref_slots, bgr[0].data_ptr(), dep[0].data_ptr(), ea.ROLE_REF)
+        fs.preprocess_device(now_slots, bgr[1].data_ptr(), 0, ea.ROLE_NOW)
+        return ctx.solve_batch(fs, ref_slots, fs, now_slots, None, sp)
+
+    for _ in range(Wm):
+        step()
+    env["barrier"]()
+    env["sampler"].begin()
+    ctx.profile_enable(True); ctx.profile_read()
+    l0 = ctx.launch_count()
+    e0, e1 = _events(torch)
+    e0.record(stream)
+    for _ in range(K):
+        poses, S = step()
+    e1.record(stream)
+    env["barrier"]()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read(); ctx.profile_enable(False)
+    launches = ctx.launch_count() - l0
+    clocks = env["sampler"].stop()
+    ms = sharding.reduce_max(ms, dist, dev)
+    pe = sum(s["n_residuals"] * s["evaluations"] for Sp in S for s in Sp)
+    ok = sum(1 for i in range(n) if 2 * np.degrees(np.arccos(min(1.0, abs(float(np.dot(poses[i][:4], gt[i][:4])))))) < 1.0 and np.abs(poses[i][4:] - gt[i][4:]).max() < 0.03)
+    ok = sharding.reduce_sum(ok, dist, dev)
+    # e2e: host frames through the host entry points in chunks of 256 pairs, poses read back per chunk
+    e2e = None
+    if not args.no_e2e:
+        CH = min(256, n)
+        hb = torch.empty((2, n, 480, 640, 3), dtype=torch.uint8, pin_memory=True); hb.copy_(bgr)
+        hd = torch.empty((n, 480, 640), dtype=torch.uint16, pin_memory=True); hd.copy_(dep[0])
+        hbn, hdn = hb.numpy(), hd.numpy()
+
+        def e2e_step():
+            for c0 in range(0, n, CH):
+                c1 = min(n, c0 + CH)
+                fs.preprocess_host(ref_slots[c0:c1], hbn[0, c0:c1], hdn[c0:c1], ea.ROLE_REF)
+                fs.preprocess_host(now_slots[c0:c1], hbn[1, c0:c1], None, ea.ROLE_NOW)
+                ctx.solve_batch(fs, ref_slots[c0:c1], fs, now_slots[c0:c1], None, sp)
+        e2e_step()
+        env["barrier"]()
+        e0.record(stream)
+        for _ in range(max(1, K // 2)):
+            e2e_step()
+        e1.record(stream)
+        env["barrier"]()
+        ms_e = sharding.reduce_max(e0.elapsed_time(e1) / max(1, K // 2), dist, dev)
+        e2e = {"value": N_TOTAL / (ms_e * 1e-3), "unit": "alignments/s", "h2d_bytes_per_step": int(n * (2 * 640 * 480 * 3 + 640 * 480 * 2)),
+               "d2h_bytes_per_step": int(n * (7 * 8 + 3 * 48)), "ms_per_step": ms_e, "note": "synchronous chunks of %d pairs (no upload / solve overlap)" % CH}
+        del hb, hd
+    if rank != 0:
+        return 0
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        th = O.hardware_threads(); m = max(2, min(th, n, 32))
+        hbs, hds = bgr[:, :m].cpu().numpy(), dep[:, :m].cpu().numpy()
+        cfg = O.pair_cfg(640, 480, synth.TUM_K, n_levels=3, stride=1); opts = O.default_options(loss_type=O.LOSS_HUBER, loss_scale=0.1)
+        pairs = [(i, m + i) for i in range(m)]                       # flat index = t * m + i
+        v_all, v_solve_all, sec = _cpu_pairs(O, hbs, hds, pairs, cfg, opts, th)
+        v_1, v_solve_1, sec1 = _cpu_pairs(O, hbs, hds, pairs[:2], cfg, opts, 1)
+        cpu = {"value": v_all, "unit": "alignments/s", "cores": th, "kind": "port", "sample": "%d of the pairs, %.1f s" % (m, sec + sec1),
+               "solve_only_alignments_per_s": v_solve_all, "one_thread_alignments_per_s": v_1, "one_thread_solve_only_alignments_per_s": v_solve_1}
+    peak, peak_src = env["peak"]
+    out = {"metric": "frame-pair alignments/sec at 640x480", "value": N_TOTAL * K / (ms * 1e-3), "unit": "alignments/s", "n_gpus": world, "steps": K, "warmup": Wm,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+           "config": {"workload": "configs[2]: batch of %d independent synthetic 640x480 frame pairs, 3-level pyramid, Huber(0.1), stride 1, Ceres-default LM" % N_TOTAL,
+                      "pairs_per_gpu": n, "l2": "every step reads %d MB of frames per GPU (> 126 MB L2)" % (n * (2 * 921600 + 614400) // 2**20),
+                      "pairs_within_1deg_3cm_of_ground_truth": int(ok), "point_evals_per_s": world * pe * K / (ms * 1e-3)},
+           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+           "roofline": _roofline(pe, prof["solve_ms"] / max(1, prof["n_solve"]), peak, peak_src, "ea_k_solve_batch",
+                                 extra={"preprocess_ms_per_step": prof["preprocess_ms"] / max(1, K)}),
+           "cpu_baseline": cpu}
+    fs.close(); ctx.close()
+    return _finish(out)
+
+
+# ------------------------------------------------------------------------------------------------------------ config 4
+def config4(args, env):
+    torch, ea, dist, dev, rank, world = env["torch"], env["ea"], env["dist"], env["dev"], env["rank"], env["world"]
+    import synth
+    from edge_alignment_b200 import sharding
+    w, h, NL, INTERVAL = 1280, 720, 4, 10
+    Kc = (1050.0, 1050.0, (w - 1) / 2.0, (h - 1) / 2.0)
+    S = args.streams if args.streams != 592 else 148          # one stream per SM unless asked otherwise
+    K, Wm = args.steps, args.warmup
+    T = Wm + K + 1; NF = min(T, 12)
+    bgr = torch.empty((NF, S, h, w, 3), dtype=torch.uint8, device=dev); dep = torch.empty((NF, S, h, w), dtype=torch.uint16, device=dev)
+    for s in range(S):
+        Rw, tw = synth.trajectory(NF, 5000 + rank * 100003 + s, max_rot_deg=0.6, max_trans=0.012)
+        bb, dd = synth.render(Rw, tw, 5000 + rank * 100003 + s, w, h, Kc, device=dev, cell=0.02, hole_frac=0.1, chunk=4)
+        bgr[:, s] = bb; dep[:, s] = dd
+    torch.cuda.synchronize()
+    ctx = ea.Context(env["local_rank"]); stream = torch.cuda.current_stream(); ctx.set_stream(stream.cuda_stream)
+    fp = ea.frame_params(width=w, height=h, n_levels=NL, fx=Kc[0], fy=Kc[1], cx=Kc[2], cy=Kc[3], max_points=w * h // 2)
+    sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=0.1)
+    tr = ea.Tracker(ctx, fp, sp, S, INTERVAL); tr.set_inputs_ready(True)
+    fb, fd = w * h * 3 * S, w * h * 2 * S
+    from bench import ring_index
+
+    def run(first, last):
+        for t in range(first, last):
+            f = ring_index(t, NF)
+            tr.step_device(bgr.data_ptr() + f * fb, dep.data_ptr() + f * fd)
+    tr.reset(); run(0, Wm + 1)
+    env["barrier"]()
+    env["sampler"].begin()
+    ctx.profile_enable(True); ctx.profile_read()
+    l0 = ctx.launch_count()
+    e0, e1 = _events(torch)
+    e0.record(stream); run(Wm + 1, T); e1.record(stream)
+    env["barrier"]()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read(); ctx.profile_enable(False)
+    launches = ctx.launch_count() - l0
+    clocks = env["sampler"].stop()
+    ms = sharding.reduce_max(ms, dist, dev)
+    # accounting pass
+    tr.reset(); run(0, Wm + 1)
+    pe = 0; npts = 0; its = 0; ns = 0
+    for t in range(Wm + 1, T):
+        run(t, t + 1)
+        _, Ss = tr.poses()
+        for i, s in enumerate(Ss):
+            pe += s.n_residuals * s.evaluations; its += s.iterations; ns += 1
+            if i % NL == 0:
+                npts += s.n_residuals
+    e2e = None
+    if not args.no_e2e:
+        NE = min(NF, 6)
+        hb = torch.empty((NE, S, h, w, 3), dtype=torch.uint8, pin_memory=True); hb.copy_(bgr[:NE])
+        hd = {f: torch.empty((S, h, w), dtype=torch.uint16, pin_memory=True) for f in sorted({ring_index(t, NE) for t in range(T) if t % INTERVAL == 0})}
+        for f, buf in hd.items():
+            buf.copy_(dep[f])
+        torch.cuda.synchronize()
+        bptr = lambda t: hb.data_ptr() + ring_index(t, NE) * fb
+        dptr = lambda t: hd[ring_index(t, NE)].data_ptr() if t % INTERVAL == 0 else 0
+        tr.reset()
+        for t in range(0, Wm + 1):
+            tr.step_host(bptr(t), dptr(t), fetch=True)
+        env["barrier"]()
+        e0.record(stream)
+        for t in range(Wm + 1, T):
+            tr.step_host(bptr(t), dptr(t), fetch=False)
+            if t > Wm + 1:
+                tr.wait(t - 1)
+        tr.wait(T - 1)
+        e1.record(stream)
+        env["barrier"]()
+        ms_e = sharding.reduce_max(e0.elapsed_time(e1), dist, dev)
+        n_key = sum(1 for t in range(Wm + 1, T) if t % INTERVAL == 0)
+        e2e = {"value": world * S * K / (ms_e * 1e-3), "unit": "alignments/s", "h2d_bytes_per_step": int((fb * K + fd * n_key) / K),
+               "d2h_bytes_per_step": int(S * (7 * 8 + NL * 48)), "ms_per_step": ms_e / K}
+        del hb, hd
+    if rank != 0:
+        return 0
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        th = O.hardware_threads(); m = max(1, min(th, S, 16))
+        hbs, hds = bgr[:2, :m].cpu().numpy(), dep[:2, :m].cpu().numpy()
+        cfg = O.pair_cfg(w, h, Kc, n_levels=NL, stride=1); opts = O.default_options(loss_type=O.LOSS_HUBER, loss_scale=0.1)
+        pairs = [(i, m + i) for i in range(m)]
+        v_all, v_solve_all, sec = _cpu_pairs(O, hbs, hds, pairs, cfg, opts, th)
+        v_1, v_solve_1, sec1 = _cpu_pairs(O, hbs, hds, pairs[:1], cfg, opts, 1)
+        cpu = {"value": v_all, "unit": "alignments/s", "cores": th, "kind": "port", "sample": "%d frame-to-frame pairs of the same sequences, %.1f s" % (m, sec + sec1),
+               "solve_only_alignments_per_s": v_solve_all, "one_thread_alignments_per_s": v_1, "one_thread_solve_only_alignments_per_s": v_solve_1}
+    peak, peak_src = env["peak"]
+    out = {"metric": "frame-pair alignments/sec at 1280x720", "value": world * S * K / (ms * 1e-3), "unit": "alignments/s", "n_gpus": world, "steps": K, "warmup": Wm,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+           "config": {"workload": "configs[3]: synthetic 1280x720 RGB-D sequences with dense edges, frame-to-keyframe tracking (key frame every %d frames), 4-level coarse-to-fine LM, Huber(0.1), stride 1" % INTERVAL,
+                      "streams_per_gpu": S, "mean_edge_points_per_frame_level0": npts / max(1, K * S),
+                      "l2": "every step reads %d MB of new frames per GPU (> 126 MB L2)" % (fb // 2**20), "mean_lm_iterations_per_level": its / max(1, ns),
+                      "point_evals_per_s": world * pe / (ms * 1e-3)},
+           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+           "roofline": _roofline(pe / max(1, K), prof["solve_ms"] / max(1, prof["n_solve"]), peak, peak_src, "ea_k_solve_batch",
+                                 extra={"preprocess_ms_per_step": prof["preprocess_ms"] / max(1, K)}),
+           "cpu_baseline": cpu}
+    tr.close(); ctx.close()
+    return _finish(out)
+
+
+# ------------------------------------------------------------------------------------------------------------ config 5
+def config5(args, env):
+    torch, ea, dist, dev, rank, world = env["torch"], env["ea"], env["dist"], env["dev"], env["rank"], env["world"]
+    import synth
+    w, h = 3840, 2160
+    Kc = (3150.0, 3150.0, (w - 1) / 2.0, (h - 1) / 2.0)
+    K, Wm = args.steps, args.warmup
+    Rw, tw = synth.trajectory(2, 9, max_rot_deg=0.3, max_trans=0.005)
+    b, d = synth.render(Rw, tw, 9, w, h, Kc, device=dev, cell=0.012, hole_frac=0.1, chunk=1)      # every rank renders the same pair (DT replicated)
+    torch.cuda.synchronize()
+    ctx = ea.Context(env["local_rank"]); stream = torch.cuda.current_stream(); ctx.set_stream(stream.cuda_stream)
+    fp = ea.frame_params(width=w, height=h, n_levels=1, fx=Kc[0], fy=Kc[1], cx=Kc[2], cy=Kc[3], max_points=w * h // 2)
+    fs = ea.FrameSet(ctx, fp, 2)
+    slots = np.array([0, 1], np.int32)
+    e0, e1 = _events(torch)
+    fs.preprocess_device(slots, b.data_ptr(), d.data_ptr(), ea.ROLE_BOTH)
+    env["barrier"]()
+    e0.record(stream)
+    for _ in range(3):
+        fs.preprocess_device(slots, b.data_ptr(), d.data_ptr(), ea.ROLE_BOTH)
+    e1.record(stream)
+    env["barrier"]()
+    pre_ms = e0.elapsed_time(e1) / 3
+    n_pts = fs.num_points(0)
+    sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=0.1)
+    ident = None
+    if world > 1:
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t = torch.tensor(list(ea.Shard.unique_id()), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        ident = bytes(t.cpu().tolist())
+    results = {}
+    from edge_alignment_b200 import sharding
+    for mode in ("kernel", "nccl"):
+        os.environ["EA_SHARD_MODE"] = mode
+        ident_m = ident
+        if world > 1 and mode == "nccl":          # a second communicator for the second shard object
+            t = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                t = torch.tensor(list(ea.Shard.unique_id()), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, 0)
+            ident_m = bytes(t.cpu().tolist())
+        sh = ea.Shard(ctx, ident_m, rank, world)
+        for _ in range(Wm):
+            pose, s = sh.solve(fs, 0, fs, 1, None, sp)
+        env["barrier"]()
+        if mode == "kernel":
+            env["sampler"].begin()
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        profs = []
+        for _ in range(K):
+            pose, s = sh.solve(fs, 0, fs, 1, None, sp)
+            profs.append(sh.profile())
+        e1.record(stream)
+        env["barrier"]()
+        ms = sharding.reduce_max(e0.elapsed_time(e1) / K, dist, dev)
+        pr = {k: float(np.mean([p[k] for p in profs])) for k in ("evaluations", "solve_ms", "eval_us", "grid_reduce_us", "allreduce_us", "lm_us")}
+        pr["in_kernel"] = profs[-1]["in_kernel"]; pr["launches_per_solve"] = (ctx.launch_count() - l0) / K
+        pr["us_per_evaluation_total"] = 1e3 * pr["solve_ms"] / max(1.0, pr["evaluations"])
+        results[mode] = {"ms_per_solve_host_to_host": ms, "device": pr, "pose": pose.tolist(), "iterations": s["iterations"], "final_cost": s["final_cost"],
+                         "termination": s["termination_name"], "n_residuals": s["n_residuals"]}
+        if mode == "kernel":
+            clocks = env["sampler"].stop()
+        sh.close()
+    # every rank must hold the same pose, bit for bit
+    same = True
+    if world > 1:
+        mine = torch.tensor(results["kernel"]["pose"], dtype=torch.float64, device=dev)
+        ref = mine.clone(); dist.broadcast(ref, 0)
+        flag = torch.tensor([1.0 if torch.equal(mine, ref) else 0.0], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item() == 1.0)
+    if rank != 0:
+        return 0
+    kern = results["kernel"]
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        hb, hd = b.cpu().numpy(), d.cpu().numpy()
+        t = time.perf_counter(); xyz, _ = O.get_aX(hb[0], hd[0], Kc); odt, _ = O.get_distance_transform(hb[1]); t_pre = time.perf_counter() - t
+        # bounded sample: every 16th point (the oracle needs ~1 us per point-evaluation on one core)
+        t = time.perf_counter(); _, so, _ = O.solve(xyz, odt, Kc, ea.IDENTITY, stride=16, options=O.default_options(loss_type=O.LOSS_HUBER, loss_scale=0.1)); t_s = time.perf_counter() - t
+        per_pe = t_s / max(1, so["n_residuals"] * (so["jac_evals"] + so["res_evals"]))
+        est = per_pe * kern["n_residuals"] * 2 * kern["device"]["evaluations"]
+        cpu = {"value": 1.0 / est, "unit": "alignments/s (solve only, extrapolated)", "cores": 1, "kind": "port",
+               "sample": "the same pair at point stride 16 (%.1f s solve, %.1f s preprocessing): %.2e s per point-evaluation on one core, scaled to %d points x %d evaluations x 2 passes"
+                         % (t_s, t_pre, per_pe, kern["n_residuals"], int(kern["device"]["evaluations"])), "preprocessing_s_both_frames": t_pre}
+    peak, peak_src = env["peak"]
+    pe = kern["n_residuals"] * kern["device"]["evaluations"]
+    out = {"metric": "frame-pair alignments/sec at 3840x2160 (one pair, point-sharded)", "value": 1e3 / kern["ms_per_solve_host_to_host"], "unit": "alignments/s",
+           "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": kern["ms_per_solve_host_to_host"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32+f64", "data": "synthetic",
+           "config": {"workload": "configs[4]: one synthetic 3840x2160 pair, single level, Huber(0.1), stride 1, Ceres-default LM, points sharded over the ranks, DT replicated",
+                      "edge_points": int(n_pts), "points_per_rank": int(n_pts // world), "preprocess_ms_both_frames": pre_ms, "ranks_bit_identical": same,
+                      "l2": "33 MB distance transform + %d MB of points per rank per evaluation; L2 126 MB" % (n_pts * 8 // world // 2**20),
+                      "in_kernel_allreduce": kern, "nccl_per_evaluation": results["nccl"],
+                      "speedup_in_kernel_over_nccl": results["nccl"]["device"]["solve_ms"] / kern["device"]["solve_ms"]},
+           "e2e": {"value": 1e3 / (kern["ms_per_solve_host_to_host"]), "unit": "alignments/s", "h2d_bytes_per_step": 7 * 8, "d2h_bytes_per_step": 7 * 8 + 48,
+                   "ms_per_step": kern["ms_per_solve_host_to_host"], "note": "ea_shard_solve takes the pose from and returns it to host memory on every call; frames are preprocessed once (preprocess_ms_both_frames)"},
+           "gpu_launches": int(round(kern["device"]["launches_per_solve"] * K)), "clocks": clocks,
+           "roofline": _roofline(pe / world, kern["device"]["solve_ms"], peak, peak_src, "k_shard_solve (persistent, cooperative)",
+                                 extra={"us_per_evaluation": {k: kern["device"][k] for k in ("eval_us", "grid_reduce_us", "allreduce_us", "lm_us", "us_per_evaluation_total")}}),
+           "cpu_baseline": cpu}
+    fs.close(); ctx.close()
+    return _finish(out)
+
+
+WORKLOADS = {"config1": config1, "config3": config3, "config4": config4, "config5": config5}
