@@ -681,7 +681,7 @@ int ea_probe_gather_device(ea_context* c, int n, ea_frameset* ref, const int32_t
 
 int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now,
                                   const int32_t* d_now_slots, double* d_poses7, const int32_t* d_pose_index,
-                                  const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries) {
+                                  const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries, bool tail_helpers) {
   if (!c || !d_ref_slots || !d_now_slots || !d_poses7) return ea_fail(EA_ERR_INVALID_ARG, "null argument");
   if (n <= 0) return EA_OK;
   EaSolveArgs A;
@@ -699,7 +699,9 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
   // persistent CTA per pair (no scheduling overhead, best L1 locality).
   if (cluster == 0) cluster = auto_cluster(c, n, 0);
   A.debug = c->d_debug;
-  A.boards = static_cast<EaHelpBoard*>(c->d_boards);
+  // tail helpers: CTAs that find the work queue empty serve the ones still solving.  They shorten the launch, not the work:
+  // a caller that has other kernels ready to take over the idle SMs (the tracker's overlapped preprocessing) turns them off.
+  A.boards = tail_helpers ? static_cast<EaHelpBoard*>(c->d_boards) : nullptr;
   e = ea_launch_solve_batch(A, cluster, c->sm_count, c->stream);
   if (c->d_debug && e == cudaSuccess) {   // development aid: synchronous read-back of the cycle counters
     const int grid = std::min(n, c->sm_count);

@@ -161,7 +161,7 @@ int ea_ensure_tmp(ea_context* c, size_t bytes);
 extern "C" int ea_check_solve_params(const ea_solve_params* sp);   // shared argument validation of every solve entry point
 int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now,
                                    const int32_t* d_now_slots, double* d_poses7, const int32_t* d_pose_index,
-                                   const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries);
+                                   const int32_t* d_order, const ea_solve_params* sp, ea_summary* d_summaries, bool tail_helpers = true);
 cudaError_t ea_launch_order_by_work(const ea_summary* d_summaries, int n, int n_levels, int32_t* d_order, cudaStream_t stream);
 int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uint8_t* d_bgr, const void* d_depth, int roles,
                        const uint8_t* d_mask = nullptr, const uint8_t* d_now_mask = nullptr, cudaStream_t stream = nullptr);

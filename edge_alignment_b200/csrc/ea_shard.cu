@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
   __shared__ unsigned long long s_ticket;
   __shared__ int s_stop;
   __shared__ EaLmState s_lm;      // the LM state of the CTA that drew the last ticket (global memory between evaluations)
+  __shared__ uint2 stage[2][THREADS];   // cp.async staging of the point stream (ea_eval_slice)
   static_assert(sizeof(EaLmState) % 8 == 0, "EaLmState is copied as 8-byte words");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = j_end - j_begin;
@@ -239,7 +240,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
       for (int i = 0; i < int(sizeof(EaPose) / 8); ++i) dst[i] = __ldcg(src + i);
     }
     if (xyz) ea_eval_slice<true, THREADS>(rd.pts, dt_pad, affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart, EA_ALTERNATE_SWEEP && !(e & 1));
-    else ea_eval_slice<false, THREADS>(rd.pts, dt_pad, affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart, EA_ALTERNATE_SWEEP && !(e & 1));
+    else {
+      const bool rev = EA_ALTERNATE_SWEEP && !(e & 1);
+      ea_eval_slice<false, THREADS>(rd.pts, dt_pad, affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart, rev, &stage[0][0], e > 1, true, EA_ALTERNATE_SWEEP ? !rev : rev);
+    }
     __syncthreads();
     if (warp == 0) {
       const double tot = ea_cta_total<THREADS / 32>(part, cpart, lane);

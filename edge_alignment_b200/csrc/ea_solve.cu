@@ -61,6 +61,11 @@ struct EaHelpBoard {                          // one per persistent CTA; zeroed 
 };
 
 struct EaSolveSmem {
+  // the kernel's arguments, for the boss functions: a __grid_constant__ parameter whose address is handed to a non-inlined
+  // function is copied to LOCAL memory first, and every access from the serial LM section then misses the L1 that the
+  // evaluation loop has just swept (measured: the LM step was ~4x slower than its dependency chains).  Shared memory is not
+  // evicted.  The inlined hot path keeps reading A from the constant bank.
+  EaSolveArgs args;
   EaMsg msg[2];
   double part[EA_MAX_CHUNKS][EA_SOLVE_WARPS][EA_NSUM];     // per chunk, per warp: lane-slot sums
   double cpart[EA_MAX_CHUNKS][EA_SOLVE_WARPS];             // per chunk, per warp: cost
@@ -213,10 +218,12 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
     }
   };
   unsigned g = 0;
+  if (tid == 0) S.args = A;
+  __syncthreads();
   if (boss) {
     EaMsg m;
     S.help_epoch = 0; S.help_fail = 0;
-    ea_boss_next(A, S, m, true);
+    ea_boss_next(S.args, S, m, true);
     if (helpers_on && m.cmd != EA_CMD_EXIT) { *reinterpret_cast<volatile int*>(&my_board->busy) = 1; __threadfence(); }
     publish(m, 0);
   }
@@ -271,7 +278,13 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
           if (!ok && lane == 0) S.help_fail = 1;
           for (int c = 0; c < cb; ++c) tot += __ldcg(&my_board->chunk[c][lane]);
         }
-        for (int c = cb; c < K; ++c) tot += ea_cta_total<THREADS / 32>(S.part[c], S.cpart[c], lane);
+        {   // the owner's chunks: four independent 16-term chains (unrolled so that they overlap), added in chunk order
+          double ct[EA_MAX_CHUNKS];
+#pragma unroll
+          for (int c = 0; c < EA_MAX_CHUNKS; ++c) ct[c] = (c >= cb && c < K) ? ea_cta_total<THREADS / 32>(S.part[c], S.cpart[c], lane) : 0.0;
+#pragma unroll
+          for (int c = 0; c < EA_MAX_CHUNKS; ++c) if (c >= cb && c < K) tot += ct[c];
+        }
         if (lane < EA_SUMS) S.sums[lane] = tot;
         if (lane == 27 && S.help_fail) S.sums[27] = 1.0;      // a helper went missing: the evaluation counts as failed
         __syncwarp();
@@ -280,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
         // (the number of registered helpers is read early: its latency hides behind the LM step)
         int reg = 0;
         if (helpers_on && lane == 31) reg = *reinterpret_cast<volatile int*>(&my_board->n_helpers);
-        ea_boss_step_warp(A, S, M, nm, lane);
+        ea_boss_step_warp(S.args, S, M, nm, lane);
         reg = __shfl_sync(0xffffffffu, reg, 31);
         if (helpers_on) {
           // share the next evaluation with the registered helpers when it has chunks to give away
@@ -315,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
         if (lane < EA_SUMS) S.sums[lane] = s;
         __syncwarp();
         EaMsg& nm = S.msg[(g + 1) & 1];
-        ea_boss_step_warp(A, S, M, nm, lane);
+        ea_boss_step_warp(S.args, S, M, nm, lane);
         for (unsigned r = 1; r < csize; ++r) {      // the other ranks' copies, word by word over DSMEM
           unsigned long long* dst = reinterpret_cast<unsigned long long*>(&cluster.map_shared_rank(&S, r)->msg[(g + 1) & 1]);
           for (int i = lane; i < int(sizeof(EaMsg) / 8); i += 32) dst[i] = reinterpret_cast<const unsigned long long*>(&nm)[i];
