@@ -212,18 +212,38 @@ __device__ __forceinline__ void ea_gather(const float* __restrict__ dt_pad, cons
 }
 // BiCubicInterpolator::Evaluate: for each grid row (== image column x_k) spline along c (== image y), then spline the
 // four results along r (== image x).  cv::normalize(NORM_MINMAX) is folded in: the interpolant is linear in the texels.
+//
+// Packed fp32x2 (sm_100 FFMA2 / FADD2 / FMUL2: two IEEE fp32 operations per issued instruction): the four column splines run
+// as two pairs, and the two row splines (of the values and of the v-derivatives) as one pair -- the same operations, in the
+// same order, with the same roundings as the scalar ea_cubic, in half the issue slots (the evaluation loop is issue-bound).
+__device__ __forceinline__ float2 ea_f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 ea_bc(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 ea_sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// two ea_cubic at once: value f and derivative d of the Catmull-Rom splines through (p0.x .. p3.x) and (p0.y .. p3.y) at x
+__device__ __forceinline__ void ea_cubic2(const float2 p0, const float2 p1, const float2 p2, const float2 p3, const float x, const float hx,
+                                          const float x15, float2& f, float2& d) {
+  const float2 a2 = __ffma2_rn(ea_bc(3.0f), ea_sub2(p1, p2), ea_sub2(p3, p0));
+  const float2 b2 = __ffma2_rn(ea_bc(4.0f), p2, __ffma2_rn(ea_bc(-5.0f), p1, __ffma2_rn(ea_bc(2.0f), p0, make_float2(-p3.x, -p3.y))));
+  const float2 c2 = ea_sub2(p2, p0);
+  f = __ffma2_rn(ea_bc(hx), __ffma2_rn(ea_bc(x), __ffma2_rn(ea_bc(x), a2, b2), c2), p1);
+  d = __ffma2_rn(ea_bc(x), __ffma2_rn(ea_bc(x15), a2, b2), __fmul2_rn(ea_bc(0.5f), c2));
+}
 __device__ __forceinline__ void ea_interp(const float (&t)[16], const float du, const float dv, const float2 affine, float& f, float& dfdu, float& dfdv) {
-  float f0, f1, f2, f3, d0, d1, d2, d3;
   const float hv = 0.5f * dv, v15 = 1.5f * dv, hu = 0.5f * du, u15 = 1.5f * du;
-  ea_cubic(t[0], t[4], t[8], t[12], dv, hv, v15, f0, d0);
-  ea_cubic(t[1], t[5], t[9], t[13], dv, hv, v15, f1, d1);
-  ea_cubic(t[2], t[6], t[10], t[14], dv, hv, v15, f2, d2);
-  ea_cubic(t[3], t[7], t[11], t[15], dv, hv, v15, f3, d3);
-  float fr, fdu;
-  ea_cubic(f0, f1, f2, f3, du, hu, u15, fr, fdu);
-  f = fmaf(fr, affine.x, affine.y);
-  dfdu = fdu * affine.x;
-  dfdv = ea_cubic_val(d0, d1, d2, d3, du, hu) * affine.x;
+  float2 f01, d01, f23, d23;      // columns 0,1 and 2,3: value and derivative along v
+  ea_cubic2(ea_f2(t[0], t[1]), ea_f2(t[4], t[5]), ea_f2(t[8], t[9]), ea_f2(t[12], t[13]), dv, hv, v15, f01, d01);
+  ea_cubic2(ea_f2(t[2], t[3]), ea_f2(t[6], t[7]), ea_f2(t[10], t[11]), ea_f2(t[14], t[15]), dv, hv, v15, f23, d23);
+  // along u: the value spline of {f_k, d_k} as one pair (-> value, d/dv), the derivative spline of f_k alone (-> d/du)
+  const float2 q0 = ea_f2(f01.x, d01.x), q1 = ea_f2(f01.y, d01.y), q2 = ea_f2(f23.x, d23.x), q3 = ea_f2(f23.y, d23.y);
+  const float2 a2 = __ffma2_rn(ea_bc(3.0f), ea_sub2(q1, q2), ea_sub2(q3, q0));
+  const float2 b2 = __ffma2_rn(ea_bc(4.0f), q2, __ffma2_rn(ea_bc(-5.0f), q1, __ffma2_rn(ea_bc(2.0f), q0, make_float2(-q3.x, -q3.y))));
+  const float2 c2 = ea_sub2(q2, q0);
+  const float2 val = __ffma2_rn(ea_bc(hu), __ffma2_rn(ea_bc(du), __ffma2_rn(ea_bc(du), a2, b2), c2), q1);
+  const float fdu = fmaf(du, fmaf(u15, a2.x, b2.x), 0.5f * c2.x);
+  f = fmaf(val.x, affine.x, affine.y);
+  const float2 g = __fmul2_rn(ea_f2(fdu, val.y), ea_bc(affine.x));
+  dfdu = g.x;
+  dfdv = g.y;
 }
 
 // Warp, project, bicubic lookup for one edge point.  dt = pixel (0,0) of the padded distance transform.

@@ -533,7 +533,7 @@ __device__ __forceinline__ uint2 ea_lds_u2(const unsigned saddr) {
 // evicted first).  Keeping more than one point per thread in flight was measured and lost (the evaluation phase is issue-
 // bound at 16 warps, profiles/r2_kernels.md).
 //
-// Chunks (chunk_iters > 0, a multiple of EA_FLUSH_EVERY): [j0, j1) starts on a chunk boundary and is cut every
+// Chunks (chunk_iters > 0, EA_FLUSH_EVERY times a power of two): [j0, j1) starts on a chunk boundary and is cut every
 // chunk_iters * THREADS residuals; chunk k of the range leaves its partials in part[k * part_stride ...] / cpart[k * ...]
 // (k counted from the range's LOW end in both directions).  A chunk's partials depend only on the chunk, not on the range it
 // was evaluated in: iterations are aligned to the chunk grid from the low end (forward) or from the virtual high end `vend`
@@ -628,12 +628,13 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
     if (((it + 1) & (EA_FLUSH_EVERY - 1)) == 0 || it + 1 == it1) {   // flush cadence on the virtual iteration grid, and at the end
       acc[27] = any_fail ? 1.0f : 0.0f;
       any_fail = false;
-      const int kc = chunk_iters > 0 ? (reverse ? n_chunks - 1 - it / chunk_iters : it / chunk_iters) : 0;   // chunk, from the range's low end
+      const int csh = 31 - __clz(chunk_iters | 1);                                                             // chunk_iters is a power of two
+      const int kc = chunk_iters > 0 ? (reverse ? n_chunks - 1 - (it >> csh) : (it >> csh)) : 0;              // chunk, from the range's low end
       double* slot = &part[size_t(kc) * part_stride + warp][lane];
       *slot += double(ea_warp_transpose_reduce(acc, lane));
 #pragma unroll
       for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
-      if (it + 1 == it1 || (chunk_iters > 0 && (it + 1) % chunk_iters == 0)) {   // the chunk is complete: its cost
+      if (it + 1 == it1 || (chunk_iters > 0 && ((it + 1) & (chunk_iters - 1)) == 0)) {   // the chunk is complete: its cost
         const double c64 = ea_warp_sum(cost64);
         if (lane == 0) cpart[size_t(kc) * part_stride + warp] = c64;
         cost64 = 0.0;
@@ -655,9 +656,13 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
 // many CTAs shared the evaluation (tail helpers, ea_solve.cu).
 #define EA_MAX_CHUNKS 4
 __device__ __forceinline__ int ea_chunking(const int n_res, const int threads, int& size) {
+  // size = unit << s with the smallest s that leaves at most EA_MAX_CHUNKS chunks (a power-of-two number of iterations per
+  // chunk: the loop finds its chunk with a shift)
   const int unit = threads * EA_FLUSH_EVERY;
   const int nb = (n_res + unit - 1) / unit;
-  size = ((nb + EA_MAX_CHUNKS - 1) / EA_MAX_CHUNKS) * unit;
+  int s = 0;
+  while (((nb + (1 << s) - 1) >> s) > EA_MAX_CHUNKS) ++s;
+  size = unit << s;
   return n_res > 0 ? (n_res + size - 1) / size : 1;
 }
 

@@ -193,6 +193,49 @@ def test_eval_parity(ea, ctx, fs5, frames, oracle, numpy_pins, a, b, stride):
             np.testing.assert_allclose(g["b"], o["b"], rtol=0, atol=2e-6 * (np.abs(o["J"]) * np.abs(o["residuals"])[:, None]).sum(0).max())
 
 
+def test_unfloored_residual_error_distribution(ea, ctx, fs5, frames, oracle, numpy_pins, capsys):
+    """north_star: per-point residuals within 1e-5 RELATIVE of the fp64 evaluation.  The other parity tests use a floor
+    (|delta| <= 1e-5 max(|r|, 0.05)); this one reports and bounds the UNFLOORED distribution on all 20 ordered pairs of the bundled
+    frames, every edge point, at a perturbed pose: the fraction of points within 1e-5 relative, the largest absolute error
+    among the small residuals (|r| < 0.05) and the largest relative error among the rest."""
+    O = oracle
+    K = frames["K"]
+    pose = numpy_pins["xpert"]
+    sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_TRIVIAL)
+    n_all = 0; n_in = 0; worst_abs_small = 0.0; worst_rel_big = 0.0; worst_abs = 0.0; n_zero = 0
+    edges = [0.0, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, np.inf]
+    hist = np.zeros(len(edges) - 1, np.int64)
+    for a in range(5):
+        xyz, _ = O.get_aX(frames["bgr"][a], frames["depth"][a], K)
+        for b in range(5):
+            if a == b:
+                continue
+            dt, _ = O.get_distance_transform(frames["bgr"][b])
+            g = ctx.eval(fs5, a, fs5, b, pose, sp, want_jac=False)
+            o = O.evaluate(xyz, dt, K, pose, stride=1, options=O.default_options(loss_type=O.LOSS_TRIVIAL))
+            ref = o["raw"]; err = np.abs(g["raw"] - ref)
+            nz = np.abs(ref) > 0
+            rel = err[nz] / np.abs(ref[nz])
+            hist += np.histogram(rel, bins=edges)[0]
+            n_zero += int((~nz).sum()); worst_abs = max(worst_abs, float(err.max()))
+            n_all += int(nz.sum()); n_in += int((rel <= 1e-5).sum())
+            small = np.abs(ref) < 0.05
+            worst_abs_small = max(worst_abs_small, float(err[small].max()))
+            big = nz & ~small
+            worst_rel_big = max(worst_rel_big, float((err[big] / np.abs(ref[big])).max()))
+            assert np.all(err[~nz] <= 2e-9)          # exact zeros of the reference (on-edge texels): within fp32 noise of the field
+    frac = n_in / n_all
+    with capsys.disabled():
+        print("\n[unfloored residual parity, 20 pairs, %d points (+%d exact zeros)] within 1e-5 relative: %.4f %%; relative-error histogram %s over bins %s; "
+              "max |err| for |r| < 0.05: %.3g; max relative error for |r| >= 0.05: %.3g; max |err| overall: %.3g"
+              % (n_all, n_zero, 100 * frac, hist.tolist(), edges, worst_abs_small, worst_rel_big, worst_abs))
+    # fp32 interpolation of a field normalised to [0, 1]: the absolute error is bounded by a few fp32 ulps of the local texel
+    # magnitude, so relative error only grows where the residual itself is tiny
+    assert frac > 0.995
+    assert worst_rel_big < 1e-5
+    assert worst_abs_small < 5e-8
+
+
 def test_eval_bypass_hooks_and_xyz_mode(ea, ctx, frames, oracle, numpy_pins):
     """Oracle-made inputs through ea_frameset_set_points / set_dt: pixel stream and fp32 XYZ stream."""
     O = oracle
