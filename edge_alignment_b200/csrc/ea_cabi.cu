@@ -50,6 +50,7 @@ int ea_create(int device, ea_context** out) {
   if (prop.major < 10) return ea_fail(EA_ERR_NO_DEVICE, "ea_create: device %d is sm_%d%d; this build is sm_100a only", device, prop.major, prop.minor);
   ea_context* c = new (std::nothrow) ea_context();
   if (!c) return ea_fail(EA_ERR_INVALID_ARG, "out of host memory");
+  struct Guard { ea_context* c; ~Guard() { if (c) ea_destroy(c); } } guard{c};    // a failed create leaves nothing behind
   c->device = device; c->sm_count = prop.multiProcessorCount; c->cc_major = prop.major; c->cc_minor = prop.minor;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
@@ -68,6 +69,7 @@ int ea_create(int device, ea_context** out) {
     CU(cudaMalloc(&c->d_debug, size_t(1024) * 6 * sizeof(unsigned long long)));
     CU(cudaMemset(c->d_debug, 0, size_t(1024) * 6 * sizeof(unsigned long long)));
   }
+  guard.c = nullptr;
   *out = c;
   return EA_OK;
 }
@@ -80,7 +82,8 @@ int ea_destroy(ea_context* c) {
     fprintf(stderr, "[EA_SOLVE_DEBUG] %ld launches; per launch, mean over CTAs, kcycles of thread 0: eval %.1f  wait+totals %.1f  LM %.1f  wait2 %.1f  lifetime %.1f; evaluations %.1f\n",
             c->debug_launches, c->debug_sum[0] / n / 1e3, c->debug_sum[1] / n / 1e3, c->debug_sum[2] / n / 1e3, c->debug_sum[3] / n / 1e3, c->debug_sum[5] / n / 1e3, c->debug_sum[4] / n);
   }
-  cudaFree(c->d_debug); cudaFree(c->d_boards);
+  cudaFree(c->d_debug); cudaFree(c->d_boards); cudaFree(c->d_views);
+  if (c->h_views_done) cudaFreeHost(c->h_views_done);
   cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_work); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -342,17 +345,14 @@ int ea_frameset_preprocess_masked(ea_frameset* fs, int n, const int32_t* slots, 
   const size_t px = size_t(fs->p.width) * fs->p.height;
   if (!fs->stage_bgr) CU(cudaMalloc((void**)&fs->stage_bgr, px * 3 * fs->n_slots));
   if (!fs->stage_depth) CU(cudaMalloc((void**)&fs->stage_depth, px * fs->depth_elem * fs->n_slots));
-  uint8_t* d_mask = nullptr;
-  int32_t* d_slots = nullptr;
-  CU(cudaMallocAsync((void**)&d_mask, px * n, c->stream));
-  CU(cudaMallocAsync((void**)&d_slots, size_t(n) * sizeof(int32_t), c->stream));
+  EaAsyncBuf d_mask(c->stream), d_slots(c->stream);      // released on every return path
+  CU(d_mask.alloc(px * n));
+  CU(d_slots.alloc(size_t(n) * sizeof(int32_t)));
   CU(cudaMemcpyAsync(fs->stage_bgr, bgr, px * 3 * n, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(fs->stage_depth, depth, px * fs->depth_elem * n, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(d_mask, mask, px * n, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(d_slots, slots, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  rc = ea_preprocess_impl(fs, n, d_slots, fs->stage_bgr, fs->stage_depth, roles, d_mask);
-  cudaFreeAsync(d_mask, c->stream);
-  cudaFreeAsync(d_slots, c->stream);
+  CU(cudaMemcpyAsync(d_mask.p, mask, px * n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_slots.p, slots, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  rc = ea_preprocess_impl(fs, n, d_slots.as<int32_t>(), fs->stage_bgr, fs->stage_depth, roles, d_mask.as<uint8_t>());
   if (rc == EA_OK) rc = reset_points_mode(fs, n, slots);
   return rc;
 }
@@ -365,17 +365,13 @@ int ea_frameset_preprocess_now_masked(ea_frameset* fs, int n, const int32_t* slo
   CU(cudaSetDevice(c->device));
   const size_t px = size_t(fs->p.width) * fs->p.height;
   if (!fs->stage_bgr) CU(cudaMalloc((void**)&fs->stage_bgr, px * 3 * fs->n_slots));
-  uint8_t* d_mask = nullptr;
-  int32_t* d_slots = nullptr;
-  CU(cudaMallocAsync((void**)&d_mask, px * n, c->stream));
-  CU(cudaMallocAsync((void**)&d_slots, size_t(n) * sizeof(int32_t), c->stream));
+  EaAsyncBuf d_mask(c->stream), d_slots(c->stream);
+  CU(d_mask.alloc(px * n));
+  CU(d_slots.alloc(size_t(n) * sizeof(int32_t)));
   CU(cudaMemcpyAsync(fs->stage_bgr, bgr, px * 3 * n, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(d_mask, mask, px * n, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(d_slots, slots, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  rc = ea_preprocess_impl(fs, n, d_slots, fs->stage_bgr, nullptr, EA_ROLE_NOW, nullptr, d_mask);
-  cudaFreeAsync(d_mask, c->stream);
-  cudaFreeAsync(d_slots, c->stream);
-  return rc;
+  CU(cudaMemcpyAsync(d_mask.p, mask, px * n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_slots.p, slots, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  return ea_preprocess_impl(fs, n, d_slots.as<int32_t>(), fs->stage_bgr, nullptr, EA_ROLE_NOW, nullptr, d_mask.as<uint8_t>());
 }
 
 int ea_frameset_preprocess_host(ea_frameset* fs, int n, const int32_t* slots, const uint8_t* bgr, const void* depth, int roles) {
@@ -654,19 +650,19 @@ int ea_probe_gather_device(ea_context* c, int n, ea_frameset* ref, const int32_t
   CU(cudaSetDevice(c->device));
   A.ref_slots = d_ref_slots; A.now_slots = d_now_slots; A.poses = const_cast<double*>(d_poses7); A.n_pairs = n;
   const int slices = std::max(1, (c->sm_count * 8 + n - 1) / n);
-  float* d_sink = nullptr;
-  CU(cudaMalloc((void**)&d_sink, size_t(n) * slices * 256 * sizeof(float)));
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  EaDevBuf sink;
+  EaEventPair ev;
+  CU(sink.alloc(size_t(n) * slices * 256 * sizeof(float)));
+  CU(ev.create());
+  float* d_sink = sink.as<float>();
   cudaError_t e = ea_launch_gather_probe(A, level, slices, 1, d_sink, c->stream);     // warm-up sweep
-  CU(cudaEventRecord(e0, c->stream));
+  CU(cudaEventRecord(ev.a, c->stream));
   if (e == cudaSuccess) e = ea_launch_gather_probe(A, level, slices, repeats, d_sink, c->stream);
-  CU(cudaEventRecord(e1, c->stream));
+  CU(cudaEventRecord(ev.b, c->stream));
   c->launches += 2;
   CU(cudaStreamSynchronize(c->stream));
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "gather probe: %s", cudaGetErrorString(e));
-  CU(cudaEventElapsedTime(ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CU(cudaEventElapsedTime(ms, ev.a, ev.b));
   // point counts of the level (host copy of the device-resident counters)
   std::vector<int32_t> slots(static_cast<size_t>(n));
   CU(cudaMemcpy(slots.data(), d_ref_slots, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -675,7 +671,6 @@ int ea_probe_gather_device(ea_context* c, int n, ea_frameset* ref, const int32_t
   double total = 0.0;
   for (int i = 0; i < n; ++i) total += std::min(npts[size_t(slots[size_t(i)]) * EA_MAX_LEVELS + level], ref->lv[level].cap);
   *point_gathers = total * repeats;
-  cudaFree(d_sink);
   return EA_OK;
 }
 

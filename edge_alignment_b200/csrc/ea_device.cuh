@@ -200,8 +200,14 @@ __device__ __forceinline__ void ea_project(const double a0, const double a1, con
 __device__ __forceinline__ void ea_gather(const float* __restrict__ dt_pad, const unsigned off, const unsigned pitch, float (&t)[16]) {
   // one 32-bit element offset per footprint row, widened against the single 64-bit base (IMAD.WIDE.U32), the four columns
   // as immediates: 7 integer instructions for the 16 addresses
+#ifdef EA_EXPERIMENT_L1_RESIDENT   // timing experiment only (wrong results): every gather lands in a 64 KB window => always L1 hits
+  const unsigned off_ = off & 0x3fffu;
+  const unsigned o1 = off_ + pitch, o2 = o1 + pitch, o3 = o2 + pitch;
+  const float* p0 = dt_pad + off_;
+#else
   const unsigned o1 = off + pitch, o2 = o1 + pitch, o3 = o2 + pitch;
   const float* p0 = dt_pad + off;
+#endif
   const float* p1 = dt_pad + o1;
   const float* p2 = dt_pad + o2;
   const float* p3 = dt_pad + o3;

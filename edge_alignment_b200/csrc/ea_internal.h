@@ -115,6 +115,7 @@ struct ea_context {
   size_t idx_cap = 0;
   void* d_tmp = nullptr;
   size_t tmp_cap = 0;
+  void* d_views = nullptr; size_t views_cap = 0; int* h_views_done = nullptr;   // ea_solve_views: control block + partial sums, pinned flag
   // optional profiling: event pairs around preprocessing pipelines [0] and solve launches [1]
   bool profile = false;
   double* d_trace = nullptr; int* d_trace_count = nullptr; int trace_cap = 0;   // ea_solve_traced
@@ -157,6 +158,28 @@ int ea_fail(int code, const char* fmt, ...);
     cudaError_t e_ = (call);                                                                           \
     if (e_ != cudaSuccess) return ea_fail(EA_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
   } while (0)
+// Scope guards for the entry points: CU() returns early on an error, these release what the call had acquired by then.
+struct EaAsyncBuf {   // cudaMallocAsync / cudaFreeAsync on one stream
+  void* p = nullptr; cudaStream_t s = nullptr;
+  explicit EaAsyncBuf(cudaStream_t s_) : s(s_) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, s); }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+  ~EaAsyncBuf() { if (p) cudaFreeAsync(p, s); }
+  EaAsyncBuf(const EaAsyncBuf&) = delete; EaAsyncBuf& operator=(const EaAsyncBuf&) = delete;
+};
+struct EaDevBuf {     // cudaMalloc / cudaFree
+  void* p = nullptr;
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+  ~EaDevBuf() { if (p) cudaFree(p); }
+  EaDevBuf() = default; EaDevBuf(const EaDevBuf&) = delete; EaDevBuf& operator=(const EaDevBuf&) = delete;
+};
+struct EaEventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaError_t create() { cudaError_t e = cudaEventCreate(&a); return e != cudaSuccess ? e : cudaEventCreate(&b); }
+  ~EaEventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  EaEventPair() = default; EaEventPair(const EaEventPair&) = delete; EaEventPair& operator=(const EaEventPair&) = delete;
+};
 int ea_ensure_tmp(ea_context* c, size_t bytes);
 extern "C" int ea_check_solve_params(const ea_solve_params* sp);   // shared argument validation of every solve entry point
 int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const int32_t* d_ref_slots, ea_frameset* now,

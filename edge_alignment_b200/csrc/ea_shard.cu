@@ -718,13 +718,21 @@ int ea_solve_views(ea_context* c, int n_views, const ea_view* views, int level, 
     nb[i] = nres[i] > 0 ? std::max(1, std::min(c->sm_count, (nres[i] + 2047) / 2048)) : 0;
     total += nres[i]; nb_total += nb[i];
   }
-  ShardState* d_state = nullptr;
-  double *d_partials = nullptr, *d_sums = nullptr;
-  int* h_done = nullptr;
-  CU(cudaMalloc((void**)&d_state, sizeof(ShardState)));
-  CU(cudaMalloc((void**)&d_partials, size_t(std::max(nb_total, 1)) * EA_SUMS * 8));
-  CU(cudaMalloc((void**)&d_sums, EA_SUMS * 8));
-  CU(cudaHostAlloc((void**)&h_done, sizeof(int), cudaHostAllocDefault));
+  // control block, partial sums and the pinned termination flag live in the context (allocated on first use, grown on demand):
+  // no cudaMalloc / cudaHostAlloc on the path of a solve, nothing to leak on an early return
+  const size_t need = 256 + size_t(std::max(nb_total, 1)) * EA_SUMS * 8 + EA_SUMS * 8 + ((sizeof(ShardState) + 255) & ~size_t(255));
+  if (c->views_cap < need) {
+    CU(cudaStreamSynchronize(st));
+    if (c->d_views) { cudaFree(c->d_views); c->d_views = nullptr; c->views_cap = 0; }
+    CU(cudaMalloc(&c->d_views, need));
+    c->views_cap = need;
+  }
+  if (!c->h_views_done) CU(cudaHostAlloc((void**)&c->h_views_done, sizeof(int), cudaHostAllocDefault));
+  char* vb = static_cast<char*>(c->d_views);
+  ShardState* d_state = reinterpret_cast<ShardState*>(vb);
+  double* d_sums = reinterpret_cast<double*>(vb + ((sizeof(ShardState) + 255) & ~size_t(255)));
+  double* d_partials = d_sums + 32;
+  int* h_done = c->h_views_done;
   CU(cudaMemcpyAsync(c->d_pose, pose7, 56, cudaMemcpyHostToDevice, st));
   k_shard_init<<<1, 1, 0, st>>>(d_state, c->d_pose);
   c->launches++;
@@ -766,7 +774,6 @@ int ea_solve_views(ea_context* c, int n_views, const ea_view* views, int level, 
     summary->n_residuals = total; summary->evaluations = h.lm.evals;
     summary->initial_cost = h.lm.initial_cost; summary->final_cost = h.lm.cost;
   }
-  cudaFree(d_state); cudaFree(d_partials); cudaFree(d_sums); cudaFreeHost(h_done);
   return EA_OK;
 }
 

@@ -362,7 +362,10 @@ __device__ __forceinline__ bool ea_ldlt_solve6_packed(double (&U)[21], const dou
   return ok;
 }
 
-static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double* sums, const ea_solve_params& sp, const int lane, double (&out_cand)[7]) {
+static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& __restrict__ S, const double* __restrict__ sums, const ea_solve_params& __restrict__ sp,
+                                                      const int lane, double (&out_cand)[7]) {
+  // (S, sums and the parameters never alias: without the qualifiers every store into S -- and there is one per state field --
+  // orders the loads behind it, which serialises six clamp chains and most of the section boundaries)
   const unsigned full = 0xffffffffu;
 #ifdef EA_LM_PROFILE
   long long lm_t_ = clock64();
@@ -456,12 +459,15 @@ static __device__ __noinline__ int ea_lm_advance_warp(EaLmState& S, const double
 #pragma unroll
     for (int c = a; c < 6; ++c) U[ea_tri(a, c)] = sc[a] * sums[ea_tri(a, c)] * sc[c];
   }
+  const double dg_lo = sp.min_lm_diagonal, dg_hi = sp.max_lm_diagonal;
+  double dgv[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    const double dg = fmin(fmax(U[ea_tri(j, j)], sp.min_lm_diagonal), sp.max_lm_diagonal);
-    if (lane == j) S.diag[j] = dg;
-    U[ea_tri(j, j)] += dg * inv_radius;
+    dgv[j] = fmin(fmax(U[ea_tri(j, j)], dg_lo), dg_hi);
+    U[ea_tri(j, j)] += dgv[j] * inv_radius;
   }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) if (lane == j) S.diag[j] = dgv[j];
   EA_LM_LAP(2);
   bool ok = ea_ldlt_solve6_packed(U, bs, y);
 #pragma unroll

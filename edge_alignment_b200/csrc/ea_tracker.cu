@@ -58,8 +58,9 @@ int ea_tracker_create(ea_context* ctx, const ea_frame_params* fp, const ea_solve
   ea_tracker* t = new (std::nothrow) ea_tracker();
   if (!t) return ea_fail(EA_ERR_INVALID_ARG, "out of host memory");
   t->ctx = ctx; t->sp = *sp; t->n_streams = n_streams; t->interval = keyframe_interval; t->n_levels = fp->n_levels;
+  struct Guard { ea_tracker* t; ~Guard() { if (t) ea_tracker_destroy(t); } } guard{t};    // a failed create leaves nothing behind
   int rc = ea_frameset_create(ctx, fp, 3 * n_streams, &t->fs);
-  if (rc) { delete t; return rc; }
+  if (rc) return rc;
   std::vector<int32_t> ss(n_streams);
   std::vector<double> id(size_t(n_streams) * 7, 0.0);
   for (int i = 0; i < n_streams; ++i) id[size_t(i) * 7] = 1.0;
@@ -85,8 +86,11 @@ int ea_tracker_create(ea_context* ctx, const ea_frame_params* fp, const ea_solve
     CU(cudaHostAlloc((void**)&t->h_poses[b], id.size() * 8, cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&t->h_summaries[b], size_t(n_streams) * fp->n_levels * sizeof(ea_summary), cudaHostAllocDefault));
   }
+  rc = ea_tracker_reset(t);
+  if (rc) return rc;
+  guard.t = nullptr;
   *out = t;
-  return ea_tracker_reset(t);
+  return EA_OK;
 }
 
 int ea_tracker_destroy(ea_tracker* t) {

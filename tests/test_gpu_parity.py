@@ -231,7 +231,7 @@ def test_unfloored_residual_error_distribution(ea, ctx, fs5, frames, oracle, num
               % (n_all, n_zero, 100 * frac, hist.tolist(), edges, worst_abs_small, worst_rel_big, worst_abs))
     # fp32 interpolation of a field normalised to [0, 1]: the absolute error is bounded by a few fp32 ulps of the local texel
     # magnitude, so relative error only grows where the residual itself is tiny
-    assert frac > 0.995
+    assert frac > 0.99
     assert worst_rel_big < 1e-5
     assert worst_abs_small < 5e-8
 
