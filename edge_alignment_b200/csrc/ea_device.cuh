@@ -53,7 +53,7 @@ struct EaPose {  // per-evaluation uniform transform, fp64
   //   EA_POINTS_XYZ:   a = (X, Y, Z), s = 1, B = I
   double A[9];
   double tt[3];
-  float t[3];        // translation, for y = p' - t in the Jacobian
+  float m2t[3];      // -2 t, for 2 (R X) = 2 p' - 2 t in the Jacobian
   float fx, fy, inv_fx, inv_fy;   // now-level intrinsics in fp32 (Jacobian)
   float cx, cy;      // now-level principal point (only the Jacobian's lever arm u' - cx uses it: fp32)
 };
@@ -90,13 +90,13 @@ __device__ __forceinline__ void ea_pose_setup(const double* x7, const EaLevelGeo
   P.tt[0] = now.fx * x7[4] + now.cx * x7[6];
   P.tt[1] = now.fy * x7[5] + now.cy * x7[6];
   P.tt[2] = x7[6];
-  P.t[0] = float(x7[4]); P.t[1] = float(x7[5]); P.t[2] = float(x7[6]);
+  P.m2t[0] = -2.0f * float(x7[4]); P.m2t[1] = -2.0f * float(x7[5]); P.m2t[2] = -2.0f * float(x7[6]);
   P.fx = float(now.fx); P.fy = float(now.fy); P.inv_fx = float(now.inv_fx); P.inv_fy = float(now.inv_fy);
   P.cx = float(now.cx); P.cy = float(now.cy);
 }
 
 struct EaPointEval {
-  float f, dfdu, dfdv;     // bicubic value and gradient (grid row == u, col == v: SEA:258)
+  float f, gu, gv;         // normalised bicubic value; gradient of the raw (pixel-unit) field (grid row == u, col == v: SEA:258)
   float ub, vb;            // u' - cx, v' - cy
   float pz, iz;            // z' and 1/z'
   bool fail;               // |z'| < 0.01  (utils.h:70-73)
@@ -120,11 +120,24 @@ __device__ __forceinline__ float ea_cubic_val(float p0, float p1, float p2, floa
   return fmaf(hx, fmaf(x, fmaf(x, a2, b2), c2), p1);
 }
 
-// floor(x) and x - floor(x): exact for |x| < 2^31 (F2I.FLOOR, I2F, one fp64 subtract, one narrowing).  Wild values
-// (only possible when the z-guard has already failed the evaluation) give unspecified but in-bounds indices.
+// floor(x) and x - floor(x), exact for |x| < 2^31, on the fp64 pipe alone: x + (2^52 + 2^51) rounded DOWN is that constant plus
+// floor(x), whose low mantissa word is floor(x) in two's complement (DADD.RM, DADD, DADD and one narrowing -- the F2I / I2F pair
+// it replaces runs on the quarter-rate conversion unit, four of them per point).  Wild values (only possible when the z-guard
+// has already failed the evaluation) give unspecified indices, which the caller clamps.
 __device__ __forceinline__ void ea_floor_frac(double x, int& i, float& frac) {
-  i = __double2int_rd(x);
-  frac = float(x - double(i));
+  const double magic = 6755399441055744.0;
+  const double t = __dadd_rd(x, magic);
+  i = __double2loint(t);
+  frac = float(x - (t - magic));
+}
+// 1 / x to within an ulp or two: hardware seed (2^-23) and one cubically convergent correction, r (1 + e + e^2) with e = 1 - x r.
+// No slow path: zero, infinite and denormal x give inf / NaN, which only a failed evaluation can meet.
+__device__ __forceinline__ double ea_rcp64(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);
+  return fma(r, e, r);
 }
 
 // Point stream element.  Pixel points are 8 bytes: integer pixel coordinates (images up to 65535 px a side) and the raw
@@ -163,10 +176,10 @@ __host__ __device__ __forceinline__ uint2 ea_pack_pixel_point(unsigned u, unsign
 
 // ---- one edge point in three stages: project (fp64) -> gather (16 texels) -> interpolate (fp32) ----------------------
 struct EaProj {
-  unsigned off;            // element offset of texel (floor(v') - 1, floor(u') - 1) from the padded image's first element
+  int off;                 // element offset of texel (floor(v') - 1, floor(u') - 1) from texel (-1, -1) of the image: iv * pitch + iu
   float du, dv;            // fractional offsets (from fp64)
   float ub, vb, pz, iz;    // u' - cx, v' - cy, z', 1/z'
-  bool fail;               // |z'| < 0.01  (utils.h:70-73)
+  int zm;                  // high word of |z'| - 0.01: negative <=> |z'| < 0.01, the evaluation fails (utils.h:70-73)
 };
 // (a0, a1, a2) = (u, v, raw depth) or (X, Y, Z)
 template <bool XYZ>
@@ -183,34 +196,40 @@ __device__ __forceinline__ void ea_project(const double a0, const double a1, con
     q1 = fma(Z, fma(P.A[3], a0, fma(P.A[4], a1, P.A[5])), P.tt[1]);
     q2 = fma(Z, fma(P.A[6], a0, fma(P.A[7], a1, P.A[8])), P.tt[2]);
   }
-  r.fail = (q2 < 0.01) && (q2 > -0.01);
-  const double iz = 1.0 / q2;
+  // the sign of an IEEE difference is exact, so this is q2 < 0.01 && q2 > -0.01 to the last bit; a running integer minimum of
+  // it is all the evaluation loop keeps of the z-guard
+  r.zm = __double2hiint(fabs(q2) - 0.01);
+  const double iz = ea_rcp64(q2);
   const double u = q0 * iz, v = q1 * iz;
   int iu, iv;
   ea_floor_frac(u, iu, r.du);
   ea_floor_frac(v, iv, r.dv);
-  // the conversion saturates; the clamp keeps the 4x4 footprint inside the padded image for any input (NaN -> 0)
+  // the clamp keeps the 4x4 footprint inside the padded image for any input
   iu = min(max(iu, 1 - EA_DT_PAD), W + 1);
   iv = min(max(iv, 1 - EA_DT_PAD), H + 1);
-  r.off = unsigned(iv + (EA_DT_PAD - 1)) * unsigned(pitch) + unsigned(iu + (EA_DT_PAD - 1));
+  r.off = iv * pitch + iu;
   r.ub = float(u) - P.cx; r.vb = float(v) - P.cy;
   r.pz = float(q2); r.iz = float(iz);
 }
-// t[4 * row + col] = dt(floor(v') - 1 + row, floor(u') - 1 + col) with Grid2D clamp-to-edge (through the padding)
-__device__ __forceinline__ void ea_gather(const float* __restrict__ dt_pad, const unsigned off, const unsigned pitch, float (&t)[16]) {
-  // one 32-bit element offset per footprint row, widened against the single 64-bit base (IMAD.WIDE.U32), the four columns
-  // as immediates: 7 integer instructions for the 16 addresses
+// The gather base of a padded distance transform whose FIRST element is dt_pad: texel (-1, -1) of the image.
+__device__ __forceinline__ const float* ea_gather_base(const float* dt_pad, const int pitch) {
+  return dt_pad + size_t(EA_DT_PAD - 1) * size_t(pitch) + (EA_DT_PAD - 1);
+}
+// t[4 * row + col] = dt(floor(v') - 1 + row, floor(u') - 1 + col) with Grid2D clamp-to-edge (through the padding).
+// base = ea_gather_base(...), off = EaProj::off
+__device__ __forceinline__ void ea_gather(const float* __restrict__ base, const int off, const int pitch, float (&t)[16]) {
+  // one 32-bit element offset per footprint row, widened against the single 64-bit base (IMAD.WIDE), the four columns as
+  // immediates: 7 integer instructions for the 16 addresses
 #ifdef EA_EXPERIMENT_L1_RESIDENT   // timing experiment only (wrong results): every gather lands in a 64 KB window => always L1 hits
-  const unsigned off_ = off & 0x3fffu;
-  const unsigned o1 = off_ + pitch, o2 = o1 + pitch, o3 = o2 + pitch;
-  const float* p0 = dt_pad + off_;
+  const int off_ = off & 0x3fff;
 #else
-  const unsigned o1 = off + pitch, o2 = o1 + pitch, o3 = o2 + pitch;
-  const float* p0 = dt_pad + off;
+  const int off_ = off;
 #endif
-  const float* p1 = dt_pad + o1;
-  const float* p2 = dt_pad + o2;
-  const float* p3 = dt_pad + o3;
+  const int o1 = off_ + pitch, o2 = o1 + pitch, o3 = o2 + pitch;
+  const float* p0 = base + off_;
+  const float* p1 = base + o1;
+  const float* p2 = base + o2;
+  const float* p3 = base + o3;
   t[0] = __ldg(p0); t[1] = __ldg(p0 + 1); t[2] = __ldg(p0 + 2); t[3] = __ldg(p0 + 3);
   t[4] = __ldg(p1); t[5] = __ldg(p1 + 1); t[6] = __ldg(p1 + 2); t[7] = __ldg(p1 + 3);
   t[8] = __ldg(p2); t[9] = __ldg(p2 + 1); t[10] = __ldg(p2 + 2); t[11] = __ldg(p2 + 3);
@@ -234,55 +253,47 @@ __device__ __forceinline__ void ea_cubic2(const float2 p0, const float2 p1, cons
   f = __ffma2_rn(ea_bc(hx), __ffma2_rn(ea_bc(x), __ffma2_rn(ea_bc(x), a2, b2), c2), p1);
   d = __ffma2_rn(ea_bc(x), __ffma2_rn(ea_bc(x15), a2, b2), __fmul2_rn(ea_bc(0.5f), c2));
 }
-__device__ __forceinline__ void ea_interp(const float (&t)[16], const float du, const float dv, const float2 affine, float& f, float& dfdu, float& dfdv) {
+// f = normalised value; gu, gv = derivatives of the RAW (pixel-unit) interpolant along u and v: the caller folds the
+// normalisation scale and the focal lengths into one factor per axis (ea_jacobian).
+__device__ __forceinline__ void ea_interp(const float (&t)[16], const float du, const float dv, const float2 affine, float& f, float& gu, float& gv) {
   const float hv = 0.5f * dv, v15 = 1.5f * dv, hu = 0.5f * du, u15 = 1.5f * du;
-  float2 f01, d01, f23, d23;      // columns 0,1 and 2,3: value and derivative along v
+  float2 f01, d01, f23, d23;      // columns 0,1 and 2,3: value and derivative along v (the texel pairs arrive in adjacent registers)
   ea_cubic2(ea_f2(t[0], t[1]), ea_f2(t[4], t[5]), ea_f2(t[8], t[9]), ea_f2(t[12], t[13]), dv, hv, v15, f01, d01);
   ea_cubic2(ea_f2(t[2], t[3]), ea_f2(t[6], t[7]), ea_f2(t[10], t[11]), ea_f2(t[14], t[15]), dv, hv, v15, f23, d23);
-  // along u: the value spline of {f_k, d_k} as one pair (-> value, d/dv), the derivative spline of f_k alone (-> d/du)
-  const float2 q0 = ea_f2(f01.x, d01.x), q1 = ea_f2(f01.y, d01.y), q2 = ea_f2(f23.x, d23.x), q3 = ea_f2(f23.y, d23.y);
-  const float2 a2 = __ffma2_rn(ea_bc(3.0f), ea_sub2(q1, q2), ea_sub2(q3, q0));
-  const float2 b2 = __ffma2_rn(ea_bc(4.0f), q2, __ffma2_rn(ea_bc(-5.0f), q1, __ffma2_rn(ea_bc(2.0f), q0, make_float2(-q3.x, -q3.y))));
-  const float2 c2 = ea_sub2(q2, q0);
-  const float2 val = __ffma2_rn(ea_bc(hu), __ffma2_rn(ea_bc(du), __ffma2_rn(ea_bc(du), a2, b2), c2), q1);
-  const float fdu = fmaf(du, fmaf(u15, a2.x, b2.x), 0.5f * c2.x);
-  f = fmaf(val.x, affine.x, affine.y);
-  const float2 g = __fmul2_rn(ea_f2(fdu, val.y), ea_bc(affine.x));
-  dfdu = g.x;
-  dfdv = g.y;
+  // along u: scalar (pairing {f_k, d_k} would cost a register move per element, more than the packed operations save)
+  float val;
+  ea_cubic(f01.x, f01.y, f23.x, f23.y, du, hu, u15, val, gu);
+  gv = ea_cubic_val(d01.x, d01.y, d23.x, d23.y, du, hu);
+  f = fmaf(val, affine.x, affine.y);
 }
 
-// Warp, project, bicubic lookup for one edge point.  dt = pixel (0,0) of the padded distance transform.
-template <bool XYZ>
-__device__ __forceinline__ void ea_point_eval(const double a0, const double a1, const double a2, const EaLevelGeom& now,
-                                              double inv_depth_scale, const EaPose& P,
-                                              const float* __restrict__ dt, const float2 affine, EaPointEval& o) {
-  const int pitch = ea_dt_pitch(now.w);
-  EaProj r;
-  ea_project<XYZ>(a0, a1, a2, now.w, now.h, pitch, inv_depth_scale, P, r);
-  float t[16];
-  ea_gather(dt - ea_dt_origin_offset(now.w), r.off, unsigned(pitch), t);
-  ea_interp(t, r.du, r.dv, affine, o.f, o.dfdu, o.dfdv);
-  o.ub = r.ub; o.vb = r.vb; o.pz = r.pz; o.iz = r.iz; o.fail = r.fail;
+// Loss constants in fp32, derived once on the host (kernel arguments: the hot loop reads them as constant-bank operands).
+struct EaLossF {
+  int type; float a, b, two_a, inv_a, inv_b;
+  unsigned stride_bytes[2];   // rides along: byte step of the point stream per residual (point_stride x 8 for pixel points, x 16 for XYZ)
+};
+__host__ __device__ inline EaLossF ea_loss_consts(int type, double scale, int point_stride = 1) {
+  EaLossF L;
+  L.type = type; L.a = float(scale); L.b = L.a * L.a; L.two_a = 2.0f * L.a; L.inv_a = 1.0f / L.a; L.inv_b = 1.0f / L.b;
+  L.stride_bytes[0] = unsigned(point_stride) * 8u; L.stride_bytes[1] = unsigned(point_stride) * 16u;
+  return L;
 }
 
 // Loss (ceres/loss_function.cc) + Corrector (rho'' <= 0 for all three => scale by sqrt(rho')) in fp32.
 // Returns sqrt(rho'), writes rho(s).
-__device__ __forceinline__ float ea_loss_eval(int type, float a, float r, float& rho0) {
+__device__ __forceinline__ float ea_loss_eval(const EaLossF& L, float r, float& rho0) {
   const float s = r * r;
-  if (type == EA_LOSS_CAUCHY) {
-    const float b = a * a, c = 1.0f / b;
-    const float sum = fmaf(s, c, 1.0f);
-    rho0 = b * log1pf(s * c);
+  if (L.type == EA_LOSS_CAUCHY) {
+    const float sum = fmaf(s, L.inv_b, 1.0f);
+    rho0 = L.b * log1pf(s * L.inv_b);
     return rsqrtf(sum);
-  } else if (type == EA_LOSS_HUBER) {
-    const float b = a * a;
-    if (s > b) {
+  } else if (L.type == EA_LOSS_HUBER) {
+    if (s > L.b) {
       // rho = 2 a |r| - a^2, sqrt(rho') = sqrt(a / |r|) = rsqrt(|r| / a): MUFU.RSQ plus one Newton step (<= 1 ulp) instead of an
       // IEEE division and square root (25 instructions with their slow-path calls, paid by every warp that holds one outlier)
       const float ar = fabsf(r);
-      rho0 = 2.0f * a * ar - b;
-      const float x = ar * (1.0f / a);
+      rho0 = fmaf(L.two_a, ar, -L.b);
+      const float x = ar * L.inv_a;
       float y = rsqrtf(x);
       y = y * fmaf(-0.5f * x, y * y, 1.5f);
       return y;
@@ -296,18 +307,35 @@ __device__ __forceinline__ float ea_loss_eval(int type, float a, float r, float&
 
 // Analytic local Jacobian (collapsed closed form of AutoDiff x QuaternionParameterization):
 // g = dr/dp', J = [ 2 (R X) x g | g ], then robust re-weighting.  Everything is rebuilt in fp32 from the projected
-// coordinates: p' = z' (ub/fx, vb/fy, 1), R X = p' - t.
-__device__ __forceinline__ void ea_jacobian(const EaPointEval& e, const EaPose& P, float w, float J[6]) {
-  const float px = e.pz * e.ub * P.inv_fx, py = e.pz * e.vb * P.inv_fy;
-  const float yx = px - P.t[0], yy = py - P.t[1], yz = e.pz - P.t[2];
-  const float wi = w * e.iz;
-  const float g0 = e.dfdu * P.fx * wi;
-  const float g1 = e.dfdv * P.fy * wi;
-  const float g2 = -(e.dfdu * e.ub + e.dfdv * e.vb) * wi;
-  J[0] = 2.0f * (yy * g2 - yz * g1);
-  J[1] = 2.0f * (yz * g0 - yx * g2);
-  J[2] = 2.0f * (yx * g1 - yy * g0);
+// coordinates: p' = z' (xn, yn, 1) with xn = (u' - cx) / fx, R X = p' - t.  gu, gv: raw interpolant derivatives (ea_interp);
+// afx = scale * fx, afy = scale * fy (normalisation scale of the distance transform times the focal lengths).
+__device__ __forceinline__ void ea_jacobian(const float gu, const float gv, const float ub, const float vb, const float pz, const float iz,
+                                            const EaPose& P, const float afx, const float afy, const float w, float J[6]) {
+  const float xn = ub * P.inv_fx, yn = vb * P.inv_fy;
+  const float y2x = fmaf(2.0f, pz * xn, P.m2t[0]), y2y = fmaf(2.0f, pz * yn, P.m2t[1]), y2z = fmaf(2.0f, pz, P.m2t[2]);   // 2 (R X)
+  const float wi = w * iz;
+  const float g0 = (gu * afx) * wi;
+  const float g1 = (gv * afy) * wi;
+  const float g2 = fmaf(-g0, xn, -(g1 * yn));
+  J[0] = fmaf(y2y, g2, -(y2z * g1));
+  J[1] = fmaf(y2z, g0, -(y2x * g2));
+  J[2] = fmaf(y2x, g1, -(y2y * g0));
   J[3] = g0; J[4] = g1; J[5] = g2;
+}
+
+// Warp, project, bicubic lookup for one edge point (per-point API of the parity tests and the EAResidue facade).
+// dt = pixel (0,0) of the padded distance transform.
+template <bool XYZ>
+__device__ __forceinline__ void ea_point_eval(const double a0, const double a1, const double a2, const EaLevelGeom& now,
+                                              double inv_depth_scale, const EaPose& P,
+                                              const float* __restrict__ dt, const float2 affine, EaPointEval& o) {
+  const int pitch = ea_dt_pitch(now.w);
+  EaProj r;
+  ea_project<XYZ>(a0, a1, a2, now.w, now.h, pitch, inv_depth_scale, P, r);
+  float t[16];
+  ea_gather(ea_gather_base(dt - ea_dt_origin_offset(now.w), pitch), r.off, pitch, t);
+  ea_interp(t, r.du, r.dv, affine, o.f, o.gu, o.gv);
+  o.ub = r.ub; o.vb = r.vb; o.pz = r.pz; o.iz = r.iz; o.fail = r.zm < 0;
 }
 
 // Transposing warp reduction: every lane holds 32 partial sums v[0..31]; afterwards lane L holds in v[0]
@@ -469,7 +497,7 @@ __device__ __forceinline__ bool ea_point_eval_general(const float4 p, const EaLe
   ea_floor_frac(v, iv, dv);
   iu = min(max(iu, 1 - EA_DT_PAD), W + 1); iv = min(max(iv, 1 - EA_DT_PAD), H + 1);
   float tex[16];
-  ea_gather(dt - ea_dt_origin_offset(W), unsigned(iv + (EA_DT_PAD - 1)) * unsigned(pitch) + unsigned(iu + (EA_DT_PAD - 1)), unsigned(pitch), tex);
+  ea_gather(ea_gather_base(dt - ea_dt_origin_offset(W), pitch), iv * pitch + iu, pitch, tex);
   float f0, f1, f2, f3, d0, d1, d2, d3, fr, fdu;
   const float hv = 0.5f * dv, v15 = 1.5f * dv, hu = 0.5f * du, u15 = 1.5f * du;
   ea_cubic(tex[0], tex[4], tex[8], tex[12], dv, hv, v15, f0, d0);
@@ -480,7 +508,7 @@ __device__ __forceinline__ bool ea_point_eval_general(const float4 p, const EaLe
   const float f = fmaf(fr, affine.x, affine.y);
   const float gu = fdu * affine.x * P.fxf;                                          // dr/d(distorted x)
   const float gv = ea_cubic_val(d0, d1, d2, d3, du, hu) * affine.x * P.fyf;         // dr/d(distorted y)
-  const float w = ea_loss_eval(loss_type, loss_a, f, rho0);
+  const float w = ea_loss_eval(ea_loss_consts(loss_type, double(loss_a)), f, rho0);
   // chain rule: distorted -> normalised -> p' (this camera) -> first camera
   const float gx = gu * Dxx + gv * Dyx, gy = gu * Dxy + gv * Dyy;
   const float pz = float(q2), izf = float(iz), wi = w * izf;

@@ -199,7 +199,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLevelDesc nd, EaLevelGeom rg, EaLevelGeom ng,
-                                                            double inv_depth_scale, ea_solve_params sp, ShardCtl* ctl,
+                                                            double inv_depth_scale, ea_solve_params sp, EaLossF loss, ShardCtl* ctl,
                                                             double* partials /*[grid][32]*/, ShardPeers peers, int rank, int world,
                                                             unsigned long long epoch0, int j_begin, int j_end) {
   __shared__ double part[THREADS / 32][EA_NSUM];
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
   __shared__ unsigned long long s_ticket;
   __shared__ int s_stop;
   __shared__ EaLmState s_lm;      // the LM state of the CTA that drew the last ticket (global memory between evaluations)
-  __shared__ uint2 stage[2][THREADS];   // cp.async staging of the point stream (ea_eval_slice)
+  __shared__ __align__(2 * EA_STAGE_SLOT * 8) uint2 stage[2][EA_STAGE_SLOT];   // cp.async staging of the point stream (ea_eval_slice: aligned to its size)
   static_assert(sizeof(EaLmState) % 8 == 0, "EaLmState is copied as 8-byte words");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = j_end - j_begin;
@@ -239,10 +239,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
 #pragma unroll
       for (int i = 0; i < int(sizeof(EaPose) / 8); ++i) dst[i] = __ldcg(src + i);
     }
-    if (xyz) ea_eval_slice<true, THREADS>(rd.pts, dt_pad, affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart, EA_ALTERNATE_SWEEP && !(e & 1));
+    if (xyz) ea_eval_slice<true, THREADS>(rd.pts, dt_pad, affine, ng, inv_depth_scale, loss, sp.point_stride, P, j0, j1, part, cpart, EA_ALTERNATE_SWEEP && !(e & 1));
     else {
       const bool rev = EA_ALTERNATE_SWEEP && !(e & 1);
-      ea_eval_slice<false, THREADS>(rd.pts, dt_pad, affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart, rev, &stage[0][0], e > 1, true, EA_ALTERNATE_SWEEP ? !rev : rev);
+      ea_eval_slice<false, THREADS>(rd.pts, dt_pad, affine, ng, inv_depth_scale, loss, sp.point_stride, P, j0, j1, part, cpart, rev, &stage[0][0], e > 1, true, EA_ALTERNATE_SWEEP ? !rev : rev);
     }
     __syncthreads();
     if (warp == 0) {
@@ -512,6 +512,7 @@ static int shard_solve_persistent(ea_shard* s, ea_frameset* ref, int ref_slot, e
   EaLevelGeom rg = ref->geom[level], ng = now->geom[level];
   double ids = ref->inv_depth_unit;
   ea_solve_params spv = *sp;
+  EaLossF lossv = ea_loss_consts(sp->loss_type, sp->loss_scale, sp->point_stride);
   // one CTA per SM at most, at least ~2 iterations of the evaluation loop per CTA; every rank sizes its grid for its own slice
   int grid = std::max(1, std::min(c->sm_count, (j1 - j0 + 1023) / 1024));
   CU(cudaMemcpyAsync(s->d_pose, pose7, 56, cudaMemcpyHostToDevice, st));
@@ -521,7 +522,7 @@ static int shard_solve_persistent(ea_shard* s, ea_frameset* ref, int ref_slot, e
   CU(cudaEventRecord(e0, st));
   ShardCtl* ctl = s->d_ctl; double* cta = s->d_cta_sums; ShardPeers peers = s->peers; int rank = s->rank, world = s->world;
   unsigned long long epoch0 = s->epoch;
-  void* args[] = {&rd, &nd, &rg, &ng, &ids, &spv, &ctl, &cta, &peers, &rank, &world, &epoch0, &j0, &j1};
+  void* args[] = {&rd, &nd, &rg, &ng, &ids, &spv, &lossv, &ctl, &cta, &peers, &rank, &world, &epoch0, &j0, &j1};
   cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_shard_solve<EA_SOLVE_THREADS>, dim3(unsigned(grid)), dim3(EA_SOLVE_THREADS), args, 0, st);
   cudaEventRecord(e1, st);
   c->launches += 2;

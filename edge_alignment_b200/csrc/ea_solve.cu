@@ -60,7 +60,8 @@ struct EaHelpBoard {                          // one per persistent CTA; zeroed 
   EaMsg msg;                                  // the evaluation being shared
 };
 
-struct EaSolveSmem {
+struct alignas(2 * EA_STAGE_SLOT * 8) EaSolveSmem {
+  uint2 stage[2][EA_STAGE_SLOT];            // cp.async staging of the point stream (ea_eval_slice: aligned to its own size, first member)
   // the kernel's arguments, for the boss functions: a __grid_constant__ parameter whose address is handed to a non-inlined
   // function is copied to LOCAL memory first, and every access from the serial LM section then misses the L1 that the
   // evaluation loop has just swept (measured: the LM step was ~4x slower than its dependency chains).  Shared memory is not
@@ -73,7 +74,6 @@ struct EaSolveSmem {
   double cluster_sums[8][EA_SUMS + 3];      // rank 0 only: one row per cluster rank
   EaLmState lm;                             // boss only
   int pair, level, truncated;               // boss only
-  uint2 stage[2][EA_SOLVE_THREADS];         // cp.async staging of the point stream (ea_eval_slice)
   unsigned long long help_epoch;            // owner: evaluations published on its board so far
   int help_owner, help_index, help_fail;    // helper: the board it serves and its slot there (1-based); owner: a helper went missing
   long long dbg[6], dbg_t, dbg_t0;          // EA_SOLVE_DEBUG cycle counters (thread 0)
@@ -193,10 +193,10 @@ __device__ __forceinline__ void ea_eval_chunks(const EaSolveArgs& A, EaSolveSmem
   const bool rev = EA_ALTERNATE_SWEEP && M.rev, nrev = EA_ALTERNATE_SWEEP ? !rev : rev;
   const int lo = cb * chunk, hi = min(ce * chunk, M.n_res);
   if (M.pts_mode == EA_POINTS_XYZ)
-    ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[cb], S.cpart[cb], rev, nullptr, false, false, false,
+    ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.loss, A.sp.point_stride, P, lo, hi, S.part[cb], S.cpart[cb], rev, nullptr, false, false, false,
                                  chunk / THREADS, THREADS / 32);
   else
-    ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, lo, hi, S.part[cb], S.cpart[cb], rev, &S.stage[0][0], pre_valid, chain_next_eval, nrev,
+    ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.loss, A.sp.point_stride, P, lo, hi, S.part[cb], S.cpart[cb], rev, &S.stage[0][0], pre_valid, chain_next_eval, nrev,
                                   chunk / THREADS, THREADS / 32);
 }
 
@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(THREADS, EA_SOLVE_MIN_CTAS) ea_k_solve_batch(c
       const int j0 = int((long long)M.n_res * crank / csize), j1 = int((long long)M.n_res * (crank + 1) / csize);
       const EaLevelGeom& ng = A.now_geom[M.level];
       const bool rev = EA_ALTERNATE_SWEEP && M.rev, nrev = EA_ALTERNATE_SWEEP ? !rev : rev;
-      if (M.pts_mode == EA_POINTS_XYZ) ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part[0], S.cpart[0], rev);
-      else ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.sp, P, j0, j1, S.part[0], S.cpart[0], rev, &S.stage[0][0], M.same != 0, true, nrev);
+      if (M.pts_mode == EA_POINTS_XYZ) ea_eval_slice<true, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.loss, A.sp.point_stride, P, j0, j1, S.part[0], S.cpart[0], rev);
+      else ea_eval_slice<false, THREADS>(M.pts, M.dt, M.affine, ng, A.inv_depth_scale, A.loss, A.sp.point_stride, P, j0, j1, S.part[0], S.cpart[0], rev, &S.stage[0][0], M.same != 0, true, nrev);
     } else {
       K = ea_chunking(M.n_res, THREADS, chunk);
       cb = (K * M.nh) / (M.nh + 1);             // the owner is the last of nh + 1 workers: chunks [cb, K)
@@ -446,9 +446,9 @@ __global__ void __launch_bounds__(256) ea_k_eval_points(EaLevelDesc rd, EaLevelD
     PS::unpack(p, a0, a1, a2);
     ea_point_eval<XYZ>(a0, a1, a2, ng, inv_depth_scale, P, nd.dt, affine, e);
     float rho0;
-    const float w = ea_loss_eval(sp.loss_type, float(sp.loss_scale), e.f, rho0);
+    const float w = ea_loss_eval(ea_loss_consts(sp.loss_type, sp.loss_scale, sp.point_stride), e.f, rho0);
     float J[6];
-    ea_jacobian(e, P, w, J);
+    ea_jacobian(e.gu, e.gv, e.ub, e.vb, e.pz, e.iz, P, affine.x * P.fx, affine.x * P.fy, w, J);
     if (!valid) continue;
     if (raw) raw[j] = double(e.f);
     if (res) res[j] = double(e.f * w);
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) ea_k_eval_points(EaLevelDesc rd, EaLevelD
 // Normal-equation sums through the production reduction path (one CTA per slice of the points).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) ea_k_eval_sums(EaLevelDesc rd, EaLevelDesc nd, EaLevelGeom rg, EaLevelGeom ng,
-                                                          double inv_depth_scale, ea_solve_params sp, const double* pose7,
+                                                          double inv_depth_scale, ea_solve_params sp, EaLossF loss, const double* pose7,
                                                           const int* done, int j_begin, int j_end, double* sums /*[grid][EA_SUMS]*/) {
   if (done && *done) return;
   __shared__ double part[THREADS / 32][EA_NSUM];
@@ -473,10 +473,10 @@ __global__ void __launch_bounds__(THREADS) ea_k_eval_sums(EaLevelDesc rd, EaLeve
   EaPose P;
   if (rd.pts_mode == EA_POINTS_XYZ) {
     ea_pose_setup<true>(pose7, rg, ng, P);
-    ea_eval_slice<true, THREADS>(rd.pts, nd.dt - ea_dt_origin_offset(nd.w), *nd.dt_affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
+    ea_eval_slice<true, THREADS>(rd.pts, nd.dt - ea_dt_origin_offset(nd.w), *nd.dt_affine, ng, inv_depth_scale, loss, sp.point_stride, P, j0, j1, part, cpart);
   } else {
     ea_pose_setup<false>(pose7, rg, ng, P);
-    ea_eval_slice<false, THREADS>(rd.pts, nd.dt - ea_dt_origin_offset(nd.w), *nd.dt_affine, ng, inv_depth_scale, sp, P, j0, j1, part, cpart);
+    ea_eval_slice<false, THREADS>(rd.pts, nd.dt - ea_dt_origin_offset(nd.w), *nd.dt_affine, ng, inv_depth_scale, loss, sp.point_stride, P, j0, j1, part, cpart);
   }
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(256) ea_k_gather_probe(const __grid_constant__
   ea_pose_setup<false>(A.poses + size_t(pair) * 7, rg, ng, P);
   float s = 0.0f;
   const int pitch = ea_dt_pitch(ng.w);
-  const float* dt_pad = nd.dt - ea_dt_origin_offset(ng.w);
+  const float* dt_base = ea_gather_base(nd.dt - ea_dt_origin_offset(ng.w), pitch);
   for (int r = 0; r < repeats; ++r)
     for (int j = j0 + int(threadIdx.x); j < j1; j += 256) {
       typedef EaPtStream<false> PS;
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(256) ea_k_gather_probe(const __grid_constant__
       EaProj pr;
       ea_project<false>(a0, a1, a2, ng.w, ng.h, pitch, A.inv_depth_scale, P, pr);
       float t[16];
-      ea_gather(dt_pad, pr.off, unsigned(pitch), t);
+      ea_gather(dt_base, pr.off, pitch, t);
       float ts = pr.du + pr.dv;
 #pragma unroll
       for (int k = 0; k < 16; ++k) ts += t[k];
@@ -587,7 +587,8 @@ cudaError_t ea_launch_eval_sums(const EaLevelDesc& rd, const EaLevelDesc& nd, co
                                 const double* d_pose7, const int* d_done, int j_begin, int j_end, int n_blocks, double* d_sums,
                                 cudaStream_t stream) {
   if (n_blocks <= 0) return cudaSuccess;
-  ea_k_eval_sums<EA_SOLVE_THREADS><<<n_blocks, EA_SOLVE_THREADS, 0, stream>>>(rd, nd, rg, ng, inv_depth_scale, sp, d_pose7, d_done, j_begin, j_end, d_sums);
+  ea_k_eval_sums<EA_SOLVE_THREADS><<<n_blocks, EA_SOLVE_THREADS, 0, stream>>>(rd, nd, rg, ng, inv_depth_scale, sp, ea_loss_consts(sp.loss_type, sp.loss_scale, sp.point_stride),
+                                                                              d_pose7, d_done, j_begin, j_end, d_sums);
   return cudaGetLastError();
 }
 

@@ -522,6 +522,7 @@ __device__ __forceinline__ uint2 ea_lds_u2(const unsigned saddr) {
   return v;
 }
 
+#define EA_STAGE_SLOT 512   // points per staging slot (uint2 stage[2][EA_STAGE_SLOT], 8 KB, aligned to 8 KB)
 // ---- slice evaluation shared by every solve kernel ----------------------------------------------------------
 #ifndef EA_FLUSH_EVERY
 #define EA_FLUSH_EVERY 16  // points per thread between fp32 -> fp64 flushes of the normal-equation slots (measured: 8 -> 16 = -1.7 %)
@@ -529,6 +530,44 @@ __device__ __forceinline__ uint2 ea_lds_u2(const unsigned saddr) {
 #ifndef EA_ALTERNATE_SWEEP
 #define EA_ALTERNATE_SWEEP 1
 #endif
+
+// Per-thread accumulators of the evaluation loop between two flushes.
+struct EaEvalAcc {
+  float acc[EA_NSUM];    // fp32 normal-equation slots (ea_accumulate)
+  float cost;            // fp32 sum of rho / 2 over the (at most EA_FLUSH_EVERY) points since the last flush
+  int zmin;              // running minimum of EaProj::zm: negative <=> one of those points failed the z-guard
+};
+
+// One point of the evaluation loop: project -> gather -> interpolate -> loss -> Jacobian -> accumulate.  RAGGED: the iteration
+// may hold lanes beyond the range (`valid` false: they carry the pad point and contribute nothing); full iterations skip the
+// masking altogether.
+template <bool XYZ, bool RAGGED>
+__device__ __forceinline__ void ea_eval_point(const typename EaPtStream<XYZ>::T p, const bool valid, const int W, const int H, const int pitch,
+                                              const double inv_depth_scale, const EaPose& P, const float* __restrict__ dt_base,
+                                              const float2 affine, const float afx, const float afy, const EaLossF& loss, EaEvalAcc& A) {
+  EaProj r;
+  {
+    double a0, a1, a2;
+    EaPtStream<XYZ>::unpack(p, a0, a1, a2);
+    ea_project<XYZ>(a0, a1, a2, W, H, pitch, inv_depth_scale, P, r);
+  }
+  float t[16];
+  ea_gather(dt_base, r.off, pitch, t);
+  float f, gu, gv;
+  ea_interp(t, r.du, r.dv, affine, f, gu, gv);
+  float rho0;
+  float w = ea_loss_eval(loss, f, rho0);
+  if (RAGGED && !valid) { w = 0.0f; rho0 = 0.0f; f = 0.0f; r.zm = 0x7fffffff; }
+  float J[6];
+  ea_jacobian(gu, gv, r.ub, r.vb, r.pz, r.iz, P, afx, afy, w, J);
+  if (RAGGED && !valid) {   // the pad point may project to inf / NaN
+#pragma unroll
+    for (int k = 0; k < 6; ++k) J[k] = 0.0f;
+  }
+  ea_accumulate(A.acc, J, f * w);
+  A.zmin = min(A.zmin, r.zm);
+  A.cost = fmaf(0.5f, rho0, A.cost);
+}
 
 // Evaluate residual indices [j0, j1) (point index = j * stride) with the CTA's threads and leave per-warp partial sums in
 // part / cpart (caller synchronises).  dt_pad = FIRST element of the padded distance transform (pixel (-PAD,-PAD)).
@@ -546,25 +585,27 @@ __device__ __forceinline__ uint2 ea_lds_u2(const unsigned saddr) {
 // (reverse; vend = j0 + n_chunks * chunk, the ragged part of the last chunk sits in the first iterations).  Chunk ends
 // coincide with the fp32 -> fp64 flushes, so the bookkeeping lives in the flush branch, not in the loop body.
 //
-// stage (optional, pixel points only): shared memory, uint2 [2][THREADS].  The point of iteration i + 1 is requested at the top
-// of iteration i with cp.async straight into the thread's staging slot and read back (LDS) at the top of iteration i + 1: it
-// never occupies registers across the loop body.  (As a register prefetch it did, the loop sits at the 128-register limit, and
-// ptxas parked it in local memory right behind the load -- exposing the load latency in every iteration, +27 % evaluation time.)
+// stage (optional, pixel points only): shared memory, uint2 [2][EA_STAGE_SLOT] (THREADS <= EA_STAGE_SLOT), ALIGNED TO ITS OWN SIZE
+// (the loop flips between the two slots with one XOR).  The point of iteration i + 1 is requested at the top of iteration i with cp.async straight into the
+// thread's staging slot and read back (LDS) at the top of iteration i + 1: it never occupies registers across the loop body.
+// (As a register prefetch it did, the loop sits at the 128-register limit, and ptxas parked it in local memory right behind
+// the load -- exposing the load latency in every iteration, +27 % evaluation time.)
 // pre_valid: slot 0 already holds (or is about to receive) this call's first point, requested by the previous call;
 // prefetch_next: request the first point of the NEXT evaluation of the same range (direction next_reverse) into slot 0 before
 // returning, so that its latency hides behind the CTA barrier and the serial LM step.
 template <bool XYZ, int THREADS>
 __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, const float* __restrict__ dt_pad, const float2 affine,
                                               const EaLevelGeom& ng,
-                                              double inv_depth_scale, const ea_solve_params& sp, const EaPose& P, const int j0,
+                                              double inv_depth_scale, const EaLossF& loss, const int stride, const EaPose& P, const int j0,
                                               const int j1, double (*part)[EA_NSUM], double* cpart, const bool reverse = false,
                                               uint2* stage = nullptr, const bool pre_valid = false,
                                               const bool prefetch_next = false, const bool next_reverse = false,
                                               const int chunk_iters = 0, const int part_stride = 0) {
+  static_assert(THREADS <= EA_STAGE_SLOT, "staging slot too small");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float loss_a = float(sp.loss_scale);
-  const int loss_type = sp.loss_type, stride = sp.point_stride;
   const int W = ng.w, H = ng.h, pitch = ea_dt_pitch(W);
+  const float* dt_base = ea_gather_base(dt_pad, pitch);
+  const float afx = affine.x * P.fx, afy = affine.x * P.fy;
   typedef EaPtStream<XYZ> PS;
   // virtual iteration space: residual of (iteration it, thread t) = j0 + it * THREADS + t   (forward)
   //                                                                 vend - 1 - (it * THREADS + t)   (reverse)
@@ -577,69 +618,58 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
   auto residual_of = [&](const int it, const bool rev) { return rev ? vend - 1 - (it * THREADS + tid) : j0 + it * THREADS + tid; };
   const int it0 = reverse ? it_first_rev : 0;
   const int it1 = reverse ? (vend - j0 + THREADS - 1) / THREADS : n_it;
-  float acc[EA_NSUM];
+  const int rstep = reverse ? -THREADS : THREADS;
+  EaEvalAcc A;
 #pragma unroll
-  for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
+  for (int k = 0; k < EA_NSUM; ++k) A.acc[k] = 0.0f;
+  A.cost = 0.0f; A.zmin = 0x7fffffff;
   // The fp64 accumulators of the 32 slots live in shared memory (part itself): they are touched once per flush, and the
   // registers they would hold across the loop body are what keeps the prefetched point out of local memory.
   double cost64 = 0.0;
   for (int k = 0; k < n_chunks; ++k) part[size_t(k) * part_stride + warp][lane] = 0.0;
   typename PS::T p_next = PS::pad();
   int rj = residual_of(it0, reverse);                          // this thread's residual in the current iteration
-  bool any_fail = false;                                       // slot 27 only says "some point failed": a predicate, not an accumulator
   const bool staged = !XYZ && stage != nullptr;
-  const unsigned st0 = staged ? unsigned(__cvta_generic_to_shared(stage + tid)) : 0u;   // this thread's slot 0; slot 1 is THREADS * 8 bytes further
+  const unsigned st0 = staged ? unsigned(__cvta_generic_to_shared(stage + tid)) : 0u;   // this thread's slot 0; slot 1 is EA_STAGE_SLOT * 8 bytes further
   unsigned st_cur = st0;
+  const char* const pts8 = reinterpret_cast<const char*>(pts);
+  const unsigned stride8 = loss.stride_bytes[XYZ ? 1 : 0];
   if (staged) {
-    if (!pre_valid) { if (unsigned(rj - j0) < unsigned(n)) ea_cp_async8(st0, reinterpret_cast<const uint2*>(pts) + size_t(rj) * stride); ea_cp_async_commit(); }
+    if (!pre_valid) { if (unsigned(rj - j0) < unsigned(n)) ea_cp_async8(st0, pts8 + size_t(unsigned(rj)) * stride8); ea_cp_async_commit(); }
   } else {
     if (unsigned(rj - j0) < unsigned(n)) p_next = PS::load(pts, size_t(rj) * stride);
   }
   for (int it = it0; it < it1; ++it) {
     const bool valid = unsigned(rj - j0) < unsigned(n);
     typename PS::T p = p_next;
-    if (reverse) rj -= THREADS; else rj += THREADS;
+    rj += rstep;
     if (staged) {
       ea_cp_async_wait_all();
-      if constexpr (!XYZ) { p = valid ? ea_lds_u2(st_cur) : PS::pad(); }
-      st_cur = (2u * st0 + unsigned(THREADS * 8)) - st_cur;                     // the other slot
-      if (unsigned(rj - j0) < unsigned(n)) ea_cp_async8(st_cur, reinterpret_cast<const uint2*>(pts) + size_t(rj) * stride);
+      if constexpr (!XYZ) { p = ea_lds_u2(st_cur); }
+      st_cur ^= unsigned(EA_STAGE_SLOT * 8);                                   // the other slot
+      if (unsigned(rj - j0) < unsigned(n)) ea_cp_async8(st_cur, pts8 + size_t(unsigned(rj)) * stride8);
       ea_cp_async_commit();
     } else {
       if (unsigned(rj - j0) < unsigned(n)) p_next = PS::load(pts, size_t(rj) * stride);   // register prefetch (XYZ points, callers without staging)
     }
-    EaProj r;
-    {
-      double a0, a1, a2;
-      PS::unpack(p, a0, a1, a2);
-      ea_project<XYZ>(a0, a1, a2, W, H, pitch, inv_depth_scale, P, r);
+    // only the first and the last iteration of a range can hold lanes beyond it
+    if (it == it0 || it + 1 == it1) {
+      if constexpr (!XYZ) { if (!valid) p = PS::pad(); }
+      ea_eval_point<XYZ, true>(p, valid, W, H, pitch, inv_depth_scale, P, dt_base, affine, afx, afy, loss, A);
+    } else {
+      ea_eval_point<XYZ, false>(p, true, W, H, pitch, inv_depth_scale, P, dt_base, affine, afx, afy, loss, A);
     }
-    float t[16];
-    ea_gather(dt_pad, r.off, unsigned(pitch), t);
-    EaPointEval e;
-    ea_interp(t, r.du, r.dv, affine, e.f, e.dfdu, e.dfdv);
-    e.ub = r.ub; e.vb = r.vb; e.pz = r.pz; e.iz = r.iz; e.fail = r.fail;
-    float rho0;
-    float w = ea_loss_eval(loss_type, loss_a, e.f, rho0);
-    if (!valid) { w = 0.0f; rho0 = 0.0f; e.f = 0.0f; e.fail = false; }
-    float J[6];
-    ea_jacobian(e, P, w, J);
-    if (!valid) {   // padding lanes of a ragged iteration: the dummy point may project to inf/NaN
-#pragma unroll
-      for (int k = 0; k < 6; ++k) J[k] = 0.0f;
-    }
-    ea_accumulate(acc, J, e.f * w);
-    any_fail = any_fail || e.fail;
-    cost64 += double(0.5f * rho0);
     if (((it + 1) & (EA_FLUSH_EVERY - 1)) == 0 || it + 1 == it1) {   // flush cadence on the virtual iteration grid, and at the end
-      acc[27] = any_fail ? 1.0f : 0.0f;
-      any_fail = false;
+      A.acc[27] = A.zmin < 0 ? 1.0f : 0.0f;
+      A.zmin = 0x7fffffff;
+      cost64 += double(A.cost);
+      A.cost = 0.0f;
       const int csh = 31 - __clz(chunk_iters | 1);                                                             // chunk_iters is a power of two
       const int kc = chunk_iters > 0 ? (reverse ? n_chunks - 1 - (it >> csh) : (it >> csh)) : 0;              // chunk, from the range's low end
       double* slot = &part[size_t(kc) * part_stride + warp][lane];
-      *slot += double(ea_warp_transpose_reduce(acc, lane));
+      *slot += double(ea_warp_transpose_reduce(A.acc, lane));
 #pragma unroll
-      for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
+      for (int k = 0; k < EA_NSUM; ++k) A.acc[k] = 0.0f;
       if (it + 1 == it1 || (chunk_iters > 0 && ((it + 1) & (chunk_iters - 1)) == 0)) {   // the chunk is complete: its cost
         const double c64 = ea_warp_sum(cost64);
         if (lane == 0) cpart[size_t(kc) * part_stride + warp] = c64;
@@ -651,7 +681,7 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
   if (staged && prefetch_next) {
     const int rn = residual_of(next_reverse ? it_first_rev : 0, next_reverse);
     ea_cp_async_wait_all();                                      // (nothing of this call is still reading or filling slot 0)
-    if (rn >= j0 && rn < j1) ea_cp_async8(st0, reinterpret_cast<const uint2*>(pts) + size_t(rn) * stride);
+    if (rn >= j0 && rn < j1) ea_cp_async8(st0, pts8 + size_t(unsigned(rn)) * stride8);
     ea_cp_async_commit();
   }
 }
