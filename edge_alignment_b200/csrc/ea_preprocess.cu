@@ -150,14 +150,17 @@ __device__ __forceinline__ unsigned e2_gray(unsigned v_bg, unsigned v_r) {
 }
 
 // TW = tile width = threads per CTA (128; 64 for levels whose width is a multiple of 64 but not of 128, where a 128-wide
-// last tile would be half empty)
-template <typename D, int TW>
+// last tile would be half empty).  REF: also write the reference-point plane (edge & depth > 0), key frames only.
+// Instruction budget (the kernel is issue-bound, not HBM-bound): staging 6, blur + gray 31, Laplacian + ballot 12-16 per pixel.
+template <typename D, int TW, bool REF>
 __global__ void __launch_bounds__(TW) k_edge_mask2(const uint8_t* __restrict__ bgr, const D* __restrict__ depth,
                                                       size_t frame_stride_px, const int32_t* __restrict__ src_slots,
                                                       const int32_t* __restrict__ dst_slots, uint32_t* __restrict__ edge_bits,
                                                       uint32_t* __restrict__ ref_bits, int w, int h, int words, int thresh, int zero_to_one) {
   constexpr int PW = TW + 8;   // packed tile: image columns x0-4 .. x0+TW+3
   constexpr int GW = TW + 4;   // gray tile: columns x0-1 .. x0+TW (+2 pad)
+  constexpr int NG = PW / 4;   // 4-pixel groups per tile row
+  constexpr int RS = TW / NG;  // tile rows staged per pass (3)
   __shared__ unsigned tile[E2_PH][PW];
   __shared__ uint8_t gray[E2_TH + 2][GW];
   const int f = blockIdx.z;
@@ -166,20 +169,29 @@ __global__ void __launch_bounds__(TW) k_edge_mask2(const uint8_t* __restrict__ b
   const int t = threadIdx.x;
   const unsigned* img = reinterpret_cast<const unsigned*>(bgr + sbase * 3);
   const int row_words = (w * 3) >> 2;
-  // ---- phase 1: 32-bit row loads, 3 words -> 4 packed pixels ----
-  for (int i = t; i < E2_PH * (PW / 4); i += TW) {
-    const int r = i / (PW / 4), g = i % (PW / 4);
+  // ---- phase 1: 32-bit row loads, 3 words -> 4 packed pixels; a thread keeps its column group and walks down the rows ----
+  {
+    const int g = t % NG, rr = t / NG;
     const int col = x0 - 4 + 4 * g;                      // first image column of the group (multiple of 4)
-    if (col < 0 || col + 3 >= w) continue;                // outside the image: never read (REFLECT_101 maps inside)
-    const int ry = reflect101(y0 - 2 + r, h);
-    const unsigned* src = img + size_t(ry) * row_words + (col * 3 >> 2);
-    const unsigned w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
-    uint4 px;
-    px.x = w0 & 0x00FFFFFFu;
-    px.y = (w0 >> 24) | ((w1 & 0x0000FFFFu) << 8);
-    px.z = (w1 >> 16) | ((w2 & 0x000000FFu) << 16);
-    px.w = w2 >> 8;
-    *reinterpret_cast<uint4*>(&tile[r][4 * g]) = px;
+    if (rr < RS && col >= 0 && col + 3 < w) {             // outside the image: never read (REFLECT_101 maps inside)
+      const unsigned* src0 = img + (col * 3 >> 2);
+#pragma unroll 2
+      for (int r = rr; r < E2_PH; r += RS) {
+        // rows y0-2 .. h+1 are all that the tile's outputs can reach (h >= 4: one reflection maps them inside); the rest stay unstaged
+        const int y = y0 - 2 + r;
+        if (y > h + 1) break;
+        int ry = abs(y);
+        ry = ry >= h ? 2 * h - 2 - ry : ry;
+        const unsigned* src = src0 + size_t(unsigned(ry) * unsigned(row_words));
+        const unsigned w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+        uint4 px;
+        px.x = w0 & 0x00FFFFFFu;
+        px.y = __funnelshift_r(w0, w1, 24) & 0x00FFFFFFu;
+        px.z = __funnelshift_r(w1, w2, 16) & 0x00FFFFFFu;
+        px.w = w2 >> 8;
+        *reinterpret_cast<uint4*>(&tile[r][4 * g]) = px;
+      }
+    }
   }
   __syncthreads();
   // ---- phase 2: per-column rolling 3x3 blur + gray ----
@@ -198,7 +210,7 @@ __global__ void __launch_bounds__(TW) k_edge_mask2(const uint8_t* __restrict__ b
       hbg0 = hbg1; hr0 = hr1; hbg1 = hbg; hr1 = hr;
     }
   }
-  // the two halo gray columns (x0-1 and x0+128): 2 x 34 values, computed directly
+  // the two halo gray columns (x0-1 and x0+TW): 2 x 34 values, computed directly
   for (int q = t; q < 2 * (E2_TH + 2); q += TW) {
     const int which = q / (E2_TH + 2), gy = q % (E2_TH + 2);
     const int hx = which ? x0 + TW : x0 - 1;
@@ -222,35 +234,35 @@ __global__ void __launch_bounds__(TW) k_edge_mask2(const uint8_t* __restrict__ b
   }
   __syncthreads();
   // ---- phase 3: Laplacian (ksize 3) + convertScaleAbs + threshold, one ballot word per warp row ----
+  // min(|v|, 255) > thresh  <=>  |v| > thresh for thresh < 255 (never true above); columns beyond the image read gray
+  // column 0 (harmless) and vote "no edge"; the row loop stops at the image's last row.
   const int x = x0 + t, lane = t & 31, wq = t >> 5;
   const bool col_ok = x < w;
-  int gl = 0, gc = 0, gr = 0;
-  if (col_ok) {
-    gl = reflect101(x - 1, w) - x0 + 1; gc = t + 1; gr = reflect101(x + 1, w) - x0 + 1;
-  }
-  int s0 = 0, s1 = 0, c1 = 0;
-  if (col_ok) {
-    s0 = gray[0][gl] + gray[0][gr];
-    s1 = gray[1][gl] + gray[1][gr]; c1 = gray[1][gc];
-  }
-  const D* dep = depth ? depth + sbase : nullptr;
-  const size_t obase = size_t(dst_slots[f]) * h * words + (x0 >> 5) + wq;
+  const int gl = col_ok ? reflect101(x - 1, w) - x0 + 1 : 0, gc = col_ok ? t + 1 : 0, gr = col_ok ? reflect101(x + 1, w) - x0 + 1 : 0;
+  const int thr = (col_ok && thresh < 255) ? thresh : 0x7fffffff;
+  const int rows = min(E2_TH, h - y0);
+  int s0 = gray[0][gl] + gray[0][gr];
+  int s1 = gray[1][gl] + gray[1][gr], c1 = gray[1][gc];
+  const bool writer = lane == 0 && (x0 >> 5) + wq < words;
+  const size_t o0 = (size_t(dst_slots[f]) * h + y0) * words + (x0 >> 5) + wq;
+  uint32_t* eo = edge_bits + o0;
+  uint32_t* ro = REF ? ref_bits + o0 : nullptr;
+  const D* dep = REF ? depth + sbase + size_t(y0) * w + (col_ok ? x : 0) : nullptr;
 #pragma unroll 4
-  for (int r = 0; r < E2_TH; ++r) {
-    const int y = y0 + r;
-    int s2 = 0, c2 = 0;
-    if (col_ok) { s2 = gray[r + 2][gl] + gray[r + 2][gr]; c2 = gray[r + 2][gc]; }
-    int v = 2 * (s0 + s2) - 8 * c1;
-    v = v < 0 ? -v : v;
-    const bool edge = col_ok && (y < h) && (min(v, 255) > thresh);
-    bool valid = false;
-    if (edge && dep) valid = zero_to_one || dep[size_t(y) * w + x] > D(0);
+  for (int r = 0; r < rows; ++r) {
+    const int s2 = gray[r + 2][gl] + gray[r + 2][gr], c2 = gray[r + 2][gc];
+    const int v = 2 * (s0 + s2) - 8 * c1;
+    const bool edge = abs(v) > thr;
     const unsigned eb = __ballot_sync(0xffffffffu, edge);
-    const unsigned rb = __ballot_sync(0xffffffffu, edge && valid);
-    if (lane == 0 && y < h && (x0 >> 5) + wq < words) {
-      edge_bits[obase + size_t(y) * words] = eb;
-      if (ref_bits) ref_bits[obase + size_t(y) * words] = rb;
+    if (REF) {
+      bool valid = false;
+      if (edge) valid = zero_to_one || dep[0] > D(0);
+      const unsigned rb = __ballot_sync(0xffffffffu, valid);
+      if (writer) *ro = rb;
+      ro += words; dep += w;
     }
+    if (writer) *eo = eb;
+    eo += words;
     s0 = s1; s1 = s2; c1 = c2;
   }
 }
@@ -842,10 +854,12 @@ static cudaError_t launch_edges_and_points(const EaPrepArgs& A, cudaStream_t str
     } else if ((L.w & 3) == 0 && L.w >= 8 && L.h >= 4) {
       if ((L.w % 128) != 0 && (L.w % 128) <= 64) {   // the last 128-wide tile would be at most half full: 64-wide tiles
         dim3 grid(unsigned((L.w + 63) / 64), unsigned((L.h + E2_TH - 1) / E2_TH), unsigned(A.n));
-        k_edge_mask2<D, 64><<<grid, 64, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
+        if (want_ref) k_edge_mask2<D, 64, true><<<grid, 64, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, L.ref_bits, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
+        else k_edge_mask2<D, 64, false><<<grid, 64, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
       } else {
         dim3 grid(unsigned((L.w + E2_TW - 1) / E2_TW), unsigned((L.h + E2_TH - 1) / E2_TH), unsigned(A.n));
-        k_edge_mask2<D, E2_TW><<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, want_ref ? L.ref_bits : nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
+        if (want_ref) k_edge_mask2<D, E2_TW, true><<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, L.ref_bits, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
+        else k_edge_mask2<D, E2_TW, false><<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
       }
     } else {   // generic byte path (any width)
       dim3 grid(unsigned((L.w + ET_W - 1) / ET_W), unsigned((L.h + ET_H - 1) / ET_H), unsigned(A.n));
