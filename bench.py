@@ -59,15 +59,16 @@ class ClockSampler(threading.Thread):
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=50):
         super().__init__(daemon=True)
         self.index = index; self.samples = []; self._halt = threading.Event(); self.proc = None
+        self.period_ms = period_ms
         self.t_begin = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.samples.append((time.time(), line.strip()))
                 if self._halt.is_set():
@@ -170,7 +171,8 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=592, help="camera streams per GPU (4 per SM)")
+    ap.add_argument("--streams", type=int, default=0, help="camera streams per GPU (default 1184 = 8 per SM for config2: the persistent "
+                    "solve kernel balances 8 pairs per CTA better than 4, profiles/r2_kernels.md; 148 for config4)")
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4", "config5"],
                     help="BASELINE.json configs[k-1]; config2 (configs[1], the tracker) is the default line")
@@ -233,7 +235,9 @@ def main():
 
     if args.workload != "config2":
         import bench_workloads
-        sampler = ClockSampler(local_rank); sampler.start()
+        # the latency workloads synchronise with the host after every call: a fast nvidia-smi poll contends for the driver with
+        # exactly those calls (measured: 1.5 -> 14 ms per config-1 pair at 50 ms), so they are sampled once a second
+        sampler = ClockSampler(local_rank, 1000 if args.workload in ("config1", "config5") else 50); sampler.start()
         env = {"torch": torch, "ea": ea, "dist": dist, "dev": dev, "rank": rank, "local_rank": local_rank, "world": world, "barrier": barrier,
                "sampler": sampler, "peak": measured_peak_hbm()}
         rc = bench_workloads.WORKLOADS[args.workload](args, env)
@@ -241,7 +245,7 @@ def main():
             dist.destroy_process_group()
         return rc
 
-    S, K, Wm = args.streams, args.steps, args.warmup
+    S, K, Wm = (args.streams or 1184), args.steps, args.warmup
     T = Wm + K + 1
     NF = min(T, RING)
     bgr_d, depth_d, _ = synth.make_sequences(S, NF, seed=1234 + rank, device=dev)     # [NF,S,h,w,3] / [NF,S,h,w] resident in HBM
@@ -254,7 +258,11 @@ def main():
     fp = ea.frame_params(n_levels=N_LEVELS)
     sp = ea.solve_params(point_stride=1, loss_type=ea.LOSS_HUBER, loss_scale=HUBER_A, cluster_size=args.cluster)
     tracker = ea.Tracker(ctx, fp, sp, S, KEYFRAME_INTERVAL)
-    tracker.set_inputs_ready(True)      # every frame is resident and complete in HBM before the timed region starts
+    # Device-resident frames run in stream order: preprocessing of frame t, then its solve with the whole GPU (tail helpers on).
+    # EA_OVERLAP=1 declares the inputs complete instead, so that frame t+1's preprocessing fills the SMs the persistent solve
+    # kernel gives up in its tail: +1.6 % alignments/s, but every solve launch then lasts 25 % longer (profiles/r2_kernels.md).
+    OVERLAP = os.environ.get("EA_OVERLAP", "0") != "0"
+    tracker.set_inputs_ready(OVERLAP)
     frame_b = W * H * 3 * S; frame_d = W * H * 2 * S
 
     def run_device(first, last):
@@ -327,7 +335,7 @@ def main():
     run_device(Wm + 1, Wm + 1 + n_iso)
     barrier()
     prof_iso = ctx.profile_read(); ctx.profile_enable(False)
-    tracker.set_inputs_ready(True)
+    tracker.set_inputs_ready(OVERLAP)
     if prof_iso["n_solve"] > 0 and prof_iso["solve_ms"] > 0:
         ms_iso = prof_iso["solve_ms"] / prof_iso["n_solve"]
         ach_iso = pe_per_launch * BYTES_PER_POINT_EVAL / (ms_iso * 1e-3) / 1e9
@@ -339,8 +347,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         # pinned host ring: E2E_RING distinct frames per stream (walked forwards and backwards like the device ring); every
-        # step still uploads a full frame set, the ring only bounds the page-locked memory (5.5 GB per rank at 592 streams)
-        NE = min(NF, E2E_RING)
+        # step still uploads a full frame set, the ring only bounds the page-locked memory
+        NE = max(3, min(NF, E2E_RING, int(5.5e9 // frame_b)))      # at most ~5.5 GB of page-locked BGR frames per rank (+ the key frames' depth)
         hb = torch.empty((NE, S, H, W, 3), dtype=torch.uint8, pin_memory=True); hb.copy_(bgr_d[:NE])
         # depth only travels for frames that become key frames: pin just those
         hd = {f: torch.empty((S, H, W), dtype=torch.uint16, pin_memory=True)

@@ -3,6 +3,7 @@
 // (src/ea.cpp:184-199), batched over n_streams independent cameras.  Every frame is preprocessed once
 // (its DT when it arrives, its edge points only if it becomes a key frame); poses are warm-started from the
 // previous frame and never leave the device between steps.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -146,6 +147,7 @@ static int tracker_step(ea_tracker* t, const uint8_t* d_bgr, const void* d_depth
   const int roles = (first ? 0 : EA_ROLE_NOW) | (becomes_key ? EA_ROLE_REF : 0);
   const int fb = t->frame & 1;
   const bool overlap = input_ready != nullptr || t->inputs_ready != 0;   // frame t+1's preprocessing may run beside frame t's solve
+  static const int force_helpers = getenv("EA_TAIL_HELPERS") ? atoi(getenv("EA_TAIL_HELPERS")) : -1;   // experiment knob
   cudaStream_t ps = t->prep_stream;
   if (input_ready) {
     CU(cudaStreamWaitEvent(ps, input_ready, 0));
@@ -166,7 +168,7 @@ static int tracker_step(ea_tracker* t, const uint8_t* d_bgr, const void* d_depth
                                        t->have_order ? t->d_order : nullptr, &t->sp, t->d_summaries,
                                        // many pairs per SM and the next frame's preprocessing waiting for the SMs the solve gives
                                        // up in its tail: helpers would only keep those SMs away from it (measured: -7 % throughput)
-                                       !(overlap && t->n_streams >= 2 * c->sm_count));
+                                       force_helpers > 0 || (force_helpers < 0 && !(overlap && t->n_streams >= 2 * c->sm_count)));
     if (rc) return rc;
     if (t->n_streams > 1 && t->n_streams <= 4096) {
       cudaError_t oe = ea_launch_order_by_work(t->d_summaries, t->n_streams, t->n_levels, t->d_order, s);

@@ -254,7 +254,7 @@ def config4(args, env):
     from edge_alignment_b200 import sharding
     w, h, NL, INTERVAL = 1280, 720, 4, 10
     Kc = (1050.0, 1050.0, (w - 1) / 2.0, (h - 1) / 2.0)
-    S = args.streams if args.streams != 592 else 148          # one stream per SM unless asked otherwise
+    S = args.streams or 148          # one stream per SM unless asked otherwise
     K, Wm = args.steps, args.warmup
     T = Wm + K + 1; NF = min(T, 12)
     bgr = torch.empty((NF, S, h, w, 3), dtype=torch.uint8, device=dev); dep = torch.empty((NF, S, h, w), dtype=torch.uint16, device=dev)

@@ -9,7 +9,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_tests.log 2>&1; echo
 timeout 600 python bench.py > $O/${TAG}_bench_default.json 2> $O/${TAG}_bench_default.err; echo "bench rc=$?"
 CMD="python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline"
 $CMD > $O/${TAG}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_ncu.csv $CMD > $O/${TAG}_ncu_list.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^(k_|ea_k)" -c 600 --csv --log-file $O/${TAG}_launches_ncu.csv $CMD > $O/${TAG}_ncu_list.log 2>&1
 echo "ncu list rc=$?"
 $CMD > $O/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:ea_k_solve_batch -s 5 -c 1 -f -o $O/${TAG}_solve_full $CMD > $O/${TAG}_ncu_full.log 2>&1
