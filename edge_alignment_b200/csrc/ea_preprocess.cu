@@ -584,8 +584,8 @@ __global__ void __launch_bounds__(1024) k_chamfer_dt(const __grid_constant__ EaP
 // instructions on scan / carry plumbing).  592 frames x 3 levels = 1 776 independent warps keep every scheduler busy
 // without any of them waiting for another.  Used when every level is at most 32 * DTW_PMAX pixels wide.
 #define DTW_PMAX 20
-template <int P, bool BACKWARD>
-__device__ __forceinline__ void dtw_row_scan(int (&d)[P], const int (&cval)[P], const int lane) {
+template <int P, bool BACKWARD, int SEG>
+__device__ __forceinline__ void dtw_row_scan(int (&d)[P], const int (&cval)[P], const int lp) {   // lp: lane within its segment
   // A single warp per scheduler cannot hide latency with other warps, so the row step is arranged for short dependency
   // chains: with the ramp HV * position taken out, the strip total is a tree minimum (feeds the warp scan at once) and the
   // strip-local prefix minimum is a two-level scan that overlaps the shuffles.
@@ -600,16 +600,16 @@ __device__ __forceinline__ void dtw_row_scan(int (&d)[P], const int (&cval)[P], 
 #pragma unroll
   for (int g = 1; g < P / 4; ++g) mt = min(mt, m[g]);
   const int run = min(mt + DT_HV * (P - 1), DT_INF);          // the strip's last pixel, ignoring upstream strips
-  const int pos = BACKWARD ? (31 - lane) : lane;
+  const int pos = BACKWARD ? (SEG - 1 - lp) : lp;
   constexpr int stepP = DT_HV * P;
   int s = run - stepP * pos;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = BACKWARD ? __shfl_down_sync(0xffffffffu, s, o) : __shfl_up_sync(0xffffffffu, s, o);
+  for (int o = 1; o < SEG; o <<= 1) {
+    const int t = BACKWARD ? __shfl_down_sync(0xffffffffu, s, o, SEG) : __shfl_up_sync(0xffffffffu, s, o, SEG);
     if (pos >= o) s = min(s, t);
   }
   const int out = s + stepP * pos;   // final value of this lane's last pixel along the scan
-  int carry = BACKWARD ? __shfl_down_sync(0xffffffffu, out, 1) : __shfl_up_sync(0xffffffffu, out, 1);
+  int carry = BACKWARD ? __shfl_down_sync(0xffffffffu, out, 1, SEG) : __shfl_up_sync(0xffffffffu, out, 1, SEG);
   if (pos == 0) carry = DT_INF;
   carry = min(carry, DT_INF);
   // strip-local prefix minimum (independent of the shuffles above)
@@ -634,16 +634,24 @@ __device__ __forceinline__ void dtw_row_scan(int (&d)[P], const int (&cval)[P], 
 #ifndef DTW_L2_AHEAD
 #define DTW_L2_AHEAD 4      // rows of L2 prefetch distance (measured: see profiles)
 #endif
-template <int P, bool FULL>
-__device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, const int slot, const int lane) {
+// SEG: lanes per frame.  A row of 32 * P pixels takes the whole warp; the coarser pyramid levels of a 640-pixel frame (320, 160,
+// 80 pixels) would leave most strips empty -- and paid 2-3x the instructions per pixel of level 0 -- so they run as 2 / 4 / 8
+// frames side by side in one warp, each on SEG = 16 / 8 / 4 lanes with the same full 20-pixel strips (segmented shuffles).
+template <int P, bool FULL, int SEG>
+__device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, const int lane) {
   const EaPrepLevel& L = A.lv[level];
-  const int w = FULL ? 32 * P : L.w, h = L.h, words = L.words;   // FULL: a compile-time width folds every bound check
+  const int lp = lane % SEG;                                       // lane within the frame's segment
+  const int fi = int(blockIdx.x) * (32 / SEG) + lane / SEG;        // frame of this segment
+  const bool frame_on = fi < A.n;
+  const int slot = A.slots[frame_on ? fi : 0];
+  const unsigned seg_mask = (0xffffffffu >> (32 - SEG)) << ((lane / SEG) * SEG);
+  const int w = FULL ? SEG * P : L.w, h = L.h, words = L.words;   // FULL: a compile-time width folds every bound check
   const uint32_t* bits = (A.use_median ? L.med_bits : L.edge_bits) + size_t(slot) * h * words;
   float* gf = ea_dt_origin(L, slot);                 // pixel (0,0) of the padded image; rows are pitch apart
   int* gi = reinterpret_cast<int*>(gf);
   const int pitch = L.dt_pitch;
-  const int x0 = lane * P;
-  const bool on = x0 < w;
+  const int x0 = lp * P;
+  const bool on = frame_on && x0 < w;
   const bool vec_ok = (P % 4 == 0) && ((w & 3) == 0);
   const int wi = x0 >> 5, sh = x0 & 31;
   const bool two = on && (wi + 1 < words);
@@ -654,15 +662,15 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
   unsigned b0 = on ? bits[wi] : 0u, b1 = two ? bits[wi + 1] : 0u;
   for (int y = 0; y < h; ++y) {
     const unsigned ebits = __funnelshift_r(b0, b1, sh);
-    if (y + DTW_L2_AHEAD < h && lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(bits + size_t(y + DTW_L2_AHEAD) * words));
+    if (y + DTW_L2_AHEAD < h && lp == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(bits + size_t(y + DTW_L2_AHEAD) * words));
     if (y + 1 < h) {   // prefetch the next row's mask words
       b0 = on ? bits[size_t(y + 1) * words + wi] : 0u;
       b1 = two ? bits[size_t(y + 1) * words + wi + 1] : 0u;
     }
-    int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
-    int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
-    if (lane == 0) pl = DT_INF;
-    if (lane == 31) pr = DT_INF;
+    int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1, SEG);
+    int pr = __shfl_down_sync(0xffffffffu, d[0], 1, SEG);
+    if (lp == 0) pl = DT_INF;
+    if (lp == SEG - 1) pr = DT_INF;
     int cval[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) {
@@ -673,7 +681,7 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
       if (!FULL && x0 + k >= w) v = DT_INF;
       cval[k] = v;     // "infinite" values stay >= DT_INF and bounded by DT_INF + DG + HV * P (the carry below is clamped every row)
     }
-    dtw_row_scan<P, false>(d, cval, lane);
+    dtw_row_scan<P, false, SEG>(d, cval, lp);
 #pragma unroll
     for (int k = 0; k < P; ++k) if (!FULL && x0 + k >= w) d[k] = DT_INF;
     if (on) dt_store_row<P, int>(gi + size_t(y) * pitch, x0, w, d, vec_ok);
@@ -694,12 +702,12 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
     if (y > 0 && on) dt_load_row<P>(gi + size_t(y - 1) * pitch, x0, w, t_next, vec_ok);
     // the forward rows were written ~1 ms ago and have left the L2: the register prefetch one row ahead does not cover a
     // DRAM round trip (ncu: 31 % of the kernel's samples waited here), so rows further up are pulled into L2 early
-    if (y >= DTW_L2_AHEAD && lane * 32 < w)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + size_t(y - DTW_L2_AHEAD) * pitch + lane * 32));
-    int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1);
-    int pr = __shfl_down_sync(0xffffffffu, d[0], 1);
-    if (lane == 0) pl = DT_INF;
-    if (lane == 31) pr = DT_INF;
+    if (y >= DTW_L2_AHEAD && frame_on && lp * 32 < w)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + size_t(y - DTW_L2_AHEAD) * pitch + lp * 32));
+    int pl = __shfl_up_sync(0xffffffffu, d[P - 1], 1, SEG);
+    int pr = __shfl_down_sync(0xffffffffu, d[0], 1, SEG);
+    if (lp == 0) pl = DT_INF;
+    if (lp == SEG - 1) pr = DT_INF;
     int cval[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) {
@@ -709,7 +717,7 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
       if (!FULL && x0 + k >= w) v = DT_INF;
       cval[k] = v;     // "infinite" values stay >= DT_INF and bounded by DT_INF + DG + HV * P (the carry below is clamped every row)
     }
-    dtw_row_scan<P, true>(d, cval, lane);
+    dtw_row_scan<P, true, SEG>(d, cval, lp);
     float outv[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) {
@@ -732,21 +740,21 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
     for (int c = 0; c < copies; ++c) {
       float* row = gf + (ptrdiff_t(y) + ptrdiff_t(c) * ystep) * pitch;
       if (on) dt_store_row<P, float>(row, x0, w, outv, vec_ok);
-      if (lane == 0) *reinterpret_cast<float4*>(row - EA_DT_PAD) = make_float4(outv[0], outv[0], outv[0], outv[0]);
+      if (lp == 0 && frame_on) *reinterpret_cast<float4*>(row - EA_DT_PAD) = make_float4(outv[0], outv[0], outv[0], outv[0]);
       if (last_strip) for (int x = w; x < pitch - EA_DT_PAD; ++x) row[x] = edge_r;
     }
     if (h == 1 && y == 0) {   // a single image row is both first and last: the rows below it as well
       for (int c = 1; c <= EA_DT_PAD; ++c) {
         float* row = gf + ptrdiff_t(c) * pitch;
         if (on) dt_store_row<P, float>(row, x0, w, outv, vec_ok);
-        if (lane == 0) *reinterpret_cast<float4*>(row - EA_DT_PAD) = make_float4(outv[0], outv[0], outv[0], outv[0]);
+        if (lp == 0 && frame_on) *reinterpret_cast<float4*>(row - EA_DT_PAD) = make_float4(outv[0], outv[0], outv[0], outv[0]);
         if (last_strip) for (int x = w; x < pitch - EA_DT_PAD; ++x) row[x] = edge_r;
       }
     }
   }
-  const unsigned mx = __reduce_max_sync(0xffffffffu, vmax);
-  const unsigned mn = __reduce_min_sync(0xffffffffu, vmin);
-  if (lane == 0) {
+  const unsigned mx = __reduce_max_sync(seg_mask, vmax);
+  const unsigned mn = __reduce_min_sync(seg_mask, vmin);
+  if (lp == 0 && frame_on) {
     A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2] = mn;
     A.dt_minmax[(slot * EA_MAX_LEVELS + level) * 2 + 1] = mx;
     // cv::normalize(NORM_MINMAX, alpha = 0, beta): scale = beta / (max - min), shift = -min * scale (double, then float)
@@ -762,13 +770,22 @@ __device__ __forceinline__ void dtw_level(const EaPrepArgs& A, const int level, 
   }
 }
 
+// lanes per frame at a level of width w: full 20-pixel strips on 16 / 8 / 4 lanes where the width allows it, else the whole warp
+__host__ __device__ __forceinline__ int dtw_seg(int w) {
+  return w == 16 * DTW_PMAX ? 16 : w == 8 * DTW_PMAX ? 8 : w == 4 * DTW_PMAX ? 4 : 32;
+}
 __global__ void __launch_bounds__(32) k_chamfer_dt_warp(const __grid_constant__ EaPrepArgs A) {
-  const int level = blockIdx.y, slot = A.slots[blockIdx.x], lane = threadIdx.x;
-  const int per = (A.lv[level].w + 31) / 32;
+  const int level = blockIdx.y, lane = threadIdx.x;
   const int w = A.lv[level].w;
-  if (per <= 8) { if (w == 256) dtw_level<8, true>(A, level, slot, lane); else dtw_level<8, false>(A, level, slot, lane); }
-  else if (per <= 12) { if (w == 384) dtw_level<12, true>(A, level, slot, lane); else dtw_level<12, false>(A, level, slot, lane); }
-  else { if (w == 32 * DTW_PMAX) dtw_level<DTW_PMAX, true>(A, level, slot, lane); else dtw_level<DTW_PMAX, false>(A, level, slot, lane); }
+  const int seg = dtw_seg(w);
+  if (int(blockIdx.x) * (32 / seg) >= A.n) return;           // the grid is sized for one frame per warp (level 0)
+  const int per = (w + 31) / 32;
+  if (seg == 16) dtw_level<DTW_PMAX, true, 16>(A, level, lane);
+  else if (seg == 8) dtw_level<DTW_PMAX, true, 8>(A, level, lane);
+  else if (seg == 4) dtw_level<DTW_PMAX, true, 4>(A, level, lane);
+  else if (per <= 8) { if (w == 256) dtw_level<8, true, 32>(A, level, lane); else dtw_level<8, false, 32>(A, level, lane); }
+  else if (per <= 12) { if (w == 384) dtw_level<12, true, 32>(A, level, lane); else dtw_level<12, false, 32>(A, level, lane); }
+  else { if (w == 32 * DTW_PMAX) dtw_level<DTW_PMAX, true, 32>(A, level, lane); else dtw_level<DTW_PMAX, false, 32>(A, level, lane); }
 }
 
 // ---- normalised copy of one DT (read-back for parity tests): dst = raw * scale + shift, exactly as cv::normalize ----

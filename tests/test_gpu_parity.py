@@ -87,6 +87,27 @@ def test_preprocess_pyramid_and_variants(ea, ctx, frames, oracle):
         fs.close()
 
 
+def test_distance_transform_frames_side_by_side(ea, ctx, frames, oracle):
+    """The coarse pyramid levels of a 640-pixel frame (320 / 160 / 80 pixels) run as 2 / 4 / 8 frames per warp in the chamfer kernel
+    (segmented shuffles): an odd number of frames in scrambled slots leaves the last warp's trailing segments empty, and every
+    frame, level and segment position must still match the oracle bit for bit."""
+    O = oracle
+    order = [4, 0, 3, 1, 2, 0, 2]                          # 7 frames (with repeats) -> segments 0..6 of the level-3 warp
+    slots = [3, 6, 0, 5, 1, 4, 2]
+    fs = ea.FrameSet(ctx, ea.frame_params(n_levels=4), len(order))
+    try:
+        fs.preprocess_host(slots, frames["bgr"][order], frames["depth"][order], ea.ROLE_NOW)
+        for slot, fi in zip(slots, order):
+            bgr = frames["bgr"][fi]
+            for l in range(4):
+                odt, omask = O.get_distance_transform(bgr)
+                np.testing.assert_array_equal(fs.edge_mask(slot, l, median=True), omask, err_msg="mask frame %d level %d" % (fi, l))
+                np.testing.assert_array_equal(fs.dt(slot, l), odt, err_msg="dt frame %d level %d" % (fi, l))
+                bgr = O.half_linear(bgr)
+    finally:
+        fs.close()
+
+
 def test_preprocess_edge_cases(ea, ctx, oracle):
     O = oracle
     rng = np.random.default_rng(3)
