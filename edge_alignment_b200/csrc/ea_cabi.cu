@@ -613,7 +613,7 @@ static int fill_solve_args(ea_context* c, ea_frameset* ref, ea_frameset* now, co
   A.inv_depth_scale = ref->inv_depth_unit;
   for (int l = 0; l < ref->p.n_levels; ++l) { A.ref_geom[l] = ref->geom[l]; A.now_geom[l] = now->geom[l]; A.ref_cap[l] = ref->lv[l].cap; }
   A.sp = *sp;
-  A.loss = ea_loss_consts(sp->loss_type, sp->loss_scale, sp->point_stride);
+  A.loss = ea_eval_consts(sp->loss_type, sp->loss_scale, sp->point_stride);
   *cluster = sp->cluster_size;
   (void)c;
   return EA_OK;

@@ -267,13 +267,14 @@ __device__ __forceinline__ void ea_interp(const float (&t)[16], const float du, 
   f = fmaf(val, affine.x, affine.y);
 }
 
-// Loss constants in fp32, derived once on the host (kernel arguments: the hot loop reads them as constant-bank operands).
-struct EaLossF {
-  int type; float a, b, two_a, inv_a, inv_b;
-  unsigned stride_bytes[2];   // rides along: byte step of the point stream per residual (point_stride x 8 for pixel points, x 16 for XYZ)
+// Per-solve constants of the evaluation loop in the form it consumes them, derived once on the host (kernel arguments: the hot
+// loop reads them as constant-bank operands instead of converting ea_solve_params' doubles in every iteration).
+struct EaEvalConsts {
+  int type; float a, b, two_a, inv_a, inv_b;   // loss: type, scale a, a^2, 2a, 1/a, 1/a^2 (fp32, IEEE-rounded as the loop used to)
+  unsigned stride_bytes[2];                    // byte step of the point stream per residual: point_stride x 8 (pixel points), x 16 (XYZ)
 };
-__host__ __device__ inline EaLossF ea_loss_consts(int type, double scale, int point_stride = 1) {
-  EaLossF L;
+__host__ __device__ inline EaEvalConsts ea_eval_consts(int type, double scale, int point_stride = 1) {
+  EaEvalConsts L;
   L.type = type; L.a = float(scale); L.b = L.a * L.a; L.two_a = 2.0f * L.a; L.inv_a = 1.0f / L.a; L.inv_b = 1.0f / L.b;
   L.stride_bytes[0] = unsigned(point_stride) * 8u; L.stride_bytes[1] = unsigned(point_stride) * 16u;
   return L;
@@ -281,7 +282,7 @@ __host__ __device__ inline EaLossF ea_loss_consts(int type, double scale, int po
 
 // Loss (ceres/loss_function.cc) + Corrector (rho'' <= 0 for all three => scale by sqrt(rho')) in fp32.
 // Returns sqrt(rho'), writes rho(s).
-__device__ __forceinline__ float ea_loss_eval(const EaLossF& L, float r, float& rho0) {
+__device__ __forceinline__ float ea_loss_eval(const EaEvalConsts& L, float r, float& rho0) {
   const float s = r * r;
   if (L.type == EA_LOSS_CAUCHY) {
     const float sum = fmaf(s, L.inv_b, 1.0f);
@@ -508,7 +509,7 @@ __device__ __forceinline__ bool ea_point_eval_general(const float4 p, const EaLe
   const float f = fmaf(fr, affine.x, affine.y);
   const float gu = fdu * affine.x * P.fxf;                                          // dr/d(distorted x)
   const float gv = ea_cubic_val(d0, d1, d2, d3, du, hu) * affine.x * P.fyf;         // dr/d(distorted y)
-  const float w = ea_loss_eval(ea_loss_consts(loss_type, double(loss_a)), f, rho0);
+  const float w = ea_loss_eval(ea_eval_consts(loss_type, double(loss_a)), f, rho0);
   // chain rule: distorted -> normalised -> p' (this camera) -> first camera
   const float gx = gu * Dxx + gv * Dyx, gy = gu * Dxy + gv * Dyy;
   const float pz = float(q2), izf = float(iz), wi = w * izf;

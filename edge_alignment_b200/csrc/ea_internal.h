@@ -32,7 +32,7 @@ struct EaSolveArgs {
   EaLevelGeom now_geom[EA_MAX_LEVELS];
   int ref_cap[EA_MAX_LEVELS];   // point-list capacity per level (guards a truncated list)
   ea_solve_params sp;
-  EaLossF loss;                 // sp's loss in fp32 (ea_loss_consts), for the evaluation loop
+  EaEvalConsts loss;                 // sp's loss in fp32 (ea_eval_consts), for the evaluation loop
 };
 
 cudaError_t ea_launch_solve_batch(const EaSolveArgs& A, int cluster_size, int sm_count, cudaStream_t stream);

@@ -199,7 +199,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLevelDesc nd, EaLevelGeom rg, EaLevelGeom ng,
-                                                            double inv_depth_scale, ea_solve_params sp, EaLossF loss, ShardCtl* ctl,
+                                                            double inv_depth_scale, ea_solve_params sp, EaEvalConsts loss, ShardCtl* ctl,
                                                             double* partials /*[grid][32]*/, ShardPeers peers, int rank, int world,
                                                             unsigned long long epoch0, int j_begin, int j_end) {
   __shared__ double part[THREADS / 32][EA_NSUM];
@@ -512,7 +512,7 @@ static int shard_solve_persistent(ea_shard* s, ea_frameset* ref, int ref_slot, e
   EaLevelGeom rg = ref->geom[level], ng = now->geom[level];
   double ids = ref->inv_depth_unit;
   ea_solve_params spv = *sp;
-  EaLossF lossv = ea_loss_consts(sp->loss_type, sp->loss_scale, sp->point_stride);
+  EaEvalConsts lossv = ea_eval_consts(sp->loss_type, sp->loss_scale, sp->point_stride);
   // one CTA per SM at most, at least ~2 iterations of the evaluation loop per CTA; every rank sizes its grid for its own slice
   int grid = std::max(1, std::min(c->sm_count, (j1 - j0 + 1023) / 1024));
   CU(cudaMemcpyAsync(s->d_pose, pose7, 56, cudaMemcpyHostToDevice, st));

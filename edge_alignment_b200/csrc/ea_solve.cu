@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) ea_k_eval_points(EaLevelDesc rd, EaLevelD
     PS::unpack(p, a0, a1, a2);
     ea_point_eval<XYZ>(a0, a1, a2, ng, inv_depth_scale, P, nd.dt, affine, e);
     float rho0;
-    const float w = ea_loss_eval(ea_loss_consts(sp.loss_type, sp.loss_scale, sp.point_stride), e.f, rho0);
+    const float w = ea_loss_eval(ea_eval_consts(sp.loss_type, sp.loss_scale, sp.point_stride), e.f, rho0);
     float J[6];
     ea_jacobian(e.gu, e.gv, e.ub, e.vb, e.pz, e.iz, P, affine.x * P.fx, affine.x * P.fy, w, J);
     if (!valid) continue;
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) ea_k_eval_points(EaLevelDesc rd, EaLevelD
 // Normal-equation sums through the production reduction path (one CTA per slice of the points).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) ea_k_eval_sums(EaLevelDesc rd, EaLevelDesc nd, EaLevelGeom rg, EaLevelGeom ng,
-                                                          double inv_depth_scale, ea_solve_params sp, EaLossF loss, const double* pose7,
+                                                          double inv_depth_scale, ea_solve_params sp, EaEvalConsts loss, const double* pose7,
                                                           const int* done, int j_begin, int j_end, double* sums /*[grid][EA_SUMS]*/) {
   if (done && *done) return;
   __shared__ double part[THREADS / 32][EA_NSUM];
@@ -587,7 +587,7 @@ cudaError_t ea_launch_eval_sums(const EaLevelDesc& rd, const EaLevelDesc& nd, co
                                 const double* d_pose7, const int* d_done, int j_begin, int j_end, int n_blocks, double* d_sums,
                                 cudaStream_t stream) {
   if (n_blocks <= 0) return cudaSuccess;
-  ea_k_eval_sums<EA_SOLVE_THREADS><<<n_blocks, EA_SOLVE_THREADS, 0, stream>>>(rd, nd, rg, ng, inv_depth_scale, sp, ea_loss_consts(sp.loss_type, sp.loss_scale, sp.point_stride),
+  ea_k_eval_sums<EA_SOLVE_THREADS><<<n_blocks, EA_SOLVE_THREADS, 0, stream>>>(rd, nd, rg, ng, inv_depth_scale, sp, ea_eval_consts(sp.loss_type, sp.loss_scale, sp.point_stride),
                                                                               d_pose7, d_done, j_begin, j_end, d_sums);
   return cudaGetLastError();
 }

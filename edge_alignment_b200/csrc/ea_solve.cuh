@@ -544,7 +544,7 @@ struct EaEvalAcc {
 template <bool XYZ, bool RAGGED>
 __device__ __forceinline__ void ea_eval_point(const typename EaPtStream<XYZ>::T p, const bool valid, const int W, const int H, const int pitch,
                                               const double inv_depth_scale, const EaPose& P, const float* __restrict__ dt_base,
-                                              const float2 affine, const float afx, const float afy, const EaLossF& loss, EaEvalAcc& A) {
+                                              const float2 affine, const float afx, const float afy, const EaEvalConsts& loss, EaEvalAcc& A) {
   EaProj r;
   {
     double a0, a1, a2;
@@ -596,7 +596,7 @@ __device__ __forceinline__ void ea_eval_point(const typename EaPtStream<XYZ>::T 
 template <bool XYZ, int THREADS>
 __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, const float* __restrict__ dt_pad, const float2 affine,
                                               const EaLevelGeom& ng,
-                                              double inv_depth_scale, const EaLossF& loss, const int stride, const EaPose& P, const int j0,
+                                              double inv_depth_scale, const EaEvalConsts& loss, const int stride, const EaPose& P, const int j0,
                                               const int j1, double (*part)[EA_NSUM], double* cpart, const bool reverse = false,
                                               uint2* stage = nullptr, const bool pre_valid = false,
                                               const bool prefetch_next = false, const bool next_reverse = false,
@@ -690,7 +690,9 @@ __device__ __forceinline__ void ea_eval_slice(const void* __restrict__ pts, cons
 // THREADS * EA_FLUSH_EVERY, so chunk ends coincide with the fp32 -> fp64 flushes).  Every chunk is reduced on its own, in a
 // fixed order, by whichever CTA evaluates it, and the chunk totals are added in chunk order: the sums do not depend on how
 // many CTAs shared the evaluation (tail helpers, ea_solve.cu).
+#ifndef EA_MAX_CHUNKS
 #define EA_MAX_CHUNKS 4
+#endif
 __device__ __forceinline__ int ea_chunking(const int n_res, const int threads, int& size) {
   // size = unit << s with the smallest s that leaves at most EA_MAX_CHUNKS chunks (a power-of-two number of iterations per
   // chunk: the loop finds its chunk with a shift)
