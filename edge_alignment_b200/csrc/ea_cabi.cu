@@ -83,7 +83,6 @@ int ea_destroy(ea_context* c) {
             c->debug_launches, c->debug_sum[0] / n / 1e3, c->debug_sum[1] / n / 1e3, c->debug_sum[2] / n / 1e3, c->debug_sum[3] / n / 1e3, c->debug_sum[5] / n / 1e3, c->debug_sum[4] / n);
   }
   cudaFree(c->d_debug); cudaFree(c->d_boards); cudaFree(c->d_views);
-  if (c->h_views_done) cudaFreeHost(c->h_views_done);
   cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_work); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;

@@ -116,7 +116,7 @@ struct ea_context {
   size_t idx_cap = 0;
   void* d_tmp = nullptr;
   size_t tmp_cap = 0;
-  void* d_views = nullptr; size_t views_cap = 0; int* h_views_done = nullptr;   // ea_solve_views: control block + partial sums, pinned flag
+  void* d_views = nullptr; size_t views_cap = 0;   // ea_solve_views: view descriptors, control block and CTA totals of the persistent kernel
   // optional profiling: event pairs around preprocessing pipelines [0] and solve launches [1]
   bool profile = false;
   double* d_trace = nullptr; int* d_trace_count = nullptr; int trace_cap = 0;   // ea_solve_traced

@@ -332,6 +332,128 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
   if (s_stop == 2 && tid == 0) ctl->error = 2;   // the release never came (a CTA of this grid or a peer rank is gone)
 }
 
+// ---- the same persistent scheme for the residual VARIANTS (ea_solve_views): any number of cameras constrain one pose ----------
+// One cooperative kernel for the whole solve: every CTA evaluates its slice of every view's point list with the general
+// per-point evaluation (rig transform and / or distortion per view), the CTA that draws the evaluation's last ticket adds the CTA
+// totals in a fixed order, runs the warp-cooperative LM step on the state in shared memory and releases the next evaluation.
+struct ViewDev {                  // one view, device-side (array in global memory)
+  EaLevelDesc rd, nd;
+  EaLevelGeom rg, ng;
+  EaViewXf X;
+  double inv_depth_scale;
+  int n_res, xyz;
+};
+__global__ void __launch_bounds__(GV_THREADS, 1) k_views_solve(const ViewDev* __restrict__ views, int n_views, ea_solve_params sp, ShardCtl* ctl,
+                                                               double* partials /*[grid][32]*/) {
+  constexpr int WARPS = GV_THREADS / 32;
+  __shared__ double part[WARPS][EA_NSUM];
+  __shared__ double cpart[WARPS];
+  __shared__ double wsum[WARPS][32];
+  __shared__ unsigned long long s_ticket;
+  __shared__ int s_stop;
+  __shared__ EaLmState s_lm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (unsigned long long e = 1;; ++e) {
+    if (tid == 0) {
+      long long spins = 0;
+      int stop = 0;
+      while (ld_acquire_gpu(&ctl->go) < e) {
+        if (++spins > EA_SHARD_SPIN_LIMIT) { stop = 2; break; }
+        __nanosleep(20);
+      }
+      if (!stop) stop = *reinterpret_cast<volatile int*>(&ctl->done);
+      s_stop = stop;
+    }
+    __syncthreads();
+    if (s_stop) break;
+    double cand[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) cand[i] = __ldcg(&ctl->lm.cand[i]);      // written by the LM warp of the previous round (L2)
+    float acc[EA_NSUM];
+#pragma unroll
+    for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
+    double acc64 = 0.0, cost64 = 0.0;
+    for (int v = 0; v < n_views; ++v) {
+      const ViewDev& V = views[v];
+      const int j0 = int((long long)V.n_res * blockIdx.x / gridDim.x), j1 = int((long long)V.n_res * (blockIdx.x + 1) / gridDim.x);
+      if (j1 <= j0) continue;                                            // (uniform per CTA)
+      EaPoseG P;
+      if (V.xyz) ea_pose_setup_general<true>(cand, V.rg, V.ng, V.X, P); else ea_pose_setup_general<false>(cand, V.rg, V.ng, V.X, P);
+      const float2 affine = *V.nd.dt_affine;
+      for (int base = j0 + warp * 32; base < j1; base += GV_THREADS) {
+        const int j = base + lane;
+        if (j < j1) {
+          float f, w, rho0, J[6];
+          bool fail;
+          if (V.xyz) {
+            const float4 p = EaPtStream<true>::as_float4(EaPtStream<true>::load(V.rd.pts, size_t(j) * sp.point_stride));
+            fail = ea_point_eval_general<true>(p, V.ng, V.inv_depth_scale, P, V.nd.dt, affine, sp.loss_type, float(sp.loss_scale), f, w, rho0, J);
+          } else {
+            const float4 p = EaPtStream<false>::as_float4(EaPtStream<false>::load(V.rd.pts, size_t(j) * sp.point_stride));
+            fail = ea_point_eval_general<false>(p, V.ng, V.inv_depth_scale, P, V.nd.dt, affine, sp.loss_type, float(sp.loss_scale), f, w, rho0, J);
+          }
+          ea_accumulate(acc, J, f * w);
+          acc[27] += fail ? 1.0f : 0.0f;
+          cost64 += double(0.5f * rho0);
+        }
+        acc64 += double(ea_warp_transpose_reduce(acc, lane));
+#pragma unroll
+        for (int k = 0; k < EA_NSUM; ++k) acc[k] = 0.0f;
+      }
+    }
+    cost64 = ea_warp_sum(cost64);
+    part[warp][lane] = acc64;
+    if (lane == 0) cpart[warp] = cost64;
+    __syncthreads();
+    if (warp == 0) {
+      const double tot = ea_cta_total<WARPS>(part, cpart, lane);
+      __stcg(&partials[size_t(blockIdx.x) * 32 + lane], lane < EA_SUMS ? tot : 0.0);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) s_ticket = atomicAdd(&ctl->ticket, 1ull);
+    }
+    __syncthreads();
+    if (s_ticket != e * gridDim.x - 1) continue;          // not the last CTA of this evaluation: wait for the next release
+    // ---- last CTA: grid reduce (fixed order: warp w adds CTAs w, w + W, ...; then the warps in order), LM, release ----
+    __threadfence();
+    {
+      double s_ = 0.0;
+      for (unsigned b = warp; b < gridDim.x; b += WARPS) s_ += __ldcg(&partials[size_t(b) * 32 + lane]);
+      wsum[warp][lane] = s_;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w2 = 0; w2 < WARPS; ++w2) tot += wsum[w2][lane];
+      wsum[0][lane] = tot;
+      {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&ctl->lm);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_lm);
+        for (int i = lane; i < int(sizeof(EaLmState) / 8); i += 32) dst[i] = __ldcg(src + i);
+      }
+      __syncwarp();
+      double next[7];
+      const int cmd = ea_lm_advance_warp(s_lm, wsum[0], sp, lane, next);      // (the next candidate is also left in s_lm.cand)
+      __syncwarp();
+      {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_lm);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&ctl->lm);
+        for (int i = lane; i < int(sizeof(EaLmState) / 8); i += 32) __stcg(dst + i, src[i]);
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        ctl->done = cmd == EA_CMD_EVAL ? 0 : 1;
+        ctl->prof[4] += 1;
+        __threadfence();
+        st_release_gpu(&ctl->go, e + 1);
+      }
+    }
+  }
+  if (s_stop == 2 && tid == 0) ctl->error = 2;   // the release never came (a CTA of this grid is gone)
+}
+
 // first evaluation's control block: LM state at the initial pose, its folded pose, evaluation 1 released
 __global__ void k_shard_ctl_init(ShardCtl* ctl, const double* pose7, EaLevelGeom rg, EaLevelGeom ng, int xyz) {
   EaLmState& L = ctl->lm;
@@ -719,55 +841,47 @@ int ea_solve_views(ea_context* c, int n_views, const ea_view* views, int level, 
     nb[i] = nres[i] > 0 ? std::max(1, std::min(c->sm_count, (nres[i] + 2047) / 2048)) : 0;
     total += nres[i]; nb_total += nb[i];
   }
-  // control block, partial sums and the pinned termination flag live in the context (allocated on first use, grown on demand):
-  // no cudaMalloc / cudaHostAlloc on the path of a solve, nothing to leak on an early return
-  const size_t need = 256 + size_t(std::max(nb_total, 1)) * EA_SUMS * 8 + EA_SUMS * 8 + ((sizeof(ShardState) + 255) & ~size_t(255));
+  // One persistent cooperative kernel for the whole solve (k_views_solve).  View descriptors, control block and CTA totals live
+  // in the context's scratch (allocated on first use, grown on demand): no allocation on the path of a solve.
+  const int grid = std::max(1, std::min(c->sm_count, (total + 1023) / 1024));
+  const size_t off_ctl = (size_t(n_views) * sizeof(ViewDev) + 255) & ~size_t(255);
+  const size_t off_part = off_ctl + ((sizeof(ShardCtl) + 255) & ~size_t(255));
+  const size_t need = off_part + size_t(grid) * 32 * 8;
   if (c->views_cap < need) {
     CU(cudaStreamSynchronize(st));
     if (c->d_views) { cudaFree(c->d_views); c->d_views = nullptr; c->views_cap = 0; }
     CU(cudaMalloc(&c->d_views, need));
     c->views_cap = need;
   }
-  if (!c->h_views_done) CU(cudaHostAlloc((void**)&c->h_views_done, sizeof(int), cudaHostAllocDefault));
   char* vb = static_cast<char*>(c->d_views);
-  ShardState* d_state = reinterpret_cast<ShardState*>(vb);
-  double* d_sums = reinterpret_cast<double*>(vb + ((sizeof(ShardState) + 255) & ~size_t(255)));
-  double* d_partials = d_sums + 32;
-  int* h_done = c->h_views_done;
-  CU(cudaMemcpyAsync(c->d_pose, pose7, 56, cudaMemcpyHostToDevice, st));
-  k_shard_init<<<1, 1, 0, st>>>(d_state, c->d_pose);
-  c->launches++;
-  const int max_evals = sp->max_num_iterations + 2;
-  int evals = 0;
-  *h_done = 0;
-  while (evals < max_evals && !*h_done) {
-    const int chunk = std::min(8, max_evals - evals);
-    for (int it = 0; it < chunk; ++it) {
-      int boff = 0;
-      for (int i = 0; i < n_views; ++i) {
-        if (!nb[i]) continue;
-        const ea_view& v = views[i];
-        const EaLevelDesc& rd = v.ref->h_desc[size_t(v.ref_slot) * EA_MAX_LEVELS + level];
-        const EaLevelDesc& nd = v.now->h_desc[size_t(v.now_slot) * EA_MAX_LEVELS + level];
-        EaViewXf X; view_xf(v, X);
-        const double ids = v.ref->inv_depth_unit;
-        if (rd.pts_mode == EA_POINTS_XYZ)
-          k_view_eval_sums<true><<<nb[i], GV_THREADS, 0, st>>>(rd, nd, v.ref->geom[level], v.now->geom[level], X, ids, *sp, d_state->cand, &d_state->done, 0, nres[i], d_partials + size_t(boff) * EA_SUMS);
-        else
-          k_view_eval_sums<false><<<nb[i], GV_THREADS, 0, st>>>(rd, nd, v.ref->geom[level], v.now->geom[level], X, ids, *sp, d_state->cand, &d_state->done, 0, nres[i], d_partials + size_t(boff) * EA_SUMS);
-        boff += nb[i];
-        c->launches++;
-      }
-      k_shard_reduce<<<1, 32, 0, st>>>(d_state, d_partials, nb_total, d_sums);
-      k_shard_lm<<<1, 32, 0, st>>>(d_state, d_sums, *sp);
-      c->launches += 2;
-    }
-    evals += chunk;
-    CU(cudaMemcpyAsync(h_done, &d_state->done, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+  ViewDev* d_vd = reinterpret_cast<ViewDev*>(vb);
+  ShardCtl* d_ctl = reinterpret_cast<ShardCtl*>(vb + off_ctl);
+  double* d_partials = reinterpret_cast<double*>(vb + off_part);
+  std::vector<ViewDev> hv(static_cast<size_t>(n_views));
+  for (int i = 0; i < n_views; ++i) {
+    const ea_view& v = views[i];
+    ViewDev& D = hv[size_t(i)];
+    D.rd = v.ref->h_desc[size_t(v.ref_slot) * EA_MAX_LEVELS + level];
+    D.nd = v.now->h_desc[size_t(v.now_slot) * EA_MAX_LEVELS + level];
+    D.rg = v.ref->geom[level]; D.ng = v.now->geom[level];
+    view_xf(v, D.X);
+    D.inv_depth_scale = v.ref->inv_depth_unit;
+    D.n_res = nres[i]; D.xyz = D.rd.pts_mode == EA_POINTS_XYZ ? 1 : 0;
   }
-  ShardState h;
-  CU(cudaMemcpy(&h, d_state, sizeof h, cudaMemcpyDeviceToHost));
+  (void)nb; (void)nb_total;
+  CU(cudaMemcpyAsync(d_vd, hv.data(), hv.size() * sizeof(ViewDev), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c->d_pose, pose7, 56, cudaMemcpyHostToDevice, st));
+  k_shard_ctl_init<<<1, 1, 0, st>>>(d_ctl, c->d_pose, hv[0].rg, hv[0].ng, hv[0].xyz);
+  ea_solve_params spv = *sp;
+  const ViewDev* vd_arg = d_vd; int nv = n_views;
+  void* args[] = {&vd_arg, &nv, &spv, &d_ctl, &d_partials};
+  cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_views_solve, dim3(unsigned(grid)), dim3(GV_THREADS), args, 0, st);
+  c->launches += 2;
+  if (le != cudaSuccess) return ea_fail(EA_ERR_CUDA, "views solve launch: %s", cudaGetErrorString(le));
+  ShardCtl h;
+  CU(cudaMemcpyAsync(&h, d_ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));      // (hv must outlive the upload)
+  if (h.error) return ea_fail(EA_ERR_CUDA, "views solve: the persistent kernel lost a CTA (bounded wait expired)");
   for (int i = 0; i < 7; ++i) pose7[i] = h.lm.x[i];
   if (summary) {
     summary->termination = h.done ? h.lm.term : EA_TERM_NO_CONVERGENCE;
