@@ -83,6 +83,11 @@ int ea_destroy(ea_context* c) {
             c->debug_launches, c->debug_sum[0] / n / 1e3, c->debug_sum[1] / n / 1e3, c->debug_sum[2] / n / 1e3, c->debug_sum[3] / n / 1e3, c->debug_sum[5] / n / 1e3, c->debug_sum[4] / n);
   }
   cudaFree(c->d_debug); cudaFree(c->d_boards); cudaFree(c->d_views);
+  for (int k = 0; k < 2; ++k) {
+    if (c->prep_pipe.aux[k]) { cudaStreamSynchronize(c->prep_pipe.aux[k]); cudaStreamDestroy(c->prep_pipe.aux[k]); }
+    if (c->prep_pipe.ev_front[k]) cudaEventDestroy(c->prep_pipe.ev_front[k]);
+    if (c->prep_pipe.ev_dt[k]) cudaEventDestroy(c->prep_pipe.ev_dt[k]);
+  }
   cudaFree(c->d_pose); cudaFree(c->d_failed); cudaFree(c->d_work); cudaFree(c->d_sums); cudaFree(c->d_idx); cudaFree(c->d_tmp);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -292,8 +297,17 @@ int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uin
   A.depth_one = fs->p.depth_type == EA_DEPTH_F32 ? 1.0f : float(fs->p.depth_scale);
   if (A.edge_detector != EA_EDGE_LAPLACIAN) A.use_median = 0;   // the Canny pipelines of the reference have no median step
   int nl = 0;
+  if (!c->prep_pipe.ready && n >= 2 * c->sm_count) {      // auxiliary lanes of the preprocessing pipeline (big batches only)
+    EaPrepPipe& P = c->prep_pipe;
+    for (int k = 0; k < 2; ++k) {
+      CU(cudaStreamCreateWithFlags(&P.aux[k], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&P.ev_front[k], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&P.ev_dt[k], cudaEventDisableTiming));
+    }
+    P.ready = true;
+  }
   EaProfileScope prof(c, 0, stream);
-  cudaError_t e = ea_launch_preprocess(A, c->sm_count, stream, &nl);
+  cudaError_t e = ea_launch_preprocess(A, c->sm_count, stream, &nl, &c->prep_pipe);
   c->launches += nl;
   if (e != cudaSuccess) return ea_fail(EA_ERR_CUDA, "preprocess launch: %s", cudaGetErrorString(e));
   return EA_OK;

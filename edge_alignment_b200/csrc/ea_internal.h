@@ -86,7 +86,14 @@ struct EaPrepArgs {
   EaScratch scratch;
 };
 // enqueue the whole preprocessing pipeline for n frames; returns number of kernel launches via *launches
-cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches);
+// Optional second lane for big batches: the distance transforms (DRAM / latency-bound, few warps) of one half of the frames run on
+// an auxiliary stream beside the edge kernels (issue-bound) of the other half.  Streams and events belong to the context.
+struct EaPrepPipe {
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_dt[2] = {nullptr, nullptr};
+  bool ready = false;
+};
+cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches, const EaPrepPipe* pipe = nullptr);
 __host__ __device__ inline float* ea_dt_origin(const EaPrepLevel& L, int slot) {   // pixel (0,0) of a slot's padded DT
   return L.dt + size_t(slot) * L.dt_slot + size_t(EA_DT_PAD) * L.dt_pitch + EA_DT_PAD;
 }
@@ -117,6 +124,7 @@ struct ea_context {
   void* d_tmp = nullptr;
   size_t tmp_cap = 0;
   void* d_views = nullptr; size_t views_cap = 0;   // ea_solve_views: view descriptors, control block and CTA totals of the persistent kernel
+  EaPrepPipe prep_pipe;           // auxiliary streams of the preprocessing pipeline (created on first use)
   // optional profiling: event pairs around preprocessing pipelines [0] and solve launches [1]
   bool profile = false;
   double* d_trace = nullptr; int* d_trace_count = nullptr; int trace_cap = 0;   // ea_solve_traced

@@ -899,46 +899,91 @@ static cudaError_t launch_edges_and_points(const EaPrepArgs& A, cudaStream_t str
   return cudaGetLastError();
 }
 
-cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches) {
-  int nl = 0;
-  const bool want_ref = (A.roles & EA_ROLE_REF) != 0, want_now = (A.roles & EA_ROLE_NOW) != 0;
-  if (want_ref && !A.in_depth) return cudaErrorInvalidValue;
-  (void)sm_count;
+// edges, reference points and the median plane of A's frames
+static cudaError_t launch_front(const EaPrepArgs& A, cudaStream_t stream, int& nl) {
+  const bool want_now = (A.roles & EA_ROLE_NOW) != 0;
   cudaError_t pe = (A.depth_type == 1) ? launch_edges_and_points<float>(A, stream, nl) : launch_edges_and_points<uint16_t>(A, stream, nl);
   if (pe != cudaSuccess) return pe;
-  if (want_now && A.dt_kind == EA_DT_EXACT) {
+  if (want_now && A.dt_kind != EA_DT_EXACT && A.use_median) {
+    const EaPrepLevel& L0 = A.lv[0];
+    dim3 grid(unsigned((L0.h * L0.words + 255) / 256), unsigned(A.n), unsigned(A.n_levels));
+    k_median_bits<<<grid, 256, 0, stream>>>(A);
+    ++nl;
+  }
+  return cudaGetLastError();
+}
+// distance transforms of A's frames (now role)
+static cudaError_t launch_dt(const EaPrepArgs& A, cudaStream_t stream, int& nl) {
+  if (A.dt_kind == EA_DT_EXACT) {
     for (int l = 0; l < A.n_levels; ++l) {
       cudaError_t ee = ea_launch_exact_edt_level(A, l, A.scratch, stream, &nl);
       if (ee != cudaSuccess) return ee;
     }
-  } else if (want_now) {
-    const EaPrepLevel& L0 = A.lv[0];
-    if (A.use_median) {
-      dim3 grid(unsigned((L0.h * L0.words + 255) / 256), unsigned(A.n), unsigned(A.n_levels));
-      k_median_bits<<<grid, 256, 0, stream>>>(A);
-      ++nl;
-    }
-    static const int env_block = getenv("EA_DT_BLOCK") ? atoi(getenv("EA_DT_BLOCK")) : 0;   // A/B knob: force the block kernel
-    if (L0.w <= 32 * DTW_PMAX && !env_block) {   // one warp per (frame, level); level 0 CTAs are scheduled first
-      k_chamfer_dt_warp<<<dim3(unsigned(A.n), unsigned(A.n_levels)), 32, 0, stream>>>(A);
-      ++nl;
-      if (launches) *launches = nl;
-      return cudaGetLastError();
-    }
-    // wider images: every level of every frame in one launch, CTA (frame, level); block sized for level 0
-    int P = (L0.w <= 4096) ? 4 : 8;
-    if (const char* e = getenv("EA_DT_P")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v > P) P = v; }   // tuning knob
-    const int threads = (((L0.w + P - 1) / P + 31) / 32) * 32;
-    if (threads > 1024) return cudaErrorInvalidValue;
-    dim3 grid(unsigned(A.n), unsigned(A.n_levels));
-    if (P == 2) k_chamfer_dt<2><<<grid, threads, 0, stream>>>(A);
-    else if (P == 4) k_chamfer_dt<4><<<grid, threads, 0, stream>>>(A);
-    else k_chamfer_dt<8><<<grid, threads, 0, stream>>>(A);
-    ++nl;
-    for (int l = 0; l < A.n_levels; ++l) { ea_launch_dt_fill_pad(A.lv[l], A.slots, A.n, stream); ++nl; }
+    return cudaGetLastError();
   }
-  if (launches) *launches = nl;
+  const EaPrepLevel& L0 = A.lv[0];
+  static const int env_block = getenv("EA_DT_BLOCK") ? atoi(getenv("EA_DT_BLOCK")) : 0;   // A/B knob: force the block kernel
+  if (L0.w <= 32 * DTW_PMAX && !env_block) {   // one warp per (frame, level); level 0 CTAs are scheduled first
+    k_chamfer_dt_warp<<<dim3(unsigned(A.n), unsigned(A.n_levels)), 32, 0, stream>>>(A);
+    ++nl;
+    return cudaGetLastError();
+  }
+  // wider images: every level of every frame in one launch, CTA (frame, level); block sized for level 0
+  int P = (L0.w <= 4096) ? 4 : 8;
+  if (const char* e = getenv("EA_DT_P")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v > P) P = v; }   // tuning knob
+  const int threads = (((L0.w + P - 1) / P + 31) / 32) * 32;
+  if (threads > 1024) return cudaErrorInvalidValue;
+  dim3 grid(unsigned(A.n), unsigned(A.n_levels));
+  if (P == 2) k_chamfer_dt<2><<<grid, threads, 0, stream>>>(A);
+  else if (P == 4) k_chamfer_dt<4><<<grid, threads, 0, stream>>>(A);
+  else k_chamfer_dt<8><<<grid, threads, 0, stream>>>(A);
+  ++nl;
+  for (int l = 0; l < A.n_levels; ++l) { ea_launch_dt_fill_pad(A.lv[l], A.slots, A.n, stream); ++nl; }
   return cudaGetLastError();
+}
+// frames [f0, f0 + n) of A as an argument block of their own (pools are indexed by slot, inputs by frame)
+static EaPrepArgs prep_slice(const EaPrepArgs& A, int f0, int n) {
+  EaPrepArgs S = A;
+  const size_t px0 = size_t(A.lv[0].w) * A.lv[0].h;
+  S.n = n; S.slots = A.slots + f0;
+  S.in_bgr = A.in_bgr + size_t(f0) * px0 * 3;
+  if (A.in_depth) S.in_depth = static_cast<const char*>(A.in_depth) + size_t(f0) * px0 * (A.depth_type == 1 ? 4 : 2);
+  if (A.in_mask) S.in_mask = A.in_mask + size_t(f0) * px0;
+  if (A.in_now_mask) S.in_now_mask = A.in_now_mask + size_t(f0) * px0;
+  return S;
+}
+
+cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches, const EaPrepPipe* pipe) {
+  int nl = 0;
+  const bool want_ref = (A.roles & EA_ROLE_REF) != 0, want_now = (A.roles & EA_ROLE_NOW) != 0;
+  if (want_ref && !A.in_depth) return cudaErrorInvalidValue;
+  // Two halves, two lanes: the chamfer kernel (DRAM- and latency-bound, ~40 % of the issue slots) of the first half runs beside
+  // the edge kernels (issue-bound, a sixth of the DRAM bandwidth) of the second half.  Only the Laplacian + chamfer pipeline (its
+  // work buffers are all indexed by slot), and only when both halves still fill the GPU: from EA_PREP_SPLIT (default 8) frames per
+  // SM; 0 turns it off.
+  static const int env_split = getenv("EA_PREP_SPLIT") ? atoi(getenv("EA_PREP_SPLIT")) : 8;
+  const bool split = env_split > 0 && pipe && pipe->ready && want_now && A.edge_detector == EA_EDGE_LAPLACIAN && A.dt_kind != EA_DT_EXACT &&
+                     A.lv[0].w <= 32 * DTW_PMAX && A.n >= env_split * sm_count;
+  cudaError_t e = cudaSuccess;
+  if (!split) {
+    e = launch_front(A, stream, nl);
+    if (e == cudaSuccess && want_now) e = launch_dt(A, stream, nl);
+  } else {
+    const int n0 = A.n / 2;
+    const EaPrepArgs H[2] = {prep_slice(A, 0, n0), prep_slice(A, n0, A.n - n0)};
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+      e = launch_front(H[k], stream, nl);
+      if (e != cudaSuccess) break;
+      e = cudaEventRecord(pipe->ev_front[k], stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(pipe->aux[k], pipe->ev_front[k], 0);
+      if (e == cudaSuccess) e = launch_dt(H[k], pipe->aux[k], nl);
+      if (e == cudaSuccess) e = cudaEventRecord(pipe->ev_dt[k], pipe->aux[k]);
+    }
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamWaitEvent(stream, pipe->ev_dt[k], 0);   // join
+  }
+  (void)sm_count;
+  if (launches) *launches = nl;
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t ea_launch_dt_normalized_copy(const float* origin, int pitch, const float2* affine, int w, int h, float* out, cudaStream_t stream) {

@@ -108,6 +108,43 @@ def test_distance_transform_frames_side_by_side(ea, ctx, frames, oracle):
         fs.close()
 
 
+def test_preprocess_two_lane_pipeline_on_big_batches(ea, ctx, oracle):
+    """From 8 frames per SM the distance transforms of the first half of a batch run on an auxiliary stream beside the edge
+    kernels of the second half (ea_launch_preprocess).  An odd, scrambled batch of small frames: the frames on either side of
+    the split, and the first and last ones, must match the oracle bit for bit -- masks, distance transforms, point lists."""
+    O = oracle
+    import torch
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    n = 8 * n_sm + 3
+    w, h = 64, 48
+    rng = np.random.default_rng(11)
+    K = (50.0, 50.0, w / 2.0, h / 2.0)
+    fp = ea.frame_params(width=w, height=h, fx=K[0], fy=K[1], cx=K[2], cy=K[3], max_points=w * h, n_levels=2)
+    fs = ea.FrameSet(ctx, fp, n)
+    try:
+        base = (rng.integers(0, 4, (16, h, w, 3)) * 64).astype(np.uint8)             # 16 distinct blocky images ...
+        shift = rng.integers(0, 16, n)
+        bgr = np.stack([np.roll(base[i % 16], int(shift[i]), axis=1) for i in range(n)])   # ... each frame its own shift
+        dep = (rng.integers(0, 3, (n, h, w)) * 700).astype(np.uint16)
+        slots = rng.permutation(n).astype(np.int32)
+        fs.preprocess_host(slots, bgr, dep, ea.ROLE_BOTH)
+        half = n // 2
+        for i in (0, 1, half - 1, half, half + 1, n - 2, n - 1):
+            s = int(slots[i])
+            b, d = bgr[i], dep[i]
+            for l in range(2):
+                Kl = fs.level_geometry(l)[2]
+                odt, omask = O.get_distance_transform(b)
+                np.testing.assert_array_equal(fs.edge_mask(s, l, median=True), omask, err_msg="mask frame %d level %d" % (i, l))
+                np.testing.assert_array_equal(fs.dt(s, l), odt, err_msg="dt frame %d level %d" % (i, l))
+                _, uvd = O.get_aX(b, d, Kl)
+                assert fs.num_points(s, l) == len(uvd)
+                np.testing.assert_array_equal(fs.points(s, l)[:, :3].astype(np.int32).reshape(-1, 3), uvd.reshape(-1, 3))
+                b, d = O.half_linear(b), O.half_nearest(d)
+    finally:
+        fs.close()
+
+
 def test_preprocess_edge_cases(ea, ctx, oracle):
     O = oracle
     rng = np.random.default_rng(3)
