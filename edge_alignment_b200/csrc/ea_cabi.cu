@@ -83,7 +83,7 @@ int ea_destroy(ea_context* c) {
             c->debug_launches, c->debug_sum[0] / n / 1e3, c->debug_sum[1] / n / 1e3, c->debug_sum[2] / n / 1e3, c->debug_sum[3] / n / 1e3, c->debug_sum[5] / n / 1e3, c->debug_sum[4] / n);
   }
   cudaFree(c->d_debug); cudaFree(c->d_boards); cudaFree(c->d_views);
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < EA_PREP_MAX_PARTS; ++k) {
     if (c->prep_pipe.aux[k]) { cudaStreamSynchronize(c->prep_pipe.aux[k]); cudaStreamDestroy(c->prep_pipe.aux[k]); }
     if (c->prep_pipe.ev_front[k]) cudaEventDestroy(c->prep_pipe.ev_front[k]);
     if (c->prep_pipe.ev_dt[k]) cudaEventDestroy(c->prep_pipe.ev_dt[k]);
@@ -299,8 +299,12 @@ int ea_preprocess_impl(ea_frameset* fs, int n, const int32_t* d_slots, const uin
   int nl = 0;
   if (!c->prep_pipe.ready && n >= 2 * c->sm_count) {      // auxiliary lanes of the preprocessing pipeline (big batches only)
     EaPrepPipe& P = c->prep_pipe;
-    for (int k = 0; k < 2; ++k) {
-      CU(cudaStreamCreateWithFlags(&P.aux[k], cudaStreamNonBlocking));
+    for (int k = 0; k < EA_PREP_MAX_PARTS; ++k) {
+      // (highest priority: the long-lived one-warp chamfer CTAs take the slots the short edge CTAs free, instead of queueing behind them)
+      int pr_lo = 0, pr_hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+      static const int env_prio = getenv("EA_PREP_PRIO") ? atoi(getenv("EA_PREP_PRIO")) : 1;
+      CU(cudaStreamCreateWithPriority(&P.aux[k], cudaStreamNonBlocking, env_prio ? pr_hi : pr_lo));
       CU(cudaEventCreateWithFlags(&P.ev_front[k], cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&P.ev_dt[k], cudaEventDisableTiming));
     }

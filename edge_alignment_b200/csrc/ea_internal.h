@@ -86,11 +86,12 @@ struct EaPrepArgs {
   EaScratch scratch;
 };
 // enqueue the whole preprocessing pipeline for n frames; returns number of kernel launches via *launches
-// Optional second lane for big batches: the distance transforms (DRAM / latency-bound, few warps) of one half of the frames run on
-// an auxiliary stream beside the edge kernels (issue-bound) of the other half.  Streams and events belong to the context.
+// Optional second lane for big batches: the distance transforms (DRAM / latency-bound, few warps) of one part of the frames run on
+// an auxiliary stream beside the edge kernels (issue-bound) of the next part.  Streams and events belong to the context.
+#define EA_PREP_MAX_PARTS 4
 struct EaPrepPipe {
-  cudaStream_t aux[2] = {nullptr, nullptr};
-  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_dt[2] = {nullptr, nullptr};
+  cudaStream_t aux[EA_PREP_MAX_PARTS] = {};
+  cudaEvent_t ev_front[EA_PREP_MAX_PARTS] = {}, ev_dt[EA_PREP_MAX_PARTS] = {};
   bool ready = false;
 };
 cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t stream, int* launches, const EaPrepPipe* pipe = nullptr);

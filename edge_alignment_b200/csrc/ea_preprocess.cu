@@ -969,17 +969,19 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
     e = launch_front(A, stream, nl);
     if (e == cudaSuccess && want_now) e = launch_dt(A, stream, nl);
   } else {
-    const int n0 = A.n / 2;
-    const EaPrepArgs H[2] = {prep_slice(A, 0, n0), prep_slice(A, n0, A.n - n0)};
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-      e = launch_front(H[k], stream, nl);
+    static const int env_parts = getenv("EA_PREP_PARTS") ? atoi(getenv("EA_PREP_PARTS")) : 2;
+    const int K = env_parts < 2 ? 2 : env_parts > EA_PREP_MAX_PARTS ? EA_PREP_MAX_PARTS : env_parts;
+    for (int k = 0; k < K && e == cudaSuccess; ++k) {
+      const int f0 = int((long long)A.n * k / K), f1 = int((long long)A.n * (k + 1) / K);
+      const EaPrepArgs H = prep_slice(A, f0, f1 - f0);
+      e = launch_front(H, stream, nl);
       if (e != cudaSuccess) break;
       e = cudaEventRecord(pipe->ev_front[k], stream);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(pipe->aux[k], pipe->ev_front[k], 0);
-      if (e == cudaSuccess) e = launch_dt(H[k], pipe->aux[k], nl);
+      if (e == cudaSuccess) e = launch_dt(H, pipe->aux[k], nl);
       if (e == cudaSuccess) e = cudaEventRecord(pipe->ev_dt[k], pipe->aux[k]);
     }
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamWaitEvent(stream, pipe->ev_dt[k], 0);   // join
+    for (int k = 0; k < K && e == cudaSuccess; ++k) e = cudaStreamWaitEvent(stream, pipe->ev_dt[k], 0);   // join
   }
   (void)sm_count;
   if (launches) *launches = nl;
