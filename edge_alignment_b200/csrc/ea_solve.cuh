@@ -522,7 +522,9 @@ __device__ __forceinline__ uint2 ea_lds_u2(const unsigned saddr) {
   return v;
 }
 
-#define EA_STAGE_SLOT 512   // points per staging slot (uint2 stage[2][EA_STAGE_SLOT], 8 KB, aligned to 8 KB)
+#ifndef EA_STAGE_SLOT
+#define EA_STAGE_SLOT 512   // points per staging slot (uint2 stage[2][EA_STAGE_SLOT], 8 KB, aligned to 8 KB); a power of two >= the CTA size
+#endif
 // ---- slice evaluation shared by every solve kernel ----------------------------------------------------------
 #ifndef EA_FLUSH_EVERY
 #define EA_FLUSH_EVERY 16  // points per thread between fp32 -> fp64 flushes of the normal-equation slots (measured: 8 -> 16 = -1.7 %)
