@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -722,6 +723,15 @@ int ea_solve_batch_device_ordered(ea_context* c, int n, ea_frameset* ref, const 
     cudaStreamSynchronize(c->stream);
     cudaMemcpy(h.data(), c->d_debug, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     for (int k = 0; k < 6; ++k) { double sum = 0; for (int b = 0; b < grid; ++b) sum += double(h[size_t(b) * 6 + k]); c->debug_sum[k] += sum / grid; }
+    {   // owner-lifetime distribution of this launch (the launch ends with the last owner): mean / 75th / 90th percentile / max
+      std::vector<double> life(static_cast<size_t>(grid));
+      double mean = 0.0;
+      for (int b = 0; b < grid; ++b) { life[size_t(b)] = double(h[size_t(b) * 6 + 5]); mean += life[size_t(b)] / grid; }
+      std::sort(life.begin(), life.end());
+      if (c->debug_launches % 7 == 3)
+        fprintf(stderr, "[EA_SOLVE_DEBUG] launch %ld: owner lifetimes (kcycles) mean %.0f  p50 %.0f  p75 %.0f  p90 %.0f  p97 %.0f  max %.0f\n", c->debug_launches,
+                mean / 1e3, life[size_t(grid / 2)] / 1e3, life[size_t(grid * 3 / 4)] / 1e3, life[size_t(grid * 9 / 10)] / 1e3, life[size_t(grid * 97 / 100)] / 1e3, life[size_t(grid - 1)] / 1e3);
+    }
     c->debug_launches++;
   }
   c->launches++;
