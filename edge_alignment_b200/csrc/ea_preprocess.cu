@@ -971,6 +971,7 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
   } else {
     static const int env_parts = getenv("EA_PREP_PARTS") ? atoi(getenv("EA_PREP_PARTS")) : 2;
     const int K = env_parts < 2 ? 2 : env_parts > EA_PREP_MAX_PARTS ? EA_PREP_MAX_PARTS : env_parts;
+    int forked = 0;                                       // parts whose distance transforms are on their lane
     for (int k = 0; k < K && e == cudaSuccess; ++k) {
       const int f0 = int((long long)A.n * k / K), f1 = int((long long)A.n * (k + 1) / K);
       const EaPrepArgs H = prep_slice(A, f0, f1 - f0);
@@ -978,10 +979,16 @@ cudaError_t ea_launch_preprocess(const EaPrepArgs& A, int sm_count, cudaStream_t
       if (e != cudaSuccess) break;
       e = cudaEventRecord(pipe->ev_front[k], stream);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(pipe->aux[k], pipe->ev_front[k], 0);
-      if (e == cudaSuccess) e = launch_dt(H, pipe->aux[k], nl);
-      if (e == cudaSuccess) e = cudaEventRecord(pipe->ev_dt[k], pipe->aux[k]);
+      if (e != cudaSuccess) break;
+      forked = k + 1;
+      e = launch_dt(H, pipe->aux[k], nl);
     }
-    for (int k = 0; k < K && e == cudaSuccess; ++k) e = cudaStreamWaitEvent(stream, pipe->ev_dt[k], 0);   // join
+    // join, also after an error: whatever reached a lane is ordered before the caller's next work on `stream`
+    for (int k = 0; k < forked; ++k) {
+      cudaError_t je = cudaEventRecord(pipe->ev_dt[k], pipe->aux[k]);
+      if (je == cudaSuccess) je = cudaStreamWaitEvent(stream, pipe->ev_dt[k], 0);
+      if (e == cudaSuccess) e = je;
+    }
   }
   (void)sm_count;
   if (launches) *launches = nl;
