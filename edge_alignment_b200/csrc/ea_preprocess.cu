@@ -156,7 +156,8 @@ template <typename D, int TW, bool REF>
 __global__ void __launch_bounds__(TW) k_edge_mask2(const uint8_t* __restrict__ bgr, const D* __restrict__ depth,
                                                       size_t frame_stride_px, const int32_t* __restrict__ src_slots,
                                                       const int32_t* __restrict__ dst_slots, uint32_t* __restrict__ edge_bits,
-                                                      uint32_t* __restrict__ ref_bits, int w, int h, int words, int thresh, int zero_to_one) {
+                                                      uint32_t* __restrict__ ref_bits, int w, int h, int words, int thresh, int zero_to_one,
+                                                      uint8_t* __restrict__ pyr_bgr, D* __restrict__ pyr_depth) {
   constexpr int PW = TW + 8;   // packed tile: image columns x0-4 .. x0+TW+3
   constexpr int GW = TW + 4;   // gray tile: columns x0-1 .. x0+TW (+2 pad)
   constexpr int NG = PW / 4;   // 4-pixel groups per tile row
@@ -194,6 +195,39 @@ __global__ void __launch_bounds__(TW) k_edge_mask2(const uint8_t* __restrict__ b
     }
   }
   __syncthreads();
+  // ---- next pyramid level from the staged tile (pyr_bgr != null): cv::resize(0.5) INTER_LINEAR == 2x2 mean, (a+b+c+d+2) >> 2 per
+  //      channel, four output pixels (12 bytes) per item; INTER_NEAREST on depth (key frames).  Saves a pass over the frame. ----
+  if (pyr_bgr) {
+    const int dw = w >> 1, dh = h >> 1;
+    const size_t dbase = size_t(dst_slots[f]) * size_t(dw) * dh;
+    for (int i = t; i < (TW / 8) * (E2_TH / 2); i += TW) {
+      const int yl = i / (TW / 8), xq = i % (TW / 8);
+      const int oy = (y0 >> 1) + yl, ox = (x0 >> 1) + 4 * xq;
+      if (oy >= dh || ox + 3 >= dw) continue;
+      const uint4 a0 = *reinterpret_cast<const uint4*>(&tile[2 * yl + 2][8 * xq + 4]), a1 = *reinterpret_cast<const uint4*>(&tile[2 * yl + 2][8 * xq + 8]);
+      const uint4 b0 = *reinterpret_cast<const uint4*>(&tile[2 * yl + 3][8 * xq + 4]), b1 = *reinterpret_cast<const uint4*>(&tile[2 * yl + 3][8 * xq + 8]);
+      const unsigned top[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bot[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      unsigned px[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        unsigned bg0, r0, bg1, r1, bg2, r2, bg3, r3;
+        e2_expand(top[2 * j], bg0, r0); e2_expand(top[2 * j + 1], bg1, r1);
+        e2_expand(bot[2 * j], bg2, r2); e2_expand(bot[2 * j + 1], bg3, r3);
+        const unsigned sbg = ((bg0 + bg1 + bg2 + bg3 + 0x00020002u) >> 2) & 0x00FF00FFu;     // {B, G} means in 16-bit lanes
+        const unsigned sr = (r0 + r1 + r2 + r3 + 2u) >> 2;
+        px[j] = __byte_perm(sbg, sr, 0x4420);                                                // B | G << 8 | R << 16
+      }
+      unsigned* d = reinterpret_cast<unsigned*>(pyr_bgr + (dbase + size_t(oy) * dw + ox) * 3);
+      d[0] = __byte_perm(px[0], px[1], 0x4210);
+      d[1] = __byte_perm(px[1], px[2], 0x5421);
+      d[2] = __byte_perm(px[2], px[3], 0x6542);
+      if (REF && pyr_depth) {
+        const D* sd = depth + sbase + size_t(2 * oy) * w + 2 * ox;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pyr_depth[dbase + size_t(oy) * dw + ox + j] = sd[2 * j];
+      }
+    }
+  }
   // ---- phase 2: per-column rolling 3x3 blur + gray ----
   const int gx = x0 + t;
   if (gx < w) {
@@ -837,6 +871,15 @@ __global__ void __launch_bounds__(256) k_unpack_mask(const uint32_t* __restrict_
 
 }  // namespace
 
+// can level l's Laplacian edge kernel (k_edge_mask2) also emit level l + 1's BGR / depth from its staged tile?
+static bool edge_kernel_fuses_pyramid(const EaPrepArgs& A, int l) {
+  if (l + 1 >= A.n_levels || A.edge_detector != EA_EDGE_LAPLACIAN) return false;
+  const EaPrepLevel& L = A.lv[l];
+  const EaPrepLevel& N = A.lv[l + 1];
+  static const int env_fuse = getenv("EA_PYR_FUSE") ? atoi(getenv("EA_PYR_FUSE")) : 1;
+  return env_fuse && (L.w & 3) == 0 && L.w >= 8 && L.h >= 4 && (N.w & 3) == 0 && (reinterpret_cast<uintptr_t>(N.bgr) & 3) == 0;
+}
+
 template <typename D>
 static cudaError_t launch_edges_and_points(const EaPrepArgs& A, cudaStream_t stream, int& nl) {
   const bool want_ref = (A.roles & EA_ROLE_REF) != 0;
@@ -845,7 +888,7 @@ static cudaError_t launch_edges_and_points(const EaPrepArgs& A, cudaStream_t str
   for (int l = 0; l < A.n_levels; ++l) {
     const EaPrepLevel& L = A.lv[l];
     const size_t pxl = size_t(L.w) * L.h;
-    if (l > 0) {
+    if (l > 0 && !edge_kernel_fuses_pyramid(A, l - 1)) {      // (otherwise level l - 1's edge kernel has already written this level)
       const EaPrepLevel& S = A.lv[l - 1];
       const uint8_t* sb = (l == 1) ? A.in_bgr : S.bgr;
       const D* sd = want_ref ? ((l == 1) ? in_depth : static_cast<const D*>(S.depth)) : nullptr;
@@ -869,14 +912,17 @@ static cudaError_t launch_edges_and_points(const EaPrepArgs& A, cudaStream_t str
       nl += k - 1;
       if (ce != cudaSuccess) return ce;
     } else if ((L.w & 3) == 0 && L.w >= 8 && L.h >= 4) {
+      const bool fuse = edge_kernel_fuses_pyramid(A, l);
+      uint8_t* nb = fuse ? A.lv[l + 1].bgr : nullptr;
+      D* nd = (fuse && want_ref) ? static_cast<D*>(A.lv[l + 1].depth) : nullptr;
       if ((L.w % 128) != 0 && (L.w % 128) <= 64) {   // the last 128-wide tile would be at most half full: 64-wide tiles
         dim3 grid(unsigned((L.w + 63) / 64), unsigned((L.h + E2_TH - 1) / E2_TH), unsigned(A.n));
-        if (want_ref) k_edge_mask2<D, 64, true><<<grid, 64, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, L.ref_bits, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
-        else k_edge_mask2<D, 64, false><<<grid, 64, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
+        if (want_ref) k_edge_mask2<D, 64, true><<<grid, 64, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, L.ref_bits, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one, nb, nd);
+        else k_edge_mask2<D, 64, false><<<grid, 64, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one, nb, nd);
       } else {
         dim3 grid(unsigned((L.w + E2_TW - 1) / E2_TW), unsigned((L.h + E2_TH - 1) / E2_TH), unsigned(A.n));
-        if (want_ref) k_edge_mask2<D, E2_TW, true><<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, L.ref_bits, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
-        else k_edge_mask2<D, E2_TW, false><<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one);
+        if (want_ref) k_edge_mask2<D, E2_TW, true><<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, L.ref_bits, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one, nb, nd);
+        else k_edge_mask2<D, E2_TW, false><<<grid, E2_TW, 0, stream>>>(b, d, pxl, ss, A.slots, L.edge_bits, nullptr, L.w, L.h, L.words, A.grad_threshold, A.zero_to_one, nb, nd);
       }
     } else {   // generic byte path (any width)
       dim3 grid(unsigned((L.w + ET_W - 1) / ET_W), unsigned((L.h + ET_H - 1) / ET_H), unsigned(A.n));
