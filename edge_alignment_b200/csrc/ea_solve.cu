@@ -592,6 +592,9 @@ cudaError_t ea_launch_eval_sums(const EaLevelDesc& rd, const EaLevelDesc& nd, co
   return cudaGetLastError();
 }
 
+#ifndef EA_ORDER_FIXED_COST
+#define EA_ORDER_FIXED_COST 8000   // measured: 0 -> 6000 -> 12000 gives 7.41 -> 7.35 -> 7.34 ms per 1184-pair launch
+#endif
 // ---- longest-first ordering for the next launch: sort pairs by the work their last solve needed -----------------
 // One CTA, bitonic sort of (work, index) in shared memory; n <= 4096.
 __global__ void __launch_bounds__(1024) ea_k_order_by_work(const ea_summary* __restrict__ summaries, int n, int n_levels, int32_t* __restrict__ order) {
@@ -604,7 +607,8 @@ __global__ void __launch_bounds__(1024) ea_k_order_by_work(const ea_summary* __r
       unsigned long long work = 0;
       for (int l = 0; l < n_levels; ++l) {
         const ea_summary s = summaries[size_t(i) * n_levels + l];
-        work += (unsigned long long)(s.n_residuals > 0 ? s.n_residuals : 0) * (unsigned long long)(s.evaluations > 0 ? s.evaluations : 0);
+        // evaluations x (points + the serial section between two evaluations in point-equivalents)
+        work += (unsigned long long)((s.n_residuals > 0 ? s.n_residuals : 0) + EA_ORDER_FIXED_COST) * (unsigned long long)(s.evaluations > 0 ? s.evaluations : 0);
       }
       if (work > 0xFFFFFFFFFFFull) work = 0xFFFFFFFFFFFull;
       k = (work << 20) | (unsigned long long)(0xFFFFF - i);       // descending work, ascending index on ties
