@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(32) k_shard_lm(ShardState* st, const double* s
 #define EA_SHARD_MAX_WORLD 8
 #define EA_SHARD_SPIN_LIMIT (1ll << 22)   // ~3 s of polling
 struct ShardXchg {                                  // lives in cudaIpc-shared device memory, one per rank
-  double data[2][EA_SHARD_MAX_WORLD][32];           // [evaluation parity][source rank][29 sums]
-  unsigned long long flag[2][EA_SHARD_MAX_WORLD];   // epoch of the evaluation whose data the slot holds
+  // Self-validating 8-byte packets {32 data bits, 32-bit epoch tag}, two per double (the "LL" idea of NCCL): a packet is one
+  // store and one load, so there is no flag to order behind the data -- no system-scope fence, no second NVLink round trip.
+  unsigned long long ll[2][EA_SHARD_MAX_WORLD][64]; // [evaluation parity][source rank][2 x 32 sums]
 };
 struct ShardPeers { ShardXchg* p[EA_SHARD_MAX_WORLD]; };
 struct ShardCtl {                                   // per-rank control block (device memory)
@@ -276,21 +277,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
       if (world > 1) {
         const int par = int(e & 1);
         const unsigned long long epoch = epoch0 + e;
-        for (int r = 0; r < world; ++r) peers.p[r]->data[par][rank][lane] = tot;       // 32 lanes x 8 B = one 256 B burst per peer
-        __threadfence_system();
-        __syncwarp();
-        if (lane < world) st_release_sys(&peers.p[lane]->flag[par][rank], epoch);
-        if (lane < world) {
+        // every lane ships its own sum to every rank (own one included) as two packets, then polls the world's packets for its slot
+        const unsigned tag = unsigned(epoch);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(tot);
+        const unsigned long long p_lo = (bits & 0xffffffffull) | ((unsigned long long)tag << 32);
+        const unsigned long long p_hi = (bits >> 32) | ((unsigned long long)tag << 32);
+        for (int r = 0; r < world; ++r) {
+          volatile unsigned long long* dst = &peers.p[r]->ll[par][rank][2 * lane];
+          dst[0] = p_lo; dst[1] = p_hi;                   // 32 lanes x 16 B = one 512 B burst per peer
+        }
+        double g = 0.0;
+        for (int r = 0; r < world; ++r) {                 // rank order: identical sums everywhere
+          const volatile unsigned long long* src = &peers.p[rank]->ll[par][r][2 * lane];
+          unsigned long long a = src[0], b = src[1];
           long long spins = 0;
-          while (ld_acquire_sys(&peers.p[rank]->flag[par][lane]) != epoch) {
+          while (unsigned(a >> 32) != tag || unsigned(b >> 32) != tag) {
             if (++spins > EA_SHARD_SPIN_LIMIT) { err = 1; break; }
+            a = src[0]; b = src[1];
           }
+          g += __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
         }
         err = __any_sync(0xffffffffu, err);
-        __syncwarp();
-        __threadfence_system();
-        double g = 0.0;
-        for (int r = 0; r < world; ++r) g += *reinterpret_cast<volatile double*>(&peers.p[rank]->data[par][r][lane]);   // rank order: identical everywhere
         tot = g;
       }
       long long t3 = clock64();
