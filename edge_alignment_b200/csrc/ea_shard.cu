@@ -206,9 +206,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
   __shared__ double part[THREADS / 32][EA_NSUM];
   __shared__ double cpart[THREADS / 32];
   __shared__ double wsum[THREADS / 32][32];
-  __shared__ unsigned long long s_ticket;
-  __shared__ int s_stop;
-  __shared__ EaLmState s_lm;      // the LM state of the CTA that drew the last ticket (global memory between evaluations)
+  __shared__ int s_stop, s_late;
+  __shared__ EaLmState s_lm;      // CTA 0 only: the LM state stays in its shared memory for the whole solve
   __shared__ __align__(2 * EA_STAGE_SLOT * 8) uint2 stage[2][EA_STAGE_SLOT];   // cp.async staging of the point stream (ea_eval_slice: aligned to its size)
   static_assert(sizeof(EaLmState) % 8 == 0, "EaLmState is copied as 8-byte words");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -217,6 +216,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
   const float2 affine = *nd.dt_affine;
   const float* dt_pad = nd.dt - ea_dt_origin_offset(nd.w);
   const bool xyz = rd.pts_mode == EA_POINTS_XYZ;
+  if (blockIdx.x == 0 && warp == 0) {   // the reducer CTA keeps the LM state (initialised by k_shard_ctl_init)
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&ctl->lm);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_lm);
+    for (int i = lane; i < int(sizeof(EaLmState) / 8); i += 32) dst[i] = __ldcg(src + i);
+  }
   for (unsigned long long e = 1;; ++e) {
     // ---- wait for the release of evaluation e (e == 1 is released by the host-side initialisation) ----
     if (tid == 0) {
@@ -252,13 +256,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
       __threadfence();
       __syncwarp();
       if (lane == 0) {
-        if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->prof[0]), (unsigned long long)(clock64() - t0));
-        s_ticket = atomicAdd(&ctl->ticket, 1ull);
+        if (blockIdx.x != 0) atomicAdd(&ctl->ticket, 1ull);      // delivered; nothing to wait for: on to the next release
+        else {
+          ctl->prof[0] += clock64() - t0;
+          // CTA 0 is the reducer of every evaluation: it waits for the other CTAs' tickets (monotonic over the solve)
+          const unsigned long long want = e * (unsigned long long)(gridDim.x - 1);
+          long long spins = 0;
+          int late = 0;
+          while (ld_acquire_gpu(&ctl->ticket) < want) { if (++spins > EA_SHARD_SPIN_LIMIT) { late = 1; break; } }
+          s_late = late;
+        }
       }
     }
+    if (blockIdx.x != 0) continue;
     __syncthreads();
-    if (s_ticket != e * gridDim.x - 1) continue;          // not the last CTA of this evaluation: wait for the next release
-    // ---- last CTA: grid reduce (fixed order: warp w adds CTAs w, w + W, ...; then the warps in order) ----
+    // ---- CTA 0: grid reduce (fixed order: warp w adds CTAs w, w + W, ...; then the warps in order) ----
     __threadfence();
     long long t1 = clock64();
     {
@@ -302,13 +314,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
       }
       long long t3 = clock64();
       wsum[0][lane] = tot;
-      {   // LM state: global -> shared (the state machine touches it a few hundred times)
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&ctl->lm);
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_lm);
-        for (int i = lane; i < int(sizeof(EaLmState) / 8); i += 32) dst[i] = __ldcg(src + i);
-      }
       __syncwarp();
       int done = 0;
+      if (s_late) err = 1;            // a CTA of this grid never delivered
       if (err) { if (lane == 0) { s_lm.term = EA_TERM_FAILURE_PEER; ctl->error = 1; } done = 1; }
       else {
         double cand[7];
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_shard_solve(EaLevelDesc rd, EaLe
         } else done = 1;
       }
       __syncwarp();
-      {
+      if (done) {   // the host reads the final state from global memory
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_lm);
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(&ctl->lm);
         for (int i = lane; i < int(sizeof(EaLmState) / 8); i += 32) __stcg(dst + i, src[i]);
