@@ -153,15 +153,17 @@ __global__ void __launch_bounds__(32) k_shard_lm(ShardState* st, const double* s
 // launch and no NCCL call per LM evaluation.
 //
 //   every CTA      evaluates its slice of this rank's point range (ea_eval_slice, the production loop) -> 29 CTA totals
-//   grid reduce    totals to global memory, one atomic ticket per CTA; the CTA that draws the last ticket adds the
-//                  per-CTA totals in a fixed order (bitwise reproducible)
-//   all-reduce     that CTA stores the rank's 29 doubles straight into every peer's exchange buffer over NVLink (peer-mapped
-//                  cudaIpc memory), fences, raises a per-source epoch flag there, waits for the world's flags in its own
-//                  buffer and adds the world's contributions in rank order: every rank obtains bit-identical sums, so all
-//                  ranks take identical LM decisions with no broadcast.  Data slots are double-buffered by evaluation parity
+//   grid reduce    totals to global memory, one atomic ticket per CTA; CTA 0 -- the reducer of every evaluation -- waits for the
+//                  tickets and adds the per-CTA totals in a fixed order (bitwise reproducible)
+//   all-reduce     CTA 0 stores the rank's sums straight into every peer's exchange buffer over NVLink (peer-mapped cudaIpc
+//                  memory) as self-validating 8-byte packets {32 data bits, 32-bit epoch tag}, two per double: one store and
+//                  one load per packet, no system-scope fence, no flag to order behind the data.  It then polls the world's
+//                  packets in its own buffer and adds the contributions in rank order: every rank obtains bit-identical sums,
+//                  so all ranks take identical LM decisions with no broadcast.  Slots are double-buffered by evaluation parity
 //                  (a rank can be at most one evaluation ahead of a peer).
-//   LM             one thread advances the Ceres-equivalent trust-region state machine (ea_lm_advance), publishes the next
-//                  candidate pose and releases the grid through an epoch word the other CTAs poll
+//   LM             CTA 0's first warp advances the Ceres-equivalent trust-region state machine on the state it keeps in shared
+//                  memory (ea_lm_advance_warp), publishes the next candidate pose and releases the grid through an epoch word
+//                  the other CTAs poll
 // Every wait is bounded (EA_SHARD_SPIN_LIMIT polls): a lost peer ends the solve with EA_TERM_FAILURE_PEER instead of hanging
 // the GPU.
 #define EA_SHARD_MAX_WORLD 8
